@@ -1,0 +1,326 @@
+/*
+ * pll.h - public API of the B200-native phylogenetic-likelihood library.
+ *
+ * This header is a fresh, ABI-compatible re-declaration of the part of the reference's public
+ * interface (reference src/pll.h) that lies on the likelihood hot path.  Constants, struct field
+ * order/types and prototypes are kept so that an existing caller recompiles against it unchanged:
+ *
+ *   sizeof(pll_partition_t) == 216 and sizeof(pll_operation_t) == 32 on x86-64
+ *   (reference src/pll.h:202-244 and :249-259).
+ *
+ * The only new surface is PLL_ATTRIB_ARCH_GPU (next to the PLL_ATTRIB_ARCH_* flags of reference
+ * src/pll.h:106-111) and the optional pll_gpu_* extension calls declared in pll_gpu.h.
+ *
+ * This build implements the GPU architecture ONLY: there is no CPU fallback.  A partition
+ * created without PLL_ATTRIB_ARCH_GPU, or on a machine without a usable CUDA device, fails with
+ * pll_errno set.
+ */
+#ifndef PLL_B200_PLL_H_
+#define PLL_B200_PLL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLL_EXPORT __attribute__((visibility("default")))
+
+/* ---- return codes (reference src/pll.h:75-79) ---- */
+#define PLL_FAILURE 0
+#define PLL_SUCCESS 1
+#define PLL_FALSE 0
+#define PLL_TRUE 1
+
+/* ---- alignment of host-side arrays (reference src/pll.h:81-83) ---- */
+#define PLL_ALIGNMENT_CPU 8
+#define PLL_ALIGNMENT_SSE 16
+#define PLL_ALIGNMENT_AVX 32
+#define PLL_ALIGNMENT_GPU 32 /* host mirrors; device arrays are 256-byte aligned */
+
+#define PLL_ASCII_SIZE 256
+
+/* ---- numerical scaling (reference src/pll.h:89-97): 2^256 and friends, all exact ---- */
+#define PLL_SCALE_FACTOR 0x1p+256
+#define PLL_SCALE_THRESHOLD 0x1p-256
+#define PLL_SCALE_FACTOR_SQRT 0x1p+128
+#define PLL_SCALE_THRESHOLD_SQRT 0x1p-128
+#define PLL_SCALE_BUFFER_NONE (-1)
+#define PLL_SCALE_RATE_MAXDIFF 4
+
+#define PLL_MISC_EPSILON 1e-8
+#define PLL_ONE_EPSILON 1e-15
+#define PLL_ONE_MIN (1 - PLL_ONE_EPSILON)
+#define PLL_ONE_MAX (1 + PLL_ONE_EPSILON)
+
+/* ---- attribute flags (reference src/pll.h:106-122) ---- */
+#define PLL_ATTRIB_ARCH_CPU 0
+#define PLL_ATTRIB_ARCH_SSE (1 << 0)
+#define PLL_ATTRIB_ARCH_AVX (1 << 1)
+#define PLL_ATTRIB_ARCH_AVX2 (1 << 2)
+#define PLL_ATTRIB_ARCH_AVX512 (1 << 3)
+#define PLL_ATTRIB_ARCH_MASK 0xF
+
+#define PLL_ATTRIB_PATTERN_TIP (1 << 4)
+
+#define PLL_ATTRIB_AB_LEWIS (1 << 5)
+#define PLL_ATTRIB_AB_FELSENSTEIN (2 << 5)
+#define PLL_ATTRIB_AB_STAMATAKIS (3 << 5)
+#define PLL_ATTRIB_AB_MASK (7 << 5)
+#define PLL_ATTRIB_AB_FLAG (1 << 8)
+
+#define PLL_ATTRIB_RATE_SCALERS (1 << 9)
+
+/* NEW: the B200 backend.  Lies outside PLL_ATTRIB_ARCH_MASK so the reference's popcount check
+ * on the SIMD bits (reference src/pll.c:413-418) is unaffected; combining it with any SIMD
+ * bit is rejected explicitly. */
+#define PLL_ATTRIB_ARCH_GPU (1 << 10)
+
+/* ---- error codes (reference src/pll.h:137-167); >= 131 are new (CUDA layer) ---- */
+#define PLL_ERROR_FILE_OPEN 100
+#define PLL_ERROR_FILE_SEEK 101
+#define PLL_ERROR_FILE_EOF 102
+#define PLL_ERROR_FASTA_ILLEGALCHAR 103
+#define PLL_ERROR_FASTA_UNPRINTABLECHAR 104
+#define PLL_ERROR_FASTA_INVALIDHEADER 105
+#define PLL_ERROR_PHYLIP_SYNTAX 106
+#define PLL_ERROR_PHYLIP_LONGSEQ 107
+#define PLL_ERROR_PHYLIP_NONALIGNED 108
+#define PLL_ERROR_PHYLIP_ILLEGALCHAR 109
+#define PLL_ERROR_PHYLIP_UNPRINTABLECHAR 110
+#define PLL_ERROR_NEWICK_SYNTAX 111
+#define PLL_ERROR_MEM_ALLOC 112
+#define PLL_ERROR_PARAM_INVALID 113
+#define PLL_ERROR_TIPDATA_ILLEGALSTATE 114
+#define PLL_ERROR_TIPDATA_ILLEGALFUNCTION 115
+#define PLL_ERROR_TREE_CONVERSION 116
+#define PLL_ERROR_INVAR_INCOMPAT 117
+#define PLL_ERROR_INVAR_PROPORTION 118
+#define PLL_ERROR_INVAR_PARAMINDEX 119
+#define PLL_ERROR_INVAR_NONEFOUND 120
+#define PLL_ERROR_AB_INVALIDMETHOD 121
+#define PLL_ERROR_AB_NOSUPPORT 122
+#define PLL_ERROR_EINVAL 130
+#define PLL_ERROR_GPU_NODEVICE 131   /* no usable CUDA device / wrong architecture */
+#define PLL_ERROR_GPU_RUNTIME 132    /* a CUDA runtime call or kernel launch failed */
+#define PLL_ERROR_GPU_UNSUPPORTED 133 /* feature not implemented by the GPU backend */
+
+#define PLL_GAMMA_RATES_MEAN 0
+#define PLL_GAMMA_RATES_MEDIAN 1
+
+#define PLL_TREE_TRAVERSE_POSTORDER 1
+#define PLL_TREE_TRAVERSE_PREORDER 2
+
+/* ---- the partition (field order and types: reference src/pll.h:202-244) ----
+ *
+ * Under PLL_ATTRIB_ARCH_GPU the big arrays live in HBM for the partition's lifetime:
+ *   clv[i], scale_buffer[i], tipchars[i]   are NULL until pll_gpu_sync_clv / _scaler /
+ *                                          _tipchars downloads a host mirror (pll_gpu.h);
+ *   pmatrix[i]                             host mirror, refreshed by pll_gpu_sync_pmatrix;
+ *   rates, rate_weights, subst_params, frequencies, prop_invar, eigen*, pattern_weights,
+ *   invariant, charmap, tipmap             are ordinary, always-valid host arrays.
+ */
+typedef struct pll_partition
+{
+  unsigned int tips;
+  unsigned int clv_buffers;
+  unsigned int states;
+  unsigned int sites;
+  unsigned int pattern_weight_sum;
+  unsigned int rate_matrices;
+  unsigned int prob_matrices;
+  unsigned int rate_cats;
+  unsigned int scale_buffers;
+  unsigned int attributes;
+
+  size_t alignment;
+  unsigned int states_padded;
+
+  double ** clv;
+  double ** pmatrix;
+  double * rates;
+  double * rate_weights;
+  double ** subst_params;
+  unsigned int ** scale_buffer;
+  double ** frequencies;
+  double * prop_invar;
+  int * invariant;
+  unsigned int * pattern_weights;
+
+  int * eigen_decomp_valid;
+  double ** eigenvecs;
+  double ** inv_eigenvecs;
+  double ** eigenvals;
+
+  unsigned int maxstates;
+  unsigned char ** tipchars;
+  unsigned char * charmap;
+  double * ttlookup;
+  unsigned int * tipmap;
+
+  int asc_bias_alloc;
+} pll_partition_t;
+
+/* ---- one CLV update (reference src/pll.h:249-259) ---- */
+typedef struct pll_operation
+{
+  unsigned int parent_clv_index;
+  int parent_scaler_index;
+  unsigned int child1_clv_index;
+  unsigned int child1_matrix_index;
+  int child1_scaler_index;
+  unsigned int child2_clv_index;
+  unsigned int child2_matrix_index;
+  int child2_scaler_index;
+} pll_operation_t;
+
+/* ---- thread-local error channel (reference src/pll.h:470-471, src/pll.c:24-25) ---- */
+PLL_EXPORT extern __thread int pll_errno;
+PLL_EXPORT extern __thread char pll_errmsg[200];
+
+/* ---- character -> state-mask maps (reference src/maps.c:26-110) ---- */
+PLL_EXPORT extern const unsigned int pll_map_bin[256];
+PLL_EXPORT extern const unsigned int pll_map_nt[256];
+PLL_EXPORT extern const unsigned int pll_map_aa[256];
+
+/* ---- empirical amino-acid models used by the BASELINE configs (reference src/maps.c) ---- */
+PLL_EXPORT extern const double pll_aa_rates_lg[190];
+PLL_EXPORT extern const double pll_aa_freqs_lg[20];
+PLL_EXPORT extern const double pll_aa_rates_lg4m[4][190];
+PLL_EXPORT extern const double pll_aa_freqs_lg4m[4][20];
+PLL_EXPORT extern const double pll_aa_rates_lg4x[4][190];
+PLL_EXPORT extern const double pll_aa_freqs_lg4x[4][20];
+
+/* ---- partition lifecycle and tip data (reference src/pll.c:399-1059) ---- */
+PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips,
+                                                  unsigned int clv_buffers,
+                                                  unsigned int states,
+                                                  unsigned int sites,
+                                                  unsigned int rate_matrices,
+                                                  unsigned int prob_matrices,
+                                                  unsigned int rate_cats,
+                                                  unsigned int scale_buffers,
+                                                  unsigned int attributes);
+
+PLL_EXPORT void pll_partition_destroy(pll_partition_t * partition);
+
+PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition,
+                                  unsigned int tip_index,
+                                  const unsigned int * map,
+                                  const char * sequence);
+
+PLL_EXPORT int pll_set_tip_clv(pll_partition_t * partition,
+                               unsigned int tip_index,
+                               const double * clv,
+                               int padding);
+
+PLL_EXPORT void pll_set_pattern_weights(pll_partition_t * partition,
+                                        const unsigned int * pattern_weights);
+
+PLL_EXPORT void * pll_aligned_alloc(size_t size, size_t alignment);
+PLL_EXPORT void pll_aligned_free(void * ptr);
+
+/* ---- model parameters (reference src/models.c:251-647) ---- */
+PLL_EXPORT void pll_set_subst_params(pll_partition_t * partition,
+                                     unsigned int params_index,
+                                     const double * params);
+
+PLL_EXPORT void pll_set_frequencies(pll_partition_t * partition,
+                                    unsigned int params_index,
+                                    const double * frequencies);
+
+PLL_EXPORT void pll_set_category_rates(pll_partition_t * partition,
+                                       const double * rates);
+
+PLL_EXPORT void pll_set_category_weights(pll_partition_t * partition,
+                                         const double * rate_weights);
+
+PLL_EXPORT int pll_update_eigen(pll_partition_t * partition,
+                                unsigned int params_index);
+
+PLL_EXPORT int pll_update_prob_matrices(pll_partition_t * partition,
+                                        const unsigned int * params_indices,
+                                        const unsigned int * matrix_indices,
+                                        const double * branch_lengths,
+                                        unsigned int count);
+
+PLL_EXPORT unsigned int pll_count_invariant_sites(pll_partition_t * partition,
+                                                  unsigned int * state_inv_count);
+
+PLL_EXPORT int pll_update_invariant_sites(pll_partition_t * partition);
+
+PLL_EXPORT int pll_update_invariant_sites_proportion(pll_partition_t * partition,
+                                                     unsigned int params_index,
+                                                     double prop_invar);
+
+/* ---- CLV updates (reference src/partials.c:177-213) ---- */
+PLL_EXPORT void pll_update_partials(pll_partition_t * partition,
+                                    const pll_operation_t * operations,
+                                    unsigned int count);
+
+/* ---- log-likelihood (reference src/likelihood.c:121-168, :478-513) ---- */
+PLL_EXPORT double pll_compute_root_loglikelihood(pll_partition_t * partition,
+                                                 unsigned int clv_index,
+                                                 int scaler_index,
+                                                 const unsigned int * freqs_indices,
+                                                 double * persite_lnl);
+
+PLL_EXPORT double pll_compute_edge_loglikelihood(pll_partition_t * partition,
+                                                 unsigned int parent_clv_index,
+                                                 int parent_scaler_index,
+                                                 unsigned int child_clv_index,
+                                                 int child_scaler_index,
+                                                 unsigned int matrix_index,
+                                                 const unsigned int * freqs_indices,
+                                                 double * persite_lnl);
+
+/* ---- branch-length derivatives (reference src/derivatives.c:164-312) ----
+ * `sumtable` is the caller's buffer exactly as in the reference (sites * rate_cats *
+ * states_padded doubles).  Under the GPU backend the table itself stays in HBM, keyed by
+ * this pointer; the host buffer is only written when PLL_GPU_SUMTABLE_HOSTCOPY=1 is set in
+ * the environment (see pll_gpu.h). */
+PLL_EXPORT int pll_update_sumtable(pll_partition_t * partition,
+                                   unsigned int parent_clv_index,
+                                   unsigned int child_clv_index,
+                                   int parent_scaler_index,
+                                   int child_scaler_index,
+                                   const unsigned int * params_indices,
+                                   double * sumtable);
+
+PLL_EXPORT int pll_compute_likelihood_derivatives(pll_partition_t * partition,
+                                                  int parent_scaler_index,
+                                                  int child_scaler_index,
+                                                  double branch_length,
+                                                  const unsigned int * params_indices,
+                                                  const double * sumtable,
+                                                  double * d_f,
+                                                  double * dd_f);
+
+/* ---- discrete Gamma rates (reference src/gamma.c:220-292) ---- */
+PLL_EXPORT int pll_compute_gamma_cats(double alpha,
+                                      unsigned int categories,
+                                      double * output_rates,
+                                      int rates_mode);
+
+/* ---- site-pattern compression (reference src/compress.c:138-286) ---- */
+PLL_EXPORT unsigned int * pll_compress_site_patterns(char ** sequence,
+                                                     const unsigned int * map,
+                                                     int count,
+                                                     int * length);
+
+/* ---- printing helpers (reference src/output.c:26-96); sync the needed mirrors first ---- */
+PLL_EXPORT void pll_show_pmatrix(const pll_partition_t * partition,
+                                 unsigned int index,
+                                 unsigned int float_precision);
+
+PLL_EXPORT void pll_show_clv(const pll_partition_t * partition,
+                             unsigned int clv_index,
+                             int scaler_index,
+                             unsigned int float_precision);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PLL_B200_PLL_H_ */

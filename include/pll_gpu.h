@@ -1,0 +1,241 @@
+/*
+ * pll_gpu.h - the drop-in boundary: a C-ABI over the sm_100a kernels.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) plg_*      the device layer.  Plain pointers and sizes, no C++/torch types.  Each
+ *                 function replaces one rung of the reference's `pll_core_*` dispatch ladders
+ *                 (the reference selects SSE/AVX/AVX2 kernels by `attrib` inside every
+ *                 pll_core_* function, e.g. reference src/core_partials.c:534-587); the
+ *                 reference interface each one stands in for is cited on the declaration.
+ *                 This is what a maintainer of the reference would bind.
+ *
+ *  (2) pll_gpu_*  optional extensions on a pll_partition_t created with PLL_ATTRIB_ARCH_GPU:
+ *                 device selection, host-mirror downloads, stream timing, launch statistics.
+ *
+ * State model: a plg_context_t owns, in HBM and for its whole lifetime, every CLV slot, scale
+ * buffer, tip-character row, P-matrix, the pattern weights and the invariant-site index; all
+ * work is enqueued on one CUDA stream per context.  void/setter calls may return after
+ * enqueue; value-returning calls synchronise.  All functions return PLG_OK (0) or a PLG_E_*
+ * code; plg_last_error() gives the thread-local message.
+ */
+#ifndef PLL_B200_PLL_GPU_H_
+#define PLL_B200_PLL_GPU_H_
+
+#include <stddef.h>
+#include "pll.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLG_OK 0
+#define PLG_E_NODEVICE 1    /* no CUDA device, or not compute capability 10.x */
+#define PLG_E_NOMEM 2       /* cudaMalloc / cudaHostAlloc failed */
+#define PLG_E_CUDA 3        /* any other CUDA runtime / launch failure */
+#define PLG_E_INVALID 4     /* bad argument */
+#define PLG_E_UNSUPPORTED 5 /* configuration not implemented on the device */
+
+typedef struct plg_context plg_context_t;
+
+/* Shape of a partition as the device layer sees it (mirrors the dimension fields of
+ * pll_partition_t, reference src/pll.h:204-217).  `sites` already includes the extra
+ * per-state columns when ascertainment-bias storage is requested. */
+typedef struct plg_dims
+{
+  unsigned int tips;
+  unsigned int clv_buffers;
+  unsigned int states;
+  unsigned int states_padded;
+  unsigned int sites;
+  unsigned int rate_cats;
+  unsigned int rate_matrices;
+  unsigned int prob_matrices;
+  unsigned int scale_buffers;
+  unsigned int attributes; /* PLL_ATTRIB_PATTERN_TIP, PLL_ATTRIB_RATE_SCALERS */
+} plg_dims_t;
+
+/* Launch / traffic counters since context creation (or the last plg_reset_stats). */
+typedef struct plg_stats
+{
+  unsigned long long kernel_launches;   /* kernels of THIS library launched */
+  unsigned long long graph_launches;    /* cudaGraphLaunch calls (each replays many kernels) */
+  unsigned long long h2d_bytes;
+  unsigned long long d2h_bytes;
+  unsigned long long partial_ops;       /* pll_operation_t entries executed */
+  unsigned long long partial_levels;    /* dependency levels they were batched into */
+  unsigned long long algorithmic_bytes; /* SURVEY.md 8(d) bytes of the partial kernels */
+} plg_stats_t;
+
+PLL_EXPORT const char * plg_last_error(void);
+
+/* Number of usable sm_100 devices (0 if none); never fails. */
+PLL_EXPORT int plg_device_count(void);
+
+/* replaces: the allocation half of pll_partition_create (reference src/pll.c:509-815).
+ * device < 0 selects the current CUDA device. */
+PLL_EXPORT int plg_create(const plg_dims_t * dims, int device, plg_context_t ** out);
+/* replaces: dealloc_partition_data (reference src/pll.c:31-111) */
+PLL_EXPORT void plg_destroy(plg_context_t * ctx);
+
+PLL_EXPORT int plg_synchronize(plg_context_t * ctx);
+
+/* ---- uploads / downloads of resident state ---------------------------------------- */
+
+/* replaces: the stores of set_tipchars_4x4 / set_tipchars (reference src/pll.c:825-903):
+ * `chars` holds ctx->sites bytes (DNA: 4-bit masks; other alphabets: charmap codes). */
+PLL_EXPORT int plg_set_tipchars(plg_context_t * ctx, unsigned int tip_index,
+                                const unsigned char * chars);
+PLL_EXPORT int plg_get_tipchars(plg_context_t * ctx, unsigned int tip_index,
+                                unsigned char * chars);
+/* replaces: partition->tipmap / maxstates maintenance (reference src/pll.c:136-397) */
+PLL_EXPORT int plg_set_tipmap(plg_context_t * ctx, const unsigned int * tipmap,
+                              unsigned int maxstates);
+/* replaces: set_tipclv / pll_set_tip_clv stores (reference src/pll.c:905-1045);
+ * `clv` is a full host CLV: sites * rate_cats * states_padded doubles. */
+PLL_EXPORT int plg_set_clv(plg_context_t * ctx, unsigned int clv_index, const double * clv);
+PLL_EXPORT int plg_get_clv(plg_context_t * ctx, unsigned int clv_index, double * clv);
+PLL_EXPORT int plg_set_scaler(plg_context_t * ctx, unsigned int scaler_index,
+                              const unsigned int * scaler);
+PLL_EXPORT int plg_get_scaler(plg_context_t * ctx, unsigned int scaler_index,
+                              unsigned int * scaler);
+/* replaces: pll_set_pattern_weights memcpy (reference src/pll.c:1047-1059) */
+PLL_EXPORT int plg_set_pattern_weights(plg_context_t * ctx, const unsigned int * weights);
+/* replaces: the tip scan of pll_update_invariant_sites (reference src/models.c:558-647):
+ * computes invariant[] on the device from the resident tips and copies it to `invariant_out`
+ * (sites ints; may be NULL to keep it device-only). */
+PLL_EXPORT int plg_update_invariant(plg_context_t * ctx, int * invariant_out);
+PLL_EXPORT int plg_set_pmatrix(plg_context_t * ctx, unsigned int matrix_index,
+                               const double * pmatrix);
+PLL_EXPORT int plg_get_pmatrix(plg_context_t * ctx, unsigned int matrix_index,
+                               double * pmatrix);
+
+/* ---- the hot path ---------------------------------------------------------------- */
+
+/* replaces: pll_core_update_pmatrix and its _4x4_avx / _20x20_avx2 rungs
+ * (reference src/core_pmatrix.c:24-250, src/core_pmatrix_avx.c:42-310,
+ * src/core_pmatrix_avx2.c:37-284).  Per-rate model data is passed already gathered by
+ * params_indices: eigenvals[r*states_padded + j], eigenvecs / inv_eigenvecs
+ * [r*states*states_padded + ...], prop_invar[r]. */
+PLL_EXPORT int plg_update_pmatrix(plg_context_t * ctx,
+                                  const unsigned int * matrix_indices,
+                                  const double * branch_lengths,
+                                  unsigned int count,
+                                  const double * rates,
+                                  const double * prop_invar,
+                                  const double * eigenvals,
+                                  const double * eigenvecs,
+                                  const double * inv_eigenvecs);
+
+/* replaces: the per-operation loop of pll_update_partials and, per operation,
+ * pll_core_create_lookup + pll_core_update_partial_tt / _ti / _ii with fill_parent_scaler and
+ * the scaling-threshold rescale (reference src/partials.c:177-213,
+ * src/core_partials.c:82-862, src/core_partials_avx.c, src/core_partials_avx2.c:568-803).
+ * The whole list is levelised by data dependency (RAW/WAR/WAW on CLV and scaler slots) and
+ * enqueued as one batch; results are identical to executing the list in array order. */
+PLL_EXPORT int plg_update_partials(plg_context_t * ctx,
+                                   const pll_operation_t * operations,
+                                   unsigned int count);
+
+/* replaces: pll_core_edge_loglikelihood_ii / _ti / _ti_4x4 (reference
+ * src/core_likelihood.c:211-1002, src/core_likelihood_avx.c:191-406,1079-1266,
+ * src/core_likelihood_avx2.c:111-547).  Tip-vs-inner is decided from the clv indices when
+ * the context has PLL_ATTRIB_PATTERN_TIP; `freqs` is [rate_cats][states_padded] gathered by
+ * freqs_indices, `prop_invar` is [rate_cats].  persite_lnl (host, sites doubles) may be NULL. */
+PLL_EXPORT int plg_edge_loglikelihood(plg_context_t * ctx,
+                                      unsigned int parent_clv_index,
+                                      int parent_scaler_index,
+                                      unsigned int child_clv_index,
+                                      int child_scaler_index,
+                                      unsigned int matrix_index,
+                                      const double * freqs,
+                                      const double * rate_weights,
+                                      const double * prop_invar,
+                                      double * persite_lnl,
+                                      double * logl_out);
+
+/* replaces: pll_core_root_loglikelihood (reference src/core_likelihood.c:25-209,
+ * src/core_likelihood_avx.c:113-189, src/core_likelihood_avx2.c:25-109) */
+PLL_EXPORT int plg_root_loglikelihood(plg_context_t * ctx,
+                                      unsigned int clv_index,
+                                      int scaler_index,
+                                      const double * freqs,
+                                      const double * rate_weights,
+                                      const double * prop_invar,
+                                      double * persite_lnl,
+                                      double * logl_out);
+
+/* replaces: pll_core_update_sumtable_ii / _ti (reference src/core_derivatives.c:125-446,
+ * src/core_derivatives_avx.c:25-207,462-645, src/core_derivatives_avx2.c:24-521).
+ * `eigenvecs` is [rate_cats][states][states_padded] gathered by params_indices.  `left_terms`
+ * is the small per-call table the reference kernels precompute before their site loop:
+ *   inner-inner: W[r][j][i] = inv_eigenvecs[r][i][j] * freqs[r][i]
+ *                (reference src/core_derivatives_avx.c:86-95)
+ *   tip-inner  : L[code][r][j] = sum over states i in `code` of inv_eigenvecs[r][i][j]*freqs[r][i]
+ *                (reference src/core_derivatives_avx.c:556-579, src/core_derivatives_avx2.c:368-410)
+ * The table is written to the device slot associated with `key` (the caller's host sumtable
+ * pointer is used as an opaque key); host_copy, if not NULL, additionally receives it. */
+PLL_EXPORT int plg_update_sumtable(plg_context_t * ctx,
+                                   unsigned int parent_clv_index,
+                                   unsigned int child_clv_index,
+                                   int parent_scaler_index,
+                                   int child_scaler_index,
+                                   const double * eigenvecs,
+                                   const double * left_terms,
+                                   const void * key,
+                                   double * host_copy);
+/* Releases the device slot of `key` (all slots are released by plg_destroy). */
+PLL_EXPORT int plg_free_sumtable(plg_context_t * ctx, const void * key);
+
+/* replaces: pll_core_likelihood_derivatives + _avx2 (reference src/core_derivatives.c:501-732,
+ * src/core_derivatives_avx2.c:523-800).  `diagptable` is the host-built
+ * [rate_cats][states][4] table {e, lk e, (lk)^2 e, 0} (reference src/core_derivatives.c:560-575).
+ * Returns d(-lnL)/dt and d2(-lnL)/dt2. */
+PLL_EXPORT int plg_likelihood_derivatives(plg_context_t * ctx,
+                                          const void * key,
+                                          const double * diagptable,
+                                          const double * rate_weights,
+                                          const double * prop_invar,
+                                          const double * freqs,
+                                          double * d_f,
+                                          double * dd_f);
+
+/* ---- measurement ------------------------------------------------------------------ */
+/* CUDA events recorded on the context's own stream (the stream the kernels run on). */
+PLL_EXPORT int plg_timer_start(plg_context_t * ctx);
+PLL_EXPORT int plg_timer_stop(plg_context_t * ctx, float * elapsed_ms);
+PLL_EXPORT int plg_get_stats(plg_context_t * ctx, plg_stats_t * out);
+PLL_EXPORT int plg_reset_stats(plg_context_t * ctx);
+/* Overwrites a device buffer larger than L2 (126 MB) on the context's stream. */
+PLL_EXPORT int plg_flush_l2(plg_context_t * ctx);
+/* Free / total device memory in bytes. */
+PLL_EXPORT int plg_mem_info(plg_context_t * ctx, size_t * free_bytes, size_t * total_bytes);
+
+/* ================= pll_gpu_*: extensions on a GPU partition ========================== */
+
+/* Device used by subsequent pll_partition_create(PLL_ATTRIB_ARCH_GPU) calls of this thread;
+ * default: $PLL_GPU_DEVICE if set, else $LOCAL_RANK if set, else the current CUDA device. */
+PLL_EXPORT int pll_gpu_set_device(int device);
+PLL_EXPORT int pll_gpu_device_count(void);
+
+/* The device context behind a GPU partition (NULL if not a GPU partition). */
+PLL_EXPORT plg_context_t * pll_gpu_context(const pll_partition_t * partition);
+
+/* Download one array into its host mirror (allocated on first use):
+ * partition->clv[i], ->scale_buffer[i], ->tipchars[i], ->pmatrix[i] become valid. */
+PLL_EXPORT int pll_gpu_sync_clv(pll_partition_t * partition, unsigned int clv_index);
+PLL_EXPORT int pll_gpu_sync_scaler(pll_partition_t * partition, unsigned int scaler_index);
+PLL_EXPORT int pll_gpu_sync_tipchars(pll_partition_t * partition, unsigned int tip_index);
+PLL_EXPORT int pll_gpu_sync_pmatrix(pll_partition_t * partition, unsigned int matrix_index);
+/* Upload the host mirror partition->pmatrix[i] / ->clv[i] to the device (tests, callers that
+ * fill P-matrices or CLVs by hand). */
+PLL_EXPORT int pll_gpu_push_pmatrix(pll_partition_t * partition, unsigned int matrix_index);
+PLL_EXPORT int pll_gpu_push_clv(pll_partition_t * partition, unsigned int clv_index);
+
+PLL_EXPORT int pll_gpu_synchronize(pll_partition_t * partition);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PLL_B200_PLL_GPU_H_ */

@@ -1,0 +1,640 @@
+/*
+ * plg_derivatives.cu - sumtable and first/second derivatives of -lnL w.r.t. a branch length
+ * (the inner loop of Newton branch-length optimisation).
+ *
+ * Replaces (AVX2-flag rungs = parity spec):
+ *   pll_core_update_sumtable_ii   4x4: reference src/core_derivatives_avx.c:25-207
+ *                                 gen: reference src/core_derivatives_avx2.c:24-272
+ *   pll_core_update_sumtable_ti   4x4: reference src/core_derivatives_avx.c:462-645
+ *                                 gen: reference src/core_derivatives_avx2.c:274-521
+ *   pll_core_likelihood_derivatives(_avx2)  reference src/core_derivatives.c:501-732,
+ *                                           src/core_derivatives_avx2.c:523-800
+ *
+ * The sumtable never leaves HBM: it is stored in a device slot keyed by the caller's host
+ * buffer address (SURVEY.md 8b "Sumtable on GPU").  Host-side precomputation of the small
+ * per-call tables (pi-weighted transposed inverse eigenvectors, per-code left terms,
+ * diagptable) is done by the C layer with the reference's operation order; the kernels
+ * consume them from the staging ring.
+ */
+#include <cmath>
+
+#include "plg_internal.cuh"
+
+#define PLG_DER_THREADS 256
+#define PLG_MAX_RATES 16
+
+struct SumArgs
+{
+  const double * clvp;       /* ii: parent CLV; ti: the inner CLV                       */
+  const double * clvc;       /* ii: child CLV                                            */
+  const unsigned char * tip; /* ti                                                       */
+  const double * left;       /* ii: W[R][K][K] = inv_eigenvecs^T * pi; ti: [codes][R][K] */
+  const double * right;      /* eigenvecs [R][K][K]                                      */
+  const unsigned int * pscale;
+  const unsigned int * cscale;
+  double * sumtable;
+  unsigned int nelem;
+  int per_rate_scaling;
+};
+
+/* per-rate residual scaling of a sumtable element (only in PLL_ATTRIB_RATE_SCALERS mode;
+ * reference src/core_derivatives_avx.c:101-118,187-191) */
+template <int R>
+__device__ __forceinline__ double rate_residual(bool valid, unsigned int e, const SumArgs & a)
+{
+  if (!a.per_rate_scaling) return 1.0;
+  unsigned int rs = 0;
+  if (valid)
+  {
+    if (a.pscale) rs += a.pscale[e];
+    if (a.cscale) rs += a.cscale[e];
+  }
+  unsigned int mn = rs;
+#pragma unroll
+  for (int off = 1; off < R; off <<= 1)
+  {
+    const unsigned int o = __shfl_xor_sync(0xffffffffu, mn, off);
+    mn = o < mn ? o : mn;
+  }
+  unsigned int diff = rs - mn;
+  if (diff > PLL_SCALE_RATE_MAXDIFF) diff = PLL_SCALE_RATE_MAXDIFF;
+  double f = 1.0;
+  for (unsigned int q = 0; q < diff; ++q) f = __dmul_rn(f, PLG_SCALE_THRESHOLD);
+  return f;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* DNA sumtables                                                                         */
+/* ------------------------------------------------------------------------------------ */
+template <int R>
+__global__ void __launch_bounds__(PLG_DER_THREADS) k_sumtable_ii_dna(const SumArgs a)
+{
+  const unsigned int k = threadIdx.x & (R - 1);
+  const unsigned int e = blockIdx.x * PLG_DER_THREADS + threadIdx.x;
+  const bool valid = e < a.nelem;
+  const double f = rate_residual<R>(valid, e, a);
+  if (!valid) return;
+  const d4 p = ld_stream(a.clvp + (size_t)e * 4);
+  const d4 c = ld_stream(a.clvc + (size_t)e * 4);
+  const double * W = a.left + k * 16;
+  const double * V = a.right + k * 16;
+  d4 s;
+  /* left_j = (W_j . p), right_j = (V_j . c), both unfused with (a0+a1)+(a2+a3)
+   * reference src/core_derivatives_avx.c:131-185 */
+  s.x = __dmul_rn(dot4_unfused(W[0], W[1], W[2], W[3], p), dot4_unfused(V[0], V[1], V[2], V[3], c));
+  s.y = __dmul_rn(dot4_unfused(W[4], W[5], W[6], W[7], p), dot4_unfused(V[4], V[5], V[6], V[7], c));
+  s.z = __dmul_rn(dot4_unfused(W[8], W[9], W[10], W[11], p), dot4_unfused(V[8], V[9], V[10], V[11], c));
+  s.w = __dmul_rn(dot4_unfused(W[12], W[13], W[14], W[15], p), dot4_unfused(V[12], V[13], V[14], V[15], c));
+  if (f != 1.0)
+  {
+    s.x = __dmul_rn(s.x, f);
+    s.y = __dmul_rn(s.y, f);
+    s.z = __dmul_rn(s.z, f);
+    s.w = __dmul_rn(s.w, f);
+  }
+  *reinterpret_cast<d4 *>(a.sumtable + (size_t)e * 4) = s;
+}
+
+template <int R>
+__global__ void __launch_bounds__(PLG_DER_THREADS) k_sumtable_ti_dna(const SumArgs a)
+{
+  const unsigned int k = threadIdx.x & (R - 1);
+  const unsigned int e = blockIdx.x * PLG_DER_THREADS + threadIdx.x;
+  const bool valid = e < a.nelem;
+  const double f = rate_residual<R>(valid, e, a);
+  if (!valid) return;
+  const d4 c = ld_stream(a.clvp + (size_t)e * 4);
+  const unsigned int code = __ldg(a.tip + e / R);
+  const double * L = a.left + ((size_t)code * R + k) * 4;
+  const double * V = a.right + k * 16;
+  /* right_j accumulates sequentially over the child states (reference
+   * src/core_derivatives_avx.c:611-620: broadcast clvc[k] times column k of V^T) */
+  double r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+  {
+    double acc = 0.0;
+    acc = __dadd_rn(acc, __dmul_rn(V[j * 4 + 0], c.x));
+    acc = __dadd_rn(acc, __dmul_rn(V[j * 4 + 1], c.y));
+    acc = __dadd_rn(acc, __dmul_rn(V[j * 4 + 2], c.z));
+    acc = __dadd_rn(acc, __dmul_rn(V[j * 4 + 3], c.w));
+    r[j] = acc;
+  }
+  d4 s;
+  s.x = __dmul_rn(L[0], r[0]);
+  s.y = __dmul_rn(L[1], r[1]);
+  s.z = __dmul_rn(L[2], r[2]);
+  s.w = __dmul_rn(L[3], r[3]);
+  if (f != 1.0)
+  {
+    s.x = __dmul_rn(s.x, f);
+    s.y = __dmul_rn(s.y, f);
+    s.z = __dmul_rn(s.z, f);
+    s.w = __dmul_rn(s.w, f);
+  }
+  *reinterpret_cast<d4 *>(a.sumtable + (size_t)e * 4) = s;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* 20-state sumtables                                                                    */
+/* ------------------------------------------------------------------------------------ */
+__device__ __forceinline__ void load20d(const double * p, double (&c)[20])
+{
+#pragma unroll
+  for (int b = 0; b < 5; ++b)
+  {
+    const d4 v = ld_stream(p + 4 * b);
+    c[4 * b + 0] = v.x;
+    c[4 * b + 1] = v.y;
+    c[4 * b + 2] = v.z;
+    c[4 * b + 3] = v.w;
+  }
+}
+
+__device__ __forceinline__ double row20_fma(const double * __restrict__ row, const double (&c)[20])
+{
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+  for (int b = 0; b < 5; ++b)
+  {
+    a0 = __fma_rn(row[4 * b + 0], c[4 * b + 0], a0);
+    a1 = __fma_rn(row[4 * b + 1], c[4 * b + 1], a1);
+    a2 = __fma_rn(row[4 * b + 2], c[4 * b + 2], a2);
+    a3 = __fma_rn(row[4 * b + 3], c[4 * b + 3], a3);
+  }
+  return hsum4(a0, a1, a2, a3);
+}
+
+template <int R>
+__global__ void __launch_bounds__(PLG_DER_THREADS) k_sumtable_ii_aa(const SumArgs a)
+{
+  extern __shared__ __align__(16) double sm[];
+  double * Ws = sm;           /* [R][20][20] */
+  double * Vs = sm + R * 400; /* [R][20][20] */
+  for (unsigned int t = threadIdx.x; t < R * 400; t += PLG_DER_THREADS)
+  {
+    Ws[t] = __ldg(a.left + t);
+    Vs[t] = __ldg(a.right + t);
+  }
+  __syncthreads();
+  const unsigned int k = threadIdx.x & (R - 1);
+  const unsigned int e = blockIdx.x * PLG_DER_THREADS + threadIdx.x;
+  const bool valid = e < a.nelem;
+  const double f = rate_residual<R>(valid, e, a);
+  if (!valid) return;
+  double p[20], c[20];
+  load20d(a.clvp + (size_t)e * 20, p);
+  load20d(a.clvc + (size_t)e * 20, c);
+  double * out = a.sumtable + (size_t)e * 20;
+  /* reference src/core_derivatives_avx2.c:158-258 */
+#pragma unroll
+  for (int jb = 0; jb < 5; ++jb)
+  {
+    d4 s;
+    s.x = __dmul_rn(row20_fma(Ws + k * 400 + (4 * jb + 0) * 20, p), row20_fma(Vs + k * 400 + (4 * jb + 0) * 20, c));
+    s.y = __dmul_rn(row20_fma(Ws + k * 400 + (4 * jb + 1) * 20, p), row20_fma(Vs + k * 400 + (4 * jb + 1) * 20, c));
+    s.z = __dmul_rn(row20_fma(Ws + k * 400 + (4 * jb + 2) * 20, p), row20_fma(Vs + k * 400 + (4 * jb + 2) * 20, c));
+    s.w = __dmul_rn(row20_fma(Ws + k * 400 + (4 * jb + 3) * 20, p), row20_fma(Vs + k * 400 + (4 * jb + 3) * 20, c));
+    if (f != 1.0)
+    {
+      s.x = __dmul_rn(s.x, f);
+      s.y = __dmul_rn(s.y, f);
+      s.z = __dmul_rn(s.z, f);
+      s.w = __dmul_rn(s.w, f);
+    }
+    *reinterpret_cast<d4 *>(out + 4 * jb) = s;
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(PLG_DER_THREADS) k_sumtable_ti_aa(const SumArgs a)
+{
+  extern __shared__ __align__(16) double sm[];
+  double * Vs = sm; /* [R][20][20] */
+  for (unsigned int t = threadIdx.x; t < R * 400; t += PLG_DER_THREADS) Vs[t] = __ldg(a.right + t);
+  __syncthreads();
+  const unsigned int k = threadIdx.x & (R - 1);
+  const unsigned int e = blockIdx.x * PLG_DER_THREADS + threadIdx.x;
+  const bool valid = e < a.nelem;
+  const double f = rate_residual<R>(valid, e, a);
+  if (!valid) return;
+  double c[20];
+  load20d(a.clvp + (size_t)e * 20, c);
+  const unsigned int code = __ldg(a.tip + e / R);
+  const double * L = a.left + ((size_t)code * R + k) * 20;
+  double * out = a.sumtable + (size_t)e * 20;
+  /* reference src/core_derivatives_avx2.c:441-512 */
+#pragma unroll
+  for (int jb = 0; jb < 5; ++jb)
+  {
+    const d4 l = *reinterpret_cast<const d4 *>(L + 4 * jb);
+    d4 s;
+    s.x = __dmul_rn(l.x, row20_fma(Vs + k * 400 + (4 * jb + 0) * 20, c));
+    s.y = __dmul_rn(l.y, row20_fma(Vs + k * 400 + (4 * jb + 1) * 20, c));
+    s.z = __dmul_rn(l.z, row20_fma(Vs + k * 400 + (4 * jb + 2) * 20, c));
+    s.w = __dmul_rn(l.w, row20_fma(Vs + k * 400 + (4 * jb + 3) * 20, c));
+    if (f != 1.0)
+    {
+      s.x = __dmul_rn(s.x, f);
+      s.y = __dmul_rn(s.y, f);
+      s.z = __dmul_rn(s.z, f);
+      s.w = __dmul_rn(s.w, f);
+    }
+    *reinterpret_cast<d4 *>(out + 4 * jb) = s;
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* derivatives                                                                           */
+/* ------------------------------------------------------------------------------------ */
+struct DerParams
+{
+  double invar_lk[PLG_MAX_RATES * 20]; /* [rate][state] = freqs * prop_invar */
+  double rate_weights[PLG_MAX_RATES];
+  double prop_invar[PLG_MAX_RATES];
+  int use_pinv;
+  int eq_weights;
+};
+
+struct DerArgs
+{
+  const double * sumtable;
+  const double * diagp; /* DNA: [R][4][4] {e, e', e'', 0}; 20 states: [R][3][20] */
+  const unsigned int * weights;
+  const int * invariant;
+  double * partials; /* 2 * gridDim.x */
+  unsigned int * counter;
+  double * result; /* [0] = d_f, [1] = dd_f */
+  unsigned int nelem;
+};
+
+template <int R, int K>
+__global__ void __launch_bounds__(PLG_DER_THREADS)
+k_derivatives(const DerArgs a, const __grid_constant__ DerParams P)
+{
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned int k = lane & (R - 1);
+  const unsigned int gbase = lane & ~(unsigned int)(R - 1);
+  const unsigned int e = blockIdx.x * PLG_DER_THREADS + threadIdx.x;
+  const bool valid = e < a.nelem;
+
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+  if (valid)
+  {
+    if (K == 4)
+    {
+      /* lanes (L, L', L'') accumulate fma(sum_j, diagp_j, acc) over the 4 states in order
+       * reference src/core_derivatives_avx2.c:634-655 */
+      const d4 s = ld_stream(a.sumtable + (size_t)e * 4);
+      const double * d = a.diagp + k * 16;
+      const double sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+      {
+        c0 = __fma_rn(sv[j], __ldg(d + j * 4 + 0), c0);
+        c1 = __fma_rn(sv[j], __ldg(d + j * 4 + 1), c1);
+        c2 = __fma_rn(sv[j], __ldg(d + j * 4 + 2), c2);
+      }
+    }
+    else
+    {
+      /* blocked: first block by mul, the other four by fma, then hadd
+       * reference src/core_derivatives_avx2.c:656-702 */
+      double s[20];
+      load20d(a.sumtable + (size_t)e * 20, s);
+      const double * d = a.diagp + k * 60;
+      double acc[3][4];
+#pragma unroll
+      for (int x = 0; x < 3; ++x)
+      {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) acc[x][l] = __dmul_rn(s[l], __ldg(d + x * 20 + l));
+#pragma unroll
+        for (int b = 1; b < 5; ++b)
+#pragma unroll
+          for (int l = 0; l < 4; ++l)
+            acc[x][l] = __fma_rn(s[4 * b + l], __ldg(d + x * 20 + 4 * b + l), acc[x][l]);
+      }
+      c0 = hsum4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+      c1 = hsum4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
+      c2 = hsum4(acc[2][0], acc[2][1], acc[2][2], acc[2][3]);
+    }
+  }
+
+  /* combine the rates of a site in order (reference src/core_derivatives_avx2.c:704-729) */
+  int inv = -1;
+  if (P.use_pinv && valid && k == 0 && a.invariant) inv = a.invariant[e / R];
+  double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+#pragma unroll
+  for (int kk = 0; kk < R; ++kk)
+  {
+    double v0 = __shfl_sync(0xffffffffu, c0, gbase + kk);
+    double v1 = __shfl_sync(0xffffffffu, c1, gbase + kk);
+    double v2 = __shfl_sync(0xffffffffu, c2, gbase + kk);
+    if (k == 0)
+    {
+      if (P.use_pinv && P.prop_invar[kk] > 0.0)
+      {
+        const double q = __dsub_rn(1.0, P.prop_invar[kk]);
+        v0 = __dmul_rn(v0, q);
+        v1 = __dmul_rn(v1, q);
+        v2 = __dmul_rn(v2, q);
+        if (inv != -1) v0 = __dadd_rn(v0, P.invar_lk[kk * K + inv]);
+      }
+      if (P.eq_weights)
+      {
+        l0 = __dadd_rn(l0, v0);
+        l1 = __dadd_rn(l1, v1);
+        l2 = __dadd_rn(l2, v2);
+      }
+      else
+      {
+        const double w = P.rate_weights[kk];
+        l0 = __fma_rn(v0, w, l0);
+        l1 = __fma_rn(v1, w, l1);
+        l2 = __fma_rn(v2, w, l2);
+      }
+    }
+  }
+
+  double df = 0.0, ddf = 0.0;
+  if (valid && k == 0)
+  {
+    /* reference src/core_derivatives_avx2.c:746-766 */
+    const double recip = __ddiv_rn(1.0, l0);
+    const double d1 = __dmul_rn(l1, recip);
+    const double d2 = __dsub_rn(__dmul_rn(d1, d1), __dmul_rn(l2, recip));
+    const double w = (double)a.weights[e / R];
+    df = -__dmul_rn(d1, w);
+    ddf = __dmul_rn(d2, w);
+  }
+
+  __shared__ double red[PLG_DER_THREADS / 32];
+  __shared__ bool is_last;
+  const double s1 = block_sum<PLG_DER_THREADS>(df, red);
+  const double s2 = block_sum<PLG_DER_THREADS>(ddf, red);
+  if (threadIdx.x == 0)
+  {
+    a.partials[2 * blockIdx.x + 0] = s1;
+    a.partials[2 * blockIdx.x + 1] = s2;
+    __threadfence();
+    const unsigned int ticket = atomicAdd(a.counter, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last)
+  {
+    __threadfence();
+    const unsigned int nb = gridDim.x;
+    const unsigned int per = (nb + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
+    const unsigned int lo = threadIdx.x * per;
+    unsigned int hi = lo + per;
+    if (hi > nb) hi = nb;
+    double t1 = 0.0, t2 = 0.0;
+    for (unsigned int b = lo; b < hi; ++b)
+    {
+      t1 = __dadd_rn(t1, __ldcg(a.partials + 2 * b));
+      t2 = __dadd_rn(t2, __ldcg(a.partials + 2 * b + 1));
+    }
+    const double r1 = block_sum<PLG_DER_THREADS>(t1, red);
+    const double r2 = block_sum<PLG_DER_THREADS>(t2, red);
+    if (threadIdx.x == 0)
+    {
+      a.result[0] = r1;
+      a.result[1] = r2;
+      *a.counter = 0u;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* host side                                                                             */
+/* ------------------------------------------------------------------------------------ */
+#define PLG_DISPATCH_R(R_, ...)                                                         \
+  switch (R_)                                                                           \
+  {                                                                                     \
+    case 1: { constexpr int RR = 1; __VA_ARGS__; } break;                                      \
+    case 2: { constexpr int RR = 2; __VA_ARGS__; } break;                                      \
+    case 4: { constexpr int RR = 4; __VA_ARGS__; } break;                                      \
+    case 8: { constexpr int RR = 8; __VA_ARGS__; } break;                                      \
+    case 16: { constexpr int RR = 16; __VA_ARGS__; } break;                                    \
+    default: plg_set_error("rate_cats=%u unsupported", R_); return PLG_E_UNSUPPORTED;   \
+  }
+
+static int sumtable_slot(plg_context * ctx, const void * key, double ** out)
+{
+  auto it = ctx->sumtables->find(key);
+  if (it != ctx->sumtables->end())
+  {
+    *out = it->second;
+    return PLG_OK;
+  }
+  double * dev = NULL;
+  PLG_CUDA(cudaMalloc(&dev, (size_t)ctx->d.sites * ctx->span * sizeof(double)));
+  (*ctx->sumtables)[key] = dev;
+  *out = dev;
+  return PLG_OK;
+}
+
+extern "C" int plg_update_sumtable(plg_context_t * ctx, unsigned int parent_clv_index,
+                                   unsigned int child_clv_index, int parent_scaler_index,
+                                   int child_scaler_index, const double * eigenvecs,
+                                   const double * left_table, const void * key,
+                                   double * host_copy)
+{
+  PLG_CHECK_CTX(ctx);
+  const unsigned int n_clv = ctx->d.tips + ctx->d.clv_buffers;
+  if (parent_clv_index >= n_clv || child_clv_index >= n_clv ||
+      parent_scaler_index >= (int)ctx->d.scale_buffers ||
+      child_scaler_index >= (int)ctx->d.scale_buffers || !key)
+  {
+    plg_set_error("plg_update_sumtable: index out of range");
+    return PLG_E_INVALID;
+  }
+  const bool ptip = plg_is_tip(ctx, parent_clv_index);
+  const bool ctip = plg_is_tip(ctx, child_clv_index);
+  if (ptip && ctip)
+  {
+    plg_set_error("plg_update_sumtable: tip-tip edge (the reference asserts, "
+                  "src/derivatives.c:195)");
+    return PLG_E_UNSUPPORTED;
+  }
+  const unsigned int R = ctx->d.rate_cats, K = ctx->d.states;
+  const unsigned int nelem = ctx->d.sites * R;
+  const unsigned int nblocks = (nelem + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
+
+  SumArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = sumtable_slot(ctx, key, &a.sumtable);
+  if (rc) return rc;
+  a.nelem = nelem;
+  a.per_rate_scaling = ctx->rate_scalers ? 1 : 0;
+
+  const size_t mat_bytes = (size_t)R * K * K * sizeof(double);
+  const bool ti = ptip || ctip;
+  const size_t codes = (K == 4) ? 16u : ctx->maxstates;
+  const size_t left_bytes = ti ? codes * R * K * sizeof(double) : mat_bytes;
+  if (plg_stage_reserve(ctx, mat_bytes + left_bytes + 1024)) return PLG_E_CUDA;
+  a.right = (const double *)plg_stage(ctx, eigenvecs, mat_bytes);
+  a.left = (const double *)plg_stage(ctx, left_table, left_bytes);
+  if (!a.right || !a.left) return PLG_E_CUDA;
+
+  if (ti)
+  {
+    const unsigned int inner = ptip ? child_clv_index : parent_clv_index;
+    const unsigned int tip = ptip ? parent_clv_index : child_clv_index;
+    a.clvp = plg_clv_ptr(ctx, inner);
+    a.tip = plg_tip_ptr(ctx, tip);
+    a.pscale = plg_scaler_ptr(ctx, ptip ? child_scaler_index : parent_scaler_index);
+    if (K == 4)
+    {
+      PLG_DISPATCH_R(R, (k_sumtable_ti_dna<RR><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(a)));
+    }
+    else
+    {
+      const size_t smem = (size_t)R * 400 * sizeof(double);
+      PLG_DISPATCH_R(R, {
+        static bool attr_done = false;
+        if (!attr_done)
+        {
+          PLG_CUDA(cudaFuncSetAttribute(k_sumtable_ti_aa<RR>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          attr_done = true;
+        }
+        k_sumtable_ti_aa<RR><<<nblocks, PLG_DER_THREADS, smem, ctx->stream>>>(a);
+      });
+    }
+  }
+  else
+  {
+    a.clvp = plg_clv_ptr(ctx, parent_clv_index);
+    a.clvc = plg_clv_ptr(ctx, child_clv_index);
+    a.pscale = plg_scaler_ptr(ctx, parent_scaler_index);
+    a.cscale = plg_scaler_ptr(ctx, child_scaler_index);
+    if (K == 4)
+    {
+      PLG_DISPATCH_R(R, (k_sumtable_ii_dna<RR><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(a)));
+    }
+    else
+    {
+      const size_t smem = (size_t)2 * R * 400 * sizeof(double);
+      PLG_DISPATCH_R(R, {
+        static bool attr_done = false;
+        if (!attr_done)
+        {
+          PLG_CUDA(cudaFuncSetAttribute(k_sumtable_ii_aa<RR>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          attr_done = true;
+        }
+        k_sumtable_ii_aa<RR><<<nblocks, PLG_DER_THREADS, smem, ctx->stream>>>(a);
+      });
+    }
+  }
+  PLG_LAUNCH_CHECK(ctx);
+
+  if (host_copy)
+  {
+    const size_t bytes = (size_t)ctx->d.sites * ctx->span * sizeof(double);
+    PLG_CUDA(cudaMemcpyAsync(host_copy, a.sumtable, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += bytes;
+  }
+  return PLG_OK;
+}
+
+extern "C" int plg_free_sumtable(plg_context_t * ctx, const void * key)
+{
+  PLG_CHECK_CTX(ctx);
+  auto it = ctx->sumtables->find(key);
+  if (it == ctx->sumtables->end()) return PLG_OK;
+  PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(it->second);
+  ctx->sumtables->erase(it);
+  return PLG_OK;
+}
+
+extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
+                                          const double * diagptable, const double * rate_weights,
+                                          const double * prop_invar, const double * freqs,
+                                          double * d_f, double * dd_f)
+{
+  PLG_CHECK_CTX(ctx);
+  auto it = ctx->sumtables->find(key);
+  if (it == ctx->sumtables->end())
+  {
+    plg_set_error("plg_likelihood_derivatives: no sumtable was computed for this buffer "
+                  "(call pll_update_sumtable first)");
+    return PLG_E_INVALID;
+  }
+  const unsigned int R = ctx->d.rate_cats, K = ctx->d.states;
+  const unsigned int nelem = ctx->d.sites * R;
+  const unsigned int nblocks = (nelem + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
+  int rc = plg_ensure_partials(ctx, 2 * (size_t)nblocks);
+  if (rc) return rc;
+
+  DerParams P;
+  memset(&P, 0, sizeof(P));
+  P.use_pinv = 0;
+  P.eq_weights = 1;
+  for (unsigned int i = 0; i < R; ++i)
+  {
+    P.rate_weights[i] = rate_weights[i];
+    P.prop_invar[i] = prop_invar[i];
+    if (prop_invar[i] > 0) P.use_pinv = 1;
+    if (rate_weights[i] != rate_weights[0]) P.eq_weights = 0;
+    for (unsigned int s = 0; s < K; ++s)
+      P.invar_lk[i * K + s] = freqs[i * ctx->d.states_padded + s] * prop_invar[i];
+  }
+  if (P.use_pinv && !ctx->has_invariant)
+  {
+    plg_set_error("derivatives with prop_invar > 0 need the invariant-site index");
+    return PLG_E_INVALID;
+  }
+
+  /* device layout of diagp: DNA keeps [R][state][4]; 20 states is transposed to
+   * [R][3][20] exactly like the reference's t_diagp (src/core_derivatives_avx2.c:598-609) */
+  double diag_host[PLG_MAX_RATES * 80];
+  size_t diag_len;
+  if (K == 4)
+  {
+    diag_len = (size_t)R * 16;
+    memcpy(diag_host, diagptable, diag_len * sizeof(double));
+  }
+  else
+  {
+    diag_len = (size_t)R * 60;
+    for (unsigned int i = 0; i < R; ++i)
+      for (unsigned int j = 0; j < K; ++j)
+        for (unsigned int x = 0; x < 3; ++x)
+          diag_host[i * 60 + x * 20 + j] = diagptable[(size_t)i * K * 4 + j * 4 + x];
+  }
+
+  DerArgs a;
+  a.sumtable = it->second;
+  a.diagp = (const double *)plg_stage(ctx, diag_host, diag_len * sizeof(double));
+  if (!a.diagp) return PLG_E_CUDA;
+  a.weights = ctx->weights;
+  a.invariant = ctx->has_invariant ? ctx->invariant : NULL;
+  a.partials = ctx->partials;
+  a.counter = ctx->counter;
+  a.result = ctx->result_dev;
+  a.nelem = nelem;
+
+  if (K == 4)
+  {
+    PLG_DISPATCH_R(R, (k_derivatives<RR, 4><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(a, P)));
+  }
+  else
+  {
+    PLG_DISPATCH_R(R, (k_derivatives<RR, 20><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(a, P)));
+  }
+  PLG_LAUNCH_CHECK(ctx);
+
+  PLG_CUDA(cudaMemcpyAsync(ctx->result_host, ctx->result_dev, 2 * sizeof(double),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+  PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.d2h_bytes += 2 * sizeof(double);
+  *d_f = ctx->result_host[0];
+  *dd_f = ctx->result_host[1];
+  return PLG_OK;
+}

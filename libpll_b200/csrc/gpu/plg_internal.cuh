@@ -1,0 +1,233 @@
+/*
+ * plg_internal.cuh - shared definitions of the device layer (not part of the public ABI).
+ *
+ * Data layout in HBM (all arrays 256-byte aligned, one cudaMalloc slab per kind):
+ *   clv      [slot][site][rate][state_padded] double   - same order as the reference CLV
+ *                                                        (reference src/pll.c:522-542)
+ *   scalers  [slot][site] u32, or [slot][site][rate] with PLL_ATTRIB_RATE_SCALERS
+ *   tipchars [tip][site] u8                              (only with PLL_ATTRIB_PATTERN_TIP)
+ *   pmatrix  [matrix][rate][row][col_padded] double      (reference src/pll.c:555-573)
+ *   weights  [site] u32, invariant [site] i32
+ */
+#ifndef PLG_INTERNAL_CUH_
+#define PLG_INTERNAL_CUH_
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+#include "pll_gpu.h"
+
+/* ------------------------------------------------------------------------------------ */
+/* error plumbing                                                                        */
+/* ------------------------------------------------------------------------------------ */
+void plg_set_error(const char * fmt, ...);
+
+#define PLG_CUDA(call)                                                                 \
+  do {                                                                                 \
+    cudaError_t err__ = (call);                                                        \
+    if (err__ != cudaSuccess) {                                                        \
+      plg_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,                 \
+                    cudaGetErrorString(err__));                                        \
+      return (err__ == cudaErrorMemoryAllocation) ? PLG_E_NOMEM : PLG_E_CUDA;          \
+    }                                                                                  \
+  } while (0)
+
+#define PLG_LAUNCH_CHECK(ctx)                                                          \
+  do {                                                                                 \
+    cudaError_t err__ = cudaGetLastError();                                            \
+    if (err__ != cudaSuccess) {                                                        \
+      plg_set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__,             \
+                    cudaGetErrorString(err__));                                        \
+      return PLG_E_CUDA;                                                               \
+    }                                                                                  \
+    (ctx)->stats.kernel_launches++;                                                    \
+  } while (0)
+
+/* ------------------------------------------------------------------------------------ */
+/* context                                                                               */
+/* ------------------------------------------------------------------------------------ */
+/* a captured, instantiated CUDA graph of one whole operation list (plg_partials.cu) */
+struct plg_graph_entry
+{
+  cudaGraphExec_t exec;
+  std::vector<unsigned char> key_bytes; /* the pll_operation_t list it was built from */
+  void * dev_tables;                    /* op / job descriptors, stable for the graph's life */
+  unsigned long long kernels;
+  unsigned long long levels;
+  unsigned long long algorithmic_bytes;
+};
+
+#define PLG_CHECK_CTX(ctx)                                                             \
+  do {                                                                                 \
+    if (!(ctx)) { plg_set_error("%s: NULL context", __func__); return PLG_E_INVALID; } \
+    PLG_CUDA(cudaSetDevice((ctx)->device));                                            \
+  } while (0)
+
+struct plg_context
+{
+  plg_dims_t d;
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+
+  bool pattern_tip;
+  bool rate_scalers;
+
+  size_t span;          /* rate_cats * states_padded (doubles per site of a CLV)          */
+  size_t clv_stride;    /* doubles between consecutive CLV slots                          */
+  size_t scaler_len;    /* u32 entries per scale buffer (sites or sites*rate_cats)        */
+  size_t scaler_stride; /* u32 entries between consecutive scale buffers                  */
+  size_t tip_stride;    /* bytes between consecutive tip-character rows                   */
+  size_t pmat_len;      /* doubles per P-matrix set: rate_cats*states*states_padded       */
+  unsigned int clv_first; /* first CLV index that has device storage                      */
+
+  double * clv;
+  unsigned int * scalers;
+  unsigned char * tipchars;
+  double * pmatrix;
+  unsigned int * weights;
+  int * invariant;
+  bool has_invariant;
+
+  unsigned int maxstates;
+  unsigned int log2_maxstates;
+  unsigned int tipmap[PLL_ASCII_SIZE];
+
+  /* pinned-host / device staging ring for small per-call constants and op tables */
+  char * stage_host;
+  char * stage_dev;
+  size_t stage_size;
+  size_t stage_off;
+
+  /* scratch: per-op tip lookup tables, reduction partials, results */
+  double * tables;
+  size_t tables_cap; /* doubles */
+  double * partials;
+  size_t partials_cap; /* doubles */
+  unsigned int * counter; /* "last block done" ticket */
+  double * result_dev;    /* 4 doubles */
+  double * result_host;   /* pinned, 4 doubles */
+  double * persite_dev;   /* sites doubles, allocated on first use */
+  double * lnl_table;     /* pi-weighted tip lookup of the edge-lnL tip-inner kernels */
+  size_t lnl_table_cap;   /* doubles */
+
+  /* device-resident sumtables keyed by the caller's host pointer */
+  std::unordered_map<const void *, double *> * sumtables;
+
+  /* cached CUDA graphs of whole operation lists, keyed by a hash of the list */
+  std::unordered_map<uint64_t, plg_graph_entry *> * graphs;
+  int use_graphs;
+
+  /* L2 flush buffer (allocated on first plg_flush_l2) */
+  char * flush_buf;
+  size_t flush_bytes;
+
+  cudaEvent_t ev_start, ev_stop;
+  plg_stats_t stats;
+};
+
+/* Copies `bytes` of host data into the staging ring and enqueues the H2D copy on the
+ * context's stream; returns the device address (256-byte aligned) or NULL on failure. */
+void * plg_stage(plg_context * ctx, const void * src, size_t bytes);
+/* Guarantees that the next `bytes` (callers add 256 per item for alignment) of plg_stage calls
+ * come from one contiguous, not-yet-recycled region of the ring.  Returns 0 on success. */
+int plg_stage_reserve(plg_context * ctx, size_t bytes);
+
+int plg_ensure_tables(plg_context * ctx, size_t doubles);
+int plg_ensure_partials(plg_context * ctx, size_t doubles);
+
+static inline double * plg_clv_ptr(const plg_context * ctx, unsigned int idx)
+{
+  return ctx->clv + (size_t)(idx - ctx->clv_first) * ctx->clv_stride;
+}
+static inline unsigned int * plg_scaler_ptr(const plg_context * ctx, int idx)
+{
+  return (idx == PLL_SCALE_BUFFER_NONE) ? NULL
+                                        : ctx->scalers + (size_t)idx * ctx->scaler_stride;
+}
+static inline unsigned char * plg_tip_ptr(const plg_context * ctx, unsigned int idx)
+{
+  return ctx->tipchars + (size_t)idx * ctx->tip_stride;
+}
+static inline double * plg_pmat_ptr(const plg_context * ctx, unsigned int idx)
+{
+  return ctx->pmatrix + (size_t)idx * ctx->pmat_len;
+}
+static inline bool plg_is_tip(const plg_context * ctx, unsigned int clv_index)
+{
+  return ctx->pattern_tip && clv_index < ctx->d.tips;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* device helpers shared by the kernels                                                  */
+/* ------------------------------------------------------------------------------------ */
+#ifdef __CUDACC__
+
+/* four consecutive states of one (site, rate): one 256-bit global access on sm_100a */
+struct __align__(32) d4
+{
+  double x, y, z, w;
+};
+
+/* streaming (read-once / write-once) 256-bit accesses that do not allocate in L1 */
+__device__ __forceinline__ d4 ld_stream(const double * p)
+{
+  d4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(double * p, d4 v)
+{
+  asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};"
+               :
+               : "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w)
+               : "memory");
+}
+
+/* The reference's 4-lane horizontal sum (unpackhi/unpacklo, add, permute2f128/blend, add;
+ * e.g. reference src/core_partials_avx.c:460-471) evaluates (a0+a1)+(a2+a3). */
+__device__ __forceinline__ double hsum4(double a0, double a1, double a2, double a3)
+{
+  return __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
+}
+
+/* unfused row * vector, the DNA kernels' building block (mul, then hsum4) */
+__device__ __forceinline__ double dot4_unfused(double m0, double m1, double m2, double m3,
+                                               const d4 & c)
+{
+  return hsum4(__dmul_rn(m0, c.x), __dmul_rn(m1, c.y), __dmul_rn(m2, c.z), __dmul_rn(m3, c.w));
+}
+
+#define PLG_SCALE_THRESHOLD 0x1p-256
+#define PLG_SCALE_FACTOR 0x1p+256
+
+/* deterministic block-wide sum: fixed shuffle tree inside each warp, then warp 0 adds the
+ * per-warp values in warp order.  Result valid in thread 0. */
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double * smem /* THREADS/32 doubles */)
+{
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+    v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, off));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  double total = 0.0;
+  if (threadIdx.x == 0)
+  {
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) total = __dadd_rn(total, smem[w]);
+  }
+  __syncthreads();
+  return total;
+}
+
+#endif /* __CUDACC__ */
+
+#endif /* PLG_INTERNAL_CUH_ */

@@ -1,0 +1,969 @@
+/*
+ * plg_partials.cu - conditional-likelihood-vector (CLV) updates: the >99 % hot loop.
+ *
+ * Replaces, for a whole pll_operation_t list at once:
+ *   pll_update_partials' per-node loop          reference src/partials.c:177-213
+ *   pll_core_create_lookup (+_4x4_avx,_20x20)   reference src/core_partials_avx.c:146-364
+ *   pll_core_update_partial_tt                   reference src/core_partials_avx.c:531-618
+ *   pll_core_update_partial_ti                   reference src/core_partials_avx.c:899-1340
+ *   pll_core_update_partial_ii                   reference src/core_partials_avx.c:366-529,
+ *                                                          src/core_partials_avx2.c:568-803
+ *   fill_parent_scaler + threshold rescale       reference src/core_partials_avx.c:24-46,490-527
+ *
+ * Work mapping.  One thread owns one (site, rate) element of the parent CLV: for DNA that is
+ * one 256-bit load per child and one 256-bit store, so a warp streams 1 KB contiguous per
+ * array per instruction.  blockIdx.y selects the operation inside a batch of mutually
+ * independent operations (one dependency level), so a level of the tree is one launch.  The
+ * per-site "all entries below 2^-256" decision is a warp ballot over the rate lanes of a
+ * site; the lane of rate 0 does the integer scaler arithmetic.
+ *
+ * Arithmetic follows the order of the reference's AVX2-flag path exactly:
+ * DNA uses unfused multiply/add with the (a0+a1)+(a2+a3) horizontal sum; 20-state
+ * inner-inner uses 4 FMA lane accumulators per row, 20-state tip-inner the unfused form.
+ * The file is compiled with -fmad=false so nothing is contracted behind our back.
+ */
+#include <algorithm>
+#include <cmath>
+
+#include "plg_internal.cuh"
+
+/* ------------------------------------------------------------------------------------ */
+/* descriptors                                                                           */
+/* ------------------------------------------------------------------------------------ */
+enum { PLG_KIND_TT = 0, PLG_KIND_TI = 1, PLG_KIND_II = 2 };
+
+struct DevOp
+{
+  double * parent;
+  const double * left;        /* ii: left child CLV                                   */
+  const double * right;       /* ii: right child CLV; ti: the inner child's CLV       */
+  const unsigned char * ltip; /* tt: left tip chars;  ti: the tip child's chars       */
+  const unsigned char * rtip; /* tt: right tip chars                                  */
+  const double * lmat;        /* ii: left P-matrix;  ti/tt: lookup table of ltip      */
+  const double * rmat;        /* ii/ti: P-matrix of `right`; tt: lookup table of rtip */
+  unsigned int * pscale;
+  const unsigned int * lscale;
+  const unsigned int * rscale;
+};
+
+struct TableJob
+{
+  const double * pmat;
+  double * out;
+};
+
+struct TipmapArg
+{
+  unsigned int map[PLL_ASCII_SIZE];
+};
+
+/* ------------------------------------------------------------------------------------ */
+/* tip lookup tables                                                                     */
+/* ------------------------------------------------------------------------------------ */
+/* DNA: table[code][rate][i] = sum over the states m in `code` of P_rate[i][m], summed as
+ * (a0+a1)+(a2+a3) with absent states contributing +0.0 - the masked-load form of reference
+ * src/core_partials_avx.c:944-984 (tip-inner) and :280-353 (tip-tip, per side). */
+__global__ void k_tip_tables_dna(const TableJob * __restrict__ jobs, unsigned int rate_cats)
+{
+  const TableJob job = jobs[blockIdx.x];
+  const unsigned int entries = 16u * rate_cats * 4u;
+  for (unsigned int t = threadIdx.x; t < entries; t += blockDim.x)
+  {
+    const unsigned int i = t & 3u;
+    const unsigned int k = (t >> 2) % rate_cats;
+    const unsigned int code = t / (rate_cats * 4u);
+    const double * row = job.pmat + (size_t)k * 16 + i * 4;
+    const double a0 = (code & 1u) ? row[0] : 0.0;
+    const double a1 = (code & 2u) ? row[1] : 0.0;
+    const double a2 = (code & 4u) ? row[2] : 0.0;
+    const double a3 = (code & 8u) ? row[3] : 0.0;
+    job.out[t] = hsum4(a0, a1, a2, a3);
+  }
+}
+
+/* 20 states: table[code][rate][i] = sequential sum, in increasing state order, of
+ * P_rate[i][m] over the states m present in tipmap[code] (reference
+ * src/core_partials_avx.c:1140-1177 and :177-220). */
+__global__ void k_tip_tables_aa(const TableJob * __restrict__ jobs, unsigned int rate_cats,
+                                unsigned int maxstates, const TipmapArg tm)
+{
+  const TableJob job = jobs[blockIdx.x];
+  const unsigned int entries = maxstates * rate_cats * 20u;
+  for (unsigned int t = threadIdx.x; t < entries; t += blockDim.x)
+  {
+    const unsigned int i = t % 20u;
+    const unsigned int k = (t / 20u) % rate_cats;
+    const unsigned int code = t / (rate_cats * 20u);
+    const unsigned int state = tm.map[code];
+    const double * row = job.pmat + (size_t)k * 400 + i * 20;
+    double s = 0.0;
+    for (unsigned int m = 0; m < 20u; ++m)
+      if ((state >> m) & 1u) s = __dadd_rn(s, row[m]);
+    job.out[t] = s;
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* scaling helpers                                                                       */
+/* ------------------------------------------------------------------------------------ */
+/* scale_mode: 0 = parent has no scaler (no scaling at all), 1 = per-site, 2 = per-rate
+ * (reference src/core_partials_avx.c:397-410). */
+
+/* Returns true if this element must be multiplied by 2^256, and performs the scaler
+ * bookkeeping.  `below` = all states of this (site, rate) element are < 2^-256.
+ * Must be called by all 32 lanes of the warp. */
+template <int R>
+__device__ __forceinline__ bool scale_decision(bool valid, bool below, int scale_mode,
+                                               unsigned int e, const DevOp & op)
+{
+  const unsigned int lane = threadIdx.x & 31u;
+  if (scale_mode == 1)
+  {
+    const unsigned int b = __ballot_sync(0xffffffffu, valid && below);
+    const unsigned int full = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
+    const unsigned int grp = (b >> (lane & ~(unsigned int)(R - 1))) & full;
+    const bool scale = (grp == full);
+    if (valid && (lane & (R - 1)) == 0)
+    {
+      const unsigned int n = e / R;
+      unsigned int s = scale ? 1u : 0u;
+      if (op.lscale) s += op.lscale[n];
+      if (op.rscale) s += op.rscale[n];
+      op.pscale[n] = s;
+    }
+    return scale;
+  }
+  if (scale_mode == 2)
+  {
+    if (valid)
+    {
+      unsigned int s = below ? 1u : 0u;
+      if (op.lscale) s += op.lscale[e];
+      if (op.rscale) s += op.rscale[e];
+      op.pscale[e] = s;
+    }
+    return below;
+  }
+  return false;
+}
+
+__device__ __forceinline__ bool all_below(const d4 & p)
+{
+  return (p.x < PLG_SCALE_THRESHOLD) & (p.y < PLG_SCALE_THRESHOLD) &
+         (p.z < PLG_SCALE_THRESHOLD) & (p.w < PLG_SCALE_THRESHOLD);
+}
+
+__device__ __forceinline__ d4 scale_up(const d4 & p)
+{
+  d4 r;
+  r.x = __dmul_rn(p.x, PLG_SCALE_FACTOR);
+  r.y = __dmul_rn(p.y, PLG_SCALE_FACTOR);
+  r.z = __dmul_rn(p.z, PLG_SCALE_FACTOR);
+  r.w = __dmul_rn(p.w, PLG_SCALE_FACTOR);
+  return r;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* DNA kernels (4 states)                                                                */
+/* ------------------------------------------------------------------------------------ */
+#define PLG_DNA_THREADS 256
+
+__device__ __forceinline__ d4 matvec4_unfused(const double (&M)[16], const d4 & c)
+{
+  d4 y;
+  y.x = dot4_unfused(M[0], M[1], M[2], M[3], c);
+  y.y = dot4_unfused(M[4], M[5], M[6], M[7], c);
+  y.z = dot4_unfused(M[8], M[9], M[10], M[11], c);
+  y.w = dot4_unfused(M[12], M[13], M[14], M[15], c);
+  return y;
+}
+
+__device__ __forceinline__ d4 mul4(const d4 & a, const d4 & b)
+{
+  d4 r;
+  r.x = __dmul_rn(a.x, b.x);
+  r.y = __dmul_rn(a.y, b.y);
+  r.z = __dmul_rn(a.z, b.z);
+  r.w = __dmul_rn(a.w, b.w);
+  return r;
+}
+
+/* inner-inner: parent[n][k][i] = (sum_j L_k[i][j] l[n][k][j]) * (sum_j R_k[i][j] r[n][k][j])
+ * reference src/core_partials_avx.c:412-528 */
+template <int R, int ITEMS>
+__global__ void __launch_bounds__(PLG_DNA_THREADS)
+k_partial_ii_dna(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mode)
+{
+  const DevOp op = ops[blockIdx.y];
+  const unsigned int k = threadIdx.x & (R - 1);
+
+  double L[16], Rm[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+  {
+    L[i] = __ldg(op.lmat + k * 16 + i);
+    Rm[i] = __ldg(op.rmat + k * 16 + i);
+  }
+
+  const unsigned int base = blockIdx.x * (PLG_DNA_THREADS * ITEMS) + threadIdx.x;
+  d4 l[ITEMS], r[ITEMS];
+  bool valid[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j)
+  {
+    const unsigned int e = base + j * PLG_DNA_THREADS;
+    valid[j] = e < nelem;
+    if (valid[j])
+    {
+      l[j] = ld_stream(op.left + (size_t)e * 4);
+      r[j] = ld_stream(op.right + (size_t)e * 4);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j)
+  {
+    const unsigned int e = base + j * PLG_DNA_THREADS;
+    d4 p;
+    bool below = false;
+    if (valid[j])
+    {
+      p = mul4(matvec4_unfused(L, l[j]), matvec4_unfused(Rm, r[j]));
+      below = all_below(p);
+    }
+    const bool scale = scale_decision<R>(valid[j], below, scale_mode, e, op);
+    if (valid[j])
+    {
+      if (scale) p = scale_up(p);
+      st_stream(op.parent + (size_t)e * 4, p);
+    }
+  }
+}
+
+/* tip-inner: parent[n][k][i] = table[tip[n]][k][i] * (sum_j R_k[i][j] r[n][k][j])
+ * reference src/core_partials_avx.c:1006-1093 */
+template <int R, int ITEMS>
+__global__ void __launch_bounds__(PLG_DNA_THREADS)
+k_partial_ti_dna(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mode)
+{
+  const DevOp op = ops[blockIdx.y];
+  const unsigned int k = threadIdx.x & (R - 1);
+
+  __shared__ d4 tab[16 * R];
+  for (unsigned int t = threadIdx.x; t < 16 * R; t += PLG_DNA_THREADS)
+    tab[t] = *reinterpret_cast<const d4 *>(op.lmat + (size_t)t * 4);
+
+  double Rm[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) Rm[i] = __ldg(op.rmat + k * 16 + i);
+  __syncthreads();
+
+  const unsigned int base = blockIdx.x * (PLG_DNA_THREADS * ITEMS) + threadIdx.x;
+  d4 r[ITEMS];
+  unsigned int code[ITEMS];
+  bool valid[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j)
+  {
+    const unsigned int e = base + j * PLG_DNA_THREADS;
+    valid[j] = e < nelem;
+    code[j] = 0;
+    if (valid[j])
+    {
+      r[j] = ld_stream(op.right + (size_t)e * 4);
+      code[j] = __ldg(op.ltip + e / R);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j)
+  {
+    const unsigned int e = base + j * PLG_DNA_THREADS;
+    d4 p;
+    bool below = false;
+    if (valid[j])
+    {
+      p = mul4(tab[code[j] * R + k], matvec4_unfused(Rm, r[j]));
+      below = all_below(p);
+    }
+    const bool scale = scale_decision<R>(valid[j], below, scale_mode, e, op);
+    if (valid[j])
+    {
+      if (scale) p = scale_up(p);
+      st_stream(op.parent + (size_t)e * 4, p);
+    }
+  }
+}
+
+/* tip-tip: parent[n][k][i] = tableL[l[n]][k][i] * tableR[r[n]][k][i]; never scales and
+ * zeroes the parent scaler (reference src/core_partials_avx.c:581-618, :262-364: the
+ * reference materialises the 16x16 product table, the products are the same numbers). */
+template <int R, int ITEMS>
+__global__ void __launch_bounds__(PLG_DNA_THREADS)
+k_partial_tt_dna(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mode)
+{
+  const DevOp op = ops[blockIdx.y];
+  const unsigned int k = threadIdx.x & (R - 1);
+
+  __shared__ d4 tabl[16 * R];
+  __shared__ d4 tabr[16 * R];
+  for (unsigned int t = threadIdx.x; t < 16 * R; t += PLG_DNA_THREADS)
+  {
+    tabl[t] = *reinterpret_cast<const d4 *>(op.lmat + (size_t)t * 4);
+    tabr[t] = *reinterpret_cast<const d4 *>(op.rmat + (size_t)t * 4);
+  }
+  __syncthreads();
+
+  const unsigned int base = blockIdx.x * (PLG_DNA_THREADS * ITEMS) + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j)
+  {
+    const unsigned int e = base + j * PLG_DNA_THREADS;
+    if (e < nelem)
+    {
+      const unsigned int n = e / R;
+      const unsigned int lc = __ldg(op.ltip + n);
+      const unsigned int rc = __ldg(op.rtip + n);
+      st_stream(op.parent + (size_t)e * 4, mul4(tabl[lc * R + k], tabr[rc * R + k]));
+      if (scale_mode == 1)
+      {
+        if (k == 0) op.pscale[n] = 0u;
+      }
+      else if (scale_mode == 2)
+        op.pscale[e] = 0u;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* 20-state kernels                                                                      */
+/* ------------------------------------------------------------------------------------ */
+#define PLG_AA_THREADS 128
+
+/* rows [4*ib, 4*ib+4) of M (20x20, row-major in shared memory) times c, with the AVX2
+ * accumulation order: per row four lane accumulators over the five column blocks, FMA
+ * (reference src/core_partials_avx2.c:671-731) or mul+add (reference
+ * src/core_partials_avx.c:1236-1286), then the (a0+a1)+(a2+a3) sum. */
+template <bool FUSED>
+__device__ __forceinline__ double row20(const double * __restrict__ Mrow, const double (&c)[20])
+{
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+  for (int b = 0; b < 5; ++b)
+  {
+    const double2 m01 = *reinterpret_cast<const double2 *>(Mrow + 4 * b);
+    const double2 m23 = *reinterpret_cast<const double2 *>(Mrow + 4 * b + 2);
+    if (FUSED)
+    {
+      a0 = __fma_rn(m01.x, c[4 * b + 0], a0);
+      a1 = __fma_rn(m01.y, c[4 * b + 1], a1);
+      a2 = __fma_rn(m23.x, c[4 * b + 2], a2);
+      a3 = __fma_rn(m23.y, c[4 * b + 3], a3);
+    }
+    else
+    {
+      a0 = __dadd_rn(a0, __dmul_rn(m01.x, c[4 * b + 0]));
+      a1 = __dadd_rn(a1, __dmul_rn(m01.y, c[4 * b + 1]));
+      a2 = __dadd_rn(a2, __dmul_rn(m23.x, c[4 * b + 2]));
+      a3 = __dadd_rn(a3, __dmul_rn(m23.y, c[4 * b + 3]));
+    }
+  }
+  return hsum4(a0, a1, a2, a3);
+}
+
+__device__ __forceinline__ void load20(const double * p, double (&c)[20])
+{
+#pragma unroll
+  for (int b = 0; b < 5; ++b)
+  {
+    const d4 v = ld_stream(p + 4 * b);
+    c[4 * b + 0] = v.x;
+    c[4 * b + 1] = v.y;
+    c[4 * b + 2] = v.z;
+    c[4 * b + 3] = v.w;
+  }
+}
+
+__device__ __forceinline__ void rescale20(double * p)
+{
+#pragma unroll
+  for (int b = 0; b < 5; ++b)
+  {
+    d4 v = *reinterpret_cast<d4 *>(p + 4 * b);
+    *reinterpret_cast<d4 *>(p + 4 * b) = scale_up(v);
+  }
+}
+
+/* inner-inner, 20 states (reference src/core_partials_avx2.c:632-802) */
+template <int R>
+__global__ void __launch_bounds__(PLG_AA_THREADS)
+k_partial_ii_aa(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mode)
+{
+  extern __shared__ __align__(16) double smem[];
+  double * Ls = smem;            /* [R][20][20] */
+  double * Rs = smem + R * 400;  /* [R][20][20] */
+  const DevOp op = ops[blockIdx.y];
+  for (unsigned int t = threadIdx.x; t < R * 400; t += PLG_AA_THREADS)
+  {
+    Ls[t] = __ldg(op.lmat + t);
+    Rs[t] = __ldg(op.rmat + t);
+  }
+  __syncthreads();
+
+  const unsigned int k = threadIdx.x & (R - 1);
+  const unsigned int e = blockIdx.x * PLG_AA_THREADS + threadIdx.x;
+  const bool valid = e < nelem;
+  bool below = true;
+  double * out = op.parent + (size_t)e * 20;
+  if (valid)
+  {
+    double l[20], r[20];
+    load20(op.left + (size_t)e * 20, l);
+    load20(op.right + (size_t)e * 20, r);
+    const double * Lk = Ls + k * 400;
+    const double * Rk = Rs + k * 400;
+#pragma unroll
+    for (int ib = 0; ib < 5; ++ib)
+    {
+      d4 p;
+      p.x = __dmul_rn(row20<true>(Lk + (4 * ib + 0) * 20, l), row20<true>(Rk + (4 * ib + 0) * 20, r));
+      p.y = __dmul_rn(row20<true>(Lk + (4 * ib + 1) * 20, l), row20<true>(Rk + (4 * ib + 1) * 20, r));
+      p.z = __dmul_rn(row20<true>(Lk + (4 * ib + 2) * 20, l), row20<true>(Rk + (4 * ib + 2) * 20, r));
+      p.w = __dmul_rn(row20<true>(Lk + (4 * ib + 3) * 20, l), row20<true>(Rk + (4 * ib + 3) * 20, r));
+      below = below && all_below(p);
+      *reinterpret_cast<d4 *>(out + 4 * ib) = p;
+    }
+  }
+  const bool scale = scale_decision<R>(valid, valid && below, scale_mode, e, op);
+  if (valid && scale) rescale20(out);
+}
+
+/* tip-inner, 20 states (reference src/core_partials_avx.c:1204-1338: the AVX kernel is what
+ * the AVX2 flag dispatches to, reference src/core_partials.c:427-444) */
+template <int R>
+__global__ void __launch_bounds__(PLG_AA_THREADS)
+k_partial_ti_aa(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mode)
+{
+  extern __shared__ __align__(16) double smem[];
+  double * Rs = smem; /* [R][20][20] */
+  const DevOp op = ops[blockIdx.y];
+  for (unsigned int t = threadIdx.x; t < R * 400; t += PLG_AA_THREADS) Rs[t] = __ldg(op.rmat + t);
+  __syncthreads();
+
+  const unsigned int k = threadIdx.x & (R - 1);
+  const unsigned int e = blockIdx.x * PLG_AA_THREADS + threadIdx.x;
+  const bool valid = e < nelem;
+  bool below = true;
+  double * out = op.parent + (size_t)e * 20;
+  if (valid)
+  {
+    double r[20];
+    load20(op.right + (size_t)e * 20, r);
+    const unsigned int code = __ldg(op.ltip + e / R);
+    const double * tab = op.lmat + ((size_t)code * R + k) * 20;
+    const double * Rk = Rs + k * 400;
+#pragma unroll
+    for (int ib = 0; ib < 5; ++ib)
+    {
+      const d4 a = *reinterpret_cast<const d4 *>(tab + 4 * ib);
+      d4 p;
+      p.x = __dmul_rn(a.x, row20<false>(Rk + (4 * ib + 0) * 20, r));
+      p.y = __dmul_rn(a.y, row20<false>(Rk + (4 * ib + 1) * 20, r));
+      p.z = __dmul_rn(a.z, row20<false>(Rk + (4 * ib + 2) * 20, r));
+      p.w = __dmul_rn(a.w, row20<false>(Rk + (4 * ib + 3) * 20, r));
+      below = below && all_below(p);
+      *reinterpret_cast<d4 *>(out + 4 * ib) = p;
+    }
+  }
+  const bool scale = scale_decision<R>(valid, valid && below, scale_mode, e, op);
+  if (valid && scale) rescale20(out);
+}
+
+/* tip-tip, 20 states (reference src/core_partials_avx.c:531-579, :225-256) */
+template <int R>
+__global__ void __launch_bounds__(PLG_AA_THREADS)
+k_partial_tt_aa(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mode)
+{
+  const DevOp op = ops[blockIdx.y];
+  const unsigned int k = threadIdx.x & (R - 1);
+  const unsigned int e = blockIdx.x * PLG_AA_THREADS + threadIdx.x;
+  if (e >= nelem) return;
+  const unsigned int n = e / R;
+  const unsigned int lc = __ldg(op.ltip + n);
+  const unsigned int rc = __ldg(op.rtip + n);
+  const double * tl = op.lmat + ((size_t)lc * R + k) * 20;
+  const double * tr = op.rmat + ((size_t)rc * R + k) * 20;
+  double * out = op.parent + (size_t)e * 20;
+#pragma unroll
+  for (int ib = 0; ib < 5; ++ib)
+  {
+    const d4 a = *reinterpret_cast<const d4 *>(tl + 4 * ib);
+    const d4 b = *reinterpret_cast<const d4 *>(tr + 4 * ib);
+    st_stream(out + 4 * ib, mul4(a, b));
+  }
+  if (scale_mode == 1)
+  {
+    if (k == 0) op.pscale[n] = 0u;
+  }
+  else if (scale_mode == 2)
+    op.pscale[e] = 0u;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* host side: levelisation, batching, launch                                             */
+/* ------------------------------------------------------------------------------------ */
+struct Group
+{
+  int kind;
+  int scale_mode;
+  unsigned int first; /* index into the sorted DevOp array */
+  unsigned int count;
+};
+
+struct Plan
+{
+  std::vector<DevOp> ops;      /* sorted by (level, kind, scale_mode) */
+  std::vector<TableJob> jobs;  /* tip lookup tables to build first */
+  std::vector<Group> groups;
+  unsigned long long levels;
+  unsigned long long algorithmic_bytes;
+  size_t table_doubles;
+};
+
+static int build_plan(plg_context * ctx, const pll_operation_t * operations, unsigned int count,
+                      Plan & plan)
+{
+  const unsigned int n_clv = ctx->d.tips + ctx->d.clv_buffers;
+  const unsigned int n_sc = ctx->d.scale_buffers;
+  const unsigned int K = ctx->d.states;
+  const unsigned int R = ctx->d.rate_cats;
+  const size_t table_len = (size_t)(K == 4 ? 16u : ctx->maxstates) * R * K;
+
+  /* dependency levels: level(op) > level of every earlier op it has a RAW, WAR or WAW
+   * relation with, on CLV slots and on scaler slots.  Executing levels in increasing order
+   * is therefore equivalent to the reference's strictly sequential loop. */
+  std::vector<int> clv_w(n_clv, -1), clv_r(n_clv, -1), sc_w(n_sc, -1), sc_r(n_sc, -1);
+
+  struct Item
+  {
+    int level, kind, scale_mode;
+    DevOp op;
+  };
+  std::vector<Item> items(count);
+  size_t n_tables = 0;
+  int max_level = -1;
+  plan.algorithmic_bytes = 0;
+
+  const size_t span_bytes = ctx->span * sizeof(double);
+  const size_t scaler_unit = ctx->rate_scalers ? 4u * R : 4u;
+
+  for (unsigned int i = 0; i < count; ++i)
+  {
+    const pll_operation_t & o = operations[i];
+    if (o.parent_clv_index >= n_clv || o.child1_clv_index >= n_clv ||
+        o.child2_clv_index >= n_clv || o.parent_clv_index < ctx->clv_first ||
+        o.child1_matrix_index >= ctx->d.prob_matrices ||
+        o.child2_matrix_index >= ctx->d.prob_matrices ||
+        o.parent_scaler_index >= (int)n_sc || o.child1_scaler_index >= (int)n_sc ||
+        o.child2_scaler_index >= (int)n_sc)
+    {
+      plg_set_error("plg_update_partials: operation %u has an index out of range", i);
+      return PLG_E_INVALID;
+    }
+    const bool t1 = plg_is_tip(ctx, o.child1_clv_index);
+    const bool t2 = plg_is_tip(ctx, o.child2_clv_index);
+    Item & it = items[i];
+    memset(&it.op, 0, sizeof(DevOp));
+    it.kind = (t1 && t2) ? PLG_KIND_TT : ((t1 || t2) ? PLG_KIND_TI : PLG_KIND_II);
+    it.op.parent = plg_clv_ptr(ctx, o.parent_clv_index);
+    it.op.pscale = plg_scaler_ptr(ctx, o.parent_scaler_index);
+    it.scale_mode = it.op.pscale ? (ctx->rate_scalers ? 2 : 1) : 0;
+
+    int level = 0;
+    auto after = [&](int l) { if (l + 1 > level) level = l + 1; };
+    /* parent slot: WAW and WAR */
+    after(clv_w[o.parent_clv_index]);
+    after(clv_r[o.parent_clv_index]);
+    if (it.op.pscale)
+    {
+      after(sc_w[o.parent_scaler_index]);
+      after(sc_r[o.parent_scaler_index]);
+    }
+
+    int read_clv[2] = {-1, -1}, read_sc[2] = {-1, -1};
+    size_t bytes = span_bytes; /* parent store */
+    if (it.kind == PLG_KIND_II)
+    {
+      it.op.left = plg_clv_ptr(ctx, o.child1_clv_index);
+      it.op.right = plg_clv_ptr(ctx, o.child2_clv_index);
+      it.op.lmat = plg_pmat_ptr(ctx, o.child1_matrix_index);
+      it.op.rmat = plg_pmat_ptr(ctx, o.child2_matrix_index);
+      read_clv[0] = (int)o.child1_clv_index;
+      read_clv[1] = (int)o.child2_clv_index;
+      if (it.op.pscale)
+      {
+        /* children scalers are only consulted when the parent has one
+         * (reference src/core_partials_avx.c:397-410) */
+        it.op.lscale = plg_scaler_ptr(ctx, o.child1_scaler_index);
+        it.op.rscale = plg_scaler_ptr(ctx, o.child2_scaler_index);
+        if (it.op.lscale) read_sc[0] = o.child1_scaler_index;
+        if (it.op.rscale) read_sc[1] = o.child2_scaler_index;
+      }
+      bytes += 2 * span_bytes;
+    }
+    else if (it.kind == PLG_KIND_TI)
+    {
+      /* which child is the tip (reference src/partials.c:91-112); the tip's scaler index
+       * is ignored */
+      const unsigned int tip = t1 ? o.child1_clv_index : o.child2_clv_index;
+      const unsigned int inner = t1 ? o.child2_clv_index : o.child1_clv_index;
+      const unsigned int tip_mat = t1 ? o.child1_matrix_index : o.child2_matrix_index;
+      const unsigned int inner_mat = t1 ? o.child2_matrix_index : o.child1_matrix_index;
+      const int inner_sc = t1 ? o.child2_scaler_index : o.child1_scaler_index;
+      it.op.ltip = plg_tip_ptr(ctx, tip);
+      it.op.right = plg_clv_ptr(ctx, inner);
+      it.op.rmat = plg_pmat_ptr(ctx, inner_mat);
+      it.op.lmat = (const double *)(uintptr_t)(n_tables * table_len); /* offset, fixed up below */
+      plan.jobs.push_back(TableJob{plg_pmat_ptr(ctx, tip_mat), (double *)(uintptr_t)(n_tables * table_len)});
+      ++n_tables;
+      read_clv[0] = (int)inner;
+      if (it.op.pscale)
+      {
+        it.op.rscale = plg_scaler_ptr(ctx, inner_sc);
+        if (it.op.rscale) read_sc[0] = inner_sc;
+      }
+      bytes += span_bytes + 1;
+    }
+    else
+    {
+      it.op.ltip = plg_tip_ptr(ctx, o.child1_clv_index);
+      it.op.rtip = plg_tip_ptr(ctx, o.child2_clv_index);
+      it.op.lmat = (const double *)(uintptr_t)(n_tables * table_len);
+      plan.jobs.push_back(TableJob{plg_pmat_ptr(ctx, o.child1_matrix_index), (double *)(uintptr_t)(n_tables * table_len)});
+      ++n_tables;
+      it.op.rmat = (const double *)(uintptr_t)(n_tables * table_len);
+      plan.jobs.push_back(TableJob{plg_pmat_ptr(ctx, o.child2_matrix_index), (double *)(uintptr_t)(n_tables * table_len)});
+      ++n_tables;
+      bytes += 2;
+    }
+    if (it.op.pscale) bytes += scaler_unit;
+    if (it.op.lscale) bytes += scaler_unit;
+    if (it.op.rscale) bytes += scaler_unit;
+    plan.algorithmic_bytes += bytes * ctx->d.sites;
+
+    for (int c = 0; c < 2; ++c)
+    {
+      if (read_clv[c] >= 0) after(clv_w[read_clv[c]]);
+      if (read_sc[c] >= 0) after(sc_w[read_sc[c]]);
+    }
+    /* `after(l)` left level = 1 + max over predecessors (0 when there is none) */
+    it.level = level;
+
+    clv_w[o.parent_clv_index] = level;
+    if (it.op.pscale) sc_w[o.parent_scaler_index] = level;
+    for (int c = 0; c < 2; ++c)
+    {
+      if (read_clv[c] >= 0 && clv_r[read_clv[c]] < level) clv_r[read_clv[c]] = level;
+      if (read_sc[c] >= 0 && sc_r[read_sc[c]] < level) sc_r[read_sc[c]] = level;
+    }
+    if (level > max_level) max_level = level;
+  }
+  plan.levels = (unsigned long long)(max_level + 1);
+  plan.table_doubles = n_tables * table_len;
+
+  /* stable sort by (level, kind, scale_mode) -> contiguous groups */
+  std::vector<unsigned int> order(count);
+  for (unsigned int i = 0; i < count; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](unsigned int a, unsigned int b) {
+    if (items[a].level != items[b].level) return items[a].level < items[b].level;
+    if (items[a].kind != items[b].kind) return items[a].kind < items[b].kind;
+    return items[a].scale_mode < items[b].scale_mode;
+  });
+  plan.ops.resize(count);
+  for (unsigned int i = 0; i < count; ++i)
+  {
+    const Item & it = items[order[i]];
+    plan.ops[i] = it.op;
+    const bool new_group = plan.groups.empty() || i == 0 ||
+                           items[order[i - 1]].level != it.level ||
+                           items[order[i - 1]].kind != it.kind ||
+                           items[order[i - 1]].scale_mode != it.scale_mode ||
+                           plan.groups.back().count >= 65535u;
+    if (new_group) plan.groups.push_back(Group{it.kind, it.scale_mode, i, 0});
+    plan.groups.back().count++;
+  }
+  return PLG_OK;
+}
+
+template <int R>
+static void launch_group(plg_context * ctx, const Group & g, const DevOp * dev_ops,
+                         unsigned int nelem)
+{
+  const DevOp * ops = dev_ops + g.first;
+  if (ctx->d.states == 4)
+  {
+    if (g.kind == PLG_KIND_II)
+    {
+      constexpr int ITEMS = 2;
+      dim3 grid((nelem + PLG_DNA_THREADS * ITEMS - 1) / (PLG_DNA_THREADS * ITEMS), g.count);
+      k_partial_ii_dna<R, ITEMS><<<grid, PLG_DNA_THREADS, 0, ctx->stream>>>(ops, nelem, g.scale_mode);
+    }
+    else if (g.kind == PLG_KIND_TI)
+    {
+      constexpr int ITEMS = 4;
+      dim3 grid((nelem + PLG_DNA_THREADS * ITEMS - 1) / (PLG_DNA_THREADS * ITEMS), g.count);
+      k_partial_ti_dna<R, ITEMS><<<grid, PLG_DNA_THREADS, 0, ctx->stream>>>(ops, nelem, g.scale_mode);
+    }
+    else
+    {
+      constexpr int ITEMS = 4;
+      dim3 grid((nelem + PLG_DNA_THREADS * ITEMS - 1) / (PLG_DNA_THREADS * ITEMS), g.count);
+      k_partial_tt_dna<R, ITEMS><<<grid, PLG_DNA_THREADS, 0, ctx->stream>>>(ops, nelem, g.scale_mode);
+    }
+  }
+  else
+  {
+    dim3 grid((nelem + PLG_AA_THREADS - 1) / PLG_AA_THREADS, g.count);
+    if (g.kind == PLG_KIND_II)
+    {
+      const size_t smem = (size_t)2 * R * 400 * sizeof(double);
+      k_partial_ii_aa<R><<<grid, PLG_AA_THREADS, smem, ctx->stream>>>(ops, nelem, g.scale_mode);
+    }
+    else if (g.kind == PLG_KIND_TI)
+    {
+      const size_t smem = (size_t)R * 400 * sizeof(double);
+      k_partial_ti_aa<R><<<grid, PLG_AA_THREADS, smem, ctx->stream>>>(ops, nelem, g.scale_mode);
+    }
+    else
+      k_partial_tt_aa<R><<<grid, PLG_AA_THREADS, 0, ctx->stream>>>(ops, nelem, g.scale_mode);
+  }
+}
+
+template <int R>
+static int set_smem_limits()
+{
+  /* 20-state kernels keep both P-matrix sets in shared memory: 2*R*3200 bytes */
+  static bool done = false;
+  if (done) return PLG_OK;
+  PLG_CUDA(cudaFuncSetAttribute(k_partial_ii_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                2 * R * 400 * (int)sizeof(double)));
+  PLG_CUDA(cudaFuncSetAttribute(k_partial_ti_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                R * 400 * (int)sizeof(double)));
+  done = true;
+  return PLG_OK;
+}
+
+static int enqueue_plan(plg_context * ctx, const Plan & plan, const DevOp * dev_ops,
+                        const TableJob * dev_jobs, unsigned long long * kernels)
+{
+  const unsigned int R = ctx->d.rate_cats;
+  const unsigned int nelem = ctx->d.sites * R;
+  unsigned long long launched = 0;
+
+  if (!plan.jobs.empty())
+  {
+    if (ctx->d.states == 4)
+      k_tip_tables_dna<<<(unsigned int)plan.jobs.size(), 256, 0, ctx->stream>>>(dev_jobs, R);
+    else
+    {
+      TipmapArg tm;
+      memcpy(tm.map, ctx->tipmap, sizeof(tm.map));
+      k_tip_tables_aa<<<(unsigned int)plan.jobs.size(), 256, 0, ctx->stream>>>(dev_jobs, R,
+                                                                                ctx->maxstates, tm);
+    }
+    ++launched;
+  }
+  for (const Group & g : plan.groups)
+  {
+    switch (R)
+    {
+      case 1: launch_group<1>(ctx, g, dev_ops, nelem); break;
+      case 2: launch_group<2>(ctx, g, dev_ops, nelem); break;
+      case 4: launch_group<4>(ctx, g, dev_ops, nelem); break;
+      case 8: launch_group<8>(ctx, g, dev_ops, nelem); break;
+      case 16: launch_group<16>(ctx, g, dev_ops, nelem); break;
+      default:
+        plg_set_error("plg_update_partials: rate_cats=%u unsupported", R);
+        return PLG_E_UNSUPPORTED;
+    }
+    ++launched;
+  }
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess)
+  {
+    plg_set_error("plg_update_partials: kernel launch failed: %s", cudaGetErrorString(err));
+    return PLG_E_CUDA;
+  }
+  *kernels = launched;
+  return PLG_OK;
+}
+
+static uint64_t fnv1a(const void * data, size_t bytes)
+{
+  const unsigned char * p = (const unsigned char *)data;
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < bytes; ++i)
+  {
+    h ^= p[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * operations,
+                                   unsigned int count)
+{
+  PLG_CHECK_CTX(ctx);
+  if (count == 0) return PLG_OK;
+  if (!operations)
+  {
+    plg_set_error("plg_update_partials: NULL operations");
+    return PLG_E_INVALID;
+  }
+  if (ctx->d.states == 20)
+  {
+    int rc = PLG_OK;
+    switch (ctx->d.rate_cats)
+    {
+      case 1: rc = set_smem_limits<1>(); break;
+      case 2: rc = set_smem_limits<2>(); break;
+      case 4: rc = set_smem_limits<4>(); break;
+      case 8: rc = set_smem_limits<8>(); break;
+      case 16: rc = set_smem_limits<16>(); break;
+    }
+    if (rc) return rc;
+  }
+
+  const size_t key_bytes = (size_t)count * sizeof(pll_operation_t);
+
+  /* ---- replay a cached graph of this exact list ---- */
+  uint64_t key = 0;
+  const bool try_graph = ctx->use_graphs && count >= 2;
+  if (try_graph)
+  {
+    key = fnv1a(operations, key_bytes) ^ ((uint64_t)ctx->maxstates << 56);
+    auto hit = ctx->graphs->find(key);
+    if (hit != ctx->graphs->end() && hit->second->key_bytes.size() == key_bytes &&
+        memcmp(hit->second->key_bytes.data(), operations, key_bytes) == 0)
+    {
+      plg_graph_entry * ge = hit->second;
+      PLG_CUDA(cudaGraphLaunch(ge->exec, ctx->stream));
+      ctx->stats.graph_launches++;
+      ctx->stats.kernel_launches += ge->kernels;
+      ctx->stats.partial_ops += count;
+      ctx->stats.partial_levels += ge->levels;
+      ctx->stats.algorithmic_bytes += ge->algorithmic_bytes;
+      return PLG_OK;
+    }
+  }
+
+  Plan plan;
+  int rc = build_plan(ctx, operations, count, plan);
+  if (rc) return rc;
+
+  if (plan.table_doubles > ctx->tables_cap)
+  {
+    /* the scratch is about to move: cached graphs hold its old address */
+    for (auto & kv : *ctx->graphs)
+    {
+      if (kv.second->exec) cudaGraphExecDestroy(kv.second->exec);
+      cudaFree(kv.second->dev_tables);
+      delete kv.second;
+    }
+    ctx->graphs->clear();
+    rc = plg_ensure_tables(ctx, plan.table_doubles);
+    if (rc) return rc;
+  }
+  /* turn table offsets into addresses */
+  for (TableJob & j : plan.jobs) j.out = ctx->tables + (uintptr_t)j.out;
+  for (size_t gi = 0; gi < plan.groups.size(); ++gi)
+  {
+    const Group & g = plan.groups[gi];
+    for (unsigned int i = g.first; i < g.first + g.count; ++i)
+    {
+      DevOp & op = plan.ops[i];
+      if (g.kind != PLG_KIND_II) op.lmat = ctx->tables + (uintptr_t)op.lmat;
+      if (g.kind == PLG_KIND_TT) op.rmat = ctx->tables + (uintptr_t)op.rmat;
+    }
+  }
+
+  const size_t ops_bytes = plan.ops.size() * sizeof(DevOp);
+  const size_t jobs_bytes = plan.jobs.size() * sizeof(TableJob);
+  const size_t ops_bytes_al = (ops_bytes + 255) / 256 * 256;
+  unsigned long long kernels = 0;
+
+  if (try_graph && ctx->graphs->size() < 64)
+  {
+    /* descriptors get a stable home, then the whole list is captured once */
+    void * dev = NULL;
+    PLG_CUDA(cudaMalloc(&dev, ops_bytes_al + jobs_bytes + 256));
+    PLG_CUDA(cudaMemcpyAsync(dev, plan.ops.data(), ops_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (jobs_bytes)
+      PLG_CUDA(cudaMemcpyAsync((char *)dev + ops_bytes_al, plan.jobs.data(), jobs_bytes,
+                               cudaMemcpyHostToDevice, ctx->stream));
+    PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.h2d_bytes += ops_bytes + jobs_bytes;
+
+    cudaGraph_t graph = NULL;
+    PLG_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_plan(ctx, plan, (const DevOp *)dev, (const TableJob *)((char *)dev + ops_bytes_al),
+                      &kernels);
+    cudaError_t cerr = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc || cerr != cudaSuccess)
+    {
+      if (graph) cudaGraphDestroy(graph);
+      cudaFree(dev);
+      if (!rc)
+      {
+        plg_set_error("plg_update_partials: graph capture failed: %s", cudaGetErrorString(cerr));
+        rc = PLG_E_CUDA;
+      }
+      return rc;
+    }
+    cudaGraphExec_t exec = NULL;
+    cerr = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (cerr != cudaSuccess)
+    {
+      cudaFree(dev);
+      plg_set_error("plg_update_partials: graph instantiate failed: %s", cudaGetErrorString(cerr));
+      return PLG_E_CUDA;
+    }
+    plg_graph_entry * ge = new plg_graph_entry();
+    ge->exec = exec;
+    ge->key_bytes.assign((const unsigned char *)operations, (const unsigned char *)operations + key_bytes);
+    ge->dev_tables = dev;
+    ge->kernels = kernels;
+    ge->levels = plan.levels;
+    ge->algorithmic_bytes = plan.algorithmic_bytes;
+    auto old = ctx->graphs->find(key);
+    if (old != ctx->graphs->end())
+    {
+      /* hash collision with a different list: replace */
+      PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaGraphExecDestroy(old->second->exec);
+      cudaFree(old->second->dev_tables);
+      delete old->second;
+    }
+    (*ctx->graphs)[key] = ge;
+    PLG_CUDA(cudaGraphLaunch(exec, ctx->stream));
+    ctx->stats.graph_launches++;
+  }
+  else
+  {
+    if (plg_stage_reserve(ctx, ops_bytes + jobs_bytes + 1024)) return PLG_E_CUDA;
+    const DevOp * dev_ops = (const DevOp *)plg_stage(ctx, plan.ops.data(), ops_bytes);
+    if (!dev_ops) return PLG_E_CUDA;
+    const TableJob * dev_jobs = NULL;
+    if (jobs_bytes)
+    {
+      dev_jobs = (const TableJob *)plg_stage(ctx, plan.jobs.data(), jobs_bytes);
+      if (!dev_jobs) return PLG_E_CUDA;
+    }
+    rc = enqueue_plan(ctx, plan, dev_ops, dev_jobs, &kernels);
+    if (rc) return rc;
+  }
+  ctx->stats.kernel_launches += kernels;
+  ctx->stats.partial_ops += count;
+  ctx->stats.partial_levels += plan.levels;
+  ctx->stats.algorithmic_bytes += plan.algorithmic_bytes;
+  return PLG_OK;
+}
