@@ -1,0 +1,178 @@
+"""Deterministic synthetic workloads: tree, branch lengths, tips,
+pattern weights and models.  Pure numpy; shared by the GPU runs, the CPU baseline and the
+parity tests so that all of them see exactly the same inputs.
+
+Tree: random-join unrooted binary topology.  Start with the T tip ids, repeatedly join two
+uniformly chosen live nodes into inner node T+k (CLV index T+k, scale buffer k; a child's
+P-matrix index is the child's CLV index) until two nodes remain; the likelihood is evaluated
+on the edge between those two.  The operations come out in creation order, which is a valid
+post-order.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from .binding import (
+    OP_DTYPE,
+    PLL_ATTRIB_PATTERN_TIP,
+    PLL_SCALE_BUFFER_NONE,
+    Partition,
+    PllLibrary,
+)
+
+DNA_ALPHABET = np.frombuffer(b"ACGT", dtype=np.uint8)
+AA_ALPHABET = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV", dtype=np.uint8)
+
+GTR_RATES = np.array([1.2, 3.1, 0.9, 1.1, 3.3, 1.0])
+GTR_FREQS = np.array([0.30, 0.20, 0.25, 0.25])
+
+
+@dataclass
+class Workload:
+    tips: int
+    sites: int
+    states: int
+    rate_cats: int = 4
+    alpha: float = 0.5
+    seed: int = 42
+    ops: np.ndarray = field(default=None, repr=False)
+    matrix_indices: np.ndarray = field(default=None, repr=False)
+    branch_lengths: np.ndarray = field(default=None, repr=False)
+    root_a: int = 0  # the two nodes of the evaluation edge
+    root_b: int = 0
+    root_matrix: int = 0
+    root_seq: np.ndarray = field(default=None, repr=False)  # [sites] state indices
+    weights: np.ndarray = field(default=None, repr=False)
+
+    # ---- derived sizes -------------------------------------------------------------
+    @property
+    def inner(self) -> int:
+        return self.tips - 2
+
+    @property
+    def prob_matrices(self) -> int:
+        return 2 * self.tips - 2
+
+    def scaler_of(self, node: int) -> int:
+        return node - self.tips if node >= self.tips else PLL_SCALE_BUFFER_NONE
+
+    def op_kinds(self):
+        """(#tip-tip, #tip-inner, #inner-inner) operations with pattern tips."""
+        t1 = self.ops["child1_clv_index"] < self.tips
+        t2 = self.ops["child2_clv_index"] < self.tips
+        tt = int(np.sum(t1 & t2))
+        ti = int(np.sum(t1 ^ t2))
+        return tt, ti, len(self.ops) - tt - ti
+
+    def algorithmic_bytes_per_site(self) -> int:
+        """ii = 3*span+12, ti = 2*span+1+8, tt = span+2+4 (per-site scalers)."""
+        span = self.rate_cats * self.states * 8
+        tt, ti, ii = self.op_kinds()
+        return ii * (3 * span + 12) + ti * (2 * span + 9) + tt * (span + 6)
+
+
+def make_workload(tips: int, sites: int, states: int = 4, rate_cats: int = 4, alpha: float = 0.5,
+                  seed: int = 42) -> Workload:
+    assert tips >= 3
+    w = Workload(tips=tips, sites=sites, states=states, rate_cats=rate_cats, alpha=alpha, seed=seed)
+    rng = np.random.default_rng(seed)
+    live = list(range(tips))
+    ops = np.zeros(tips - 2, dtype=OP_DTYPE)
+    for k in range(tips - 2):
+        i = int(rng.integers(0, len(live)))
+        a = live.pop(i)
+        j = int(rng.integers(0, len(live)))
+        b = live.pop(j)
+        parent = tips + k
+        ops[k] = (parent, k, a, a, w.scaler_of(a), b, b, w.scaler_of(b))
+        live.append(parent)
+    w.ops = ops
+    # an inner node plays "parent" of the evaluation edge (a tip-tip edge cannot occur: T >= 3)
+    a, b = live
+    if a < tips:
+        a, b = b, a
+    w.root_a, w.root_b = a, b
+    w.root_matrix = b
+    rng_b = np.random.default_rng(seed + 2)
+    w.matrix_indices = np.arange(w.prob_matrices, dtype=np.uint32)
+    w.branch_lengths = rng_b.uniform(0.01, 0.21, size=w.prob_matrices)
+    rng_r = np.random.default_rng(seed + 1)
+    w.root_seq = rng_r.integers(0, states, size=sites, dtype=np.uint8)
+    rng_w = np.random.default_rng(seed + 3)
+    w.weights = rng_w.integers(1, 5, size=sites, dtype=np.uint32)
+    return w
+
+
+def tip_sequence(w: Workload, tip: int, lo: int = 0, hi: Optional[int] = None) -> bytes:
+    """Characters of one tip for sites [lo, hi): root state w.p. 0.7 else uniform; 1 % full
+    ambiguity (N / X), 0.5 % two-state ambiguity (R,Y / B,Z).  Site-sliceable: the value at a
+    site does not depend on the slice asked for."""
+    hi = w.sites if hi is None else hi
+    rng = np.random.default_rng([w.seed + 1, tip])
+    u = rng.random(w.sites, dtype=np.float32)
+    alt = rng.integers(0, w.states, size=w.sites, dtype=np.uint8)
+    u2 = rng.random(w.sites, dtype=np.float32)
+    sl = slice(lo, hi)
+    idx = np.where(u[sl] < 0.7, w.root_seq[sl], alt[sl])
+    alphabet = DNA_ALPHABET if w.states == 4 else AA_ALPHABET
+    chars = alphabet[idx]
+    amb_full = ord("N") if w.states == 4 else ord("X")
+    amb2 = (ord("R"), ord("Y")) if w.states == 4 else (ord("B"), ord("Z"))
+    u2s = u2[sl]
+    chars = np.where(u2s < 0.01, np.uint8(amb_full), chars)
+    two = (u2s >= 0.01) & (u2s < 0.015)
+    chars = np.where(two & (alt[sl] & 1 == 0), np.uint8(amb2[0]), chars)
+    chars = np.where(two & (alt[sl] & 1 == 1), np.uint8(amb2[1]), chars)
+    return chars.astype(np.uint8).tobytes()
+
+
+def model_for(lib: PllLibrary, w: Workload, variant: str = "default"):
+    """(rate_matrices, [(subst_params, freqs)], params_indices, rates, rate_weights)."""
+    rates = lib.gamma_rates(w.alpha, w.rate_cats)
+    weights = np.full(w.rate_cats, 1.0 / w.rate_cats)
+    if w.states == 4:
+        return 1, [(GTR_RATES, GTR_FREQS)], np.zeros(w.rate_cats, np.uint32), rates, weights
+    if variant == "lg4m":
+        assert w.rate_cats == 4
+        r = lib.aa_table("pll_aa_rates_lg4m", (4, 190))
+        f = lib.aa_table("pll_aa_freqs_lg4m", (4, 20))
+        return 4, [(r[i], f[i]) for i in range(4)], np.arange(4, dtype=np.uint32), rates, weights
+    r = lib.aa_table("pll_aa_rates_lg", (190,))
+    f = lib.aa_table("pll_aa_freqs_lg", (20,))
+    return 1, [(r, f)], np.zeros(w.rate_cats, np.uint32), rates, weights
+
+
+def build_partition(lib: PllLibrary, w: Workload, attributes: int, lo: int = 0,
+                    hi: Optional[int] = None, variant: str = "default",
+                    rates: Optional[np.ndarray] = None) -> tuple[Partition, np.ndarray]:
+    """Creates a partition over sites [lo, hi) of the workload, sets model, tips and weights.
+    Returns (partition, params_indices).  `rates` lets a caller impose category rates computed
+    elsewhere (parity tests give both libraries the same doubles)."""
+    hi = w.sites if hi is None else hi
+    n_rm, models, pidx, g_rates, g_weights = model_for(lib, w, variant)
+    pattern_tip = bool(attributes & PLL_ATTRIB_PATTERN_TIP)
+    part = lib.partition(tips=w.tips, clv_buffers=w.inner, states=w.states, sites=hi - lo,
+                         rate_matrices=n_rm, prob_matrices=w.prob_matrices, rate_cats=w.rate_cats,
+                         scale_buffers=w.inner, attributes=attributes)
+    for i, (sp, fr) in enumerate(models):
+        part.set_frequencies(i, fr)
+        part.set_subst_params(i, sp)
+    part.set_category_rates(g_rates if rates is None else rates)
+    part.set_category_weights(g_weights)
+    for t in range(w.tips):
+        part.set_tip_states(t, tip_sequence(w, t, lo, hi))
+    part.set_pattern_weights(w.weights[lo:hi])
+    del pattern_tip
+    return part, pidx
+
+
+def full_evaluation(part: Partition, w: Workload, pidx: np.ndarray) -> float:
+    """One full-tree log-likelihood evaluation: all P-matrices, the whole post-order
+    traversal, the edge log-likelihood (SURVEY.md 8(d) metric ii)."""
+    part.update_prob_matrices(pidx, w.matrix_indices, w.branch_lengths)
+    part.update_partials(w.ops)
+    return part.edge_loglikelihood(w.root_a, w.scaler_of(w.root_a), w.root_b, w.scaler_of(w.root_b),
+                                   w.root_matrix, pidx)
