@@ -45,6 +45,6 @@ for it in range(a.iters):
     ms_l = part.timer_stop()
     gbs = st["algorithmic_bytes"] / ms / 1e6
     print(f"iter {it}: traversal {ms:.3f} ms  {gbs:.0f} GB/s algorithmic  "
-          f"{len(w.ops)*a.sites/ms/1e3:.3e} site-updates/s  kernels={st['kernel_launches']} "
+          f"{len(w.ops)*a.sites/(ms*1e-3):.3e} site-updates/s  kernels={st['kernel_launches']} "
           f"levels={st['partial_levels']}  edge lnL {ms_l:.3f} ms  lnL={lnl:.6f}", flush=True)
 part.destroy()
