@@ -26,6 +26,7 @@
 #include <cmath>
 
 #include "plg_internal.cuh"
+#include "plg_async.cuh"
 
 /* ------------------------------------------------------------------------------------ */
 /* descriptors                                                                           */
@@ -331,6 +332,189 @@ k_partial_tt_dna(const DevOp * __restrict__ ops, unsigned int nelem, int scale_m
         op.pscale[e] = 0u;
     }
   }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* DNA streaming kernels: persistent CTAs + TMA bulk-copy pipeline                       */
+/* ------------------------------------------------------------------------------------ */
+/*
+ * The tip-inner and inner-inner updates are pure streaming (0.6 flop/B): what limits them is
+ * the number of bytes in flight per SM, not arithmetic.  These kernels therefore decouple the
+ * memory pipeline from the register file:
+ *   - the grid is persistent (a few CTAs per SM); the (operation, tile) space of a whole
+ *     dependency level is flattened and cut into one contiguous chunk per CTA;
+ *   - one elected thread feeds a PLG_IN_STAGES-deep ring of shared-memory tiles with 1-D TMA
+ *     bulk copies (cp.async.bulk, completion on "full" mbarriers); consumers release a stage
+ *     through an "empty" mbarrier as soon as they have pulled their 32-byte element into
+ *     registers, so copies for the next tiles are always outstanding;
+ *   - every thread owns one (site, rate) element per tile, with its rate's P-matrix rows in
+ *     registers for the whole chunk (reloaded only when the chunk crosses into the next
+ *     operation);
+ *   - results go back through a shared-memory ring and TMA bulk stores (full-line writes),
+ *     or directly with 256-bit stores when TMA_STORE is false.
+ * Arithmetic, voting and scaler bookkeeping are exactly those of the simple kernels above.
+ */
+#define PLG_TILE 256
+#define PLG_IN_STAGES 4
+#define PLG_OUT_STAGES 3
+#ifndef PLG_TMA_STORE
+#define PLG_TMA_STORE true /* results leave through shared memory + TMA bulk stores */
+#endif
+
+template <int R, int KIND, bool TMA_STORE>
+struct StreamSmem
+{
+  d4 in_r[PLG_IN_STAGES][PLG_TILE];
+  d4 in_l[KIND == PLG_KIND_II ? PLG_IN_STAGES : 1][KIND == PLG_KIND_II ? PLG_TILE : 1];
+  d4 out[TMA_STORE ? PLG_OUT_STAGES : 1][TMA_STORE ? PLG_TILE : 1];
+  d4 tab[KIND == PLG_KIND_TI ? 16 * R : 1];
+  unsigned char tips[KIND == PLG_KIND_TI ? PLG_IN_STAGES : 1][PLG_TILE];
+  uint64_t full[PLG_IN_STAGES];
+  uint64_t empty[PLG_IN_STAGES];
+};
+
+template <int R, int KIND, bool TMA_STORE>
+__global__ void __launch_bounds__(PLG_TILE, 2)
+k_partial_stream_dna(const DevOp * __restrict__ ops, unsigned int nelem, unsigned int ntiles,
+                     unsigned int total_tiles, int scale_mode)
+{
+  using namespace plg_async;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StreamSmem<R, KIND, TMA_STORE> & sm = *reinterpret_cast<StreamSmem<R, KIND, TMA_STORE> *>(smem_raw);
+
+  const unsigned int tid = threadIdx.x;
+  const unsigned int k = tid & (R - 1);
+
+  /* this CTA's contiguous chunk of the flattened (operation, tile) space */
+  const unsigned int per = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const unsigned int q0 = blockIdx.x * per;
+  if (q0 >= total_tiles) return;
+  const unsigned int q1 = (q0 + per < total_tiles) ? q0 + per : total_tiles;
+  const unsigned int n = q1 - q0;
+
+  if (tid == 0)
+  {
+#pragma unroll
+    for (int s = 0; s < PLG_IN_STAGES; ++s)
+    {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], PLG_TILE / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  /* producer: TMA copies for the j-th tile of the chunk into stage j % PLG_IN_STAGES */
+  auto issue = [&](unsigned int j) {
+    const unsigned int q = q0 + j;
+    const unsigned int o = q / ntiles;
+    const unsigned int e0 = (q - o * ntiles) * PLG_TILE;
+    const unsigned int cnt = (nelem - e0 < PLG_TILE) ? nelem - e0 : PLG_TILE;
+    const unsigned int s = j % PLG_IN_STAGES;
+    const DevOp * op = ops + o;
+    const unsigned int bytes = cnt * 32u;
+    if (KIND == PLG_KIND_II)
+    {
+      mbar_arrive_expect_tx(&sm.full[s], 2 * bytes);
+      bulk_g2s(sm.in_l[s], op->left + (size_t)e0 * 4, bytes, &sm.full[s]);
+      bulk_g2s(sm.in_r[s], op->right + (size_t)e0 * 4, bytes, &sm.full[s]);
+    }
+    else
+    {
+      const unsigned int tip_bytes = ((cnt / R) + 15u) & ~15u;
+      mbar_arrive_expect_tx(&sm.full[s], bytes + tip_bytes);
+      bulk_g2s(sm.in_r[s], op->right + (size_t)e0 * 4, bytes, &sm.full[s]);
+      bulk_g2s(sm.tips[s], op->ltip + e0 / R, tip_bytes, &sm.full[s]);
+    }
+  };
+
+  if (tid == 0)
+  {
+    const unsigned int pre = n < PLG_IN_STAGES ? n : PLG_IN_STAGES;
+    for (unsigned int j = 0; j < pre; ++j) issue(j);
+  }
+
+  double L[16], Rm[16];
+  DevOp op;
+  unsigned int cur_op = 0xffffffffu;
+
+  for (unsigned int j = 0; j < n; ++j)
+  {
+    const unsigned int q = q0 + j;
+    const unsigned int o = q / ntiles;
+    const unsigned int tile = q - o * ntiles;
+    if (o != cur_op)
+    {
+      /* chunk crossed into the next operation (block-uniform): new pointers and matrices */
+      cur_op = o;
+      op = ops[o];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+      {
+        const d4 rr = *reinterpret_cast<const d4 *>(op.rmat + k * 16 + i * 4);
+        Rm[4 * i + 0] = rr.x; Rm[4 * i + 1] = rr.y; Rm[4 * i + 2] = rr.z; Rm[4 * i + 3] = rr.w;
+        if (KIND == PLG_KIND_II)
+        {
+          const d4 ll = *reinterpret_cast<const d4 *>(op.lmat + k * 16 + i * 4);
+          L[4 * i + 0] = ll.x; L[4 * i + 1] = ll.y; L[4 * i + 2] = ll.z; L[4 * i + 3] = ll.w;
+        }
+      }
+      if (KIND == PLG_KIND_TI)
+      {
+        __syncthreads(); /* nobody still reads the previous operation's table */
+        for (unsigned int t = tid; t < 16 * R; t += PLG_TILE)
+          sm.tab[t] = *reinterpret_cast<const d4 *>(op.lmat + (size_t)t * 4);
+        __syncthreads();
+      }
+    }
+
+    const unsigned int s = j % PLG_IN_STAGES;
+    mbar_wait(&sm.full[s], (j / PLG_IN_STAGES) & 1u);
+    const d4 r = sm.in_r[s][tid];
+    d4 l;
+    unsigned int code = 0;
+    if (KIND == PLG_KIND_II) l = sm.in_l[s][tid];
+    else code = sm.tips[s][tid / R] & 15u; /* lanes past the end of a short tile see stale bytes */
+    __syncwarp();
+    if ((tid & 31u) == 0) mbar_arrive(&sm.empty[s]);
+
+    if (tid == 0 && j >= 1 && j - 1 + PLG_IN_STAGES < n)
+    {
+      /* stage of the previous tile: every warp released it an iteration ago */
+      mbar_wait(&sm.empty[(j - 1) % PLG_IN_STAGES], ((j - 1) / PLG_IN_STAGES) & 1u);
+      issue(j - 1 + PLG_IN_STAGES);
+    }
+
+    const unsigned int e = tile * PLG_TILE + tid;
+    const bool valid = e < nelem;
+    d4 p;
+    if (KIND == PLG_KIND_II) p = mul4(matvec4_unfused(L, l), matvec4_unfused(Rm, r));
+    else p = mul4(sm.tab[code * R + k], matvec4_unfused(Rm, r));
+    const bool below = valid && all_below(p);
+    const bool scale = scale_decision<R>(valid, below, scale_mode, e, op);
+    if (scale) p = scale_up(p);
+
+    if (TMA_STORE)
+    {
+      const unsigned int so = j % PLG_OUT_STAGES;
+      sm.out[so][tid] = p;
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0)
+      {
+        const unsigned int e0 = tile * PLG_TILE;
+        const unsigned int cnt = (nelem - e0 < PLG_TILE) ? nelem - e0 : PLG_TILE;
+        bulk_s2g(op.parent + (size_t)e0 * 4, sm.out[so], cnt * 32u);
+        bulk_commit();
+        /* the store issued one tile ago has finished reading its buffer; the next barrier
+         * publishes that to the CTA two tiles before the buffer is written again */
+        bulk_wait_read<1>();
+      }
+    }
+    else if (valid)
+      st_stream(op.parent + (size_t)e * 4, p);
+  }
+  if (TMA_STORE && tid == 0) bulk_wait_read<0>();
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -700,17 +884,24 @@ static void launch_group(plg_context * ctx, const Group & g, const DevOp * dev_o
   const DevOp * ops = dev_ops + g.first;
   if (ctx->d.states == 4)
   {
-    if (g.kind == PLG_KIND_II)
+    if (g.kind == PLG_KIND_II || g.kind == PLG_KIND_TI)
     {
-      constexpr int ITEMS = 2;
-      dim3 grid((nelem + PLG_DNA_THREADS * ITEMS - 1) / (PLG_DNA_THREADS * ITEMS), g.count);
-      k_partial_ii_dna<R, ITEMS><<<grid, PLG_DNA_THREADS, 0, ctx->stream>>>(ops, nelem, g.scale_mode);
-    }
-    else if (g.kind == PLG_KIND_TI)
-    {
-      constexpr int ITEMS = 4;
-      dim3 grid((nelem + PLG_DNA_THREADS * ITEMS - 1) / (PLG_DNA_THREADS * ITEMS), g.count);
-      k_partial_ti_dna<R, ITEMS><<<grid, PLG_DNA_THREADS, 0, ctx->stream>>>(ops, nelem, g.scale_mode);
+      const unsigned int ntiles = (nelem + PLG_TILE - 1) / PLG_TILE;
+      const unsigned long long total = (unsigned long long)ntiles * g.count;
+      unsigned int blocks = (unsigned int)ctx->sm_count * 2u;
+      if (total < blocks) blocks = (unsigned int)total;
+      if (g.kind == PLG_KIND_II)
+      {
+        const size_t smem = sizeof(StreamSmem<R, PLG_KIND_II, PLG_TMA_STORE>);
+        k_partial_stream_dna<R, PLG_KIND_II, PLG_TMA_STORE><<<blocks, PLG_TILE, smem, ctx->stream>>>(
+            ops, nelem, ntiles, (unsigned int)total, g.scale_mode);
+      }
+      else
+      {
+        const size_t smem = sizeof(StreamSmem<R, PLG_KIND_TI, PLG_TMA_STORE>);
+        k_partial_stream_dna<R, PLG_KIND_TI, PLG_TMA_STORE><<<blocks, PLG_TILE, smem, ctx->stream>>>(
+            ops, nelem, ntiles, (unsigned int)total, g.scale_mode);
+      }
     }
     else
     {
@@ -740,9 +931,16 @@ static void launch_group(plg_context * ctx, const Group & g, const DevOp * dev_o
 template <int R>
 static int set_smem_limits()
 {
-  /* 20-state kernels keep both P-matrix sets in shared memory: 2*R*3200 bytes */
+  /* opt in to > 48 KB of dynamic shared memory: the DNA streaming rings and the 20-state
+   * kernels' P-matrix sets (2*R*3200 bytes) */
   static bool done = false;
   if (done) return PLG_OK;
+  PLG_CUDA(cudaFuncSetAttribute(k_partial_stream_dna<R, PLG_KIND_II, PLG_TMA_STORE>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(StreamSmem<R, PLG_KIND_II, PLG_TMA_STORE>)));
+  PLG_CUDA(cudaFuncSetAttribute(k_partial_stream_dna<R, PLG_KIND_TI, PLG_TMA_STORE>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(StreamSmem<R, PLG_KIND_TI, PLG_TMA_STORE>)));
   PLG_CUDA(cudaFuncSetAttribute(k_partial_ii_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 2 * R * 400 * (int)sizeof(double)));
   PLG_CUDA(cudaFuncSetAttribute(k_partial_ti_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -818,7 +1016,6 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
     plg_set_error("plg_update_partials: NULL operations");
     return PLG_E_INVALID;
   }
-  if (ctx->d.states == 20)
   {
     int rc = PLG_OK;
     switch (ctx->d.rate_cats)
