@@ -1,0 +1,416 @@
+#!/usr/bin/env python3
+"""Headline benchmark: full post-order CLV traversal + edge log-likelihood of a synthetic
+1,000-taxon x 1M-pattern GTR+G4 DNA partition per B200 (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W          # this repository's CUDA path
+    python bench.py --impl reference ...                   # the reference's own AVX2 CPU path
+
+One "step" = one full-tree evaluation: all P-matrices, the whole traversal
+(`pll_update_partials` over T-2 operations) and `pll_compute_edge_loglikelihood`.  With N > 1
+(torchrun, one rank per GPU) the site patterns are sharded: every rank owns a contiguous slice
+of 1M patterns of EVERY CLV (weak scaling: the alignment has N x 1M patterns) and only the
+per-rank partial lnL crosses NVLink (one scalar NCCL all-reduce per step).
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  value        CLV site-updates/s, device-timed (CUDA events on the library's own stream) with
+               everything resident in HBM: traversal + edge lnL, P-matrices already on device
+  e2e          the same metric through the public pll.h API from HOST buffers, wall-clocked:
+               each step uploads fresh branch lengths / matrix indices / the operations array
+               (pinned staging -> HBM), recomputes all P-matrices, traverses, reads lnL back
+  roofline     dominant kernel (inner-inner CLV update): algorithmic bytes / CUDA-event time
+               per launch, measured live in profiling mode, against MEASURED_PEAKS.json
+  cpu_baseline the reference (oracle/_ref) timed on this box's host cores on a bounded sample
+  lnl_evals_per_s  full-tree lnL evaluations/s (1 / e2e step time) - BASELINE.json's 2nd metric
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CLV site-updates/sec (full post-order traversal + edge logL, GTR+G4 DNA)"
+UNIT = "site-updates/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ----------------------------------------------------------------------------------------
+# CPU baseline = the reference's own AVX2 path on host cores
+# ----------------------------------------------------------------------------------------
+def _ref_library():
+    from libpll_b200.binding import PllLibrary
+
+    path = os.path.join(ROOT, "oracle", "_ref", "libpll_ref.so")
+    if os.path.exists(path):
+        return PllLibrary(path, is_gpu=False), "reference"
+    return None, "port"
+
+
+def cpu_traversal_rate(w_full, threads: int, sites_per_thread: int, reps: int, warm: int = 1,
+                       use_mean: bool = False):
+    """Downstream convention for the single-threaded reference: `threads`
+    host threads, each owning an independent partition over a contiguous slice of
+    `sites_per_thread` patterns of the SAME workload; time = slowest thread.  Returns
+    (site-updates/s, seconds per step, lnL of the sample)."""
+    from libpll_b200 import synthetic as S
+    from libpll_b200.binding import PLL_ATTRIB_ARCH_AVX2, PLL_ATTRIB_PATTERN_TIP
+
+    ref, kind = _ref_library()
+    if ref is None:
+        from oracle import port as oracle_port
+
+        return oracle_port.cpu_traversal_rate(w_full, threads, sites_per_thread, reps) + (kind,)
+
+    parts = [None] * threads
+    pidx = None
+
+    def setup(t):
+        nonlocal pidx
+        lo = t * sites_per_thread
+        parts[t], pidx_t = S.build_partition(ref, w_full, PLL_ATTRIB_ARCH_AVX2 | PLL_ATTRIB_PATTERN_TIP,
+                                             lo=lo, hi=lo + sites_per_thread)
+        pidx = pidx_t
+
+    ths = [threading.Thread(target=setup, args=(t,)) for t in range(threads)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+
+    times = np.zeros((threads, warm + reps))
+    lnl = np.zeros(threads)
+    barrier = threading.Barrier(threads)
+
+    def work(t):
+        for r in range(warm + reps):
+            barrier.wait()
+            t0 = time.perf_counter()
+            lnl[t] = S.full_evaluation(parts[t], w_full, pidx)  # ctypes releases the GIL
+            times[t, r] = time.perf_counter() - t0
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    for p in parts:
+        p.destroy()
+    step = times[:, warm:].max(axis=0)  # slowest thread per repetition
+    t = float(step.mean()) if use_mean else float(step.min())
+    rate = len(w_full.ops) * threads * sites_per_thread / t
+    return rate, t, float(lnl.sum()), kind
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ----------------------------------------------------------------------------------------
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's own CPU implementation of the path on host cores."""
+    if rank != 0:
+        return
+    from libpll_b200 import synthetic as S
+
+    cores = host_cores()
+    w = S.make_workload(args.tips, args.sites_per_gpu * max(world, 1), states=4)
+    spt = args.cpu_sites_per_thread
+    # warmup + steps: each "step" is one traversal of the bounded sample on all cores
+    rate, best, lnl, kind = cpu_traversal_rate(w, cores, spt, reps=args.steps, warm=args.warmup,
+                                               use_mean=True)
+    sample = (f"{cores} threads x {spt} patterns each ({cores * spt} of {w.sites} patterns), "
+              f"{len(w.ops)} operations per traversal, mean of {args.steps} steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": best * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"synthetic {args.tips}-taxon x {w.sites}-pattern GTR+G4 DNA, "
+                               "full post-order traversal + edge logL (bounded CPU sample)",
+                   "attributes": "PLL_ATTRIB_ARCH_AVX2|PLL_ATTRIB_PATTERN_TIP"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+def run_gpu(args, rank: int, world: int, local_rank: int):
+    import torch  # plumbing only: torch.distributed (NCCL) for the scalar all-reduce / barriers
+
+    import libpll_b200
+    from libpll_b200 import synthetic as S
+    from libpll_b200.binding import PLL_ATTRIB_ARCH_GPU, PLL_ATTRIB_PATTERN_TIP
+
+    lib = libpll_b200.load()
+    if lib.plg_device_count() == 0:
+        raise SystemExit("bench.py: no B200 visible - the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    lib.pll_gpu_set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allreduce_max(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allreduce_sum(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    S_gpu = args.sites_per_gpu
+    w = S.make_workload(args.tips, S_gpu * world, states=4)
+    lo, hi = rank * S_gpu, (rank + 1) * S_gpu
+    t0 = time.time()
+    part, pidx = S.build_partition(lib, w, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP, lo=lo, hi=hi)
+    if rank == 0:
+        log(f"[bench] setup {time.time() - t0:.1f}s: {args.tips} tips x {S_gpu} patterns per GPU, "
+            f"ops tt/ti/ii = {w.op_kinds()}, {w.algorithmic_bytes_per_site()} algorithmic B per pattern")
+    root = (w.root_a, w.scaler_of(w.root_a), w.root_b, w.scaler_of(w.root_b), w.root_matrix, pidx)
+    n_ops = len(w.ops)
+
+    # ---- leg A: resident (device-timed) ------------------------------------------------
+    part.update_prob_matrices(pidx, w.matrix_indices, w.branch_lengths)
+
+    def resident_step():
+        part.update_partials(w.ops)
+        return allreduce_sum(part.edge_loglikelihood(*root))
+
+    for _ in range(max(args.warmup, 3)):
+        lnl = resident_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    part.reset_stats()
+    sampler.start()
+    part.timer_start()
+    for _ in range(args.steps):
+        lnl = resident_step()
+    ms = part.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    stats = part.stats()
+    ms = allreduce_max(ms)
+    ms_per_step = ms / args.steps
+    value = n_ops * S_gpu * world / (ms_per_step * 1e-3)
+
+    # ---- leg B: end to end through the public API, host buffers, wall clock -------------
+    rng = np.random.default_rng(1234 + rank)
+
+    def e2e_step(i):
+        # fresh host inputs every step: branch lengths change, so every P-matrix is recomputed
+        bl = w.branch_lengths * (1.0 + 1e-3 * ((i % 7) - 3))
+        ops = w.ops.copy()
+        part.update_prob_matrices(pidx, w.matrix_indices, bl)
+        part.update_partials(ops)
+        return allreduce_sum(part.edge_loglikelihood(*root))
+
+    for i in range(max(args.warmup, 3)):
+        e2e_step(i)
+    barrier()
+    part.reset_stats()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_lnl = e2e_step(i)
+    barrier()
+    e2e_s = allreduce_max(time.perf_counter() - t0) / args.steps
+    e2e_stats = part.stats()
+    e2e_value = n_ops * S_gpu * world / e2e_s
+
+    # ---- leg C: roofline of the dominant kernel, CUDA events per launch ------------------
+    part.set_profiling(True)
+    part.reset_stats()
+    for _ in range(3):
+        part.update_partials(w.ops)
+    prof = part.stats()
+    part.set_profiling(False)
+    kinds = ["tip-tip", "tip-inner", "inner-inner"]
+    shares = {}
+    tot_ns = sum(prof["kind_ns"]) or 1
+    for i, name in enumerate(kinds):
+        if prof["kind_launches"][i]:
+            shares[name] = {
+                "share_of_traversal": prof["kind_ns"][i] / tot_ns,
+                "GBps": prof["kind_bytes"][i] / max(prof["kind_ns"][i], 1),
+                "launches_per_traversal": prof["kind_launches"][i] // 3,
+            }
+    dom = int(np.argmax(prof["kind_ns"]))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    achieved = prof["kind_bytes"][dom] / max(prof["kind_ns"][dom], 1)
+    roofline = {
+        "bound": "hbm", "kernel": f"k_partial_stream_dna ({kinds[dom]})", "achieved": achieved,
+        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "traffic": None,
+        "algorithmic_bytes_per_launch": prof["kind_bytes"][dom] / max(prof["kind_launches"][dom], 1),
+        "avg_launch_ms": prof["kind_ns"][dom] / max(prof["kind_launches"][dom], 1) * 1e-6,
+        "whole_traversal_GBps": stats["algorithmic_bytes"] / args.steps / (ms_per_step * 1e-3) / 1e9,
+        "whole_traversal_frac_of_8TBps_nominal": stats["algorithmic_bytes"] / args.steps / (ms_per_step * 1e-3) / 8e12,
+        "by_kind": shares,
+    }
+    # DRAM traffic per launch: ratio (dram bytes / algorithmic byte) of this kernel from the
+    # committed `ncu` capture (profiles/traffic.json) times this launch's algorithmic bytes
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ratio = traffic[kinds[dom]]["dram_bytes_per_algorithmic_byte"]
+        roofline["traffic"] = ratio * roofline["algorithmic_bytes_per_launch"]
+        roofline["traffic_source"] = traffic[kinds[dom]]["source"]
+    except Exception:
+        pass
+
+    part.destroy()
+
+    # ---- leg D: CPU baseline (rank 0, N = 1 only) ---------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        spt = args.cpu_sites_per_thread
+        try:
+            rate, best, cpu_lnl, kind = cpu_traversal_rate(w, cores, spt, reps=2, warm=1)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": f"{cores} threads x {spt} patterns each of the same workload "
+                             f"({len(w.ops)} ops per traversal), best of 2, {best:.2f} s per step"}
+        except Exception as e:  # pragma: no cover
+            cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "unavailable", "sample": str(e)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"synthetic {args.tips}-taxon x {S_gpu * world}-pattern GTR+G4 DNA "
+                            f"({S_gpu} patterns per GPU), full post-order traversal + edge logL",
+                "attributes": "PLL_ATTRIB_ARCH_GPU|PLL_ATTRIB_PATTERN_TIP, per-site scalers",
+                "operations": n_ops, "rate_cats": 4,
+                "l2": "no flush needed: each step streams %.0f GB per GPU through a 126 MB L2" %
+                      (stats["algorithmic_bytes"] / args.steps / 1e9),
+                "sharding": "site patterns, scalar NCCL all-reduce of lnL" if world > 1 else "single GPU",
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": e2e_stats["h2d_bytes"] // args.steps,
+                    "d2h_bytes_per_step": e2e_stats["d2h_bytes"] // args.steps,
+                    "ms_per_step": e2e_s * 1e3},
+            "lnl_evals_per_s": 1.0 / e2e_s,
+            "gpu_launches": stats["kernel_launches"],
+            "graph_launches": stats["graph_launches"],
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "lnl": lnl,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
+    ap.add_argument("--tips", type=int, default=1000)
+    ap.add_argument("--sites-per-gpu", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sites-per-thread", type=int, default=10_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

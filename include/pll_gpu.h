@@ -65,6 +65,13 @@ typedef struct plg_stats
   unsigned long long partial_ops;       /* pll_operation_t entries executed */
   unsigned long long partial_levels;    /* dependency levels they were batched into */
   unsigned long long algorithmic_bytes; /* SURVEY.md 8(d) bytes of the partial kernels */
+  /* filled only while plg_set_profiling(ctx, 1) is active: per kind of CLV update
+   * (0 = tip-tip, 1 = tip-inner, 2 = inner-inner) the device time between CUDA events
+   * recorded around each launch on the context's stream, the algorithmic bytes those
+   * launches moved and their number */
+  unsigned long long kind_ns[3];
+  unsigned long long kind_bytes[3];
+  unsigned long long kind_launches[3];
 } plg_stats_t;
 
 PLL_EXPORT const char * plg_last_error(void);
@@ -205,6 +212,9 @@ PLL_EXPORT int plg_likelihood_derivatives(plg_context_t * ctx,
 PLL_EXPORT int plg_timer_start(plg_context_t * ctx);
 PLL_EXPORT int plg_timer_stop(plg_context_t * ctx, float * elapsed_ms);
 PLL_EXPORT int plg_get_stats(plg_context_t * ctx, plg_stats_t * out);
+/* Per-launch event timing of plg_update_partials (disables graph replay while on; each call
+ * then synchronises).  For roofline measurement inside a benchmark, not for production. */
+PLL_EXPORT int plg_set_profiling(plg_context_t * ctx, int enable);
 PLL_EXPORT int plg_reset_stats(plg_context_t * ctx);
 /* Overwrites a device buffer larger than L2 (126 MB) on the context's stream. */
 PLL_EXPORT int plg_flush_l2(plg_context_t * ctx);

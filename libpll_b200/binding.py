@@ -119,6 +119,9 @@ class PlgStats(C.Structure):
         ("partial_ops", C.c_ulonglong),
         ("partial_levels", C.c_ulonglong),
         ("algorithmic_bytes", C.c_ulonglong),
+        ("kind_ns", C.c_ulonglong * 3),
+        ("kind_bytes", C.c_ulonglong * 3),
+        ("kind_launches", C.c_ulonglong * 3),
     ]
 
 
@@ -175,6 +178,7 @@ _GPU_API = {
     "plg_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "plg_get_stats": (C.c_int, [C.c_void_p, C.POINTER(PlgStats)]),
     "plg_reset_stats": (C.c_int, [C.c_void_p]),
+    "plg_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "plg_flush_l2": (C.c_int, [C.c_void_p]),
     "plg_mem_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "plg_synchronize": (C.c_int, [C.c_void_p]),
@@ -462,7 +466,14 @@ class Partition:
     def stats(self) -> dict:
         st = PlgStats()
         assert self.lib.plg_get_stats(self.ctx(), C.byref(st)) == 0
-        return {name: int(getattr(st, name)) for name, _ in PlgStats._fields_}
+        out = {}
+        for name, typ in PlgStats._fields_:
+            v = getattr(st, name)
+            out[name] = int(v) if typ is C.c_ulonglong else [int(x) for x in v]
+        return out
+
+    def set_profiling(self, on: bool):
+        assert self.lib.plg_set_profiling(self.ctx(), int(on)) == 0
 
     def reset_stats(self):
         assert self.lib.plg_reset_stats(self.ctx()) == 0

@@ -133,6 +133,8 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   ctx->use_graphs = g ? atoi(g) : 1;
   ctx->flush_buf = NULL; ctx->flush_bytes = 0;
   ctx->stream = NULL; ctx->ev_start = NULL; ctx->ev_stop = NULL;
+  ctx->profiling = 0;
+  ctx->prof_events = new std::vector<cudaEvent_t>();
 
 #define PLG_CREATE_CUDA(call)                                                          \
   do {                                                                                 \
@@ -237,6 +239,11 @@ extern "C" void plg_destroy(plg_context_t * ctx)
   cudaFree(ctx->flush_buf);
   if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
   if (ctx->result_host) cudaFreeHost(ctx->result_host);
+  if (ctx->prof_events)
+  {
+    for (cudaEvent_t e : *ctx->prof_events) cudaEventDestroy(e);
+    delete ctx->prof_events;
+  }
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
   if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -559,6 +566,13 @@ extern "C" int plg_get_stats(plg_context_t * ctx, plg_stats_t * out)
 {
   if (!ctx || !out) return PLG_E_INVALID;
   *out = ctx->stats;
+  return PLG_OK;
+}
+
+extern "C" int plg_set_profiling(plg_context_t * ctx, int enable)
+{
+  if (!ctx) return PLG_E_INVALID;
+  ctx->profiling = enable ? 1 : 0;
   return PLG_OK;
 }
 

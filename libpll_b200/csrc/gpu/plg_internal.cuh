@@ -127,6 +127,8 @@ struct plg_context
   size_t flush_bytes;
 
   cudaEvent_t ev_start, ev_stop;
+  int profiling;
+  std::vector<cudaEvent_t> * prof_events;
   plg_stats_t stats;
 };
 

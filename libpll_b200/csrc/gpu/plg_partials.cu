@@ -700,6 +700,7 @@ struct Group
   int scale_mode;
   unsigned int first; /* index into the sorted DevOp array */
   unsigned int count;
+  unsigned long long bytes; /* algorithmic bytes of the group */
 };
 
 struct Plan
@@ -729,6 +730,7 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
   struct Item
   {
     int level, kind, scale_mode;
+    unsigned long long bytes;
     DevOp op;
   };
   std::vector<Item> items(count);
@@ -831,7 +833,8 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
     if (it.op.pscale) bytes += scaler_unit;
     if (it.op.lscale) bytes += scaler_unit;
     if (it.op.rscale) bytes += scaler_unit;
-    plan.algorithmic_bytes += bytes * ctx->d.sites;
+    it.bytes = (unsigned long long)bytes * ctx->d.sites;
+    plan.algorithmic_bytes += it.bytes;
 
     for (int c = 0; c < 2; ++c)
     {
@@ -871,8 +874,9 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
                            items[order[i - 1]].kind != it.kind ||
                            items[order[i - 1]].scale_mode != it.scale_mode ||
                            plan.groups.back().count >= 65535u;
-    if (new_group) plan.groups.push_back(Group{it.kind, it.scale_mode, i, 0});
+    if (new_group) plan.groups.push_back(Group{it.kind, it.scale_mode, i, 0, 0});
     plan.groups.back().count++;
+    plan.groups.back().bytes += it.bytes;
   }
   return PLG_OK;
 }
@@ -969,8 +973,25 @@ static int enqueue_plan(plg_context * ctx, const Plan & plan, const DevOp * dev_
     }
     ++launched;
   }
+  const bool prof = ctx->profiling != 0;
+  if (prof)
+  {
+    while (ctx->prof_events->size() < plan.groups.size() + 1)
+    {
+      cudaEvent_t ev;
+      if (cudaEventCreate(&ev) != cudaSuccess)
+      {
+        plg_set_error("plg_update_partials: cudaEventCreate failed");
+        return PLG_E_CUDA;
+      }
+      ctx->prof_events->push_back(ev);
+    }
+  }
+  size_t gi = 0;
   for (const Group & g : plan.groups)
   {
+    if (prof) cudaEventRecord((*ctx->prof_events)[gi], ctx->stream);
+    ++gi;
     switch (R)
     {
       case 1: launch_group<1>(ctx, g, dev_ops, nelem); break;
@@ -989,6 +1010,20 @@ static int enqueue_plan(plg_context * ctx, const Plan & plan, const DevOp * dev_
   {
     plg_set_error("plg_update_partials: kernel launch failed: %s", cudaGetErrorString(err));
     return PLG_E_CUDA;
+  }
+  if (prof)
+  {
+    cudaEventRecord((*ctx->prof_events)[gi], ctx->stream);
+    PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < plan.groups.size(); ++i)
+    {
+      float ms = 0.f;
+      PLG_CUDA(cudaEventElapsedTime(&ms, (*ctx->prof_events)[i], (*ctx->prof_events)[i + 1]));
+      const int kind = plan.groups[i].kind;
+      ctx->stats.kind_ns[kind] += (unsigned long long)((double)ms * 1e6);
+      ctx->stats.kind_bytes[kind] += plan.groups[i].bytes;
+      ctx->stats.kind_launches[kind] += 1;
+    }
   }
   *kernels = launched;
   return PLG_OK;
@@ -1033,7 +1068,7 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
 
   /* ---- replay a cached graph of this exact list ---- */
   uint64_t key = 0;
-  const bool try_graph = ctx->use_graphs && count >= 2;
+  const bool try_graph = ctx->use_graphs && !ctx->profiling && count >= 2;
   if (try_graph)
   {
     key = fnv1a(operations, key_bytes) ^ ((uint64_t)ctx->maxstates << 56);

@@ -106,27 +106,34 @@ def make_workload(tips: int, sites: int, states: int = 4, rate_cats: int = 4, al
     return w
 
 
+TIP_BLOCK = 1 << 16  # sites per independently seeded block (makes tips site-sliceable)
+
+
 def tip_sequence(w: Workload, tip: int, lo: int = 0, hi: Optional[int] = None) -> bytes:
     """Characters of one tip for sites [lo, hi): root state w.p. 0.7 else uniform; 1 % full
-    ambiguity (N / X), 0.5 % two-state ambiguity (R,Y / B,Z).  Site-sliceable: the value at a
-    site does not depend on the slice asked for."""
+    ambiguity (N / X), 0.5 % two-state ambiguity (R,Y / B,Z).  Generated in independently
+    seeded blocks of TIP_BLOCK sites, so the value at a site does not depend on the slice
+    asked for and a rank only generates the slice it owns."""
     hi = w.sites if hi is None else hi
-    rng = np.random.default_rng([w.seed + 1, tip])
-    u = rng.random(w.sites, dtype=np.float32)
-    alt = rng.integers(0, w.states, size=w.sites, dtype=np.uint8)
-    u2 = rng.random(w.sites, dtype=np.float32)
-    sl = slice(lo, hi)
-    idx = np.where(u[sl] < 0.7, w.root_seq[sl], alt[sl])
     alphabet = DNA_ALPHABET if w.states == 4 else AA_ALPHABET
-    chars = alphabet[idx]
-    amb_full = ord("N") if w.states == 4 else ord("X")
-    amb2 = (ord("R"), ord("Y")) if w.states == 4 else (ord("B"), ord("Z"))
-    u2s = u2[sl]
-    chars = np.where(u2s < 0.01, np.uint8(amb_full), chars)
-    two = (u2s >= 0.01) & (u2s < 0.015)
-    chars = np.where(two & (alt[sl] & 1 == 0), np.uint8(amb2[0]), chars)
-    chars = np.where(two & (alt[sl] & 1 == 1), np.uint8(amb2[1]), chars)
-    return chars.astype(np.uint8).tobytes()
+    amb_full = np.uint8(ord("N") if w.states == 4 else ord("X"))
+    amb2 = (np.uint8(ord("R")), np.uint8(ord("Y"))) if w.states == 4 else (np.uint8(ord("B")), np.uint8(ord("Z")))
+    out = np.empty(hi - lo, dtype=np.uint8)
+    for blk in range(lo // TIP_BLOCK, (hi + TIP_BLOCK - 1) // TIP_BLOCK):
+        b0, b1 = blk * TIP_BLOCK, min((blk + 1) * TIP_BLOCK, w.sites)
+        rng = np.random.default_rng([w.seed + 1, tip, blk])
+        n = b1 - b0
+        u = rng.random(n, dtype=np.float32)
+        alt = rng.integers(0, w.states, size=n, dtype=np.uint8)
+        u2 = rng.random(n, dtype=np.float32)
+        chars = alphabet[np.where(u < 0.7, w.root_seq[b0:b1], alt)]
+        chars[u2 < 0.01] = amb_full
+        two = (u2 >= 0.01) & (u2 < 0.015)
+        chars[two & ((alt & 1) == 0)] = amb2[0]
+        chars[two & ((alt & 1) == 1)] = amb2[1]
+        s0, s1 = max(lo, b0), min(hi, b1)
+        out[s0 - lo:s1 - lo] = chars[s0 - b0:s1 - b0]
+    return out.tobytes()
 
 
 def model_for(lib: PllLibrary, w: Workload, variant: str = "default"):
