@@ -308,6 +308,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     prof = part.stats()
     part.set_profiling(False)
     kinds = ["tip-tip", "tip-inner", "inner-inner"]
+    KERNEL_NAMES = ["k_partial_tt_dna", "k_partial_stream_dna<TI>", "k_partial_stream_dna<II>"]
     shares = {}
     tot_ns = sum(prof["kind_ns"]) or 1
     for i, name in enumerate(kinds):
@@ -327,7 +328,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     achieved = prof["kind_bytes"][dom] / max(prof["kind_ns"][dom], 1)
     roofline = {
-        "bound": "hbm", "kernel": f"k_partial_stream_dna ({kinds[dom]})", "achieved": achieved,
+        "bound": "hbm", "kernel": f"{KERNEL_NAMES[dom]} ({kinds[dom]})", "achieved": achieved,
         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "traffic": None,
         "algorithmic_bytes_per_launch": prof["kind_bytes"][dom] / max(prof["kind_launches"][dom], 1),

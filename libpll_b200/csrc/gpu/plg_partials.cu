@@ -301,35 +301,47 @@ template <int R, int ITEMS>
 __global__ void __launch_bounds__(PLG_DNA_THREADS)
 k_partial_tt_dna(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mode)
 {
+  /* one thread per HALF element (two states, 16 bytes): a warp's store instruction then
+   * covers 512 contiguous bytes in full 32-byte sectors */
   const DevOp op = ops[blockIdx.y];
-  const unsigned int k = threadIdx.x & (R - 1);
-
-  __shared__ d4 tabl[16 * R];
-  __shared__ d4 tabr[16 * R];
-  for (unsigned int t = threadIdx.x; t < 16 * R; t += PLG_DNA_THREADS)
+  __shared__ double2 tabl[16 * R * 2];
+  __shared__ double2 tabr[16 * R * 2];
+  for (unsigned int t = threadIdx.x; t < 16 * R * 2; t += PLG_DNA_THREADS)
   {
-    tabl[t] = *reinterpret_cast<const d4 *>(op.lmat + (size_t)t * 4);
-    tabr[t] = *reinterpret_cast<const d4 *>(op.rmat + (size_t)t * 4);
+    tabl[t] = *reinterpret_cast<const double2 *>(op.lmat + (size_t)t * 2);
+    tabr[t] = *reinterpret_cast<const double2 *>(op.rmat + (size_t)t * 2);
   }
   __syncthreads();
 
+  const unsigned int nhalf = nelem * 2u;
   const unsigned int base = blockIdx.x * (PLG_DNA_THREADS * ITEMS) + threadIdx.x;
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j)
   {
-    const unsigned int e = base + j * PLG_DNA_THREADS;
-    if (e < nelem)
+    const unsigned int hidx = base + j * PLG_DNA_THREADS; /* half-element index */
+    if (hidx < nhalf)
     {
+      const unsigned int e = hidx >> 1;
+      const unsigned int kh = hidx & (2 * R - 1); /* (rate, half) within the site */
       const unsigned int n = e / R;
       const unsigned int lc = __ldg(op.ltip + n);
       const unsigned int rc = __ldg(op.rtip + n);
-      st_stream(op.parent + (size_t)e * 4, mul4(tabl[lc * R + k], tabr[rc * R + k]));
+      const double2 a = tabl[lc * 2 * R + kh];
+      const double2 b = tabr[rc * 2 * R + kh];
+      double2 p;
+      p.x = __dmul_rn(a.x, b.x);
+      p.y = __dmul_rn(a.y, b.y);
+      asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(op.parent + (size_t)hidx * 2),
+                   "d"(p.x), "d"(p.y)
+                   : "memory");
       if (scale_mode == 1)
       {
-        if (k == 0) op.pscale[n] = 0u;
+        if (kh == 0) op.pscale[n] = 0u;
       }
       else if (scale_mode == 2)
-        op.pscale[e] = 0u;
+      {
+        if ((hidx & 1u) == 0) op.pscale[e] = 0u;
+      }
     }
   }
 }
@@ -343,47 +355,97 @@ k_partial_tt_dna(const DevOp * __restrict__ ops, unsigned int nelem, int scale_m
  * memory pipeline from the register file:
  *   - the grid is persistent (a few CTAs per SM); the (operation, tile) space of a whole
  *     dependency level is flattened and cut into one contiguous chunk per CTA;
- *   - one elected thread feeds a PLG_IN_STAGES-deep ring of shared-memory tiles with 1-D TMA
+ *   - one elected thread feeds a STAGES-deep ring of shared-memory tiles with 1-D TMA
  *     bulk copies (cp.async.bulk, completion on "full" mbarriers); consumers release a stage
  *     through an "empty" mbarrier as soon as they have pulled their 32-byte element into
  *     registers, so copies for the next tiles are always outstanding;
  *   - every thread owns one (site, rate) element per tile, with its rate's P-matrix rows in
  *     registers for the whole chunk (reloaded only when the chunk crosses into the next
  *     operation);
- *   - results go back through a shared-memory ring and TMA bulk stores (full-line writes),
- *     or directly with 256-bit stores when TMA_STORE is false.
+ *   - results leave with 256-bit streaming stores straight from registers (a shared-memory
+ *     ring + TMA bulk stores was measured 8 % slower: it costs a CTA barrier per tile).
  * Arithmetic, voting and scaler bookkeeping are exactly those of the simple kernels above.
  */
-#define PLG_TILE 256
-#define PLG_IN_STAGES 4
-#define PLG_OUT_STAGES 3
-#ifndef PLG_TMA_STORE
-#define PLG_TMA_STORE true /* results leave through shared memory + TMA bulk stores */
+#define PLG_STREAM_THREADS 256
+#define PLG_STREAM_TILE 256 /* elements per tile: 8 KB per CLV array per stage */
+#define PLG_II_STAGES 4     /* x 16 KB */
+#define PLG_TI_STAGES 6     /* x  8 KB */
+#ifndef PLG_II_MINB
+#define PLG_II_MINB 2 /* resident CTAs per SM */
+#endif
+#ifndef PLG_TI_MINB
+#define PLG_TI_MINB 3
 #endif
 
-template <int R, int KIND, bool TMA_STORE>
+template <int R, int KIND, int STAGES>
 struct StreamSmem
 {
-  d4 in_r[PLG_IN_STAGES][PLG_TILE];
-  d4 in_l[KIND == PLG_KIND_II ? PLG_IN_STAGES : 1][KIND == PLG_KIND_II ? PLG_TILE : 1];
-  d4 out[TMA_STORE ? PLG_OUT_STAGES : 1][TMA_STORE ? PLG_TILE : 1];
-  d4 tab[KIND == PLG_KIND_TI ? 16 * R : 1];
-  unsigned char tips[KIND == PLG_KIND_TI ? PLG_IN_STAGES : 1][PLG_TILE];
-  uint64_t full[PLG_IN_STAGES];
-  uint64_t empty[PLG_IN_STAGES];
+  d4 in_r[STAGES][PLG_STREAM_TILE];
+  d4 in_l[KIND == PLG_KIND_II ? STAGES : 1][KIND == PLG_KIND_II ? PLG_STREAM_TILE : 1];
+  double2 tab[KIND == PLG_KIND_TI ? 16 * R * 2 : 1];
+  unsigned char tips[KIND == PLG_KIND_TI ? STAGES : 1][PLG_STREAM_TILE];
+  unsigned int sc_l[KIND == PLG_KIND_II ? STAGES : 1][PLG_STREAM_TILE]; /* child scalers of the tile */
+  unsigned int sc_r[STAGES][PLG_STREAM_TILE];
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
 };
 
-template <int R, int KIND, bool TMA_STORE>
-__global__ void __launch_bounds__(PLG_TILE, 2)
+/* scaler bookkeeping for the half-element mapping: the 2R lanes of a site vote */
+template <int R>
+__device__ __forceinline__ bool scale_decision_half(bool valid, bool below, int scale_mode,
+                                                    unsigned int hidx, unsigned int child_sum,
+                                                    const DevOp & op)
+{
+  const unsigned int lane = threadIdx.x & 31u;
+  if (scale_mode == 1)
+  {
+    constexpr unsigned int W = 2 * R; /* lanes per site */
+    const unsigned int b = __ballot_sync(0xffffffffu, valid && below);
+    const unsigned int full = (W >= 32) ? 0xffffffffu : ((1u << W) - 1u);
+    const unsigned int grp = (b >> (lane & ~(W - 1))) & full;
+    const bool scale = (grp == full);
+    if (valid && (lane & (W - 1)) == 0)
+    {
+      op.pscale[hidx / W] = child_sum + (scale ? 1u : 0u);
+    }
+    return scale;
+  }
+  if (scale_mode == 2)
+  {
+    /* per-rate: the two halves of an element are adjacent lanes */
+    const unsigned int b = __ballot_sync(0xffffffffu, valid && below);
+    const bool both = ((b >> (lane & ~1u)) & 3u) == 3u;
+    if (valid && (lane & 1u) == 0) op.pscale[hidx >> 1] = child_sum + (both ? 1u : 0u);
+    return both;
+  }
+  return false;
+}
+
+__device__ __forceinline__ void st_stream2(double * p, double x, double y)
+{
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(x), "d"(y) : "memory");
+}
+
+/*
+ * One thread per HALF element: (site, rate, state pair).  Each thread keeps the two rows of
+ * its rate's P-matrices that it needs in registers, reads the full 4-state child vectors
+ * from the shared-memory stage and emits one 128-bit store, so that every store instruction
+ * of a warp covers 512 contiguous bytes in whole 32-byte sectors (measured +7 % write
+ * bandwidth over 256-bit per-thread stores, which the LSU splits into half-sector passes).
+ */
+template <int R, int KIND, int STAGES, int MINB>
+__global__ void __launch_bounds__(PLG_STREAM_THREADS, MINB)
 k_partial_stream_dna(const DevOp * __restrict__ ops, unsigned int nelem, unsigned int ntiles,
                      unsigned int total_tiles, int scale_mode)
 {
   using namespace plg_async;
+  constexpr unsigned int TILE = PLG_STREAM_TILE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  StreamSmem<R, KIND, TMA_STORE> & sm = *reinterpret_cast<StreamSmem<R, KIND, TMA_STORE> *>(smem_raw);
+  StreamSmem<R, KIND, STAGES> & sm = *reinterpret_cast<StreamSmem<R, KIND, STAGES> *>(smem_raw);
 
   const unsigned int tid = threadIdx.x;
-  const unsigned int k = tid & (R - 1);
+  const unsigned int h = tid & 1u;              /* which state pair */
+  const unsigned int k = (tid >> 1) & (R - 1);  /* which rate       */
 
   /* this CTA's contiguous chunk of the flattened (operation, tile) space */
   const unsigned int per = (total_tiles + gridDim.x - 1) / gridDim.x;
@@ -395,46 +457,54 @@ k_partial_stream_dna(const DevOp * __restrict__ ops, unsigned int nelem, unsigne
   if (tid == 0)
   {
 #pragma unroll
-    for (int s = 0; s < PLG_IN_STAGES; ++s)
+    for (int s = 0; s < STAGES; ++s)
     {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], PLG_TILE / 32);
+      mbar_init(&sm.empty[s], PLG_STREAM_THREADS / 32);
     }
     fence_barrier_init();
   }
   __syncthreads();
 
-  /* producer: TMA copies for the j-th tile of the chunk into stage j % PLG_IN_STAGES */
+  /* producer: TMA copies for the j-th tile of the chunk into stage j % STAGES */
   auto issue = [&](unsigned int j) {
     const unsigned int q = q0 + j;
     const unsigned int o = q / ntiles;
-    const unsigned int e0 = (q - o * ntiles) * PLG_TILE;
-    const unsigned int cnt = (nelem - e0 < PLG_TILE) ? nelem - e0 : PLG_TILE;
-    const unsigned int s = j % PLG_IN_STAGES;
+    const unsigned int e0 = (q - o * ntiles) * TILE;
+    const unsigned int cnt = (nelem - e0 < TILE) ? nelem - e0 : TILE;
+    const unsigned int s = j % STAGES;
     const DevOp * op = ops + o;
     const unsigned int bytes = cnt * 32u;
+    /* child scalers of the tile ride along (no global loads in the consumer loop) */
+    const unsigned int sc_off = (scale_mode == 2) ? e0 : e0 / R;
+    const unsigned int sc_bytes = (((scale_mode == 2) ? cnt : cnt / R) * 4u + 15u) & ~15u;
+    const unsigned int * lsc = (scale_mode != 0 && KIND == PLG_KIND_II) ? op->lscale : nullptr;
+    const unsigned int * rsc = (scale_mode != 0) ? op->rscale : nullptr;
+    const unsigned int sc_total = (lsc ? sc_bytes : 0u) + (rsc ? sc_bytes : 0u);
     if (KIND == PLG_KIND_II)
     {
-      mbar_arrive_expect_tx(&sm.full[s], 2 * bytes);
+      mbar_arrive_expect_tx(&sm.full[s], 2 * bytes + sc_total);
       bulk_g2s(sm.in_l[s], op->left + (size_t)e0 * 4, bytes, &sm.full[s]);
       bulk_g2s(sm.in_r[s], op->right + (size_t)e0 * 4, bytes, &sm.full[s]);
+      if (lsc) bulk_g2s(sm.sc_l[s], lsc + sc_off, sc_bytes, &sm.full[s]);
     }
     else
     {
       const unsigned int tip_bytes = ((cnt / R) + 15u) & ~15u;
-      mbar_arrive_expect_tx(&sm.full[s], bytes + tip_bytes);
+      mbar_arrive_expect_tx(&sm.full[s], bytes + tip_bytes + sc_total);
       bulk_g2s(sm.in_r[s], op->right + (size_t)e0 * 4, bytes, &sm.full[s]);
       bulk_g2s(sm.tips[s], op->ltip + e0 / R, tip_bytes, &sm.full[s]);
     }
+    if (rsc) bulk_g2s(sm.sc_r[s], rsc + sc_off, sc_bytes, &sm.full[s]);
   };
 
   if (tid == 0)
   {
-    const unsigned int pre = n < PLG_IN_STAGES ? n : PLG_IN_STAGES;
+    const unsigned int pre = n < STAGES ? n : STAGES;
     for (unsigned int j = 0; j < pre; ++j) issue(j);
   }
 
-  double L[16], Rm[16];
+  double L[8], Rm[8]; /* rows 2h and 2h+1 of this thread's rate */
   DevOp op;
   unsigned int cur_op = 0xffffffffu;
 
@@ -449,72 +519,84 @@ k_partial_stream_dna(const DevOp * __restrict__ ops, unsigned int nelem, unsigne
       cur_op = o;
       op = ops[o];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 2; ++i)
       {
-        const d4 rr = *reinterpret_cast<const d4 *>(op.rmat + k * 16 + i * 4);
+        const d4 rr = *reinterpret_cast<const d4 *>(op.rmat + k * 16 + (2 * h + i) * 4);
         Rm[4 * i + 0] = rr.x; Rm[4 * i + 1] = rr.y; Rm[4 * i + 2] = rr.z; Rm[4 * i + 3] = rr.w;
         if (KIND == PLG_KIND_II)
         {
-          const d4 ll = *reinterpret_cast<const d4 *>(op.lmat + k * 16 + i * 4);
+          const d4 ll = *reinterpret_cast<const d4 *>(op.lmat + k * 16 + (2 * h + i) * 4);
           L[4 * i + 0] = ll.x; L[4 * i + 1] = ll.y; L[4 * i + 2] = ll.z; L[4 * i + 3] = ll.w;
         }
       }
       if (KIND == PLG_KIND_TI)
       {
         __syncthreads(); /* nobody still reads the previous operation's table */
-        for (unsigned int t = tid; t < 16 * R; t += PLG_TILE)
-          sm.tab[t] = *reinterpret_cast<const d4 *>(op.lmat + (size_t)t * 4);
+        for (unsigned int t = tid; t < 16 * R * 2; t += PLG_STREAM_THREADS)
+          sm.tab[t] = *reinterpret_cast<const double2 *>(op.lmat + (size_t)t * 2);
         __syncthreads();
       }
     }
 
-    const unsigned int s = j % PLG_IN_STAGES;
-    mbar_wait(&sm.full[s], (j / PLG_IN_STAGES) & 1u);
-    const d4 r = sm.in_r[s][tid];
-    d4 l;
-    unsigned int code = 0;
-    if (KIND == PLG_KIND_II) l = sm.in_l[s][tid];
-    else code = sm.tips[s][tid / R] & 15u; /* lanes past the end of a short tile see stale bytes */
+    const unsigned int s = j % STAGES;
+    mbar_wait(&sm.full[s], (j / STAGES) & 1u);
+    d4 r[2], l[2];
+    unsigned int code[2], csum[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+    {
+      const unsigned int el = (tid + i * PLG_STREAM_THREADS) >> 1; /* element within the tile */
+      r[i] = sm.in_r[s][el];
+      if (KIND == PLG_KIND_II) l[i] = sm.in_l[s][el];
+      /* lanes past the end of a short tile see stale bytes: keep the index in range */
+      else code[i] = sm.tips[s][el / R] & 15u;
+      csum[i] = 0u;
+      if (scale_mode != 0)
+      {
+        const unsigned int si = (scale_mode == 2) ? el : el / R;
+        if (KIND == PLG_KIND_II && op.lscale) csum[i] += sm.sc_l[s][si];
+        if (op.rscale) csum[i] += sm.sc_r[s][si];
+      }
+    }
     __syncwarp();
     if ((tid & 31u) == 0) mbar_arrive(&sm.empty[s]);
 
-    if (tid == 0 && j >= 1 && j - 1 + PLG_IN_STAGES < n)
+    if (tid == 0 && j >= 1 && j - 1 + STAGES < n)
     {
       /* stage of the previous tile: every warp released it an iteration ago */
-      mbar_wait(&sm.empty[(j - 1) % PLG_IN_STAGES], ((j - 1) / PLG_IN_STAGES) & 1u);
-      issue(j - 1 + PLG_IN_STAGES);
+      mbar_wait(&sm.empty[(j - 1) % STAGES], ((j - 1) / STAGES) & 1u);
+      issue(j - 1 + STAGES);
     }
 
-    const unsigned int e = tile * PLG_TILE + tid;
-    const bool valid = e < nelem;
-    d4 p;
-    if (KIND == PLG_KIND_II) p = mul4(matvec4_unfused(L, l), matvec4_unfused(Rm, r));
-    else p = mul4(sm.tab[code * R + k], matvec4_unfused(Rm, r));
-    const bool below = valid && all_below(p);
-    const bool scale = scale_decision<R>(valid, below, scale_mode, e, op);
-    if (scale) p = scale_up(p);
-
-    if (TMA_STORE)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
     {
-      const unsigned int so = j % PLG_OUT_STAGES;
-      sm.out[so][tid] = p;
-      fence_proxy_async_smem();
-      __syncthreads();
-      if (tid == 0)
+      const unsigned int hidx = tile * (2 * TILE) + tid + i * PLG_STREAM_THREADS;
+      const bool valid = hidx < 2 * nelem;
+      const double y0 = dot4_unfused(Rm[0], Rm[1], Rm[2], Rm[3], r[i]);
+      const double y1 = dot4_unfused(Rm[4], Rm[5], Rm[6], Rm[7], r[i]);
+      double x0, x1;
+      if (KIND == PLG_KIND_II)
       {
-        const unsigned int e0 = tile * PLG_TILE;
-        const unsigned int cnt = (nelem - e0 < PLG_TILE) ? nelem - e0 : PLG_TILE;
-        bulk_s2g(op.parent + (size_t)e0 * 4, sm.out[so], cnt * 32u);
-        bulk_commit();
-        /* the store issued one tile ago has finished reading its buffer; the next barrier
-         * publishes that to the CTA two tiles before the buffer is written again */
-        bulk_wait_read<1>();
+        x0 = dot4_unfused(L[0], L[1], L[2], L[3], l[i]);
+        x1 = dot4_unfused(L[4], L[5], L[6], L[7], l[i]);
       }
+      else
+      {
+        const double2 t = sm.tab[(code[i] * R + k) * 2 + h];
+        x0 = t.x;
+        x1 = t.y;
+      }
+      double p0 = __dmul_rn(x0, y0), p1 = __dmul_rn(x1, y1);
+      const bool below = valid && (p0 < PLG_SCALE_THRESHOLD) & (p1 < PLG_SCALE_THRESHOLD);
+      if (scale_decision_half<R>(valid, below, scale_mode, hidx, csum[i], op))
+      {
+        p0 = __dmul_rn(p0, PLG_SCALE_FACTOR);
+        p1 = __dmul_rn(p1, PLG_SCALE_FACTOR);
+      }
+      if (valid) st_stream2(op.parent + (size_t)hidx * 2, p0, p1);
     }
-    else if (valid)
-      st_stream(op.parent + (size_t)e * 4, p);
   }
-  if (TMA_STORE && tid == 0) bulk_wait_read<0>();
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -890,27 +972,30 @@ static void launch_group(plg_context * ctx, const Group & g, const DevOp * dev_o
   {
     if (g.kind == PLG_KIND_II || g.kind == PLG_KIND_TI)
     {
-      const unsigned int ntiles = (nelem + PLG_TILE - 1) / PLG_TILE;
+      unsigned int blocks =
+          (unsigned int)ctx->sm_count * (g.kind == PLG_KIND_II ? PLG_II_MINB : PLG_TI_MINB);
+      const unsigned int ntiles = (nelem + PLG_STREAM_TILE - 1) / PLG_STREAM_TILE;
       const unsigned long long total = (unsigned long long)ntiles * g.count;
-      unsigned int blocks = (unsigned int)ctx->sm_count * 2u;
       if (total < blocks) blocks = (unsigned int)total;
       if (g.kind == PLG_KIND_II)
       {
-        const size_t smem = sizeof(StreamSmem<R, PLG_KIND_II, PLG_TMA_STORE>);
-        k_partial_stream_dna<R, PLG_KIND_II, PLG_TMA_STORE><<<blocks, PLG_TILE, smem, ctx->stream>>>(
-            ops, nelem, ntiles, (unsigned int)total, g.scale_mode);
+        const size_t smem = sizeof(StreamSmem<R, PLG_KIND_II, PLG_II_STAGES>);
+        k_partial_stream_dna<R, PLG_KIND_II, PLG_II_STAGES, PLG_II_MINB>
+            <<<blocks, PLG_STREAM_THREADS, smem, ctx->stream>>>(ops, nelem, ntiles, (unsigned int)total,
+                                                               g.scale_mode);
       }
       else
       {
-        const size_t smem = sizeof(StreamSmem<R, PLG_KIND_TI, PLG_TMA_STORE>);
-        k_partial_stream_dna<R, PLG_KIND_TI, PLG_TMA_STORE><<<blocks, PLG_TILE, smem, ctx->stream>>>(
-            ops, nelem, ntiles, (unsigned int)total, g.scale_mode);
+        const size_t smem = sizeof(StreamSmem<R, PLG_KIND_TI, PLG_TI_STAGES>);
+        k_partial_stream_dna<R, PLG_KIND_TI, PLG_TI_STAGES, PLG_TI_MINB>
+            <<<blocks, PLG_STREAM_THREADS, smem, ctx->stream>>>(ops, nelem, ntiles, (unsigned int)total,
+                                                               g.scale_mode);
       }
     }
     else
     {
-      constexpr int ITEMS = 4;
-      dim3 grid((nelem + PLG_DNA_THREADS * ITEMS - 1) / (PLG_DNA_THREADS * ITEMS), g.count);
+      constexpr int ITEMS = 8;
+      dim3 grid((2 * nelem + PLG_DNA_THREADS * ITEMS - 1) / (PLG_DNA_THREADS * ITEMS), g.count);
       k_partial_tt_dna<R, ITEMS><<<grid, PLG_DNA_THREADS, 0, ctx->stream>>>(ops, nelem, g.scale_mode);
     }
   }
@@ -939,12 +1024,12 @@ static int set_smem_limits()
    * kernels' P-matrix sets (2*R*3200 bytes) */
   static bool done = false;
   if (done) return PLG_OK;
-  PLG_CUDA(cudaFuncSetAttribute(k_partial_stream_dna<R, PLG_KIND_II, PLG_TMA_STORE>,
+  PLG_CUDA(cudaFuncSetAttribute(k_partial_stream_dna<R, PLG_KIND_II, PLG_II_STAGES, PLG_II_MINB>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(StreamSmem<R, PLG_KIND_II, PLG_TMA_STORE>)));
-  PLG_CUDA(cudaFuncSetAttribute(k_partial_stream_dna<R, PLG_KIND_TI, PLG_TMA_STORE>,
+                                (int)sizeof(StreamSmem<R, PLG_KIND_II, PLG_II_STAGES>)));
+  PLG_CUDA(cudaFuncSetAttribute(k_partial_stream_dna<R, PLG_KIND_TI, PLG_TI_STAGES, PLG_TI_MINB>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(StreamSmem<R, PLG_KIND_TI, PLG_TMA_STORE>)));
+                                (int)sizeof(StreamSmem<R, PLG_KIND_TI, PLG_TI_STAGES>)));
   PLG_CUDA(cudaFuncSetAttribute(k_partial_ii_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 2 * R * 400 * (int)sizeof(double)));
   PLG_CUDA(cudaFuncSetAttribute(k_partial_ti_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
