@@ -16,8 +16,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 
 
 def pytest_configure(config):
@@ -59,7 +60,8 @@ def ref_lib():
 
 
 @pytest.fixture(scope="session")
-def port():
+def port_lib():
+    """ctypes handle of the oracle's C restatement (oracle/libpll_oracle.so)."""
     from oracle import port as oracle_port
 
     return oracle_port.load()

@@ -1,0 +1,173 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/cases.json from the REFERENCE itself (oracle/_ref/libpll_ref.so, built
+from /root/reference by oracle/Makefile).  Run here, in the build container; the JSON it writes
+is committed and travels to the GPU box, where /root/reference does not exist.
+
+Each case restates, through the pll.h API, one of the reference's own self-contained tests or
+examples (inputs are embedded in their sources), executes it on the reference with
+PLL_ATTRIB_ARCH_AVX2 (with and without PLL_ATTRIB_PATTERN_TIP) and records every output at
+full double precision.  Where the reference ships an expected value in text form
+(test/out/*.out, examples' documented output) the script ASSERTS the freshly computed number
+against that text, so the fixture is pinned to the reference's own golden files:
+
+  case                     restates                                    pinned to
+  test_00010_NMDU_lkcalc   test/src/00010_NMDU_lkcalc.c:33-210         test/out/00010_NMDU_lkcalc.out
+  test_00011_NMAU_lkcalc   test/src/00011_NMAU_lkcalc.c                test/out/00011_NMAU_lkcalc.out
+  example_unrooted         examples/unrooted/unrooted.c:32-212         lnL -33.387713 / -34.550204 / -36.830297
+  example_newton           examples/newton/newton.c:31-243             0.6 -> 2.607098 in 7 iterations
+  derivatives_grid         test/src/derivatives.c recipe (alpha x pinv x cats x branch lengths)
+
+usage: python tests/golden/make_golden.py
+"""
+import json
+import os
+import re
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from libpll_b200.binding import (PLL_ATTRIB_ARCH_AVX2, PLL_ATTRIB_PATTERN_TIP, OP_DTYPE, PllLibrary)  # noqa: E402
+
+REF = "/root/reference"
+ref = PllLibrary(os.path.join(ROOT, "oracle", "_ref", "libpll_ref.so"), is_gpu=False)
+NONE = -1
+
+
+def aa(name, shape):
+    return ref.aa_table(name, shape).tolist()
+
+
+def op(parent, ps, c1, m1, s1, c2, m2, s2):
+    return [parent, ps, c1, m1, s1, c2, m2, s2]
+
+
+CASES = []
+
+# ---- test 00010: DNA, 5 taxa x 12 sites, HKY-like GTR, Gamma4 alpha 0.5 -----------------------
+CASES.append(dict(
+    name="test_00010_NMDU_lkcalc", states=4, tips=5, clv_buffers=4, sites=12, rate_matrices=1,
+    prob_matrices=7, rate_cats=4, scale_buffers=0, alpha=0.5,
+    freqs=[[0.3, 0.4, 0.1, 0.2]], subst=[[1, 2.5, 1, 1, 2.5, 1]],
+    seqs=["WAC-CTA-ATCT", "CCC-TTA-ATGT", "A-C-TAG-CTCT", "CTCTTAA-A-CG", "CAC-TCA-A-TG"],
+    steps=[
+        dict(do="pmatrix", params=[0, 0, 0, 0], matrices=[0, 1, 2, 3], lengths=[0.1, 0.2, 1, 1]),
+        dict(do="partials", ops=[op(5, NONE, 0, 1, NONE, 1, 1, NONE), op(6, NONE, 5, 0, NONE, 2, 1, NONE),
+                                 op(7, NONE, 3, 1, NONE, 4, 1, NONE)]),
+        dict(do="get_pmatrix", index=0), dict(do="get_pmatrix", index=1),
+        dict(do="get_clv", index=5), dict(do="get_clv", index=6), dict(do="get_clv", index=7),
+        dict(do="edge", args=[6, NONE, 7, NONE, 0], freqs_indices=[0, 0, 0, 0], tag="inner-inner"),
+        dict(do="partials", ops=[op(7, NONE, 6, 0, NONE, 3, 1, NONE)]),
+        dict(do="edge", args=[7, NONE, 4, NONE, 1], freqs_indices=[0, 0, 0, 0], tag="tip-inner"),
+    ],
+    printed={"inner-inner": -58.887310, "tip-inner": -58.887310}, out_file="test/out/00010_NMDU_lkcalc.out"))
+
+# ---- test 00011: amino acids (Dayhoff), 5 taxa x 15 sites ------------------------------------
+dayhoff_r = ref.aa_table("pll_aa_rates_dayhoff", (190,)).tolist()
+dayhoff_f = ref.aa_table("pll_aa_freqs_dayhoff", (20,)).tolist()
+CASES.append(dict(
+    name="test_00011_NMAU_lkcalc", states=20, tips=5, clv_buffers=4, sites=15, rate_matrices=1,
+    prob_matrices=7, rate_cats=4, scale_buffers=0, alpha=0.5,
+    freqs=[dayhoff_f], subst=[dayhoff_r],
+    seqs=["PIGLRVTLRRDRMWI", "IQGMDITIVT-----", "--AFALLQKIGMPFE", "MDISIVT------TA", "GLSEQTVFHEIDQDK"],
+    steps=None, out_file="test/out/00011_NMAU_lkcalc.out"))
+
+# ---- examples/unrooted and examples/newton: 4 taxa x 6 sites, JC-rates GTR, Gamma4 alpha 1 ------
+EX = dict(states=4, tips=4, clv_buffers=2, sites=6, rate_matrices=1, prob_matrices=5, rate_cats=4,
+          scale_buffers=2, alpha=1.0, freqs=[[0.17, 0.19, 0.25, 0.39]], subst=[[1, 1, 1, 1, 1, 1]],
+          seqs=["WAAAAB", "CACACD", "AGGACA", "CGTAGT"])
+EX_PM = dict(do="pmatrix", params=[0, 0, 0, 0], matrices=[0, 1, 2, 3, 4], lengths=[0.2, 0.4, 0.3, 0.5, 0.6])
+EX_OPS = dict(do="partials", ops=[op(4, 0, 0, 0, NONE, 1, 1, NONE), op(5, 1, 2, 2, NONE, 3, 3, NONE)])
+EX_EDGE = dict(do="edge", args=[4, 0, 5, 1, 4], freqs_indices=[0, 0, 0, 0])
+CASES.append(dict(name="example_unrooted", **EX, steps=[
+    EX_PM, EX_OPS, dict(do="get_clv", index=4), dict(do="get_clv", index=5),
+    dict(EX_EDGE, tag="Log-L"),
+    dict(do="pinv", index=0, value=0.5), EX_PM, EX_OPS, dict(EX_EDGE, tag="Log-L (Inv+Gamma 0.5)"),
+    dict(do="pinv", index=0, value=0.75), EX_PM, EX_OPS, dict(EX_EDGE, tag="Log-L (Inv+Gamma 0.75)"),
+], printed={"Log-L": -33.387713, "Log-L (Inv+Gamma 0.5)": -34.550204, "Log-L (Inv+Gamma 0.75)": -36.830297}))
+
+CASES.append(dict(name="example_newton", **EX, steps=[
+    EX_PM, EX_OPS,
+    dict(do="newton", edge=[4, 5, 0, 1], params=[0, 0, 0, 0], start=0.6, max_iter=32, eps=1e-5,
+         printed_final=2.607098, printed_iterations=7),
+]))
+
+# ---- derivatives grid (recipe of reference test/src/derivatives.c:44-48 on the 00010 data) ------
+deriv_steps = [
+    dict(do="pmatrix", params=[0, 0, 0, 0], matrices=[0, 1, 2, 3], lengths=[0.1, 0.2, 1, 1]),
+    dict(do="partials", ops=[op(5, NONE, 0, 1, NONE, 1, 1, NONE), op(6, NONE, 5, 0, NONE, 2, 1, NONE),
+                             op(7, NONE, 3, 1, NONE, 4, 1, NONE)]),
+    dict(do="sumtable", key="ii", edge=[6, 7, NONE, NONE], params=[0, 0, 0, 0]),
+    dict(do="sumtable", key="ti", edge=[6, 3, NONE, NONE], params=[0, 0, 0, 0]),
+]
+for t in (0.1, 0.5, 0.9, 1.2, 1.5, 1.8, 2.1, 5.0, 25.0):
+    deriv_steps.append(dict(do="derivs", key="ii", t=t, params=[0, 0, 0, 0]))
+    deriv_steps.append(dict(do="derivs", key="ti", t=t, params=[0, 0, 0, 0]))
+for alpha in (0.1, 0.75, 1.5):
+    for pinv in (0.0, 0.3, 0.6):
+        CASES.append(dict(
+            name=f"derivatives_grid_a{alpha}_p{pinv}", states=4, tips=5, clv_buffers=4, sites=12,
+            rate_matrices=1, prob_matrices=7, rate_cats=4, scale_buffers=0, alpha=alpha,
+            freqs=[[0.3, 0.4, 0.1, 0.2]], subst=[[1, 2.5, 1, 1, 2.5, 1]],
+            seqs=["WAC-CTA-ATCT", "CCC-TTA-ATGT", "A-C-TAG-CTCT", "CTCTTAA-A-CG", "CAC-TCA-A-TG"],
+            steps=([dict(do="pinv", index=0, value=pinv)] if pinv > 0 else []) + deriv_steps))
+
+# test 00011 shares the step list of 00010
+CASES[1]["steps"] = [dict(s) for s in CASES[0]["steps"]]
+CASES[1]["printed"] = {"inner-inner": -227.371279, "tip-inner": -227.371279}
+
+
+# ------------------------------------------------------------------------------------------
+def run_case(lib, case, attributes):
+    """Executes a case through the pll.h API of `lib`; returns the list of outputs, one entry
+    per step that produces something.  (tests/golden_runner.py holds the same interpreter for
+    the libraries under test.)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_runner import execute
+
+    return execute(lib, case, attributes)
+
+
+def parse_printed(path, tags):
+    text = open(os.path.join(REF, path)).read()
+    out = {}
+    for tag in tags:
+        m = re.search(re.escape(tag) + r"\s+logL:\s+(-?\d+\.\d+)", text)
+        if m:
+            out[tag] = float(m.group(1))
+    return out
+
+
+def main():
+    golden = []
+    for case in CASES:
+        entry = dict(case)
+        entry["expect"] = {}
+        entry["rates"] = ref.gamma_rates(case["alpha"], case["rate_cats"]).tolist()
+        for label, attr in (("tv", PLL_ATTRIB_ARCH_AVX2 | PLL_ATTRIB_PATTERN_TIP), ("notv", PLL_ATTRIB_ARCH_AVX2)):
+            entry["expect"][label] = run_case(ref, case, attr)
+        # pin to the reference's text fixtures
+        printed = dict(case.get("printed", {}))
+        if case.get("out_file"):
+            from_file = parse_printed(case["out_file"], list(printed))
+            for tag, v in from_file.items():
+                assert abs(v - printed[tag]) < 1e-9, (case["name"], tag, v, printed[tag])
+            assert from_file, f"no lnL lines found in {case['out_file']}"
+        for label in ("tv", "notv"):
+            for out in entry["expect"][label]:
+                if out.get("tag") in printed:
+                    assert abs(out["logl"] - printed[out["tag"]]) < 5e-7, (case["name"], out["tag"], out["logl"])
+                if out.get("kind") == "newton":
+                    step = [s for s in case["steps"] if s["do"] == "newton"][0]
+                    assert abs(out["final"] - step["printed_final"]) < 5e-7, out
+                    assert out["iterations"] == step["printed_iterations"], out
+        golden.append(entry)
+        print("ok", case["name"])
+    path = os.path.join(ROOT, "tests", "golden", "cases.json")
+    json.dump(golden, open(path, "w"))
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
