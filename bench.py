@@ -38,6 +38,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+print_json = print
+
 METRIC = "CLV site-updates/sec (full post-order traversal + edge logL, GTR+G4 DNA)"
 UNIT = "site-updates/s"
 
@@ -201,7 +203,7 @@ def run_reference(args, rank: int, world: int):
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print_json(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------
@@ -388,12 +390,24 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             "cpu_baseline": cpu,
             "lnl": lnl,
         }
-        print(json.dumps(line), flush=True)
+        print_json(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
 
 def main():
+    # Only the JSON line may reach stdout: libraries (NCCL's version banner, for one) write
+    # there too, so fd 1 is pointed at stderr for the whole run and the line goes to the
+    # saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: str):
+        os.write(real_stdout, (line + "\n").encode())
+
+    global print_json
+    print_json = emit
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

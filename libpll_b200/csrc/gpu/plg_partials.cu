@@ -603,6 +603,9 @@ k_partial_stream_dna(const DevOp * __restrict__ ops, unsigned int nelem, unsigne
 /* 20-state kernels                                                                      */
 /* ------------------------------------------------------------------------------------ */
 #define PLG_AA_THREADS 128
+/* shared-memory stride of one rate's 20x20 matrix, in doubles: 404 (not 400) so that the R
+ * matrices the lanes of a warp read from start 8 banks apart instead of all in the same bank */
+#define PLG_AA_MSTRIDE 404
 
 /* rows [4*ib, 4*ib+4) of M (20x20, row-major in shared memory) times c, with the AVX2
  * accumulation order: per row four lane accumulators over the five column blocks, FMA
@@ -665,12 +668,12 @@ k_partial_ii_aa(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mo
 {
   extern __shared__ __align__(16) double smem[];
   double * Ls = smem;            /* [R][20][20] */
-  double * Rs = smem + R * 400;  /* [R][20][20] */
+  double * Rs = smem + R * PLG_AA_MSTRIDE; /* [R][20][20] */
   const DevOp op = ops[blockIdx.y];
   for (unsigned int t = threadIdx.x; t < R * 400; t += PLG_AA_THREADS)
   {
-    Ls[t] = __ldg(op.lmat + t);
-    Rs[t] = __ldg(op.rmat + t);
+    Ls[(t / 400) * PLG_AA_MSTRIDE + t % 400] = __ldg(op.lmat + t);
+    Rs[(t / 400) * PLG_AA_MSTRIDE + t % 400] = __ldg(op.rmat + t);
   }
   __syncthreads();
 
@@ -684,8 +687,8 @@ k_partial_ii_aa(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mo
     double l[20], r[20];
     load20(op.left + (size_t)e * 20, l);
     load20(op.right + (size_t)e * 20, r);
-    const double * Lk = Ls + k * 400;
-    const double * Rk = Rs + k * 400;
+    const double * Lk = Ls + k * PLG_AA_MSTRIDE;
+    const double * Rk = Rs + k * PLG_AA_MSTRIDE;
 #pragma unroll
     for (int ib = 0; ib < 5; ++ib)
     {
@@ -711,7 +714,8 @@ k_partial_ti_aa(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mo
   extern __shared__ __align__(16) double smem[];
   double * Rs = smem; /* [R][20][20] */
   const DevOp op = ops[blockIdx.y];
-  for (unsigned int t = threadIdx.x; t < R * 400; t += PLG_AA_THREADS) Rs[t] = __ldg(op.rmat + t);
+  for (unsigned int t = threadIdx.x; t < R * 400; t += PLG_AA_THREADS)
+    Rs[(t / 400) * PLG_AA_MSTRIDE + t % 400] = __ldg(op.rmat + t);
   __syncthreads();
 
   const unsigned int k = threadIdx.x & (R - 1);
@@ -725,7 +729,7 @@ k_partial_ti_aa(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mo
     load20(op.right + (size_t)e * 20, r);
     const unsigned int code = __ldg(op.ltip + e / R);
     const double * tab = op.lmat + ((size_t)code * R + k) * 20;
-    const double * Rk = Rs + k * 400;
+    const double * Rk = Rs + k * PLG_AA_MSTRIDE;
 #pragma unroll
     for (int ib = 0; ib < 5; ++ib)
     {
@@ -1004,12 +1008,12 @@ static void launch_group(plg_context * ctx, const Group & g, const DevOp * dev_o
     dim3 grid((nelem + PLG_AA_THREADS - 1) / PLG_AA_THREADS, g.count);
     if (g.kind == PLG_KIND_II)
     {
-      const size_t smem = (size_t)2 * R * 400 * sizeof(double);
+      const size_t smem = (size_t)2 * R * PLG_AA_MSTRIDE * sizeof(double);
       k_partial_ii_aa<R><<<grid, PLG_AA_THREADS, smem, ctx->stream>>>(ops, nelem, g.scale_mode);
     }
     else if (g.kind == PLG_KIND_TI)
     {
-      const size_t smem = (size_t)R * 400 * sizeof(double);
+      const size_t smem = (size_t)R * PLG_AA_MSTRIDE * sizeof(double);
       k_partial_ti_aa<R><<<grid, PLG_AA_THREADS, smem, ctx->stream>>>(ops, nelem, g.scale_mode);
     }
     else
@@ -1031,9 +1035,9 @@ static int set_smem_limits()
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(StreamSmem<R, PLG_KIND_TI, PLG_TI_STAGES>)));
   PLG_CUDA(cudaFuncSetAttribute(k_partial_ii_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                2 * R * 400 * (int)sizeof(double)));
+                                2 * R * PLG_AA_MSTRIDE * (int)sizeof(double)));
   PLG_CUDA(cudaFuncSetAttribute(k_partial_ti_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                R * 400 * (int)sizeof(double)));
+                                R * PLG_AA_MSTRIDE * (int)sizeof(double)));
   done = true;
   return PLG_OK;
 }
