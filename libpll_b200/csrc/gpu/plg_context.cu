@@ -131,6 +131,8 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   ctx->graphs = new std::unordered_map<uint64_t, plg_graph_entry *>();
   const char * g = getenv("PLL_GPU_GRAPHS");
   ctx->use_graphs = g ? atoi(g) : 1;
+  const char * ex = getenv("PLL_GPU_AA_EXACT");
+  ctx->aa_exact = (ex && *ex && *ex != '0') ? 1 : 0;
   ctx->flush_buf = NULL; ctx->flush_bytes = 0;
   ctx->stream = NULL; ctx->ev_start = NULL; ctx->ev_stop = NULL;
   ctx->profiling = 0;

@@ -778,6 +778,237 @@ k_partial_tt_aa(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mo
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* 20-state kernels on the FP64 tensor cores (DMMA m8n8k4)                               */
+/* ------------------------------------------------------------------------------------ */
+/*
+ * The (sites x rates) x 20 x 20 products are the one GEMM-shaped piece of the path.  On the
+ * vector pipe every FMA needs a P-matrix operand replicated to 32 lanes through shared memory
+ * (LDS-bound: measured 1.8 TB/s, 17 % of the FP64 peak); DMMA keeps the matrix distributed
+ * across the lanes of a warp as A fragments and reads each CLV entry exactly once as a B
+ * fragment straight from HBM (8 full 32-byte sectors per request), so the loop is
+ * tensor-/HBM-bound instead.  Measured peaks on this B200: DFMA 33.8 TFLOP/s, DMMA 37.1.
+ *
+ *   Y[i][s] = sum_j P_k[i][j] * c[s][k][j]      M = parent states (20, padded to 3 x 8)
+ *                                               N = 8 sites per warp-tile, K = 20 = 5 x 4
+ *   A fragment (mt, ks): lane holds P[8mt + lane/4][4ks + lane%4]   (shared memory, per op)
+ *   B fragment (ks)    : lane holds c[site lane/4][4ks + lane%4]    (one LDG.64 each)
+ *   D fragment (mt)    : lane holds Y[8mt + lane/4][site 2(lane%4) + {0,1}]
+ *
+ * A warp owns 8 sites and loops over the rates; results are stored as they are produced and
+ * re-read for the (rare) x 2^256 rescale, exactly like the reference's per-site loop
+ * (reference src/core_partials_avx2.c:788-801).  The summation order inside a DMMA differs
+ * from the AVX2 lane order, so CLVs agree with the reference to ~1e-16 relative instead of bit
+ * for bit; PLL_GPU_AA_EXACT=1 selects the vector-pipe kernels above, which are bit-exact.
+ */
+#define PLG_DMMA_THREADS 256
+
+__device__ __forceinline__ void dmma884(double & d0, double & d1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double ldg_stream64(const double * p)
+{
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+/* KIND: PLG_KIND_II (two matrix products) or PLG_KIND_TI (tip table x one matrix product) */
+template <int R, int KIND>
+__global__ void __launch_bounds__(PLG_DMMA_THREADS, 2)
+k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int sites, int scale_mode)
+{
+  extern __shared__ __align__(16) double afrag[]; /* [child][rate][mt*5+ks][lane] */
+  constexpr int NCHILD = (KIND == PLG_KIND_II) ? 2 : 1;
+  const DevOp op = ops[blockIdx.y];
+  const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned int g = lane >> 2, q = lane & 3u;
+
+  /* P matrices -> A fragments (rows 20..23 of the third M tile are zero padding) */
+  for (unsigned int t = threadIdx.x; t < NCHILD * R * 15 * 32; t += PLG_DMMA_THREADS)
+  {
+    const unsigned int l = t & 31u, f = (t >> 5) % 15, kc = (t >> 5) / 15; /* kc = child*R + k */
+    const unsigned int row = 8 * (f / 5) + (l >> 2), col = 4 * (f % 5) + (l & 3u);
+    const double * M = (NCHILD == 2 && kc < (unsigned)R) ? op.lmat : op.rmat;
+    const unsigned int k = kc % R;
+    afrag[t] = (row < 20) ? __ldg(M + (size_t)k * 400 + row * 20 + col) : 0.0;
+  }
+  __syncthreads();
+  const double * AL = afrag;                               /* left child (ii only)  */
+  const double * AR = afrag + (NCHILD - 1) * R * 15 * 32;  /* right / inner child   */
+
+  const unsigned int units = (sites + 7) / 8;
+  const unsigned int warps_total = gridDim.x * (PLG_DMMA_THREADS / 32);
+  for (unsigned int u = blockIdx.x * (PLG_DMMA_THREADS / 32) + warp; u < units; u += warps_total)
+  {
+    const unsigned int site_b = 8 * u + g;            /* site whose CLV entries this lane loads */
+    const bool load_ok = site_b < sites;
+    const unsigned int site_d0 = 8 * u + 2 * q;       /* the two sites of this lane's D columns */
+    const bool ok0 = site_d0 < sites, ok1 = site_d0 + 1 < sites;
+
+    /* scaler inputs of the unit's 8 sites: lane t < 8 looks after site 8u + t */
+    unsigned int child_sum = 0;
+    if (scale_mode == 1 && lane < 8 && 8 * u + lane < sites)
+    {
+      if (KIND == PLG_KIND_II && op.lscale) child_sum += op.lscale[8 * u + lane];
+      if (op.rscale) child_sum += op.rscale[8 * u + lane];
+    }
+    unsigned int code0 = 0, code1 = 0;
+    if (KIND == PLG_KIND_TI)
+    {
+      if (ok0) code0 = __ldg(op.ltip + site_d0);
+      if (ok1) code1 = __ldg(op.ltip + site_d0 + 1);
+    }
+
+    bool below0 = true, below1 = true; /* per-site mode: every entry of the site so far */
+    double bl[5], br[5];
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks)
+    {
+      const size_t off = ((size_t)site_b * R + 0) * 20 + 4 * ks + q;
+      br[ks] = load_ok ? ldg_stream64(op.right + off) : 0.0;
+      if (KIND == PLG_KIND_II) bl[ks] = load_ok ? ldg_stream64(op.left + off) : 0.0;
+    }
+
+#pragma unroll 1
+    for (int k = 0; k < R; ++k)
+    {
+      /* prefetch the next rate's B fragments while this rate's products run */
+      double nl[5], nr[5];
+      if (k + 1 < R)
+      {
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks)
+        {
+          const size_t off = ((size_t)site_b * R + (k + 1)) * 20 + 4 * ks + q;
+          nr[ks] = load_ok ? ldg_stream64(op.right + off) : 0.0;
+          if (KIND == PLG_KIND_II) nl[ks] = load_ok ? ldg_stream64(op.left + off) : 0.0;
+        }
+      }
+
+      double y[3][2], x[3][2];
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt)
+      {
+        y[mt][0] = y[mt][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks)
+          dmma884(y[mt][0], y[mt][1], AR[((size_t)k * 15 + mt * 5 + ks) * 32 + lane], br[ks]);
+        if (KIND == PLG_KIND_II)
+        {
+          x[mt][0] = x[mt][1] = 0.0;
+#pragma unroll
+          for (int ks = 0; ks < 5; ++ks)
+            dmma884(x[mt][0], x[mt][1], AL[((size_t)k * 15 + mt * 5 + ks) * 32 + lane], bl[ks]);
+        }
+        else
+        {
+          const unsigned int row = 8 * mt + g;
+          x[mt][0] = (row < 20) ? __ldg(op.lmat + ((size_t)code0 * R + k) * 20 + row) : 0.0;
+          x[mt][1] = (row < 20) ? __ldg(op.lmat + ((size_t)code1 * R + k) * 20 + row) : 0.0;
+        }
+      }
+
+      /* products, threshold test, store */
+      bool b0 = true, b1 = true;
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt)
+      {
+        const unsigned int row = 8 * mt + g;
+        const double p0 = __dmul_rn(x[mt][0], y[mt][0]);
+        const double p1 = __dmul_rn(x[mt][1], y[mt][1]);
+        if (row < 20)
+        {
+          b0 = b0 && (p0 < PLG_SCALE_THRESHOLD);
+          b1 = b1 && (p1 < PLG_SCALE_THRESHOLD);
+          if (ok0) op.parent[((size_t)site_d0 * R + k) * 20 + row] = p0;
+          if (ok1) op.parent[((size_t)(site_d0 + 1) * R + k) * 20 + row] = p1;
+        }
+      }
+      if (scale_mode == 2)
+      {
+        /* per-rate: all 20 rows of (site, rate) below -> rescale that block now */
+        const unsigned int m0 = __ballot_sync(0xffffffffu, b0), m1 = __ballot_sync(0xffffffffu, b1);
+        const unsigned int rows_mask = 0x11111111u << q;
+        const bool s0 = (m0 & rows_mask) == rows_mask, s1 = (m1 & rows_mask) == rows_mask;
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt)
+        {
+          const unsigned int row = 8 * mt + g;
+          if (row < 20)
+          {
+            if (s0 && ok0) op.parent[((size_t)site_d0 * R + k) * 20 + row] *= PLG_SCALE_FACTOR;
+            if (s1 && ok1) op.parent[((size_t)(site_d0 + 1) * R + k) * 20 + row] *= PLG_SCALE_FACTOR;
+          }
+        }
+        if (g == 0)
+        {
+          if (ok0)
+          {
+            const size_t e = (size_t)site_d0 * R + k;
+            op.pscale[e] = (s0 ? 1u : 0u) + ((KIND == PLG_KIND_II && op.lscale) ? op.lscale[e] : 0u) +
+                           (op.rscale ? op.rscale[e] : 0u);
+          }
+          if (ok1)
+          {
+            const size_t e = (size_t)(site_d0 + 1) * R + k;
+            op.pscale[e] = (s1 ? 1u : 0u) + ((KIND == PLG_KIND_II && op.lscale) ? op.lscale[e] : 0u) +
+                           (op.rscale ? op.rscale[e] : 0u);
+          }
+        }
+      }
+      below0 = below0 && b0;
+      below1 = below1 && b1;
+      if (k + 1 < R)
+      {
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks)
+        {
+          br[ks] = nr[ks];
+          if (KIND == PLG_KIND_II) bl[ks] = nl[ks];
+        }
+      }
+    }
+
+    if (scale_mode == 1)
+    {
+      /* per-site: every entry (all rates, all rows) of a site below the threshold */
+      const unsigned int m0 = __ballot_sync(0xffffffffu, below0), m1 = __ballot_sync(0xffffffffu, below1);
+      unsigned int votes = 0; /* bit t = site 8u + t must be rescaled */
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq)
+      {
+        const unsigned int rows_mask = 0x11111111u << qq;
+        if ((m0 & rows_mask) == rows_mask) votes |= 1u << (2 * qq);
+        if ((m1 & rows_mask) == rows_mask) votes |= 1u << (2 * qq + 1);
+      }
+      if (votes)
+      {
+        __syncwarp(); /* this warp's own stores above are visible to its lanes */
+#pragma unroll 1
+        for (int k = 0; k < R; ++k)
+#pragma unroll
+          for (int mt = 0; mt < 3; ++mt)
+          {
+            const unsigned int row = 8 * mt + g;
+            if (row < 20)
+            {
+              if (((votes >> (2 * q)) & 1u) && ok0)
+                op.parent[((size_t)site_d0 * R + k) * 20 + row] *= PLG_SCALE_FACTOR;
+              if (((votes >> (2 * q + 1)) & 1u) && ok1)
+                op.parent[((size_t)(site_d0 + 1) * R + k) * 20 + row] *= PLG_SCALE_FACTOR;
+            }
+          }
+      }
+      if (lane < 8 && 8 * u + lane < sites) op.pscale[8 * u + lane] = child_sum + ((votes >> lane) & 1u);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* host side: levelisation, batching, launch                                             */
 /* ------------------------------------------------------------------------------------ */
 struct Group
@@ -1003,6 +1234,22 @@ static void launch_group(plg_context * ctx, const Group & g, const DevOp * dev_o
       k_partial_tt_dna<R, ITEMS><<<grid, PLG_DNA_THREADS, 0, ctx->stream>>>(ops, nelem, g.scale_mode);
     }
   }
+  else if (!ctx->aa_exact && g.kind != PLG_KIND_TT)
+  {
+    /* tensor-core path: persistent over 8-site units, one grid row per operation */
+    const unsigned int units = (ctx->d.sites + 7) / 8;
+    unsigned int bx = (units + 7) / 8;
+    const unsigned int cap = (unsigned int)ctx->sm_count * 2u;
+    if (g.count * (unsigned long long)bx > cap) bx = (cap + g.count - 1) / g.count;
+    if (bx == 0) bx = 1;
+    dim3 grid(bx, g.count);
+    if (g.kind == PLG_KIND_II)
+      k_partial_dmma_aa<R, PLG_KIND_II><<<grid, PLG_DMMA_THREADS, (size_t)2 * R * 15 * 32 * sizeof(double),
+                                          ctx->stream>>>(ops, ctx->d.sites, g.scale_mode);
+    else
+      k_partial_dmma_aa<R, PLG_KIND_TI><<<grid, PLG_DMMA_THREADS, (size_t)R * 15 * 32 * sizeof(double),
+                                          ctx->stream>>>(ops, ctx->d.sites, g.scale_mode);
+  }
   else
   {
     dim3 grid((nelem + PLG_AA_THREADS - 1) / PLG_AA_THREADS, g.count);
@@ -1034,6 +1281,12 @@ static int set_smem_limits()
   PLG_CUDA(cudaFuncSetAttribute(k_partial_stream_dna<R, PLG_KIND_TI, PLG_TI_STAGES, PLG_TI_MINB>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(StreamSmem<R, PLG_KIND_TI, PLG_TI_STAGES>)));
+  PLG_CUDA(cudaFuncSetAttribute(k_partial_dmma_aa<R, PLG_KIND_II>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                2 * R * 15 * 32 * (int)sizeof(double)));
+  PLG_CUDA(cudaFuncSetAttribute(k_partial_dmma_aa<R, PLG_KIND_TI>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                R * 15 * 32 * (int)sizeof(double)));
   PLG_CUDA(cudaFuncSetAttribute(k_partial_ii_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 2 * R * PLG_AA_MSTRIDE * (int)sizeof(double)));
   PLG_CUDA(cudaFuncSetAttribute(k_partial_ti_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,

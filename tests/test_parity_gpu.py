@@ -42,9 +42,28 @@ def _share_pmatrices(pg, pr, w, pidx):
     return worst
 
 
+@pytest.fixture(params=["exact", "dmma"])
+def aa_mode(request, monkeypatch):
+    """20-state CLV updates have two device implementations: the vector-pipe kernels that follow
+    the reference's AVX2 lane order (bit-exact CLVs) and the default DMMA tensor-core kernels
+    (CLVs to ~1e-16 relative).  The library reads PLL_GPU_AA_EXACT at partition creation."""
+    monkeypatch.setenv("PLL_GPU_AA_EXACT", "1" if request.param == "exact" else "0")
+    return request.param
+
+
+def _assert_clv(a, b, exact, what):
+    if exact:
+        assert a.tobytes() == b.tobytes(), f"{what} differs (max abs {np.max(np.abs(a - b))})"
+    else:
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=0, err_msg=what)
+
+
 @pytest.mark.parametrize("states,tips,sites", [(4, 12, 1000), (4, 60, 4099), (20, 10, 777), (20, 40, 1031)])
 @pytest.mark.parametrize("pattern_tip", [True, False])
-def test_traversal_bit_exact(gpu_lib, ref_lib, states, tips, sites, pattern_tip):
+def test_traversal_bit_exact(gpu_lib, ref_lib, states, tips, sites, pattern_tip, aa_mode):
+    if states == 4 and aa_mode == "dmma":
+        pytest.skip("DNA has a single implementation")
+    exact = states == 4 or aa_mode == "exact"
     w = S.make_workload(tips, sites, states=states, seed=7 + tips)
     extra = PLL_ATTRIB_PATTERN_TIP if pattern_tip else 0
     pg, pr, pidx = _pair(gpu_lib, ref_lib, w, extra)
@@ -55,8 +74,7 @@ def test_traversal_bit_exact(gpu_lib, ref_lib, states, tips, sites, pattern_tip)
     pr.update_partials(w.ops)
     for k in range(w.inner):
         np.testing.assert_array_equal(pg.get_scaler(k), pr.get_scaler(k), err_msg=f"scaler {k}")
-        a, b = pg.get_clv(w.tips + k), pr.get_clv(w.tips + k)
-        assert a.tobytes() == b.tobytes(), f"CLV {w.tips + k} differs (max abs {np.max(np.abs(a - b))})"
+        _assert_clv(pg.get_clv(w.tips + k), pr.get_clv(w.tips + k), exact, f"CLV {w.tips + k}")
 
     ps_g, ps_r = np.zeros(sites), np.zeros(sites)
     args = (w.root_a, w.scaler_of(w.root_a), w.root_b, w.scaler_of(w.root_b), w.root_matrix, pidx)
@@ -105,8 +123,11 @@ def _caterpillar(tips, sites, states, seed):
 
 
 @pytest.mark.parametrize("states,rate_scalers", [(4, False), (4, True), (20, False), (20, True)])
-def test_scaling_long_tree(gpu_lib, ref_lib, states, rate_scalers):
-    tips, sites = (400, 64) if states == 4 else (160, 32)
+def test_scaling_long_tree(gpu_lib, ref_lib, states, rate_scalers, aa_mode):
+    if states == 4 and aa_mode == "dmma":
+        pytest.skip("DNA has a single implementation")
+    exact = states == 4 or aa_mode == "exact"
+    tips, sites = (400, 64) if states == 4 else (160, 37)
     w = _caterpillar(tips, sites, states, seed=5)
     extra = PLL_ATTRIB_PATTERN_TIP | (PLL_ATTRIB_RATE_SCALERS if rate_scalers else 0)
     pg, pr, pidx = _pair(gpu_lib, ref_lib, w, extra)
@@ -120,8 +141,7 @@ def test_scaling_long_tree(gpu_lib, ref_lib, states, rate_scalers):
         total += int(b.sum())
     assert total > 0, "the test tree must actually trigger rescaling"
     top = w.root_a
-    a, b = pg.get_clv(top), pr.get_clv(top)
-    assert a.tobytes() == b.tobytes()
+    _assert_clv(pg.get_clv(top), pr.get_clv(top), exact, "top CLV")
     args = (w.root_a, w.scaler_of(w.root_a), w.root_b, w.scaler_of(w.root_b), w.root_matrix, pidx)
     lg, lr = pg.edge_loglikelihood(*args), pr.edge_loglikelihood(*args)
     assert np.isfinite(lr)
