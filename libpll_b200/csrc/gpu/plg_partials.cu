@@ -747,34 +747,38 @@ k_partial_ti_aa(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mo
   if (valid && scale) rescale20(out);
 }
 
-/* tip-tip, 20 states (reference src/core_partials_avx.c:531-579, :225-256) */
+/* tip-tip, 20 states (reference src/core_partials_avx.c:531-579, :225-256): one thread per
+ * 16-byte chunk (two states) of the parent CLV, so every store instruction of a warp covers 512
+ * contiguous bytes; the two per-side tables stay hot in L1 */
+#define PLG_AA_TT_ITEMS 4
 template <int R>
-__global__ void __launch_bounds__(PLG_AA_THREADS)
+__global__ void __launch_bounds__(256)
 k_partial_tt_aa(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mode)
 {
   const DevOp op = ops[blockIdx.y];
-  const unsigned int k = threadIdx.x & (R - 1);
-  const unsigned int e = blockIdx.x * PLG_AA_THREADS + threadIdx.x;
-  if (e >= nelem) return;
-  const unsigned int n = e / R;
-  const unsigned int lc = __ldg(op.ltip + n);
-  const unsigned int rc = __ldg(op.rtip + n);
-  const double * tl = op.lmat + ((size_t)lc * R + k) * 20;
-  const double * tr = op.rmat + ((size_t)rc * R + k) * 20;
-  double * out = op.parent + (size_t)e * 20;
+  const unsigned long long nchunks = (unsigned long long)nelem * 10ull; /* 16-byte chunks */
+  const unsigned long long base = (unsigned long long)blockIdx.x * (256 * PLG_AA_TT_ITEMS) + threadIdx.x;
 #pragma unroll
-  for (int ib = 0; ib < 5; ++ib)
+  for (int j = 0; j < PLG_AA_TT_ITEMS; ++j)
   {
-    const d4 a = *reinterpret_cast<const d4 *>(tl + 4 * ib);
-    const d4 b = *reinterpret_cast<const d4 *>(tr + 4 * ib);
-    st_stream(out + 4 * ib, mul4(a, b));
+    const unsigned long long c = base + (unsigned long long)j * 256;
+    if (c >= nchunks) break;
+    const unsigned int n = (unsigned int)(c / (R * 10));  /* site                          */
+    const unsigned int w = (unsigned int)(c % (R * 10));  /* chunk within the site: k*10+p */
+    const unsigned int lc = __ldg(op.ltip + n);
+    const unsigned int rc = __ldg(op.rtip + n);
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(op.lmat + (size_t)lc * R * 20) + w);
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(op.rmat + (size_t)rc * R * 20) + w);
+    st_stream2(op.parent + c * 2, __dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y));
+    if (scale_mode == 1)
+    {
+      if (w == 0) op.pscale[n] = 0u;
+    }
+    else if (scale_mode == 2)
+    {
+      if (w % 10 == 0) op.pscale[(size_t)n * R + w / 10] = 0u;
+    }
   }
-  if (scale_mode == 1)
-  {
-    if (k == 0) op.pscale[n] = 0u;
-  }
-  else if (scale_mode == 2)
-    op.pscale[e] = 0u;
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -788,11 +792,14 @@ k_partial_tt_aa(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mo
  * fragment straight from HBM (8 full 32-byte sectors per request), so the loop is
  * tensor-/HBM-bound instead.  Measured peaks on this B200: DFMA 33.8 TFLOP/s, DMMA 37.1.
  *
- *   Y[i][s] = sum_j P_k[i][j] * c[s][k][j]      M = parent states (20, padded to 3 x 8)
- *                                               N = 8 sites per warp-tile, K = 20 = 5 x 4
- *   A fragment (mt, ks): lane holds P[8mt + lane/4][4ks + lane%4]   (shared memory, per op)
- *   B fragment (ks)    : lane holds c[site lane/4][4ks + lane%4]    (one LDG.64 each)
- *   D fragment (mt)    : lane holds Y[8mt + lane/4][site 2(lane%4) + {0,1}]
+ *   Y[s][i] = sum_j c[s][k][j] * P_k[i][j]      M = 8 sites per warp-tile,
+ *                                               N = parent states (20, padded to 3 x 8), K = 20
+ *   The 20 child states are fed in 5 k-steps with the permutation j(ks, q) = 4q + ks for
+ *   ks < 4 and 16 + q for ks = 4 (any order works as long as A and B agree), so that
+ *   A fragment (ks)    : lane (g, q) holds c[site g][j(ks, q)] - its four ks < 4 values are
+ *                        32 contiguous bytes: ONE 256-bit load + one 64-bit load per (site, rate)
+ *   B fragment (nt, ks): lane holds P[8nt + g][j(ks, q)]             (shared memory, per op)
+ *   D fragment (nt)    : lane holds Y[site g][8nt + 2q + {0,1}]      -> 128-bit stores
  *
  * A warp owns 8 sites and loops over the rates; results are stored as they are produced and
  * re-read for the (rare) x 2^256 rescale, exactly like the reference's per-site loop
@@ -816,196 +823,247 @@ __device__ __forceinline__ double ldg_stream64(const double * p)
   return v;
 }
 
+/* the five A-fragment values of one (site, rate): states 4q..4q+3 and 16+q */
+struct afrag5
+{
+  double2 lo0, lo1;
+  double hi;
+};
+
+/* D(8 sites x 8 states) += A(8 x 20) . B(20 x 8) for one N tile */
+__device__ __forceinline__ void dmma_row(double & d0, double & d1, const afrag5 & a,
+                                         const double * __restrict__ bfrag /* [5][32] */, unsigned int lane)
+{
+  dmma884(d0, d1, a.lo0.x, bfrag[0 * 32 + lane]);
+  dmma884(d0, d1, a.lo0.y, bfrag[1 * 32 + lane]);
+  dmma884(d0, d1, a.lo1.x, bfrag[2 * 32 + lane]);
+  dmma884(d0, d1, a.lo1.y, bfrag[3 * 32 + lane]);
+  dmma884(d0, d1, a.hi, bfrag[4 * 32 + lane]);
+}
+
+__device__ __forceinline__ void cp_async16(void * dst_smem, const void * src_gmem)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem))),
+               "l"(src_gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+/* Each warp streams its own 8-site units through a private 2-deep ring in shared memory
+ * (cp.async, 16-byte chunks, rows padded to PLG_DMMA_PITCH doubles so that the A-fragment
+ * reads are bank-conflict free): ~20 KB in flight per warp, independent of register use. */
+#define PLG_DMMA_WARPS 8
+template <int R>
+struct dmma_geom
+{
+  static constexpr int ROW = R * 20;        /* doubles per site                       */
+  static constexpr int PITCH = ROW + 2;     /* padded: (PITCH*2) % 32 == 4 words      */
+  static constexpr int UNIT = 8 * PITCH;    /* doubles per child per unit (8 sites)   */
+};
+
 /* KIND: PLG_KIND_II (two matrix products) or PLG_KIND_TI (tip table x one matrix product) */
 template <int R, int KIND>
-__global__ void __launch_bounds__(PLG_DMMA_THREADS, 2)
-k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int sites, int scale_mode)
+__global__ void __launch_bounds__(PLG_DMMA_WARPS * 32, 1)
+k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned int sites, int scale_mode)
 {
-  extern __shared__ __align__(16) double afrag[]; /* [child][rate][mt*5+ks][lane] */
+  extern __shared__ __align__(16) double smem_d[];
   constexpr int NCHILD = (KIND == PLG_KIND_II) ? 2 : 1;
-  const DevOp op = ops[blockIdx.y];
+  using G = dmma_geom<R>;
+  double * bfrag = smem_d;                                   /* [child][rate][nt][ks][lane] */
   const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned int g = lane >> 2, q = lane & 3u;
+  double * ring = smem_d + NCHILD * R * 15 * 32 + (size_t)warp * 2 * NCHILD * G::UNIT; /* [2][child][8][PITCH] */
+  const unsigned int units = (sites + 7) / 8;
+  const size_t total_doubles = (size_t)sites * G::ROW;
 
-  /* P matrices -> A fragments (rows 20..23 of the third M tile are zero padding) */
-  for (unsigned int t = threadIdx.x; t < NCHILD * R * 15 * 32; t += PLG_DMMA_THREADS)
+  /* the (operation, unit) space of the whole launch is flattened and cut into one contiguous
+   * chunk per CTA (no partial second wave); a chunk is walked one operation segment at a time */
+  const unsigned long long total_units = (unsigned long long)n_ops * units;
+  const unsigned long long per = (total_units + gridDim.x - 1) / gridDim.x;
+  const unsigned long long f_begin = blockIdx.x * per;
+  const unsigned long long f_end = (f_begin + per < total_units) ? f_begin + per : total_units;
+
+  for (unsigned long long f_seg = f_begin; f_seg < f_end;)
+  {
+  const unsigned int op_idx = (unsigned int)(f_seg / units);
+  const unsigned int u_seg = (unsigned int)(f_seg - (unsigned long long)op_idx * units);
+  const unsigned long long seg_len_ll = ((unsigned long long)units - u_seg < f_end - f_seg)
+                                            ? (unsigned long long)units - u_seg : f_end - f_seg;
+  const unsigned int u_stop = u_seg + (unsigned int)seg_len_ll; /* units [u_seg, u_stop) of op_idx */
+  f_seg += seg_len_ll;
+  const DevOp op = ops[op_idx];
+
+  __syncthreads(); /* previous segment's fragments no longer in use */
+  /* P matrices -> B fragments (parent states 20..23 of the third N tile are zero padding) */
+  for (unsigned int t = threadIdx.x; t < NCHILD * R * 15 * 32; t += PLG_DMMA_WARPS * 32)
   {
     const unsigned int l = t & 31u, f = (t >> 5) % 15, kc = (t >> 5) / 15; /* kc = child*R + k */
-    const unsigned int row = 8 * (f / 5) + (l >> 2), col = 4 * (f % 5) + (l & 3u);
+    const unsigned int nt = f / 5, ks = f % 5;
+    const unsigned int row = 8 * nt + (l >> 2);
+    const unsigned int col = (ks < 4) ? 4 * (l & 3u) + ks : 16 + (l & 3u);
     const double * M = (NCHILD == 2 && kc < (unsigned)R) ? op.lmat : op.rmat;
     const unsigned int k = kc % R;
-    afrag[t] = (row < 20) ? __ldg(M + (size_t)k * 400 + row * 20 + col) : 0.0;
+    bfrag[t] = (row < 20) ? __ldg(M + (size_t)k * 400 + row * 20 + col) : 0.0;
   }
   __syncthreads();
-  const double * AL = afrag;                               /* left child (ii only)  */
-  const double * AR = afrag + (NCHILD - 1) * R * 15 * 32;  /* right / inner child   */
+  const double * BL = bfrag;                               /* left child (ii only) */
+  const double * BR = bfrag + (NCHILD - 1) * R * 15 * 32;  /* right / inner child  */
 
-  const unsigned int units = (sites + 7) / 8;
-  const unsigned int warps_total = gridDim.x * (PLG_DMMA_THREADS / 32);
-  for (unsigned int u = blockIdx.x * (PLG_DMMA_THREADS / 32) + warp; u < units; u += warps_total)
-  {
-    const unsigned int site_b = 8 * u + g;            /* site whose CLV entries this lane loads */
-    const bool load_ok = site_b < sites;
-    const unsigned int site_d0 = 8 * u + 2 * q;       /* the two sites of this lane's D columns */
-    const bool ok0 = site_d0 < sites, ok1 = site_d0 + 1 < sites;
+  const unsigned int stride = PLG_DMMA_WARPS;
+  const unsigned int u_first = u_seg + warp;
 
-    /* scaler inputs of the unit's 8 sites: lane t < 8 looks after site 8u + t */
-    unsigned int child_sum = 0;
-    if (scale_mode == 1 && lane < 8 && 8 * u + lane < sites)
+  /* asynchronous copy of unit u (both children) into ring slot `slot` */
+  auto fetch = [&](unsigned int u, unsigned int slot) {
+    if (u < u_stop)
     {
-      if (KIND == PLG_KIND_II && op.lscale) child_sum += op.lscale[8 * u + lane];
-      if (op.rscale) child_sum += op.rscale[8 * u + lane];
-    }
-    unsigned int code0 = 0, code1 = 0;
-    if (KIND == PLG_KIND_TI)
-    {
-      if (ok0) code0 = __ldg(op.ltip + site_d0);
-      if (ok1) code1 = __ldg(op.ltip + site_d0 + 1);
-    }
-
-    bool below0 = true, below1 = true; /* per-site mode: every entry of the site so far */
-    double bl[5], br[5];
+      const size_t base = (size_t)u * 8 * G::ROW; /* doubles */
 #pragma unroll
-    for (int ks = 0; ks < 5; ++ks)
-    {
-      const size_t off = ((size_t)site_b * R + 0) * 20 + 4 * ks + q;
-      br[ks] = load_ok ? ldg_stream64(op.right + off) : 0.0;
-      if (KIND == PLG_KIND_II) bl[ks] = load_ok ? ldg_stream64(op.left + off) : 0.0;
+      for (int c = 0; c < NCHILD; ++c)
+      {
+        const double * src = (NCHILD == 2 && c == 0) ? op.left : op.right;
+        double * dst = ring + ((size_t)slot * NCHILD + c) * G::UNIT;
+        for (unsigned int i = lane; i < 8 * G::ROW / 2; i += 32) /* 16-byte chunks */
+        {
+          const size_t off = base + 2 * (size_t)i;
+          if (off < total_doubles) cp_async16(dst + (i / (G::ROW / 2)) * G::PITCH + 2 * (i % (G::ROW / 2)), src + off);
+        }
+      }
     }
+    cp_async_commit();
+  };
 
-#pragma unroll 1
+  fetch(u_first, 0);
+  fetch(u_first + stride, 1);
+  unsigned int slot = 0;
+  for (unsigned int u = u_first; u < u_stop; u += stride, slot ^= 1u)
+  {
+    const unsigned int site = 8 * u + g; /* this lane's site: A rows and D rows alike */
+    const bool ok = site < sites;
+    const size_t site_off = (size_t)site * G::ROW;
+
+    unsigned int child_sum = 0, code = 0;
+    if (scale_mode == 1 && q == 0 && ok)
+    {
+      if (KIND == PLG_KIND_II && op.lscale) child_sum += op.lscale[site];
+      if (op.rscale) child_sum += op.rscale[site];
+    }
+    if (KIND == PLG_KIND_TI && ok) code = __ldg(op.ltip + site);
+
+    cp_async_wait<1>(); /* this unit's copies have landed (the next unit's may be in flight) */
+    __syncwarp();
+    const double * rowL = ring + ((size_t)slot * NCHILD + 0) * G::UNIT + g * G::PITCH;
+    const double * rowR = ring + ((size_t)slot * NCHILD + (NCHILD - 1)) * G::UNIT + g * G::PITCH;
+
+    bool below_site = true;
+#pragma unroll
     for (int k = 0; k < R; ++k)
     {
-      /* prefetch the next rate's B fragments while this rate's products run */
-      double nl[5], nr[5];
-      if (k + 1 < R)
+      afrag5 ar, al;
+      ar.lo0 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 4 * q);
+      ar.lo1 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 4 * q + 2);
+      ar.hi = rowR[k * 20 + 16 + q];
+      if (KIND == PLG_KIND_II)
       {
-#pragma unroll
-        for (int ks = 0; ks < 5; ++ks)
-        {
-          const size_t off = ((size_t)site_b * R + (k + 1)) * 20 + 4 * ks + q;
-          nr[ks] = load_ok ? ldg_stream64(op.right + off) : 0.0;
-          if (KIND == PLG_KIND_II) nl[ks] = load_ok ? ldg_stream64(op.left + off) : 0.0;
-        }
+        al.lo0 = *reinterpret_cast<const double2 *>(rowL + k * 20 + 4 * q);
+        al.lo1 = *reinterpret_cast<const double2 *>(rowL + k * 20 + 4 * q + 2);
+        al.hi = rowL[k * 20 + 16 + q];
       }
 
-      double y[3][2], x[3][2];
+      double p[3][2];
+      bool below = true;
 #pragma unroll
-      for (int mt = 0; mt < 3; ++mt)
+      for (int nt = 0; nt < 3; ++nt)
       {
-        y[mt][0] = y[mt][1] = 0.0;
-#pragma unroll
-        for (int ks = 0; ks < 5; ++ks)
-          dmma884(y[mt][0], y[mt][1], AR[((size_t)k * 15 + mt * 5 + ks) * 32 + lane], br[ks]);
+        double y0 = 0.0, y1 = 0.0, x0 = 0.0, x1 = 0.0;
+        dmma_row(y0, y1, ar, BR + ((size_t)k * 15 + nt * 5) * 32, lane);
+        const unsigned int row = 8 * nt + 2 * q; /* first of this lane's two parent states */
         if (KIND == PLG_KIND_II)
+          dmma_row(x0, x1, al, BL + ((size_t)k * 15 + nt * 5) * 32, lane);
+        else if (row < 20)
         {
-          x[mt][0] = x[mt][1] = 0.0;
-#pragma unroll
-          for (int ks = 0; ks < 5; ++ks)
-            dmma884(x[mt][0], x[mt][1], AL[((size_t)k * 15 + mt * 5 + ks) * 32 + lane], bl[ks]);
+          const double2 t = __ldg(reinterpret_cast<const double2 *>(op.lmat + ((size_t)code * R + k) * 20 + row));
+          x0 = t.x;
+          x1 = t.y;
         }
-        else
-        {
-          const unsigned int row = 8 * mt + g;
-          x[mt][0] = (row < 20) ? __ldg(op.lmat + ((size_t)code0 * R + k) * 20 + row) : 0.0;
-          x[mt][1] = (row < 20) ? __ldg(op.lmat + ((size_t)code1 * R + k) * 20 + row) : 0.0;
-        }
-      }
-
-      /* products, threshold test, store */
-      bool b0 = true, b1 = true;
-#pragma unroll
-      for (int mt = 0; mt < 3; ++mt)
-      {
-        const unsigned int row = 8 * mt + g;
-        const double p0 = __dmul_rn(x[mt][0], y[mt][0]);
-        const double p1 = __dmul_rn(x[mt][1], y[mt][1]);
+        p[nt][0] = __dmul_rn(x0, y0);
+        p[nt][1] = __dmul_rn(x1, y1);
         if (row < 20)
         {
-          b0 = b0 && (p0 < PLG_SCALE_THRESHOLD);
-          b1 = b1 && (p1 < PLG_SCALE_THRESHOLD);
-          if (ok0) op.parent[((size_t)site_d0 * R + k) * 20 + row] = p0;
-          if (ok1) op.parent[((size_t)(site_d0 + 1) * R + k) * 20 + row] = p1;
+          below = below && (p[nt][0] < PLG_SCALE_THRESHOLD) && (p[nt][1] < PLG_SCALE_THRESHOLD);
+          if (ok) st_stream2(op.parent + site_off + k * 20 + row, p[nt][0], p[nt][1]);
         }
       }
       if (scale_mode == 2)
       {
-        /* per-rate: all 20 rows of (site, rate) below -> rescale that block now */
-        const unsigned int m0 = __ballot_sync(0xffffffffu, b0), m1 = __ballot_sync(0xffffffffu, b1);
-        const unsigned int rows_mask = 0x11111111u << q;
-        const bool s0 = (m0 & rows_mask) == rows_mask, s1 = (m1 & rows_mask) == rows_mask;
+        /* per-rate: all 20 states of (site, rate) below -> rescale that block now */
+        const unsigned int m = __ballot_sync(0xffffffffu, below);
+        const bool sc = ((m >> (lane & ~3u)) & 0xFu) == 0xFu;
+        if (sc && ok)
 #pragma unroll
-        for (int mt = 0; mt < 3; ++mt)
+          for (int nt = 0; nt < 3; ++nt)
+          {
+            const unsigned int row = 8 * nt + 2 * q;
+            if (row < 20)
+              st_stream2(op.parent + site_off + k * 20 + row, __dmul_rn(p[nt][0], PLG_SCALE_FACTOR),
+                         __dmul_rn(p[nt][1], PLG_SCALE_FACTOR));
+          }
+        if (q == 0 && ok)
         {
-          const unsigned int row = 8 * mt + g;
-          if (row < 20)
-          {
-            if (s0 && ok0) op.parent[((size_t)site_d0 * R + k) * 20 + row] *= PLG_SCALE_FACTOR;
-            if (s1 && ok1) op.parent[((size_t)(site_d0 + 1) * R + k) * 20 + row] *= PLG_SCALE_FACTOR;
-          }
-        }
-        if (g == 0)
-        {
-          if (ok0)
-          {
-            const size_t e = (size_t)site_d0 * R + k;
-            op.pscale[e] = (s0 ? 1u : 0u) + ((KIND == PLG_KIND_II && op.lscale) ? op.lscale[e] : 0u) +
-                           (op.rscale ? op.rscale[e] : 0u);
-          }
-          if (ok1)
-          {
-            const size_t e = (size_t)(site_d0 + 1) * R + k;
-            op.pscale[e] = (s1 ? 1u : 0u) + ((KIND == PLG_KIND_II && op.lscale) ? op.lscale[e] : 0u) +
-                           (op.rscale ? op.rscale[e] : 0u);
-          }
+          const size_t e = (size_t)site * R + k;
+          op.pscale[e] = (sc ? 1u : 0u) + ((KIND == PLG_KIND_II && op.lscale) ? op.lscale[e] : 0u) +
+                         (op.rscale ? op.rscale[e] : 0u);
         }
       }
-      below0 = below0 && b0;
-      below1 = below1 && b1;
-      if (k + 1 < R)
-      {
-#pragma unroll
-        for (int ks = 0; ks < 5; ++ks)
-        {
-          br[ks] = nr[ks];
-          if (KIND == PLG_KIND_II) bl[ks] = nl[ks];
-        }
-      }
+      below_site = below_site && below;
     }
+
+    /* the slot is free again: start fetching the unit after next into it */
+    __syncwarp();
+    fetch(u + 2 * stride, slot);
 
     if (scale_mode == 1)
     {
-      /* per-site: every entry (all rates, all rows) of a site below the threshold */
-      const unsigned int m0 = __ballot_sync(0xffffffffu, below0), m1 = __ballot_sync(0xffffffffu, below1);
-      unsigned int votes = 0; /* bit t = site 8u + t must be rescaled */
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq)
+      /* per-site: every entry (all rates, all states) of the site below the threshold; the
+       * four lanes of a site hold all of them */
+      const unsigned int m = __ballot_sync(0xffffffffu, below_site);
+      const bool sc = ((m >> (lane & ~3u)) & 0xFu) == 0xFu;
+      if (sc && ok)
       {
-        const unsigned int rows_mask = 0x11111111u << qq;
-        if ((m0 & rows_mask) == rows_mask) votes |= 1u << (2 * qq);
-        if ((m1 & rows_mask) == rows_mask) votes |= 1u << (2 * qq + 1);
-      }
-      if (votes)
-      {
-        __syncwarp(); /* this warp's own stores above are visible to its lanes */
+        /* rare: re-read what this lane stored and scale it (reference rescales in place too) */
 #pragma unroll 1
         for (int k = 0; k < R; ++k)
 #pragma unroll
-          for (int mt = 0; mt < 3; ++mt)
+          for (int nt = 0; nt < 3; ++nt)
           {
-            const unsigned int row = 8 * mt + g;
+            const unsigned int row = 8 * nt + 2 * q;
             if (row < 20)
             {
-              if (((votes >> (2 * q)) & 1u) && ok0)
-                op.parent[((size_t)site_d0 * R + k) * 20 + row] *= PLG_SCALE_FACTOR;
-              if (((votes >> (2 * q + 1)) & 1u) && ok1)
-                op.parent[((size_t)(site_d0 + 1) * R + k) * 20 + row] *= PLG_SCALE_FACTOR;
+              double2 * dst = reinterpret_cast<double2 *>(op.parent + site_off + k * 20 + row);
+              double2 v = *dst;
+              v.x = __dmul_rn(v.x, PLG_SCALE_FACTOR);
+              v.y = __dmul_rn(v.y, PLG_SCALE_FACTOR);
+              *dst = v;
             }
           }
       }
-      if (lane < 8 && 8 * u + lane < sites) op.pscale[8 * u + lane] = child_sum + ((votes >> lane) & 1u);
+      if (q == 0 && ok) op.pscale[site] = child_sum + (sc ? 1u : 0u);
     }
   }
+  cp_async_wait<0>();
+  } /* segment */
+}
+
+template <int R, int KIND>
+static constexpr size_t dmma_smem_bytes()
+{
+  constexpr int NCHILD = (KIND == PLG_KIND_II) ? 2 : 1;
+  return ((size_t)NCHILD * R * 15 * 32 + (size_t)PLG_DMMA_WARPS * 2 * NCHILD * dmma_geom<R>::UNIT) * sizeof(double);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -1234,21 +1292,23 @@ static void launch_group(plg_context * ctx, const Group & g, const DevOp * dev_o
       k_partial_tt_dna<R, ITEMS><<<grid, PLG_DNA_THREADS, 0, ctx->stream>>>(ops, nelem, g.scale_mode);
     }
   }
-  else if (!ctx->aa_exact && g.kind != PLG_KIND_TT)
+  else if (!ctx->aa_exact && g.kind != PLG_KIND_TT && dmma_smem_bytes<R, PLG_KIND_II>() <= 227 * 1024)
   {
-    /* tensor-core path: persistent over 8-site units, one grid row per operation */
+    /* tensor-core path: persistent CTAs over the flattened (operation, 8-site unit) space;
+     * resident CTAs per SM by shared memory: 1 (inner-inner, 199 KB) or 2 (tip-inner, 99 KB) */
     const unsigned int units = (ctx->d.sites + 7) / 8;
-    unsigned int bx = (units + 7) / 8;
-    const unsigned int cap = (unsigned int)ctx->sm_count * 2u;
-    if (g.count * (unsigned long long)bx > cap) bx = (cap + g.count - 1) / g.count;
-    if (bx == 0) bx = 1;
-    dim3 grid(bx, g.count);
+    const unsigned long long total = (unsigned long long)units * g.count;
+    unsigned long long blocks = (unsigned long long)ctx->sm_count * (g.kind == PLG_KIND_II ? 1u : 2u);
+    const unsigned long long want = (total + PLG_DMMA_WARPS - 1) / PLG_DMMA_WARPS;
+    if (want < blocks) blocks = want ? want : 1;
     if (g.kind == PLG_KIND_II)
-      k_partial_dmma_aa<R, PLG_KIND_II><<<grid, PLG_DMMA_THREADS, (size_t)2 * R * 15 * 32 * sizeof(double),
-                                          ctx->stream>>>(ops, ctx->d.sites, g.scale_mode);
+      k_partial_dmma_aa<R, PLG_KIND_II><<<(unsigned int)blocks, PLG_DMMA_WARPS * 32,
+                                          dmma_smem_bytes<R, PLG_KIND_II>(), ctx->stream>>>(
+          ops, g.count, ctx->d.sites, g.scale_mode);
     else
-      k_partial_dmma_aa<R, PLG_KIND_TI><<<grid, PLG_DMMA_THREADS, (size_t)R * 15 * 32 * sizeof(double),
-                                          ctx->stream>>>(ops, ctx->d.sites, g.scale_mode);
+      k_partial_dmma_aa<R, PLG_KIND_TI><<<(unsigned int)blocks, PLG_DMMA_WARPS * 32,
+                                          dmma_smem_bytes<R, PLG_KIND_TI>(), ctx->stream>>>(
+          ops, g.count, ctx->d.sites, g.scale_mode);
   }
   else
   {
@@ -1264,7 +1324,11 @@ static void launch_group(plg_context * ctx, const Group & g, const DevOp * dev_o
       k_partial_ti_aa<R><<<grid, PLG_AA_THREADS, smem, ctx->stream>>>(ops, nelem, g.scale_mode);
     }
     else
-      k_partial_tt_aa<R><<<grid, PLG_AA_THREADS, 0, ctx->stream>>>(ops, nelem, g.scale_mode);
+    {
+      const unsigned long long nchunks = (unsigned long long)nelem * 10ull;
+      dim3 gtt((unsigned int)((nchunks + 256 * PLG_AA_TT_ITEMS - 1) / (256 * PLG_AA_TT_ITEMS)), g.count);
+      k_partial_tt_aa<R><<<gtt, 256, 0, ctx->stream>>>(ops, nelem, g.scale_mode);
+    }
   }
 }
 
@@ -1281,12 +1345,15 @@ static int set_smem_limits()
   PLG_CUDA(cudaFuncSetAttribute(k_partial_stream_dna<R, PLG_KIND_TI, PLG_TI_STAGES, PLG_TI_MINB>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(StreamSmem<R, PLG_KIND_TI, PLG_TI_STAGES>)));
-  PLG_CUDA(cudaFuncSetAttribute(k_partial_dmma_aa<R, PLG_KIND_II>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                2 * R * 15 * 32 * (int)sizeof(double)));
-  PLG_CUDA(cudaFuncSetAttribute(k_partial_dmma_aa<R, PLG_KIND_TI>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                R * 15 * 32 * (int)sizeof(double)));
+  if (dmma_smem_bytes<R, PLG_KIND_II>() <= 227 * 1024)
+  {
+    PLG_CUDA(cudaFuncSetAttribute(k_partial_dmma_aa<R, PLG_KIND_II>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)dmma_smem_bytes<R, PLG_KIND_II>()));
+    PLG_CUDA(cudaFuncSetAttribute(k_partial_dmma_aa<R, PLG_KIND_TI>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)dmma_smem_bytes<R, PLG_KIND_TI>()));
+  }
   PLG_CUDA(cudaFuncSetAttribute(k_partial_ii_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 2 * R * PLG_AA_MSTRIDE * (int)sizeof(double)));
   PLG_CUDA(cudaFuncSetAttribute(k_partial_ti_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
