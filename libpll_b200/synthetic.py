@@ -46,11 +46,13 @@ class Workload:
     root_matrix: int = 0
     root_seq: np.ndarray = field(default=None, repr=False)  # [sites] state indices
     weights: np.ndarray = field(default=None, repr=False)
+    n_slots: int = 0  # > 0: inner CLVs / scalers live in this many recycled slots
 
     # ---- derived sizes -------------------------------------------------------------
     @property
     def inner(self) -> int:
-        return self.tips - 2
+        """CLV buffers / scale buffers to allocate."""
+        return self.n_slots if self.n_slots else self.tips - 2
 
     @property
     def prob_matrices(self) -> int:
@@ -107,6 +109,77 @@ def make_workload(tips: int, sites: int, states: int = 4, rate_cats: int = 4, al
 
 
 TIP_BLOCK = 1 << 16  # sites per independently seeded block (makes tips site-sliceable)
+
+
+def recycle_slots(w: Workload, max_slots: int) -> Workload:
+    """Re-indexes the inner CLVs / scale buffers of a workload onto a pool of `max_slots`
+    recycled slots (SURVEY.md section 7 "Capacity": 5,000 x 10M cannot keep every CLV).
+
+    The tree is walked depth-first from the evaluation edge, larger subtree first
+    (Sethi-Ullman order), a node's slot is taken when its operation is emitted and its
+    children's slots return to the pool right after.  P-matrix indices stay node indices.
+    The result is an ordinary pll_operation_t list - slot reuse is legal pll.h API use - whose
+    later operations overwrite slots earlier ones read (WAR/WAW hazards the batched scheduler
+    must honour).  Raises if `max_slots` is too small for the tree."""
+    import sys
+
+    T = w.tips
+    children = {int(o["parent_clv_index"]): (int(o["child1_clv_index"]), int(o["child2_clv_index"])) for o in w.ops}
+    size = {}
+
+    def subtree(n):
+        if n < T:
+            size[n] = 1
+        else:
+            a, b = children[n]
+            size[n] = 1 + subtree(a) + subtree(b)
+        return size[n]
+
+    old = sys.getrecursionlimit()
+    sys.setrecursionlimit(max(old, 4 * T + 100))
+    try:
+        for r in (w.root_a, w.root_b):
+            subtree(r)
+        free = list(range(max_slots - 1, -1, -1))
+        slot = {}
+        new_ops = []
+
+        def emit(n):
+            if n < T:
+                return
+            a, b = children[n]
+            first, second = (a, b) if size[a] >= size[b] else (b, a)
+            emit(first)
+            emit(second)
+            if not free:
+                raise ValueError(f"max_slots={max_slots} is too small for this tree")
+            slot[n] = free.pop()
+
+            def idx(c):
+                return c if c < T else T + slot[c]
+
+            def sc(c):
+                return PLL_SCALE_BUFFER_NONE if c < T else slot[c]
+
+            new_ops.append((T + slot[n], slot[n], idx(a), a, sc(a), idx(b), b, sc(b)))
+            for c in (a, b):
+                if c >= T:
+                    free.append(slot[c])
+
+        emit(w.root_a)
+        emit(w.root_b)
+    finally:
+        sys.setrecursionlimit(old)
+
+    out = Workload(tips=w.tips, sites=w.sites, states=w.states, rate_cats=w.rate_cats, alpha=w.alpha, seed=w.seed)
+    out.ops = np.array(new_ops, dtype=OP_DTYPE)
+    out.matrix_indices, out.branch_lengths = w.matrix_indices, w.branch_lengths
+    out.root_seq, out.weights = w.root_seq, w.weights
+    out.root_a = w.root_a if w.root_a < T else T + slot[w.root_a]
+    out.root_b = w.root_b if w.root_b < T else T + slot[w.root_b]
+    out.root_matrix = w.root_matrix
+    out.n_slots = max_slots
+    return out
 
 
 def tip_sequence(w: Workload, tip: int, lo: int = 0, hi: Optional[int] = None) -> bytes:

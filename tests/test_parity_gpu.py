@@ -192,3 +192,58 @@ def test_edge_lnl_with_invariant_sites(gpu_lib, ref_lib):
     assert abs(lg - lr) <= RTOL * abs(lr), (lg, lr)
     pg.destroy()
     pr.destroy()
+
+
+@pytest.mark.parametrize("states,tips,sites,slots", [(4, 150, 1500, 10), (4, 64, 700, 7), (20, 60, 300, 8)])
+def test_slot_recycling_hazards(gpu_lib, ref_lib, states, tips, sites, slots):
+    """CLV / scaler slots recycled by the caller (legal pll.h use, needed for 5,000 x 10M):
+    later operations overwrite slots earlier ones read, so the batched scheduler has to honour
+    WAR and WAW hazards, not only RAW.  Same list on the reference (strictly sequential)."""
+    w = S.recycle_slots(S.make_workload(tips, sites, states=states, seed=23), slots)
+    pg, pr, pidx = _pair(gpu_lib, ref_lib, w, PLL_ATTRIB_PATTERN_TIP)
+    _share_pmatrices(pg, pr, w, pidx)
+    for _ in range(2):  # second call replays the cached CUDA graph
+        pg.update_partials(w.ops)
+    pr.update_partials(w.ops)
+    for k in range(slots):
+        np.testing.assert_array_equal(pg.get_scaler(k), pr.get_scaler(k), err_msg=f"scaler slot {k}")
+        np.testing.assert_allclose(pg.get_clv(w.tips + k), pr.get_clv(w.tips + k), rtol=1e-12, atol=0)
+    args = (w.root_a, w.scaler_of(w.root_a), w.root_b, w.scaler_of(w.root_b), w.root_matrix, pidx)
+    lg, lr = pg.edge_loglikelihood(*args), pr.edge_loglikelihood(*args)
+    assert abs(lg - lr) <= RTOL * abs(lr), (lg, lr)
+    pg.destroy()
+    pr.destroy()
+
+
+def test_full_width_properties(gpu_lib, ref_lib):
+    """Size-independent properties at a pattern count the CPU oracle cannot cover in seconds
+    (500k patterns, 25 GB of CLVs): the per-pattern lnLs add up to the total; the lnL of the
+    whole alignment equals the sum over two half partitions (what site sharding relies on);
+    a 3,000-pattern window is checked against the reference pattern by pattern; repeated
+    evaluations are bit-reproducible."""
+    tips, sites = 48, 500_000
+    w = S.make_workload(tips, sites, states=4, seed=31)
+    pg, pidx = S.build_partition(gpu_lib, w, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP)
+    total = S.full_evaluation(pg, w, pidx)
+    again = S.full_evaluation(pg, w, pidx)
+    assert total == again
+    persite = np.zeros(sites)
+    args = (w.root_a, w.scaler_of(w.root_a), w.root_b, w.scaler_of(w.root_b), w.root_matrix, pidx)
+    assert pg.edge_loglikelihood(*args, persite=persite) == total
+    assert abs(np.sum(persite) - total) <= 1e-11 * abs(total)
+    pg.destroy()
+
+    halves = 0.0
+    for lo, hi in ((0, 250_048), (250_048, sites)):
+        ph, _ = S.build_partition(gpu_lib, w, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP, lo=lo, hi=hi)
+        halves += S.full_evaluation(ph, w, pidx)
+        ph.destroy()
+    assert abs(halves - total) <= 1e-11 * abs(total)
+
+    lo, hi = 123_456, 126_456
+    pr, _ = S.build_partition(ref_lib, w, PLL_ATTRIB_ARCH_AVX2 | PLL_ATTRIB_PATTERN_TIP, lo=lo, hi=hi)
+    S.full_evaluation(pr, w, pidx)
+    ps_ref = np.zeros(hi - lo)
+    pr.edge_loglikelihood(*args, persite=ps_ref)
+    pr.destroy()
+    np.testing.assert_allclose(persite[lo:hi], ps_ref, rtol=RTOL, atol=0)
