@@ -245,7 +245,16 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         return float(t.item())
 
     S_gpu = args.sites_per_gpu
-    w = S.make_workload(args.tips, S_gpu * world, states=4)
+    if args.workload == "c5":
+        # BASELINE.json configs[4]: 5,000 taxa x 10M patterns sharded over the GPUs (strong
+        # scaling: the alignment is fixed), CLVs / scalers in a pool of recycled slots
+        args.tips, total_sites = 5000, 10_000_000
+        S_gpu = (total_sites // world + 63) // 64 * 64
+        w = S.recycle_slots(S.make_workload(args.tips, S_gpu * world, states=4), args.slots)
+        distinct = [S.tip_sequence(w, t, rank * S_gpu, (rank + 1) * S_gpu) for t in range(args.distinct_tips)]
+        S.tip_sequence = lambda w_, t, lo=0, hi=None: distinct[t % len(distinct)]
+    else:
+        w = S.make_workload(args.tips, S_gpu * world, states=4)
     lo, hi = rank * S_gpu, (rank + 1) * S_gpu
     t0 = time.time()
     part, pidx = S.build_partition(lib, w, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP, lo=lo, hi=hi)
@@ -368,10 +377,13 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if args.workload == "c5" else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
             "config": {
                 "workload": f"synthetic {args.tips}-taxon x {S_gpu * world}-pattern GTR+G4 DNA "
-                            f"({S_gpu} patterns per GPU), full post-order traversal + edge logL",
+                            f"({S_gpu} patterns per GPU), full post-order traversal + edge logL"
+                            + (f", {args.slots} recycled CLV slots, {args.distinct_tips} distinct tip rows"
+                               if args.workload == "c5" else ""),
                 "attributes": "PLL_ATTRIB_ARCH_GPU|PLL_ATTRIB_PATTERN_TIP, per-site scalers",
                 "operations": n_ops, "rate_cats": 4,
                 "l2": "no flush needed: each step streams %.0f GB per GPU through a 126 MB L2" %
@@ -417,6 +429,12 @@ def main():
     ap.add_argument("--sites-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--cpu-sites-per-thread", type=int, default=10_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2: 1000 taxa x 1M patterns per GPU (weak scaling, the judged default); "
+                         "c5: 5000 taxa x 10M patterns sharded over the GPUs with CLV-slot recycling")
+    ap.add_argument("--slots", type=int, default=64, help="c5: recycled CLV / scaler slots")
+    ap.add_argument("--distinct-tips", type=int, default=64,
+                    help="c5: number of distinct synthetic tip rows (tips reuse them cyclically)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -268,6 +268,11 @@ struct DerArgs
   unsigned int nelem;
 };
 
+/* Persistent: a few CTAs per SM walk the (site, rate) elements with a grid stride, every
+ * thread keeping its running d_f / dd_f in registers; one deterministic block tree at the
+ * end and a last-block final sum (fixed grid => bit-reproducible).  A Newton iteration is
+ * latency-bound (132 B per pattern), so the kernel is a single launch with no atomics on
+ * doubles and two loads in flight per thread. */
 template <int R, int K>
 __global__ void __launch_bounds__(PLG_DER_THREADS)
 k_derivatives(const DerArgs a, const __grid_constant__ DerParams P)
@@ -275,98 +280,113 @@ k_derivatives(const DerArgs a, const __grid_constant__ DerParams P)
   const unsigned int lane = threadIdx.x & 31u;
   const unsigned int k = lane & (R - 1);
   const unsigned int gbase = lane & ~(unsigned int)(R - 1);
-  const unsigned int e = blockIdx.x * PLG_DER_THREADS + threadIdx.x;
-  const bool valid = e < a.nelem;
+  const unsigned int stride = gridDim.x * PLG_DER_THREADS;
 
-  double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-  if (valid)
+  /* this thread's rate: diagptable rows in registers (DNA) */
+  double dg[K == 4 ? 12 : 1];
+  if (K == 4)
   {
-    if (K == 4)
-    {
-      /* lanes (L, L', L'') accumulate fma(sum_j, diagp_j, acc) over the 4 states in order
-       * reference src/core_derivatives_avx2.c:634-655 */
-      const d4 s = ld_stream(a.sumtable + (size_t)e * 4);
-      const double * d = a.diagp + k * 16;
-      const double sv[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-      {
-        c0 = __fma_rn(sv[j], __ldg(d + j * 4 + 0), c0);
-        c1 = __fma_rn(sv[j], __ldg(d + j * 4 + 1), c1);
-        c2 = __fma_rn(sv[j], __ldg(d + j * 4 + 2), c2);
-      }
-    }
-    else
-    {
-      /* blocked: first block by mul, the other four by fma, then hadd
-       * reference src/core_derivatives_avx2.c:656-702 */
-      double s[20];
-      load20d(a.sumtable + (size_t)e * 20, s);
-      const double * d = a.diagp + k * 60;
-      double acc[3][4];
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int x = 0; x < 3; ++x)
-      {
-#pragma unroll
-        for (int l = 0; l < 4; ++l) acc[x][l] = __dmul_rn(s[l], __ldg(d + x * 20 + l));
-#pragma unroll
-        for (int b = 1; b < 5; ++b)
-#pragma unroll
-          for (int l = 0; l < 4; ++l)
-            acc[x][l] = __fma_rn(s[4 * b + l], __ldg(d + x * 20 + 4 * b + l), acc[x][l]);
-      }
-      c0 = hsum4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
-      c1 = hsum4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
-      c2 = hsum4(acc[2][0], acc[2][1], acc[2][2], acc[2][3]);
-    }
-  }
-
-  /* combine the rates of a site in order (reference src/core_derivatives_avx2.c:704-729) */
-  int inv = -1;
-  if (P.use_pinv && valid && k == 0 && a.invariant) inv = a.invariant[e / R];
-  double l0 = 0.0, l1 = 0.0, l2 = 0.0;
-#pragma unroll
-  for (int kk = 0; kk < R; ++kk)
-  {
-    double v0 = __shfl_sync(0xffffffffu, c0, gbase + kk);
-    double v1 = __shfl_sync(0xffffffffu, c1, gbase + kk);
-    double v2 = __shfl_sync(0xffffffffu, c2, gbase + kk);
-    if (k == 0)
-    {
-      if (P.use_pinv && P.prop_invar[kk] > 0.0)
-      {
-        const double q = __dsub_rn(1.0, P.prop_invar[kk]);
-        v0 = __dmul_rn(v0, q);
-        v1 = __dmul_rn(v1, q);
-        v2 = __dmul_rn(v2, q);
-        if (inv != -1) v0 = __dadd_rn(v0, P.invar_lk[kk * K + inv]);
-      }
-      if (P.eq_weights)
-      {
-        l0 = __dadd_rn(l0, v0);
-        l1 = __dadd_rn(l1, v1);
-        l2 = __dadd_rn(l2, v2);
-      }
-      else
-      {
-        const double w = P.rate_weights[kk];
-        l0 = __fma_rn(v0, w, l0);
-        l1 = __fma_rn(v1, w, l1);
-        l2 = __fma_rn(v2, w, l2);
-      }
-    }
+      for (int x = 0; x < 3; ++x) dg[j * 3 + x] = __ldg(a.diagp + k * 16 + j * 4 + x);
   }
 
   double df = 0.0, ddf = 0.0;
-  if (valid && k == 0)
+  /* all lanes of a warp run the same number of iterations (shuffles inside) */
+  const unsigned int first = blockIdx.x * PLG_DER_THREADS + threadIdx.x;
+  const unsigned int warp_first = first - lane;
+  for (unsigned int e0 = warp_first; e0 < a.nelem; e0 += stride)
   {
-    /* reference src/core_derivatives_avx2.c:746-766 */
-    const double recip = __ddiv_rn(1.0, l0);
-    const double d1 = __dmul_rn(l1, recip);
-    const double d2 = __dsub_rn(__dmul_rn(d1, d1), __dmul_rn(l2, recip));
-    const double w = (double)a.weights[e / R];
-    df = -__dmul_rn(d1, w);
-    ddf = __dmul_rn(d2, w);
+    const unsigned int e = e0 + lane;
+    const bool valid = e < a.nelem;
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    if (valid)
+    {
+      if (K == 4)
+      {
+        /* lanes (L, L', L'') accumulate fma(sum_j, diagp_j, acc) over the 4 states in order
+         * reference src/core_derivatives_avx2.c:634-655 */
+        const d4 s = ld_stream(a.sumtable + (size_t)e * 4);
+        const double sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+          c0 = __fma_rn(sv[j], dg[j * 3 + 0], c0);
+          c1 = __fma_rn(sv[j], dg[j * 3 + 1], c1);
+          c2 = __fma_rn(sv[j], dg[j * 3 + 2], c2);
+        }
+      }
+      else
+      {
+        /* blocked: first block by mul, the other four by fma, then hadd
+         * reference src/core_derivatives_avx2.c:656-702 */
+        double s[20];
+        load20d(a.sumtable + (size_t)e * 20, s);
+        const double * d = a.diagp + k * 60;
+        double acc[3][4];
+#pragma unroll
+        for (int x = 0; x < 3; ++x)
+        {
+#pragma unroll
+          for (int l = 0; l < 4; ++l) acc[x][l] = __dmul_rn(s[l], __ldg(d + x * 20 + l));
+#pragma unroll
+          for (int b = 1; b < 5; ++b)
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+              acc[x][l] = __fma_rn(s[4 * b + l], __ldg(d + x * 20 + 4 * b + l), acc[x][l]);
+        }
+        c0 = hsum4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+        c1 = hsum4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
+        c2 = hsum4(acc[2][0], acc[2][1], acc[2][2], acc[2][3]);
+      }
+    }
+
+    /* combine the rates of a site in order (reference src/core_derivatives_avx2.c:704-729) */
+    int inv = -1;
+    if (P.use_pinv && valid && k == 0 && a.invariant) inv = a.invariant[e / R];
+    double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < R; ++kk)
+    {
+      double v0 = __shfl_sync(0xffffffffu, c0, gbase + kk);
+      double v1 = __shfl_sync(0xffffffffu, c1, gbase + kk);
+      double v2 = __shfl_sync(0xffffffffu, c2, gbase + kk);
+      if (k == 0)
+      {
+        if (P.use_pinv && P.prop_invar[kk] > 0.0)
+        {
+          const double q = __dsub_rn(1.0, P.prop_invar[kk]);
+          v0 = __dmul_rn(v0, q);
+          v1 = __dmul_rn(v1, q);
+          v2 = __dmul_rn(v2, q);
+          if (inv != -1) v0 = __dadd_rn(v0, P.invar_lk[kk * K + inv]);
+        }
+        if (P.eq_weights)
+        {
+          l0 = __dadd_rn(l0, v0);
+          l1 = __dadd_rn(l1, v1);
+          l2 = __dadd_rn(l2, v2);
+        }
+        else
+        {
+          const double w = P.rate_weights[kk];
+          l0 = __fma_rn(v0, w, l0);
+          l1 = __fma_rn(v1, w, l1);
+          l2 = __fma_rn(v2, w, l2);
+        }
+      }
+    }
+    if (valid && k == 0)
+    {
+      /* reference src/core_derivatives_avx2.c:746-766 */
+      const double recip = __ddiv_rn(1.0, l0);
+      const double d1 = __dmul_rn(l1, recip);
+      const double d2 = __dsub_rn(__dmul_rn(d1, d1), __dmul_rn(l2, recip));
+      const double w = (double)a.weights[e / R];
+      df = __dsub_rn(df, __dmul_rn(d1, w));
+      ddf = __dadd_rn(ddf, __dmul_rn(d2, w));
+    }
   }
 
   __shared__ double red[PLG_DER_THREADS / 32];
@@ -568,7 +588,9 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
   }
   const unsigned int R = ctx->d.rate_cats, K = ctx->d.states;
   const unsigned int nelem = ctx->d.sites * R;
-  const unsigned int nblocks = (nelem + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
+  unsigned int nblocks = (nelem + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
+  const unsigned int cap = (unsigned int)ctx->sm_count * 8u; /* persistent: 8 CTAs per SM */
+  if (nblocks > cap) nblocks = cap;
   int rc = plg_ensure_partials(ctx, 2 * (size_t)nblocks);
   if (rc) return rc;
 
