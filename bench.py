@@ -271,12 +271,14 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         part.update_partials(w.ops)
         return allreduce_sum(part.edge_loglikelihood(*root))
 
+    # clocks are sampled from the warm-up on: nvidia-smi needs ~0.2 s to deliver its first
+    # sample and the timed region of a short run is not much longer (same load throughout)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         lnl = resident_step()
-    sampler = ClockSampler(local_rank)
     barrier()
     part.reset_stats()
-    sampler.start()
     part.timer_start()
     for _ in range(args.steps):
         lnl = resident_step()
