@@ -367,9 +367,16 @@ k_partial_tt_dna(const DevOp * __restrict__ ops, unsigned int nelem, int scale_m
  * Arithmetic, voting and scaler bookkeeping are exactly those of the simple kernels above.
  */
 #define PLG_STREAM_THREADS 256
-#define PLG_STREAM_TILE 256 /* elements per tile: 8 KB per CLV array per stage */
-#define PLG_II_STAGES 4     /* x 16 KB */
-#define PLG_TI_STAGES 6     /* x  8 KB */
+#define PLG_II_TILE 256     /* elements per tile: 8 KB per CLV array per stage */
+#ifndef PLG_TI_TILE
+#define PLG_TI_TILE 256
+#endif
+#ifndef PLG_II_STAGES
+#define PLG_II_STAGES 4 /* x 16 KB */
+#endif
+#ifndef PLG_TI_STAGES
+#define PLG_TI_STAGES 4     /* x 16 KB */
+#endif
 #ifndef PLG_II_MINB
 #define PLG_II_MINB 2 /* resident CTAs per SM */
 #endif
@@ -380,12 +387,13 @@ k_partial_tt_dna(const DevOp * __restrict__ ops, unsigned int nelem, int scale_m
 template <int R, int KIND, int STAGES>
 struct StreamSmem
 {
-  d4 in_r[STAGES][PLG_STREAM_TILE];
-  d4 in_l[KIND == PLG_KIND_II ? STAGES : 1][KIND == PLG_KIND_II ? PLG_STREAM_TILE : 1];
+  static constexpr int TILE_E = (KIND == PLG_KIND_II) ? PLG_II_TILE : PLG_TI_TILE;
+  d4 in_r[STAGES][TILE_E];
+  d4 in_l[KIND == PLG_KIND_II ? STAGES : 1][KIND == PLG_KIND_II ? TILE_E : 1];
   double2 tab[KIND == PLG_KIND_TI ? 16 * R * 2 : 1];
-  unsigned char tips[KIND == PLG_KIND_TI ? STAGES : 1][PLG_STREAM_TILE];
-  unsigned int sc_l[KIND == PLG_KIND_II ? STAGES : 1][PLG_STREAM_TILE]; /* child scalers of the tile */
-  unsigned int sc_r[STAGES][PLG_STREAM_TILE];
+  unsigned char tips[KIND == PLG_KIND_TI ? STAGES : 1][TILE_E];
+  unsigned int sc_l[KIND == PLG_KIND_II ? STAGES : 1][TILE_E]; /* child scalers of the tile */
+  unsigned int sc_r[STAGES][TILE_E];
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
 };
@@ -439,7 +447,8 @@ k_partial_stream_dna(const DevOp * __restrict__ ops, unsigned int nelem, unsigne
                      unsigned int total_tiles, int scale_mode)
 {
   using namespace plg_async;
-  constexpr unsigned int TILE = PLG_STREAM_TILE;
+  constexpr unsigned int TILE = StreamSmem<R, KIND, STAGES>::TILE_E;
+  constexpr int EPT = 2 * TILE / PLG_STREAM_THREADS; /* half elements per thread per tile */
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StreamSmem<R, KIND, STAGES> & sm = *reinterpret_cast<StreamSmem<R, KIND, STAGES> *>(smem_raw);
 
@@ -540,10 +549,10 @@ k_partial_stream_dna(const DevOp * __restrict__ ops, unsigned int nelem, unsigne
 
     const unsigned int s = j % STAGES;
     mbar_wait(&sm.full[s], (j / STAGES) & 1u);
-    d4 r[2], l[2];
-    unsigned int code[2], csum[2];
+    d4 r[EPT], l[EPT];
+    unsigned int code[EPT], csum[EPT];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < EPT; ++i)
     {
       const unsigned int el = (tid + i * PLG_STREAM_THREADS) >> 1; /* element within the tile */
       r[i] = sm.in_r[s][el];
@@ -569,7 +578,7 @@ k_partial_stream_dna(const DevOp * __restrict__ ops, unsigned int nelem, unsigne
     }
 
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < EPT; ++i)
     {
       const unsigned int hidx = tile * (2 * TILE) + tid + i * PLG_STREAM_THREADS;
       const bool valid = hidx < 2 * nelem;
@@ -1267,7 +1276,8 @@ static void launch_group(plg_context * ctx, const Group & g, const DevOp * dev_o
     {
       unsigned int blocks =
           (unsigned int)ctx->sm_count * (g.kind == PLG_KIND_II ? PLG_II_MINB : PLG_TI_MINB);
-      const unsigned int ntiles = (nelem + PLG_STREAM_TILE - 1) / PLG_STREAM_TILE;
+      const unsigned int tile_e = (g.kind == PLG_KIND_II) ? PLG_II_TILE : PLG_TI_TILE;
+      const unsigned int ntiles = (nelem + tile_e - 1) / tile_e;
       const unsigned long long total = (unsigned long long)ntiles * g.count;
       if (total < blocks) blocks = (unsigned int)total;
       if (g.kind == PLG_KIND_II)
