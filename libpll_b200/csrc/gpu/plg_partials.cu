@@ -867,7 +867,17 @@ __device__ __forceinline__ void cp_async_wait()
 /* Each warp streams its own 8-site units through a private 2-deep ring in shared memory
  * (cp.async, 16-byte chunks, rows padded to PLG_DMMA_PITCH doubles so that the A-fragment
  * reads are bank-conflict free): ~20 KB in flight per warp, independent of register use. */
-#define PLG_DMMA_WARPS 8
+/* inner-inner: 12 warps, one ring slot each (A fragments of a whole unit are pulled into
+ * registers first, so the slot is refilled a full unit ahead); tip-inner: 8 warps x 2 slots,
+ * two CTAs per SM */
+#define PLG_DMMA_WARPS_II 12
+#define PLG_DMMA_WARPS_TI 8
+template <int KIND>
+struct dmma_cfg
+{
+  static constexpr int WARPS = (KIND == PLG_KIND_II) ? PLG_DMMA_WARPS_II : PLG_DMMA_WARPS_TI;
+  static constexpr int NSLOT = (KIND == PLG_KIND_II) ? 1 : 2;
+};
 template <int R>
 struct dmma_geom
 {
@@ -878,18 +888,29 @@ struct dmma_geom
 
 /* KIND: PLG_KIND_II (two matrix products) or PLG_KIND_TI (tip table x one matrix product) */
 template <int R, int KIND>
-__global__ void __launch_bounds__(PLG_DMMA_WARPS * 32, 1)
+__global__ void __launch_bounds__(dmma_cfg<KIND>::WARPS * 32, 1)
 k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned int sites, int scale_mode)
 {
   extern __shared__ __align__(16) double smem_d[];
   constexpr int NCHILD = (KIND == PLG_KIND_II) ? 2 : 1;
+  constexpr int PLG_DMMA_WARPS = dmma_cfg<KIND>::WARPS;
+  constexpr int NSLOT = dmma_cfg<KIND>::NSLOT;
   using G = dmma_geom<R>;
   double * bfrag = smem_d;                                   /* [child][rate][nt][ks][lane] */
   const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned int g = lane >> 2, q = lane & 3u;
-  double * ring = smem_d + NCHILD * R * 15 * 32 + (size_t)warp * 2 * NCHILD * G::UNIT; /* [2][child][8][PITCH] */
+  double * ring = smem_d + NCHILD * R * 15 * 32 + (size_t)warp * NSLOT * NCHILD * G::UNIT; /* [slot][child][8][PITCH] */
+  uint64_t * full = reinterpret_cast<uint64_t *>(smem_d + NCHILD * R * 15 * 32 +
+                                                 (size_t)PLG_DMMA_WARPS * NSLOT * NCHILD * G::UNIT) + 2 * warp;
   const unsigned int units = (sites + 7) / 8;
-  const size_t total_doubles = (size_t)sites * G::ROW;
+  if (lane == 0)
+  {
+    plg_async::mbar_init(&full[0], 1);
+    plg_async::mbar_init(&full[1], 1);
+    plg_async::fence_barrier_init();
+  }
+  __syncwarp();
+  unsigned int it = 0; /* this warp's unit counter: ring slot = it % NSLOT, barrier phase = (it / NSLOT) & 1 */
 
   /* the (operation, unit) space of the whole launch is flattened and cut into one contiguous
    * chunk per CTA (no partial second wave); a chunk is walked one operation segment at a time */
@@ -910,7 +931,7 @@ k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned i
 
   __syncthreads(); /* previous segment's fragments no longer in use */
   /* P matrices -> B fragments (parent states 20..23 of the third N tile are zero padding) */
-  for (unsigned int t = threadIdx.x; t < NCHILD * R * 15 * 32; t += PLG_DMMA_WARPS * 32)
+  for (unsigned int t = threadIdx.x; t < NCHILD * R * 15 * 32; t += blockDim.x)
   {
     const unsigned int l = t & 31u, f = (t >> 5) % 15, kc = (t >> 5) / 15; /* kc = child*R + k */
     const unsigned int nt = f / 5, ks = f % 5;
@@ -927,31 +948,33 @@ k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned i
   const unsigned int stride = PLG_DMMA_WARPS;
   const unsigned int u_first = u_seg + warp;
 
-  /* asynchronous copy of unit u (both children) into ring slot `slot` */
+  /* TMA row copies of unit u (8 sites x NCHILD children, 640-byte rows into padded rows) into
+   * ring slot `slot`; completion is signalled on the warp's own mbarrier */
   auto fetch = [&](unsigned int u, unsigned int slot) {
     if (u < u_stop)
     {
-      const size_t base = (size_t)u * 8 * G::ROW; /* doubles */
-#pragma unroll
-      for (int c = 0; c < NCHILD; ++c)
+      const unsigned int first_site = 8 * u;
+      const unsigned int nrows = (sites - first_site < 8) ? sites - first_site : 8;
+      if (lane == 0) plg_async::mbar_arrive_expect_tx(&full[slot], nrows * NCHILD * G::ROW * 8u);
+      __syncwarp();
+      if (lane < 8 * NCHILD)
       {
-        const double * src = (NCHILD == 2 && c == 0) ? op.left : op.right;
-        double * dst = ring + ((size_t)slot * NCHILD + c) * G::UNIT;
-        for (unsigned int i = lane; i < 8 * G::ROW / 2; i += 32) /* 16-byte chunks */
+        const unsigned int c = lane >> 3, row = lane & 7u;
+        if (row < nrows)
         {
-          const size_t off = base + 2 * (size_t)i;
-          if (off < total_doubles) cp_async16(dst + (i / (G::ROW / 2)) * G::PITCH + 2 * (i % (G::ROW / 2)), src + off);
+          const double * src = ((NCHILD == 2 && c == 0) ? op.left : op.right) + (size_t)(first_site + row) * G::ROW;
+          double * dst = ring + ((size_t)slot * NCHILD + c) * G::UNIT + row * G::PITCH;
+          plg_async::bulk_g2s(dst, src, G::ROW * 8u, &full[slot]);
         }
       }
     }
-    cp_async_commit();
   };
 
-  fetch(u_first, 0);
-  fetch(u_first + stride, 1);
-  unsigned int slot = 0;
-  for (unsigned int u = u_first; u < u_stop; u += stride, slot ^= 1u)
+  fetch(u_first, it % NSLOT);
+  if (NSLOT == 2) fetch(u_first + stride, (it + 1) % NSLOT);
+  for (unsigned int u = u_first; u < u_stop; u += stride, ++it)
   {
+    const unsigned int slot = it % NSLOT;
     const unsigned int site = 8 * u + g; /* this lane's site: A rows and D rows alike */
     const bool ok = site < sites;
     const size_t site_off = (size_t)site * G::ROW;
@@ -964,44 +987,80 @@ k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned i
     }
     if (KIND == PLG_KIND_TI && ok) code = __ldg(op.ltip + site);
 
-    cp_async_wait<1>(); /* this unit's copies have landed (the next unit's may be in flight) */
-    __syncwarp();
+    plg_async::mbar_wait(&full[slot], (it / NSLOT) & 1u); /* this unit's rows have landed */
     const double * rowL = ring + ((size_t)slot * NCHILD + 0) * G::UNIT + g * G::PITCH;
     const double * rowR = ring + ((size_t)slot * NCHILD + (NCHILD - 1)) * G::UNIT + g * G::PITCH;
+
+    /* single-slot ring: pull the whole unit's A fragments into registers, then hand the slot
+     * straight back to the TMA for the next unit */
+    afrag5 pre_r[NSLOT == 1 ? R : 1], pre_l[NSLOT == 1 ? R : 1];
+    if (NSLOT == 1)
+    {
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+      {
+        pre_r[k].lo0 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 4 * q);
+        pre_r[k].lo1 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 4 * q + 2);
+        pre_r[k].hi = rowR[k * 20 + 16 + q];
+        if (KIND == PLG_KIND_II)
+        {
+          pre_l[k].lo0 = *reinterpret_cast<const double2 *>(rowL + k * 20 + 4 * q);
+          pre_l[k].lo1 = *reinterpret_cast<const double2 *>(rowL + k * 20 + 4 * q + 2);
+          pre_l[k].hi = rowL[k * 20 + 16 + q];
+        }
+      }
+      __syncwarp();
+      fetch(u + stride, slot);
+    }
 
     bool below_site = true;
 #pragma unroll
     for (int k = 0; k < R; ++k)
     {
-      afrag5 ar, al;
-      ar.lo0 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 4 * q);
-      ar.lo1 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 4 * q + 2);
-      ar.hi = rowR[k * 20 + 16 + q];
-      if (KIND == PLG_KIND_II)
+      afrag5 ar, al = {};
+      if (NSLOT == 1)
       {
-        al.lo0 = *reinterpret_cast<const double2 *>(rowL + k * 20 + 4 * q);
-        al.lo1 = *reinterpret_cast<const double2 *>(rowL + k * 20 + 4 * q + 2);
-        al.hi = rowL[k * 20 + 16 + q];
+        ar = pre_r[k];
+        if (KIND == PLG_KIND_II) al = pre_l[k];
       }
+      else
+      {
+        ar.lo0 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 4 * q);
+        ar.lo1 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 4 * q + 2);
+        ar.hi = rowR[k * 20 + 16 + q];
+      }
+
+      /* six independent accumulator chains (3 N tiles x {left, right}) advance one k-step
+       * at a time, so that consecutive DMMAs never depend on each other */
+      double y[3][2], x[3][2];
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) y[nt][0] = y[nt][1] = x[nt][0] = x[nt][1] = 0.0;
+      const double av_r[5] = {ar.lo0.x, ar.lo0.y, ar.lo1.x, ar.lo1.y, ar.hi};
+      const double av_l[5] = {al.lo0.x, al.lo0.y, al.lo1.x, al.lo1.y, al.hi};
+#pragma unroll
+      for (int ks = 0; ks < 5; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt)
+        {
+          dmma884(y[nt][0], y[nt][1], av_r[ks], BR[((size_t)k * 15 + nt * 5 + ks) * 32 + lane]);
+          if (KIND == PLG_KIND_II)
+            dmma884(x[nt][0], x[nt][1], av_l[ks], BL[((size_t)k * 15 + nt * 5 + ks) * 32 + lane]);
+        }
 
       double p[3][2];
       bool below = true;
 #pragma unroll
       for (int nt = 0; nt < 3; ++nt)
       {
-        double y0 = 0.0, y1 = 0.0, x0 = 0.0, x1 = 0.0;
-        dmma_row(y0, y1, ar, BR + ((size_t)k * 15 + nt * 5) * 32, lane);
         const unsigned int row = 8 * nt + 2 * q; /* first of this lane's two parent states */
-        if (KIND == PLG_KIND_II)
-          dmma_row(x0, x1, al, BL + ((size_t)k * 15 + nt * 5) * 32, lane);
-        else if (row < 20)
+        if (KIND == PLG_KIND_TI && row < 20)
         {
           const double2 t = __ldg(reinterpret_cast<const double2 *>(op.lmat + ((size_t)code * R + k) * 20 + row));
-          x0 = t.x;
-          x1 = t.y;
+          x[nt][0] = t.x;
+          x[nt][1] = t.y;
         }
-        p[nt][0] = __dmul_rn(x0, y0);
-        p[nt][1] = __dmul_rn(x1, y1);
+        p[nt][0] = __dmul_rn(x[nt][0], y[nt][0]);
+        p[nt][1] = __dmul_rn(x[nt][1], y[nt][1]);
         if (row < 20)
         {
           below = below && (p[nt][0] < PLG_SCALE_THRESHOLD) && (p[nt][1] < PLG_SCALE_THRESHOLD);
@@ -1033,8 +1092,11 @@ k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned i
     }
 
     /* the slot is free again: start fetching the unit after next into it */
-    __syncwarp();
-    fetch(u + 2 * stride, slot);
+    if (NSLOT == 2)
+    {
+      __syncwarp();
+      fetch(u + 2 * stride, slot);
+    }
 
     if (scale_mode == 1)
     {
@@ -1064,7 +1126,7 @@ k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned i
       if (q == 0 && ok) op.pscale[site] = child_sum + (sc ? 1u : 0u);
     }
   }
-  cp_async_wait<0>();
+  __syncwarp();
   } /* segment */
 }
 
@@ -1072,7 +1134,9 @@ template <int R, int KIND>
 static constexpr size_t dmma_smem_bytes()
 {
   constexpr int NCHILD = (KIND == PLG_KIND_II) ? 2 : 1;
-  return ((size_t)NCHILD * R * 15 * 32 + (size_t)PLG_DMMA_WARPS * 2 * NCHILD * dmma_geom<R>::UNIT) * sizeof(double);
+  return ((size_t)NCHILD * R * 15 * 32 +
+          (size_t)dmma_cfg<KIND>::WARPS * dmma_cfg<KIND>::NSLOT * NCHILD * dmma_geom<R>::UNIT) * sizeof(double) +
+         (size_t)dmma_cfg<KIND>::WARPS * 2 * sizeof(uint64_t);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -1305,20 +1369,19 @@ static void launch_group(plg_context * ctx, const Group & g, const DevOp * dev_o
   else if (!ctx->aa_exact && g.kind != PLG_KIND_TT && dmma_smem_bytes<R, PLG_KIND_II>() <= 227 * 1024)
   {
     /* tensor-core path: persistent CTAs over the flattened (operation, 8-site unit) space;
-     * resident CTAs per SM by shared memory: 1 (inner-inner, 199 KB) or 2 (tip-inner, 99 KB) */
+     * resident CTAs per SM by shared memory: 1 (inner-inner) or 2 (tip-inner) */
     const unsigned int units = (ctx->d.sites + 7) / 8;
     const unsigned long long total = (unsigned long long)units * g.count;
+    const unsigned int warps = (g.kind == PLG_KIND_II) ? PLG_DMMA_WARPS_II : PLG_DMMA_WARPS_TI;
     unsigned long long blocks = (unsigned long long)ctx->sm_count * (g.kind == PLG_KIND_II ? 1u : 2u);
-    const unsigned long long want = (total + PLG_DMMA_WARPS - 1) / PLG_DMMA_WARPS;
+    const unsigned long long want = (total + warps - 1) / warps;
     if (want < blocks) blocks = want ? want : 1;
     if (g.kind == PLG_KIND_II)
-      k_partial_dmma_aa<R, PLG_KIND_II><<<(unsigned int)blocks, PLG_DMMA_WARPS * 32,
-                                          dmma_smem_bytes<R, PLG_KIND_II>(), ctx->stream>>>(
-          ops, g.count, ctx->d.sites, g.scale_mode);
+      k_partial_dmma_aa<R, PLG_KIND_II><<<(unsigned int)blocks, warps * 32, dmma_smem_bytes<R, PLG_KIND_II>(),
+                                          ctx->stream>>>(ops, g.count, ctx->d.sites, g.scale_mode);
     else
-      k_partial_dmma_aa<R, PLG_KIND_TI><<<(unsigned int)blocks, PLG_DMMA_WARPS * 32,
-                                          dmma_smem_bytes<R, PLG_KIND_TI>(), ctx->stream>>>(
-          ops, g.count, ctx->d.sites, g.scale_mode);
+      k_partial_dmma_aa<R, PLG_KIND_TI><<<(unsigned int)blocks, warps * 32, dmma_smem_bytes<R, PLG_KIND_TI>(),
+                                          ctx->stream>>>(ops, g.count, ctx->d.sites, g.scale_mode);
   }
   else
   {
