@@ -253,6 +253,15 @@ class PllLibrary:
             raise PllError(self.errmsg())
         return out
 
+    @staticmethod
+    def make_map(table: dict):
+        """char -> state-set mask table (the `map` argument of pll_set_tip_states) for alphabets
+        other than pll_map_nt / pll_map_aa; `table` maps one-character strings to masks."""
+        arr = (C.c_uint * 256)()
+        for ch, mask in table.items():
+            arr[ord(ch)] = int(mask)
+        return arr
+
     def partition(self, **kw) -> "Partition":
         return Partition(self, **kw)
 

@@ -57,22 +57,24 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   }
   *out = NULL;
 
-  if (dims->states != 4 && dims->states != 20)
+  /* 4 and 20 states with 1/2/4/8/16 rate categories run the specialised kernels; any other
+   * alphabet / category count runs the generic kernels of plg_generic.cu */
+  if (dims->states < 2 || dims->rate_cats == 0)
   {
-    plg_set_error("plg_create: %u states not supported by the GPU backend (4 and 20 are)",
-                  dims->states);
-    return PLG_E_UNSUPPORTED;
-  }
-  if (dims->states_padded != dims->states)
-  {
-    plg_set_error("plg_create: states_padded must equal states for 4/20 states");
+    plg_set_error("plg_create: states=%u rate_cats=%u is not a valid partition", dims->states,
+                  dims->rate_cats);
     return PLG_E_INVALID;
   }
-  if (dims->rate_cats == 0 || dims->rate_cats > 16 ||
-      (dims->rate_cats & (dims->rate_cats - 1)) != 0)
+  if (dims->states_padded < dims->states || (dims->states_padded & 3u) ||
+      ((dims->states == 4 || dims->states == 20) && dims->states_padded != dims->states))
   {
-    plg_set_error("plg_create: rate_cats=%u not supported (1, 2, 4, 8 or 16)",
-                  dims->rate_cats);
+    plg_set_error("plg_create: states_padded=%u invalid for %u states (multiple of 4, >= states; "
+                  "equal to states for 4 and 20)", dims->states_padded, dims->states);
+    return PLG_E_INVALID;
+  }
+  if ((dims->attributes & PLL_ATTRIB_PATTERN_TIP) && dims->states > 32)
+  {
+    plg_set_error("plg_create: pattern tips need states <= 32 (state sets are 32-bit masks)");
     return PLG_E_UNSUPPORTED;
   }
   if (dims->sites == 0)
@@ -472,11 +474,6 @@ extern "C" int plg_get_pmatrix(plg_context_t * ctx, unsigned int idx, double * p
 /* ------------------------------------------------------------------------------------ */
 /* invariant-site index                                                                  */
 /* ------------------------------------------------------------------------------------ */
-struct TipmapArg
-{
-  unsigned int map[PLL_ASCII_SIZE];
-};
-
 /* one thread per site: AND of the state masks of all tips, then "exactly one bit" -> index
  * (reference src/models.c:593-645).  use_map selects tipmap[code] (non-DNA alphabets). */
 __global__ void k_invariant_tipchars(const unsigned char * __restrict__ tipchars,

@@ -480,6 +480,38 @@ extern "C" int plg_update_sumtable(plg_context_t * ctx, unsigned int parent_clv_
     return PLG_E_UNSUPPORTED;
   }
   const unsigned int R = ctx->d.rate_cats, K = ctx->d.states;
+  if (!plg_fast_path(ctx))
+  {
+    const unsigned int Kp = ctx->d.states_padded;
+    double * table = NULL;
+    int grc = sumtable_slot(ctx, key, &table);
+    if (grc) return grc;
+    const bool gti = ptip || ctip;
+    const size_t gmat = (size_t)R * K * Kp * sizeof(double);
+    const size_t gleft = gti ? (size_t)(K == 4 ? 16u : ctx->maxstates) * R * Kp * sizeof(double) : gmat;
+    if (plg_stage_reserve(ctx, gmat + gleft + 1024)) return PLG_E_CUDA;
+    const double * d_evecs = (const double *)plg_stage(ctx, eigenvecs, gmat);
+    const double * d_left = (const double *)plg_stage(ctx, left_table, gleft);
+    if (!d_evecs || !d_left) return PLG_E_CUDA;
+    if (gti)
+      grc = plg_gen_sumtable(ctx, plg_clv_ptr(ctx, ptip ? child_clv_index : parent_clv_index), NULL,
+                             plg_tip_ptr(ctx, ptip ? parent_clv_index : child_clv_index),
+                             plg_scaler_ptr(ctx, ptip ? child_scaler_index : parent_scaler_index), NULL,
+                             d_evecs, d_left, table);
+    else
+      grc = plg_gen_sumtable(ctx, plg_clv_ptr(ctx, parent_clv_index), plg_clv_ptr(ctx, child_clv_index), NULL,
+                             plg_scaler_ptr(ctx, parent_scaler_index), plg_scaler_ptr(ctx, child_scaler_index),
+                             d_evecs, d_left, table);
+    if (grc) return grc;
+    if (host_copy)
+    {
+      const size_t bytes = (size_t)ctx->d.sites * ctx->span * sizeof(double);
+      PLG_CUDA(cudaMemcpyAsync(host_copy, table, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+      ctx->stats.d2h_bytes += bytes;
+    }
+    return PLG_OK;
+  }
   const unsigned int nelem = ctx->d.sites * R;
   const unsigned int nblocks = (nelem + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
 
@@ -586,6 +618,8 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
                   "(call pll_update_sumtable first)");
     return PLG_E_INVALID;
   }
+  if (!plg_fast_path(ctx))
+    return plg_gen_derivatives(ctx, it->second, diagptable, rate_weights, prop_invar, freqs, d_f, dd_f);
   const unsigned int R = ctx->d.rate_cats, K = ctx->d.states;
   const unsigned int nelem = ctx->d.sites * R;
   unsigned int nblocks = (nelem + PLG_DER_THREADS - 1) / PLG_DER_THREADS;

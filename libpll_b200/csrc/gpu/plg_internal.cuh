@@ -133,6 +133,61 @@ struct plg_context
   plg_stats_t stats;
 };
 
+/* ---- descriptors shared by the CLV-update kernels (plg_partials.cu, plg_generic.cu) ---- */
+enum { PLG_KIND_TT = 0, PLG_KIND_TI = 1, PLG_KIND_II = 2 };
+
+struct DevOp
+{
+  double * parent;
+  const double * left;        /* ii: left child CLV                                   */
+  const double * right;       /* ii: right child CLV; ti: the inner child's CLV       */
+  const unsigned char * ltip; /* tt: left tip chars;  ti: the tip child's chars       */
+  const unsigned char * rtip; /* tt: right tip chars                                  */
+  const double * lmat;        /* ii: left P-matrix;  ti/tt: lookup table of ltip      */
+  const double * rmat;        /* ii/ti: P-matrix of `right`; tt: lookup table of rtip */
+  unsigned int * pscale;
+  const unsigned int * lscale;
+  const unsigned int * rscale;
+};
+
+struct TableJob
+{
+  const double * pmat;
+  double * out;
+};
+
+struct TipmapArg
+{
+  unsigned int map[PLL_ASCII_SIZE];
+};
+
+/* the generic (any state count / any number of rate categories) device path, plg_generic.cu */
+static inline bool plg_is_pow2(unsigned int v) { return v && !(v & (v - 1)); }
+static inline bool plg_fast_path(const plg_context * ctx);
+int plg_gen_tables(plg_context * ctx, const TableJob * dev_jobs, unsigned int njobs);
+int plg_gen_partials(plg_context * ctx, int kind, int scale_mode, const DevOp * dev_ops, unsigned int count);
+int plg_gen_pmatrix(plg_context * ctx, const unsigned int * d_idx, const double * d_bl, unsigned int count,
+                    const double * evals, const double * evecs, const double * ievecs, const double * rates,
+                    const double * pinv);
+struct GenLnl
+{
+  const double * clvp;
+  const double * clvc;       /* ii */
+  const unsigned char * tip; /* ti */
+  const double * pmat;       /* edge: P-matrix set */
+  const unsigned int * pscale;
+  const unsigned int * cscale;
+  int root;                  /* 1: root lnL (no P-matrix, single CLV) */
+};
+int plg_gen_loglikelihood(plg_context * ctx, const GenLnl & g, const double * freqs, const double * rate_weights,
+                          const double * prop_invar, double * persite_lnl, double * logl_out);
+int plg_gen_sumtable(plg_context * ctx, const double * clvp, const double * clvc, const unsigned char * tip,
+                     const unsigned int * pscale, const unsigned int * cscale, const double * dev_evecs,
+                     const double * dev_left, double * sumtable);
+int plg_gen_derivatives(plg_context * ctx, const double * sumtable, const double * diagptable,
+                        const double * rate_weights, const double * prop_invar, const double * freqs,
+                        double * d_f, double * dd_f);
+
 /* Copies `bytes` of host data into the staging ring and enqueues the H2D copy on the
  * context's stream; returns the device address (256-byte aligned) or NULL on failure. */
 void * plg_stage(plg_context * ctx, const void * src, size_t bytes);
@@ -163,6 +218,13 @@ static inline double * plg_pmat_ptr(const plg_context * ctx, unsigned int idx)
 static inline bool plg_is_tip(const plg_context * ctx, unsigned int clv_index)
 {
   return ctx->pattern_tip && clv_index < ctx->d.tips;
+}
+/* specialised kernels exist for 4 and 20 states with 1/2/4/8/16 rate categories; everything
+ * else runs on the generic kernels of plg_generic.cu */
+static inline bool plg_fast_path(const plg_context * ctx)
+{
+  return (ctx->d.states == 4 || ctx->d.states == 20) && ctx->d.rate_cats <= 16 &&
+         (ctx->d.rate_cats & (ctx->d.rate_cats - 1)) == 0;
 }
 
 /* ------------------------------------------------------------------------------------ */

@@ -513,6 +513,26 @@ extern "C" int plg_edge_loglikelihood(plg_context_t * ctx, unsigned int parent_c
                   "(nor by the reference, src/likelihood.c:489-501)");
     return PLG_E_UNSUPPORTED;
   }
+  if (!plg_fast_path(ctx))
+  {
+    GenLnl g;
+    memset(&g, 0, sizeof(g));
+    g.pmat = plg_pmat_ptr(ctx, matrix_index);
+    if (ptip || ctip)
+    {
+      g.clvp = plg_clv_ptr(ctx, ptip ? child_clv_index : parent_clv_index);
+      g.tip = plg_tip_ptr(ctx, ptip ? parent_clv_index : child_clv_index);
+      g.pscale = plg_scaler_ptr(ctx, ptip ? child_scaler_index : parent_scaler_index);
+    }
+    else
+    {
+      g.clvp = plg_clv_ptr(ctx, parent_clv_index);
+      g.clvc = plg_clv_ptr(ctx, child_clv_index);
+      g.pscale = plg_scaler_ptr(ctx, parent_scaler_index);
+      g.cscale = plg_scaler_ptr(ctx, child_scaler_index);
+    }
+    return plg_gen_loglikelihood(ctx, g, freqs, rate_weights, prop_invar, persite_lnl, logl_out);
+  }
 
   LnlParams P;
   int rc = fill_params(ctx, freqs, rate_weights, prop_invar, P);
@@ -605,6 +625,15 @@ extern "C" int plg_root_loglikelihood(plg_context_t * ctx, unsigned int clv_inde
   {
     plg_set_error("plg_root_loglikelihood: index out of range");
     return PLG_E_INVALID;
+  }
+  if (!plg_fast_path(ctx))
+  {
+    GenLnl g;
+    memset(&g, 0, sizeof(g));
+    g.clvp = plg_clv_ptr(ctx, clv_index);
+    g.pscale = plg_scaler_ptr(ctx, scaler_index);
+    g.root = 1;
+    return plg_gen_loglikelihood(ctx, g, freqs, rate_weights, prop_invar, persite_lnl, logl_out);
   }
   LnlParams P;
   int rc = fill_params(ctx, freqs, rate_weights, prop_invar, P);

@@ -31,33 +31,6 @@
 /* ------------------------------------------------------------------------------------ */
 /* descriptors                                                                           */
 /* ------------------------------------------------------------------------------------ */
-enum { PLG_KIND_TT = 0, PLG_KIND_TI = 1, PLG_KIND_II = 2 };
-
-struct DevOp
-{
-  double * parent;
-  const double * left;        /* ii: left child CLV                                   */
-  const double * right;       /* ii: right child CLV; ti: the inner child's CLV       */
-  const unsigned char * ltip; /* tt: left tip chars;  ti: the tip child's chars       */
-  const unsigned char * rtip; /* tt: right tip chars                                  */
-  const double * lmat;        /* ii: left P-matrix;  ti/tt: lookup table of ltip      */
-  const double * rmat;        /* ii/ti: P-matrix of `right`; tt: lookup table of rtip */
-  unsigned int * pscale;
-  const unsigned int * lscale;
-  const unsigned int * rscale;
-};
-
-struct TableJob
-{
-  const double * pmat;
-  double * out;
-};
-
-struct TipmapArg
-{
-  unsigned int map[PLL_ASCII_SIZE];
-};
-
 /* ------------------------------------------------------------------------------------ */
 /* tip lookup tables                                                                     */
 /* ------------------------------------------------------------------------------------ */
@@ -1168,7 +1141,7 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
   const unsigned int n_sc = ctx->d.scale_buffers;
   const unsigned int K = ctx->d.states;
   const unsigned int R = ctx->d.rate_cats;
-  const size_t table_len = (size_t)(K == 4 ? 16u : ctx->maxstates) * R * K;
+  const size_t table_len = (size_t)(K == 4 ? 16u : ctx->maxstates) * R * ctx->d.states_padded;
 
   /* dependency levels: level(op) > level of every earlier op it has a RAW, WAR or WAW
    * relation with, on CLV slots and on scaler slots.  Executing levels in increasing order
@@ -1442,9 +1415,15 @@ static int enqueue_plan(plg_context * ctx, const Plan & plan, const DevOp * dev_
   const unsigned int nelem = ctx->d.sites * R;
   unsigned long long launched = 0;
 
+  const bool fast = plg_fast_path(ctx);
   if (!plan.jobs.empty())
   {
-    if (ctx->d.states == 4)
+    if (!fast)
+    {
+      int rc = plg_gen_tables(ctx, dev_jobs, (unsigned int)plan.jobs.size());
+      if (rc) return rc;
+    }
+    else if (ctx->d.states == 4)
       k_tip_tables_dna<<<(unsigned int)plan.jobs.size(), 256, 0, ctx->stream>>>(dev_jobs, R);
     else
     {
@@ -1474,7 +1453,9 @@ static int enqueue_plan(plg_context * ctx, const Plan & plan, const DevOp * dev_
   {
     if (prof) cudaEventRecord((*ctx->prof_events)[gi], ctx->stream);
     ++gi;
-    switch (R)
+    if (!fast)
+      plg_gen_partials(ctx, g.kind, g.scale_mode, dev_ops + g.first, g.count);
+    else switch (R)
     {
       case 1: launch_group<1>(ctx, g, dev_ops, nelem); break;
       case 2: launch_group<2>(ctx, g, dev_ops, nelem); break;

@@ -172,8 +172,14 @@ extern "C" int plg_update_pmatrix(plg_context_t * ctx, const unsigned int * matr
       k_pmatrix_dna<<<(threads + 127) / 128, 128, 0, ctx->stream>>>(ctx->pmatrix, ctx->pmat_len,
                                                                      d_idx, d_bl, c, R, m);
     }
-    else
+    else if (K == 20)
       k_pmatrix_aa<<<c * R, 256, 0, ctx->stream>>>(ctx->pmatrix, ctx->pmat_len, d_idx, d_bl, R, m);
+    else
+    {
+      int rc = plg_gen_pmatrix(ctx, d_idx, d_bl, c, m.eigenvals, m.eigenvecs, m.inv_eigenvecs, m.rates,
+                               m.prop_invar);
+      if (rc) return rc;
+    }
     PLG_LAUNCH_CHECK(ctx);
   }
   return PLG_OK;

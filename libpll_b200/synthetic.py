@@ -26,6 +26,29 @@ from .binding import (
 DNA_ALPHABET = np.frombuffer(b"ACGT", dtype=np.uint8)
 AA_ALPHABET = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV", dtype=np.uint8)
 
+GENERIC_LETTERS = b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdef"  # alphabets other than DNA / amino acids
+
+
+def generic_map(states: int) -> dict:
+    """char -> state-set mask for a synthetic alphabet of `states` (<= 32) letters: '-' is the
+    full ambiguity, '1' = first two states, '2' = last two states."""
+    assert 2 <= states <= 32
+    m = {chr(GENERIC_LETTERS[i]): 1 << i for i in range(states)}
+    m["-"] = (1 << states) - 1
+    m["1"] = 0b11
+    m["2"] = 0b11 << (states - 2)
+    return m
+
+
+def _alphabet(states: int):
+    """(letters, full-ambiguity char, two two-state ambiguity chars)"""
+    if states == 4:
+        return DNA_ALPHABET, ord("N"), (ord("R"), ord("Y"))
+    if states == 20:
+        return AA_ALPHABET, ord("X"), (ord("B"), ord("Z"))
+    return np.frombuffer(GENERIC_LETTERS[:states], dtype=np.uint8), ord("-"), (ord("1"), ord("2"))
+
+
 GTR_RATES = np.array([1.2, 3.1, 0.9, 1.1, 3.3, 1.0])
 GTR_FREQS = np.array([0.30, 0.20, 0.25, 0.25])
 
@@ -188,9 +211,9 @@ def tip_sequence(w: Workload, tip: int, lo: int = 0, hi: Optional[int] = None) -
     seeded blocks of TIP_BLOCK sites, so the value at a site does not depend on the slice
     asked for and a rank only generates the slice it owns."""
     hi = w.sites if hi is None else hi
-    alphabet = DNA_ALPHABET if w.states == 4 else AA_ALPHABET
-    amb_full = np.uint8(ord("N") if w.states == 4 else ord("X"))
-    amb2 = (np.uint8(ord("R")), np.uint8(ord("Y"))) if w.states == 4 else (np.uint8(ord("B")), np.uint8(ord("Z")))
+    alphabet, amb_full, amb2 = _alphabet(w.states)
+    amb_full = np.uint8(amb_full)
+    amb2 = (np.uint8(amb2[0]), np.uint8(amb2[1]))
     out = np.empty(hi - lo, dtype=np.uint8)
     for blk in range(lo // TIP_BLOCK, (hi + TIP_BLOCK - 1) // TIP_BLOCK):
         b0, b1 = blk * TIP_BLOCK, min((blk + 1) * TIP_BLOCK, w.sites)
@@ -215,6 +238,13 @@ def model_for(lib: PllLibrary, w: Workload, variant: str = "default"):
     weights = np.full(w.rate_cats, 1.0 / w.rate_cats)
     if w.states == 4:
         return 1, [(GTR_RATES, GTR_FREQS)], np.zeros(w.rate_cats, np.uint32), rates, weights
+    if w.states != 20:
+        # any other alphabet: a seeded reversible model (exchangeabilities in [0.5, 3], last one 1)
+        rng = np.random.default_rng([w.seed + 2, w.states])
+        r = rng.uniform(0.5, 3.0, w.states * (w.states - 1) // 2)
+        r[-1] = 1.0
+        f = rng.uniform(0.5, 1.5, w.states)
+        return 1, [(r, f / f.sum())], np.zeros(w.rate_cats, np.uint32), rates, weights
     if variant == "lg4m":
         assert w.rate_cats == 4
         r = lib.aa_table("pll_aa_rates_lg4m", (4, 190))
@@ -242,8 +272,9 @@ def build_partition(lib: PllLibrary, w: Workload, attributes: int, lo: int = 0,
         part.set_subst_params(i, sp)
     part.set_category_rates(g_rates if rates is None else rates)
     part.set_category_weights(g_weights)
+    amap = None if w.states in (4, 20) else lib.make_map(generic_map(w.states))
     for t in range(w.tips):
-        part.set_tip_states(t, tip_sequence(w, t, lo, hi))
+        part.set_tip_states(t, tip_sequence(w, t, lo, hi), amap)
     part.set_pattern_weights(w.weights[lo:hi])
     del pattern_tip
     return part, pidx

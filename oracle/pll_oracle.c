@@ -9,8 +9,11 @@
  * oracle/Makefile) on random inputs, and the assembled pipeline against the reference's
  * golden outputs (tests/golden/, derived from reference test/out and examples).
  *
- * Supported: states 4 (the reference's *_4x4_avx kernels) and 20 (its AVX2 generic / 20x20
- * kernels), states_padded == states, any rate_cats, per-site and per-rate scaling.
+ * Supported: states 4 (the reference's *_4x4_avx kernels), 20 (its AVX2 generic / 20x20
+ * kernels) and any other alphabet up to 64 states in the operation order of the reference's
+ * plain-C code (src/core_partials.c:510-663, src/core_likelihood.c:163-209, 617-725, 905-1010,
+ * src/core_derivatives.c:240-262, 415-440, 449-500, src/core_pmatrix.c:146-250);
+ * states_padded == states, any rate_cats, per-site and per-rate scaling.
  * Compile with -ffp-contract=off: every fused multiply-add below is an explicit fma().
  *
  * Signatures mirror the reference's pll_core_* prototypes (reference src/pll.h:829-1027,
@@ -40,6 +43,14 @@ static double row_dot(const double * row, const double * v, unsigned int K, int 
 {
   double a[4] = {0.0, 0.0, 0.0, 0.0};
   unsigned int b, l;
+  if (K != 4 && K != 20)
+  {
+    /* any other alphabet: the plain sequential sum of the reference's non-SIMD code
+     * (e.g. reference src/core_partials.c:630-640) */
+    double s = 0.0;
+    for (b = 0; b < K; ++b) s += row[b] * v[b];
+    return s;
+  }
   for (b = 0; b < K; b += 4)
     for (l = 0; l < 4; ++l) a[l] = fused ? fma(row[b + l], v[b + l], a[l]) : a[l] + row[b + l] * v[b + l];
   return hsum4(a[0], a[1], a[2], a[3]);
@@ -58,9 +69,9 @@ int orc_core_update_pmatrix(double ** pmatrix, unsigned int states, unsigned int
 {
   const unsigned int K = states;
   unsigned int i, n, j, c, m;
-  double e[20], T[400];
+  double e[64], T[4096];
   (void)attrib;
-  if (K != 4 && K != 20) return 0;
+  if (K > 64) return 0;
   for (i = 0; i < count; ++i)
   {
     double * pmat = pmatrix[matrix_indices[i]];
@@ -91,6 +102,12 @@ int orc_core_update_pmatrix(double ** pmatrix, unsigned int states, unsigned int
           if (K == 4)
             s = hsum4(T[j * 4 + 0] * V[0 + c], T[j * 4 + 1] * V[4 + c], T[j * 4 + 2] * V[8 + c],
                       T[j * 4 + 3] * V[12 + c]) + ((j == c) ? 1.0 : 0.0);
+          else if (K != 20)
+          {
+            /* plain loop, identity added first (reference src/core_pmatrix.c:225-236) */
+            s = (j == c) ? 1.0 : 0.0;
+            for (m = 0; m < K; ++m) s += T[j * K + m] * V[m * K + c];
+          }
           else
           {
             /* first column block by mul, the rest by fmadd (reference
@@ -375,6 +392,12 @@ double orc_core_edge_loglikelihood_ii(unsigned int states, unsigned int sites, u
         for (j = 0; j < 4; ++j)
           t[j] = (f[j] * hsum4(M[j * 4] * c[0], M[j * 4 + 1] * c[1], M[j * 4 + 2] * c[2], M[j * 4 + 3] * c[3])) * p[j];
         terma_r = hsum4(t[0], t[1], t[2], t[3]);
+      }
+      else if (K != 20)
+      {
+        /* reference src/core_likelihood.c:947-958 */
+        terma_r = 0;
+        for (j = 0; j < K; ++j) terma_r += p[j] * f[j] * row_dot(M + j * K, c, K, 0);
       }
       else
       {
@@ -675,6 +698,15 @@ int orc_core_likelihood_derivatives(unsigned int states, unsigned int sites, uns
         {
           cat[x] = 0.0;
           for (j = 0; j < 4; ++j) cat[x] = fma(s[j], diagp[((size_t)i * 4 + j) * 4 + x], cat[x]);
+        }
+      }
+      else if (K != 20)
+      {
+        /* reference src/core_derivatives.c:472-480 */
+        for (x = 0; x < 3; ++x)
+        {
+          cat[x] = 0.0;
+          for (j = 0; j < K; ++j) cat[x] += s[j] * diagp[((size_t)i * K + j) * 4 + x];
         }
       }
       else

@@ -400,8 +400,8 @@ class _PortPartitionAPI:
     def set_pattern_weights(self, w):
         self.pp.weights = np.ascontiguousarray(w, dtype=np.uint32)
 
-    def set_tip_states(self, tip, seq):
-        self.pp.set_tip_states(tip, seq, self._map)
+    def set_tip_states(self, tip, seq, amap=None):
+        self.pp.set_tip_states(tip, seq, self._map if amap is None else amap)
 
     def update_invariant_sites_proportion(self, idx, pinv):
         if self.pp.invariant is None:
@@ -449,6 +449,13 @@ class PortAsLibrary:
     def gamma_rates(self, alpha, cats, mode=0):
         assert mode == 0
         return gamma_mean_rates(alpha, cats)
+
+    @staticmethod
+    def make_map(table):
+        m = np.zeros(256, dtype=np.uint32)
+        for ch, mask in table.items():
+            m[ord(ch)] = mask
+        return m
 
     def partition(self, **kw):
         return _PortPartitionAPI(**kw)

@@ -16,6 +16,8 @@ against that text, so the fixture is pinned to the reference's own golden files:
   example_unrooted         examples/unrooted/unrooted.c:32-212         lnL -33.387713 / -34.550204 / -36.830297
   example_newton           examples/newton/newton.c:31-243             0.6 -> 2.607098 in 7 iterations
   derivatives_grid         test/src/derivatives.c recipe (alpha x pinv x cats x branch lengths)
+  test_00012_NMOU_lkcalc   test/src/00012_NMOU_lkcalc.c:33-235 (7 states) test/out/00012_NMOU_lkcalc.out
+  derivatives_oddstates    test/src/derivatives-oddstates.c:44-330 (5 st.) test/out/derivatives-oddstates.out
 
 usage: python tests/golden/make_golden.py
 """
@@ -113,6 +115,61 @@ for alpha in (0.1, 0.75, 1.5):
             seqs=["WAC-CTA-ATCT", "CCC-TTA-ATGT", "A-C-TAG-CTCT", "CTCTTAA-A-CG", "CAC-TCA-A-TG"],
             steps=([dict(do="pinv", index=0, value=pinv)] if pinv > 0 else []) + deriv_steps))
 
+# ---- test 00012: 7 states ("odd" alphabet A..G, E ambiguous), generic kernels ------------------
+def odd_map(n_states):
+    """reference test/src/00012_NMOU_lkcalc.c:32-44 (7 states) and test/src/common.c:8-19 (5 states)"""
+    gap = (1 << n_states) - 1 if n_states == 5 else 0x3f
+    m = {"*": gap, "-": gap, "?": gap}
+    for ch, v in zip("ABCDEFG", (1, 2, 4, 8, 0x0c, 0x10, 0x20)):
+        if n_states == 5 and ch in "FG":
+            continue
+        m[ch] = v
+        m[ch.lower()] = v
+    return m
+
+
+CASES.append(dict(
+    name="test_00012_NMOU_lkcalc", states=7, tips=5, clv_buffers=4, sites=12, rate_matrices=1,
+    prob_matrices=7, rate_cats=4, scale_buffers=0, alpha=0.5, map=odd_map(7),
+    freqs=[[0.12, 0.14, 0.13, 0.11, 0.15, 0.13, 0.12]],
+    subst=[[0.5, 2.0, 3.0, 4.0, 5.0, 1.1, 1.2, 1.3, 1.4, 1.5, 2.1, 2.2, 2.3, 2.4, 2.5, 3.1, 3.2, 3.3, 3.4, 3.5, 1.0]],
+    seqs=["AAB-CCD-EFAA", "ACC-FBA-ABGG", "A-C-GAG-GCCF", "ADCFCAA-A-CG", "ABC-BCA-A-BG"],
+    steps=[dict(s) for s in CASES[0]["steps"]],
+    printed={"inner-inner": -95.791417, "tip-inner": -95.791417}, out_file="test/out/00012_NMOU_lkcalc.out"))
+
+# ---- derivatives with 5 states: 1, 2 and 4 categories, alpha x pinv x 9 branch lengths ---------
+ODD_BRANCHES = (0.1, 0.2, 0.5, 0.9, 1.5, 5, 10, 50, 90)
+for cats in (1, 2, 4):
+    for alpha in (0.1, 0.75, 1.5):
+        for pinv in (0.0, 0.3, 0.9):
+            pr = [0] * cats
+            steps = ([dict(do="pinv", index=0, value=pinv)] if pinv > 0 else []) + [
+                dict(do="pmatrix", params=pr, matrices=[0, 1, 2, 3], lengths=[0.1, 0.2, 0.3, 0.4]),
+                dict(do="partials", ops=[op(5, NONE, 0, 1, NONE, 1, 1, NONE), op(6, NONE, 5, 0, NONE, 2, 1, NONE),
+                                         op(7, NONE, 3, 1, NONE, 4, 1, NONE)]),
+                dict(do="edge", args=[6, NONE, 7, NONE, 0], freqs_indices=pr),
+                dict(do="sumtable", key="ii", edge=[6, 7, NONE, NONE], params=pr)]
+            for t in ODD_BRANCHES:
+                steps += [dict(do="derivs", key="ii", t=t, params=pr),
+                          dict(do="pmatrix", params=pr, matrices=[0], lengths=[t]),
+                          dict(do="edge", args=[6, NONE, 7, NONE, 0], freqs_indices=pr, tag=f"Branch {t}")]
+            steps += [dict(do="pmatrix", params=pr, matrices=[0], lengths=[0.1]),
+                      dict(do="partials", ops=[op(7, NONE, 6, 0, NONE, 3, 0, NONE)]),
+                      dict(do="edge", args=[4, NONE, 7, NONE, 1], freqs_indices=pr),
+                      dict(do="sumtable", key="ti", edge=[4, 7, NONE, NONE], params=pr)]
+            for t in ODD_BRANCHES:
+                steps += [dict(do="derivs", key="ti", t=t, params=pr),
+                          dict(do="pmatrix", params=pr, matrices=[1], lengths=[t]),
+                          dict(do="edge", args=[4, NONE, 7, NONE, 1], freqs_indices=pr, tag=f"Branch(Tip) {t}")]
+            CASES.append(dict(
+                name=f"derivatives_oddstates_c{cats}_a{alpha}_p{pinv}", states=5, tips=5, clv_buffers=4, sites=20,
+                rate_matrices=1, prob_matrices=7, rate_cats=cats, scale_buffers=0, alpha=alpha, map=odd_map(5),
+                freqs=[[0.3, 0.25, 0.1, 0.2, 0.15]],
+                subst=[[1.452176, 0.937951, 0.462880, 0.617729, 1.745312, 0.937951, 0.462880, 0.617729, 1.745312, 1.0]],
+                seqs=["DAACBCECBA--ABBCBAAB", "CACCABECBA--ABBEBCBB", "AE-C-BECAE--CBBCBACB",
+                      "CEBCBBECAA--AB-C-AAE", "CEACBBECCA--AB-B-AAE"],
+                steps=steps, odd_block=dict(alpha=alpha, cats=cats, pinv=pinv)))
+
 # test 00011 shares the step list of 00010
 CASES[1]["steps"] = [dict(s) for s in CASES[0]["steps"]]
 CASES[1]["printed"] = {"inner-inner": -227.371279, "tip-inner": -227.371279}
@@ -139,6 +196,27 @@ def parse_printed(path, tags):
     return out
 
 
+def parse_odd_block(alpha, cats, pinv):
+    """(lnL, d_f, dd_f) rows printed by the reference for one block of derivatives-oddstates.out"""
+    text = open(os.path.join(REF, "test/out/derivatives-oddstates.out")).read()
+    head = " TEST alpha(ncats) = %6.2f(%2d) ; pinv = %.2f" % (alpha, cats, pinv)
+    block = text[text.index(head):].split(" TEST alpha")[1]
+    rows = re.findall(r"Branch(?:\(Tip\))?\s+[\d.]+ :\s+(-?[\d.]+)\s+(-?[\d.e+-]+)\s+(-?[\d.e+-]+)", block)
+    assert len(rows) == 18, (head, len(rows))
+    return [tuple(float(x) for x in r) for r in rows]
+
+
+def check_odd_block(case, outs):
+    want = parse_odd_block(**case["odd_block"])
+    d = [o for o in outs if o["kind"] == "derivs"]
+    e = [o for o in outs if o["kind"] == "edge" and o.get("tag")]
+    assert len(d) == 18 and len(e) == 18
+    for (lnl, d1, d2), od, oe in zip(want, d, e):
+        assert abs(oe["logl"] - lnl) < 5e-7, (case["name"], oe["logl"], lnl)
+        assert abs(od["d_f"] - d1) <= 6e-5 * abs(d1) + 1e-18, (case["name"], od, d1)
+        assert abs(od["dd_f"] - d2) <= 6e-5 * abs(d2) + 1e-40, (case["name"], od, d2)
+
+
 def main():
     golden = []
     for case in CASES:
@@ -162,6 +240,8 @@ def main():
                     step = [s for s in case["steps"] if s["do"] == "newton"][0]
                     assert abs(out["final"] - step["printed_final"]) < 5e-7, out
                     assert out["iterations"] == step["printed_iterations"], out
+            if "odd_block" in case:
+                check_odd_block(case, entry["expect"][label])
         golden.append(entry)
         print("ok", case["name"])
     path = os.path.join(ROOT, "tests", "golden", "cases.json")

@@ -33,8 +33,14 @@ def execute(lib, case, attributes):
         part.set_category_rates(case["rates"])
     else:
         part.set_category_rates(lib.gamma_rates(case["alpha"], case["rate_cats"]))
+    amap = None
+    if "map" in case:  # alphabets other than DNA / amino acids carry their own char -> state-set map
+        amap = lib.make_map(case["map"])
     for t, seq in enumerate(case["seqs"]):
-        part.set_tip_states(t, seq.encode())
+        if amap is None:
+            part.set_tip_states(t, seq.encode())
+        else:
+            part.set_tip_states(t, seq.encode(), amap)
     out = _run_steps(part, case)
     part.destroy()
     return out
@@ -50,9 +56,9 @@ def _run_steps(part, case):
         elif do == "partials":
             part.update_partials(_ops(st["ops"]))
         elif do == "get_pmatrix":
-            out.append(dict(kind="pmatrix", index=st["index"], values=part.get_pmatrix(st["index"]).reshape(-1).tolist()))
+            out.append(dict(kind="pmatrix", index=st["index"], values=part.get_pmatrix(st["index"])[..., :case["states"]].reshape(-1).tolist()))
         elif do == "get_clv":
-            out.append(dict(kind="clv", index=st["index"], values=part.get_clv(st["index"]).reshape(-1).tolist()))
+            out.append(dict(kind="clv", index=st["index"], values=part.get_clv(st["index"])[..., :case["states"]].reshape(-1).tolist()))
         elif do == "edge":
             ps = np.zeros(case["sites"])
             a = st["args"]
