@@ -19,6 +19,7 @@
 #define PLL_B200_PLL_H_
 
 #include <stddef.h>
+#include <stdio.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -175,6 +176,44 @@ typedef struct pll_operation
   int child2_scaler_index;
 } pll_operation_t;
 
+/* ---- unrooted tree: a tip is one record (next == NULL); an inner node is a ring of three
+ * records linked by `next`, each facing one neighbour through `back`
+ * (reference src/pll.h:312-334) ---- */
+typedef struct pll_unode_s
+{
+  char * label;
+  double length;
+  unsigned int node_index;
+  unsigned int clv_index;
+  int scaler_index;
+  unsigned int pmatrix_index;
+  struct pll_unode_s * next;
+  struct pll_unode_s * back;
+  void * data;
+} pll_unode_t;
+
+typedef struct pll_utree_s
+{
+  unsigned int tip_count;
+  unsigned int inner_count;
+  unsigned int edge_count;
+  pll_unode_t ** nodes; /* tips first, then inner nodes in post-order, the parse root last */
+} pll_utree_t;
+
+/* ---- FASTA reader state (reference src/pll.h:85,282-292) ---- */
+#define PLL_LINEALLOC 2048
+typedef struct pll_fasta
+{
+  FILE * fp;
+  char line[PLL_LINEALLOC];
+  const unsigned int * chrstatus;
+  long no;
+  long filesize;
+  long lineno;
+  long stripped_count;
+  long stripped[256];
+} pll_fasta_t;
+
 /* ---- thread-local error channel (reference src/pll.h:470-471, src/pll.c:24-25) ---- */
 PLL_EXPORT extern __thread int pll_errno;
 PLL_EXPORT extern __thread char pll_errmsg[200];
@@ -183,6 +222,11 @@ PLL_EXPORT extern __thread char pll_errmsg[200];
 PLL_EXPORT extern const unsigned int pll_map_bin[256];
 PLL_EXPORT extern const unsigned int pll_map_nt[256];
 PLL_EXPORT extern const unsigned int pll_map_aa[256];
+
+/* ---- character status tables of the file readers: 0 stripped, 1 kept, 2 fatal, 3 silently
+ * stripped (reference src/maps.c:117-168) ---- */
+PLL_EXPORT extern const unsigned int pll_map_fasta[256];
+PLL_EXPORT extern const unsigned int pll_map_phylip[256];
 
 /* ---- empirical amino-acid models used by the BASELINE configs (reference src/maps.c) ---- */
 PLL_EXPORT extern const double pll_aa_rates_lg[190];
@@ -308,6 +352,63 @@ PLL_EXPORT unsigned int * pll_compress_site_patterns(char ** sequence,
                                                      const unsigned int * map,
                                                      int count,
                                                      int * length);
+
+/* ---- FASTA reader (reference src/fasta.c:39-323, prototypes src/pll.h:668-681) ---- */
+PLL_EXPORT pll_fasta_t * pll_fasta_open(const char * filename, const unsigned int * map);
+PLL_EXPORT int pll_fasta_getnext(pll_fasta_t * fd, char ** head, long * head_len, char ** seq,
+                                 long * seq_len, long * seqno);
+PLL_EXPORT void pll_fasta_close(pll_fasta_t * fd);
+PLL_EXPORT long pll_fasta_getfilesize(const pll_fasta_t * fd);
+PLL_EXPORT long pll_fasta_getfilepos(pll_fasta_t * fd);
+PLL_EXPORT int pll_fasta_rewind(pll_fasta_t * fd);
+
+/* ---- unrooted trees: Newick reader, traversal, traversal -> operations
+ * (reference src/parse_utree.y:71-524, src/utree.c:217-442, prototypes src/pll.h:702-760).
+ * Hand-written and non-recursive here (no flex/bison, no call-stack depth on deep trees). ---- */
+PLL_EXPORT pll_utree_t * pll_utree_parse_newick(const char * filename);
+PLL_EXPORT pll_utree_t * pll_utree_parse_newick_string(const char * s);
+PLL_EXPORT void pll_utree_destroy(pll_utree_t * tree, void (*cb_destroy)(void *));
+PLL_EXPORT void pll_utree_graph_destroy(pll_unode_t * root, void (*cb_destroy)(void *));
+PLL_EXPORT void pll_utree_reset_template_indices(pll_unode_t * node, unsigned int tip_count);
+PLL_EXPORT pll_utree_t * pll_utree_wraptree(pll_unode_t * root, unsigned int tip_count);
+PLL_EXPORT char * pll_utree_export_newick(const pll_unode_t * root,
+                                          char * (*cb_serialize)(const pll_unode_t *));
+PLL_EXPORT int pll_utree_traverse(pll_unode_t * root,
+                                  int traversal,
+                                  int (*cbtrav)(pll_unode_t *),
+                                  pll_unode_t ** outbuffer,
+                                  unsigned int * trav_size);
+PLL_EXPORT int pll_utree_every(pll_utree_t * tree, int (*cb)(pll_unode_t *));
+PLL_EXPORT void pll_utree_create_operations(pll_unode_t * const * trav_buffer,
+                                            unsigned int trav_buffer_size,
+                                            double * branches,
+                                            unsigned int * pmatrix_indices,
+                                            pll_operation_t * ops,
+                                            unsigned int * matrix_count,
+                                            unsigned int * ops_count);
+
+/* NEW (no reference counterpart): operation list of a FULL traversal towards the edge
+ * (root, root->back) that recycles CLV / scaler slots, for partitions created with fewer
+ * clv_buffers / scale_buffers than inner nodes (at 5 000 taxa x 10 M patterns one CLV is
+ * 1.28 GB).  Subtrees are evaluated larger-demand-first, so `max_slots` >= the tree's Strahler
+ * number + 1 (<= log2(tips) + 2) always suffices; *slots_used receives the exact need and the
+ * call fails with PLL_ERROR_PARAM_INVALID if it exceeds max_slots.  Inner node results go to
+ * CLV tip_count + slot and scaler slot; tips keep clv_index / PLL_SCALE_BUFFER_NONE;
+ * P-matrix indices and branches are the tree's own (all 2T-3 of them are listed).
+ * edge_clv[2] / edge_scaler[2] receive where the two ends of the evaluation edge ended up
+ * ([0] = root, [1] = root->back).  The tree must carry the default index template
+ * (pll_utree_parse_newick* or pll_utree_reset_template_indices). */
+PLL_EXPORT int pll_utree_create_operations_recycled(pll_unode_t * root,
+                                                    unsigned int tip_count,
+                                                    unsigned int max_slots,
+                                                    double * branches,
+                                                    unsigned int * pmatrix_indices,
+                                                    pll_operation_t * ops,
+                                                    unsigned int * matrix_count,
+                                                    unsigned int * ops_count,
+                                                    unsigned int * edge_clv,
+                                                    int * edge_scaler,
+                                                    unsigned int * slots_used);
 
 /* ---- printing helpers (reference src/output.c:26-96); sync the needed mirrors first ---- */
 PLL_EXPORT void pll_show_pmatrix(const pll_partition_t * partition,

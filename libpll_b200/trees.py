@@ -1,0 +1,202 @@
+"""ctypes mirror of the tree / file front-end of pll.h (include/pll.h: pll_unode_t, pll_utree_t,
+pll_utree_*, pll_fasta_*).  Works with any library exporting that API with the reference's struct
+layouts: a tree parsed by one such library can be handed to another's traversal functions in the
+same process - that is how tests/test_utree_cpu.py pins parity with the reference."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .binding import OP_DTYPE, PllError, PllLibrary
+
+PLL_TREE_TRAVERSE_POSTORDER = 1
+PLL_TREE_TRAVERSE_PREORDER = 2
+
+
+class UNode(C.Structure):
+    pass
+
+
+UNode._fields_ = [
+    ("label", C.c_char_p),
+    ("length", C.c_double),
+    ("node_index", C.c_uint),
+    ("clv_index", C.c_uint),
+    ("scaler_index", C.c_int),
+    ("pmatrix_index", C.c_uint),
+    ("next", C.POINTER(UNode)),
+    ("back", C.POINTER(UNode)),
+    ("data", C.c_void_p),
+]
+UNODE_P = C.POINTER(UNode)
+
+
+class UTree(C.Structure):
+    _fields_ = [
+        ("tip_count", C.c_uint),
+        ("inner_count", C.c_uint),
+        ("edge_count", C.c_uint),
+        ("nodes", C.POINTER(UNODE_P)),
+    ]
+
+
+UTREE_P = C.POINTER(UTree)
+TRAV_CB = C.CFUNCTYPE(C.c_int, UNODE_P)
+
+_TREE_API = {
+    "pll_utree_parse_newick": (UTREE_P, [C.c_char_p]),
+    "pll_utree_parse_newick_string": (UTREE_P, [C.c_char_p]),
+    "pll_utree_destroy": (None, [UTREE_P, C.c_void_p]),
+    "pll_utree_reset_template_indices": (None, [UNODE_P, C.c_uint]),
+    "pll_utree_wraptree": (UTREE_P, [UNODE_P, C.c_uint]),
+    "pll_utree_export_newick": (C.c_void_p, [UNODE_P, C.c_void_p]),
+    "pll_utree_traverse": (C.c_int, [UNODE_P, C.c_int, TRAV_CB, C.POINTER(UNODE_P), C.POINTER(C.c_uint)]),
+    "pll_utree_create_operations": (None, [C.POINTER(UNODE_P), C.c_uint, C.POINTER(C.c_double),
+                                           C.POINTER(C.c_uint), C.c_void_p, C.POINTER(C.c_uint),
+                                           C.POINTER(C.c_uint)]),
+    "pll_utree_create_operations_recycled": (C.c_int, [UNODE_P, C.c_uint, C.c_uint, C.POINTER(C.c_double),
+                                                       C.POINTER(C.c_uint), C.c_void_p, C.POINTER(C.c_uint),
+                                                       C.POINTER(C.c_uint), C.POINTER(C.c_uint),
+                                                       C.POINTER(C.c_int), C.POINTER(C.c_uint)]),
+    "pll_fasta_open": (C.c_void_p, [C.c_char_p, C.POINTER(C.c_uint)]),
+    "pll_fasta_getnext": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_long),
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_long), C.POINTER(C.c_long)]),
+    "pll_fasta_close": (None, [C.c_void_p]),
+}
+
+_libc = C.CDLL(None)
+_libc.free.argtypes = [C.c_void_p]
+
+
+def bind(lib: PllLibrary) -> PllLibrary:
+    """Adds the tree / file functions to a loaded PllLibrary (symbols a library lacks are listed
+    in lib.missing; the reference built without bison has no Newick reader)."""
+    if getattr(lib, "_trees_bound", False):
+        return lib
+    for name, (res, args) in _TREE_API.items():
+        lib._bind(name, res, args)
+    lib._trees_bound = True
+    return lib
+
+
+@TRAV_CB
+def full_traversal(_node):
+    return 1
+
+
+class Tree:
+    """An unrooted tree owned by `lib` (pll_utree_parse_newick_string .. pll_utree_destroy)."""
+
+    def __init__(self, lib: PllLibrary, newick: str | None = None, path: str | None = None):
+        self.lib = bind(lib)
+        if newick is not None:
+            self.ptr = lib.pll_utree_parse_newick_string(newick.encode())
+        else:
+            self.ptr = lib.pll_utree_parse_newick(path.encode())
+        if not self.ptr:
+            raise PllError(f"[{lib.errno()}] {lib.errmsg()}")
+        self.t = self.ptr.contents
+
+    def destroy(self):
+        if self.ptr:
+            self.lib.pll_utree_destroy(self.ptr, None)
+            self.ptr = None
+
+    @property
+    def tips(self) -> int:
+        return self.t.tip_count
+
+    @property
+    def inner(self) -> int:
+        return self.t.inner_count
+
+    def node(self, i: int):
+        return self.t.nodes[i]
+
+    @property
+    def root(self):
+        """The inner node the Newick string was rooted at (last entry of nodes[])."""
+        return self.t.nodes[self.t.tip_count + self.t.inner_count - 1]
+
+    def tip_labels(self) -> list[str]:
+        return [self.t.nodes[i].contents.label.decode() for i in range(self.tips)]
+
+    def records(self):
+        """(label, length, node_index, clv_index, scaler_index, pmatrix_index) of every record:
+        tips, then the three ring records of each inner node."""
+        out = []
+        for i in range(self.tips + self.inner):
+            n = self.t.nodes[i]
+            ring = [n] if not n.contents.next else [n, n.contents.next, n.contents.next.contents.next]
+            for r in ring:
+                c = r.contents
+                out.append((c.label.decode() if c.label else None, c.length, c.node_index, c.clv_index,
+                            c.scaler_index, c.pmatrix_index))
+        return out
+
+    def traverse(self, lib: PllLibrary | None = None, root=None, order=PLL_TREE_TRAVERSE_POSTORDER, cb=full_traversal):
+        """Traversal buffer computed by `lib` (default: the owner) - a ctypes array of node pointers."""
+        lib = bind(lib or self.lib)
+        buf = (UNODE_P * (self.tips + self.inner))()
+        n = C.c_uint(0)
+        if not lib.pll_utree_traverse(root or self.root, order, cb, buf, C.byref(n)):
+            raise PllError(lib.errmsg())
+        return buf, n.value
+
+    def operations(self, lib: PllLibrary | None = None, root=None):
+        """(ops, matrix_indices, branch_lengths) of a full post-order traversal, from `lib`."""
+        lib = bind(lib or self.lib)
+        buf, n = self.traverse(lib, root)
+        branches = np.zeros(2 * self.tips - 3)
+        matrices = np.zeros(2 * self.tips - 3, dtype=np.uint32)
+        ops = np.zeros(self.inner, dtype=OP_DTYPE)
+        nm, no = C.c_uint(0), C.c_uint(0)
+        lib.pll_utree_create_operations(buf, n, branches.ctypes.data_as(C.POINTER(C.c_double)),
+                                        matrices.ctypes.data_as(C.POINTER(C.c_uint)), ops.ctypes.data,
+                                        C.byref(nm), C.byref(no))
+        return ops[:no.value], matrices[:nm.value], branches[:nm.value]
+
+    def operations_recycled(self, max_slots: int, root=None):
+        """(ops, matrix_indices, branch_lengths, edge_clv[2], edge_scaler[2], slots_used)."""
+        lib = self.lib
+        branches = np.zeros(2 * self.tips - 3)
+        matrices = np.zeros(2 * self.tips - 3, dtype=np.uint32)
+        ops = np.zeros(self.inner, dtype=OP_DTYPE)
+        nm, no, used = C.c_uint(0), C.c_uint(0), C.c_uint(0)
+        eclv, esc = (C.c_uint * 2)(), (C.c_int * 2)()
+        ok = lib.pll_utree_create_operations_recycled(root or self.root, self.tips, max_slots,
+                                                      branches.ctypes.data_as(C.POINTER(C.c_double)),
+                                                      matrices.ctypes.data_as(C.POINTER(C.c_uint)), ops.ctypes.data,
+                                                      C.byref(nm), C.byref(no), eclv, esc, C.byref(used))
+        if not ok:
+            raise PllError(f"[{lib.errno()}] {lib.errmsg()} (needs {used.value} slots)")
+        return ops[:no.value], matrices[:nm.value], branches[:nm.value], list(eclv), list(esc), used.value
+
+    def export_newick(self, lib: PllLibrary | None = None) -> str:
+        lib = bind(lib or self.lib)
+        p = lib.pll_utree_export_newick(self.root, None)
+        if not p:
+            raise PllError(lib.errmsg())
+        s = C.string_at(p).decode()
+        _libc.free(p)
+        return s
+
+
+def read_fasta(lib: PllLibrary, path: str, status_table=None):
+    """[(header, sequence)] read by `lib`'s FASTA reader, plus (stripped_count, errno at the end)."""
+    bind(lib)
+    table = status_table if status_table is not None else (C.c_uint * 256).in_dll(lib.dll, "pll_map_fasta")
+    fd = lib.pll_fasta_open(path.encode(), table)
+    if not fd:
+        raise PllError(f"[{lib.errno()}] {lib.errmsg()}")
+    out = []
+    head, seq = C.c_void_p(), C.c_void_p()
+    hl, sl, no = C.c_long(), C.c_long(), C.c_long()
+    while lib.pll_fasta_getnext(fd, C.byref(head), C.byref(hl), C.byref(seq), C.byref(sl), C.byref(no)):
+        out.append((C.string_at(head, hl.value).decode(), C.string_at(seq, sl.value).decode(), no.value))
+        _libc.free(head)
+        _libc.free(seq)
+    err = lib.errno()
+    lib.pll_fasta_close(fd)
+    return out, err

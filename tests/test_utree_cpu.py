@@ -1,0 +1,269 @@
+"""CPU tests of the caller side of the path: Newick reader, index
+template, traversal, traversal -> operations, slot recycling, FASTA reader - the host C code of
+libpll_b200/csrc/host/pll_utree.c and pll_fasta.c.  No GPU is needed (no partition is created
+on the product library here).
+
+Pins: (1) tests/golden/lg4_example.json, recorded from the reference on its own example data;
+(2) the reference's pll_utree_traverse / pll_utree_create_operations / pll_utree_export_newick /
+FASTA reader (oracle/_ref) run IN PROCESS on trees parsed by this library - the struct layouts
+are identical, so operation lists must match bit for bit; (3) the reference's likelihood of
+recycled-slot operation lists, which must be bit-identical to the plain list's."""
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import libpll_b200
+from libpll_b200 import trees as T
+from libpll_b200.binding import PLL_ATTRIB_ARCH_AVX2, PLL_ATTRIB_PATTERN_TIP, PllError
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LG4 = json.load(open(os.path.join(ROOT, "tests", "golden", "lg4_example.json")))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return T.bind(libpll_b200.load())
+
+
+@pytest.fixture(scope="module")
+def ref(ref_lib):
+    return T.bind(ref_lib)
+
+
+def random_newick(tips, seed, caterpillar=False, labels=True):
+    rng = np.random.default_rng(seed)
+    if caterpillar and tips > 3:
+        # ((((t0,t1),t2),t3)...,t[T-2],t[T-1]); built by one join (string surgery is quadratic)
+        lens = rng.uniform(0.01, 0.3, 2 * tips)
+        inner = ("(" * (tips - 3) + f"t0:{lens[0]:.6f},t1:{lens[1]:.6f}"
+                 + "".join(f"):{lens[tips + i]:.6f},t{i}:{lens[i]:.6f}" for i in range(2, tips - 2))
+                 + f"):{lens[tips]:.6f}")
+        return f"({inner},t{tips - 2}:{lens[tips - 2]:.6f},t{tips - 1}:{lens[tips - 1]:.6f});"
+    nodes = [f"t{i}:{rng.uniform(0.01, 0.3):.6f}" for i in range(tips)]
+    if not labels:
+        nodes = [f"{i}:{rng.uniform(0.01, 0.3):.6f}" for i in range(tips)]
+    while len(nodes) > 3:
+        if caterpillar:
+            a, b = nodes.pop(0), nodes.pop(0)
+            nodes.insert(0, f"({a},{b}):{rng.uniform(0.01, 0.3):.6f}")
+        else:
+            i = int(rng.integers(0, len(nodes)))
+            a = nodes.pop(i)
+            j = int(rng.integers(0, len(nodes)))
+            b = nodes.pop(j)
+            nodes.append(f"({a},{b}):{rng.uniform(0.01, 0.3):.6f}")
+    return f"({nodes[0]},{nodes[1]},{nodes[2]});"
+
+
+# ---- golden: the reference's lg4 example ----------------------------------------------------
+def test_newick_reader_and_template_match_golden(lib):
+    t = T.Tree(lib, newick=LG4["newick"])
+    assert t.tips == LG4["tip_count"] and t.inner == t.tips - 2 and t.t.edge_count == 2 * t.tips - 3
+    got = t.records()
+    assert len(got) == len(LG4["records"])
+    for g, w in zip(got, LG4["records"]):
+        assert g[0] == w[0] and g[1] == w[1] and list(g[2:]) == list(w[2:]), (g, w)
+    t.destroy()
+
+
+def test_operations_match_golden(lib):
+    t = T.Tree(lib, newick=LG4["newick"])
+    ops, mi, bl = t.operations()
+    assert [list(int(x) for x in o) for o in ops.tolist()] == LG4["ops"]
+    assert mi.tolist() == LG4["matrices"]
+    assert bl.tolist() == LG4["branches"]
+    r = t.root.contents
+    assert [r.clv_index, r.scaler_index, r.back.contents.clv_index, r.back.contents.scaler_index,
+            r.pmatrix_index] == LG4["edge"]
+    t.destroy()
+
+
+def test_fasta_reader_matches_golden(lib, tmp_path):
+    p = tmp_path / "example.fas"
+    p.write_text(LG4["fasta_text"])
+    got, err = T.read_fasta(lib, str(p))
+    assert err == 102  # PLL_ERROR_FILE_EOF ends the loop, as in examples/lg4/lg4.c:172-174
+    assert [list(x) for x in got] == LG4["fasta"]
+
+
+# ---- in-process parity with the reference's tree functions ----------------------------------
+@pytest.mark.parametrize("tips,seed,caterpillar", [(3, 1, False), (4, 2, False), (17, 3, False), (200, 4, False),
+                                                   (1000, 5, False), (300, 6, True)])
+def test_traversal_and_operations_match_reference(lib, ref, tips, seed, caterpillar):
+    t = T.Tree(lib, newick=random_newick(tips, seed, caterpillar))
+    for root_index in {tips + t.inner - 1, tips, tips + t.inner // 2}:
+        root = t.node(root_index)
+        for order in (T.PLL_TREE_TRAVERSE_POSTORDER, T.PLL_TREE_TRAVERSE_PREORDER):
+            a, na = t.traverse(lib, root, order)
+            b, nb = t.traverse(ref, root, order)
+            assert na == nb == 2 * tips - 2
+            assert [C.addressof(a[i].contents) for i in range(na)] == [C.addressof(b[i].contents) for i in range(nb)]
+        o1, m1, b1 = t.operations(lib, root)
+        o2, m2, b2 = t.operations(ref, root)
+        assert o1.tobytes() == o2.tobytes() and m1.tobytes() == m2.tobytes() and b1.tobytes() == b2.tobytes()
+    assert t.export_newick(lib) == t.export_newick(ref)
+    t.destroy()
+
+
+def test_partial_traversal_callback(lib, ref):
+    """cbtrav prunes subtrees (reference examples/partial-traversal/partial.c:60-100)."""
+    t = T.Tree(lib, newick=random_newick(60, 11))
+
+    @T.TRAV_CB
+    def only_small_clv(node):
+        n = node.contents
+        return 1 if (not n.next) or n.clv_index % 5 != 3 else 0
+
+    for order in (T.PLL_TREE_TRAVERSE_POSTORDER, T.PLL_TREE_TRAVERSE_PREORDER):
+        a, na = t.traverse(lib, order=order, cb=only_small_clv)
+        b, nb = t.traverse(ref, order=order, cb=only_small_clv)
+        assert na == nb and 0 < na < 2 * 60 - 2
+        assert [C.addressof(a[i].contents) for i in range(na)] == [C.addressof(b[i].contents) for i in range(nb)]
+    t.destroy()
+
+
+def test_export_parse_round_trip(lib):
+    nw = random_newick(80, 21)
+    t = T.Tree(lib, newick=nw)
+    out = t.export_newick()
+    t2 = T.Tree(lib, newick=out)
+    assert t2.export_newick() == out
+    assert t2.tip_labels() == t.tip_labels()
+    assert [r[2:] for r in t2.records()] == [r[2:] for r in t.records()]
+    t.destroy()
+    t2.destroy()
+
+
+def test_deep_tree_needs_no_recursion(lib):
+    """A 200 000-taxon caterpillar: the reference's recursive walks would need ~200 000 stack
+    frames; the reader, template, traversal, operations and export here are all iterative."""
+    tips = 200_000
+    t = T.Tree(lib, newick=random_newick(tips, 3, caterpillar=True))
+    assert t.tips == tips
+    ops, mi, bl = t.operations()
+    assert len(ops) == tips - 2 and len(mi) == 2 * tips - 3
+    assert len(t.export_newick()) > tips * 10
+    t.destroy()
+
+
+def test_lexer_details(lib):
+    # quoted labels, numeric labels, labels that start like numbers, inner labels, whitespace
+    nw = "( 'a b':0.1 ,\n\"c,d\":2e-1,\t(12:1,1e5x:.5)in1:0.25 )root:7 ;"
+    t = T.Tree(lib, newick=nw)
+    assert t.tip_labels() == ["a b", "c,d", "12", "1e5x"]
+    recs = t.records()
+    assert [r[1] for r in recs[:4]] == [0.1, 0.2, 1.0, 0.5]
+    assert recs[4][0] == "in1" and recs[4][1] == 0.25
+    assert recs[7][0] == "root"
+    t.destroy()
+    # missing lengths are 0 (examples set them afterwards, lg4.c:37-62)
+    t = T.Tree(lib, newick="(a,b,(c,d));")
+    assert all(r[1] == 0.0 for r in t.records())
+    t.destroy()
+
+
+@pytest.mark.parametrize("bad", ["(a,b);", "(a,b,c,d);", "(a,b,(c,d,e));", "(a,b,c)", "(a,b,(c,d);", "a;",
+                                 "(a,b,c):;", "(a:x,b,c);", "(a,b,[c]);", "((a,b),(c,d));", "", "(a,,b);",
+                                 "(a,b,'c);"])
+def test_syntax_errors(lib, bad):
+    with pytest.raises(PllError) as e:
+        T.Tree(lib, newick=bad)
+    assert "[111]" in str(e.value)  # PLL_ERROR_NEWICK_SYNTAX
+
+
+def test_fasta_reader_matches_reference(lib, ref, tmp_path):
+    text = (">seq one\r\nACGT acgt\r\nNN--??\r\n"
+            ">two|x\nAC*GT!!\nj o J O 12\n\n"
+            ">three\n>four\nA\n")
+    p = tmp_path / "x.fas"
+    p.write_bytes(text.encode())
+    a, ea = T.read_fasta(lib, str(p))
+    b, eb = T.read_fasta(ref, str(p))
+    assert a == b and ea == eb == 102
+    assert a[1][1] == "ACGTJO12" and a[2][1] == ""
+    # fatal character and bad header: same error codes as the reference
+    for content, code in ((">a\nAC.GT\n", 103), (">a\nAC\x01GT\n", 104), ("ACGT\n", 105)):
+        p.write_bytes(content.encode())
+        _, ea = T.read_fasta(lib, str(p))
+        _, eb = T.read_fasta(ref, str(p))
+        assert ea == eb == code
+    with pytest.raises(PllError):
+        T.read_fasta(lib, str(tmp_path / "missing.fas"))
+    for name in ("pll_map_fasta", "pll_map_phylip"):
+        ours = list((C.c_uint * 256).in_dll(lib.dll, name))
+        theirs = list((C.c_uint * 256).in_dll(ref.dll, name))
+        assert ours == theirs
+
+
+# ---- slot recycling -------------------------------------------------------------------------
+def _check_recycled(ops, tips, slots):
+    """every operation reads tips or slots written before and not yet overwritten"""
+    holder = {}
+    for op in ops:
+        for c in (int(op["child1_clv_index"]), int(op["child2_clv_index"])):
+            if c >= tips:
+                assert holder.get(c) == "live", "child slot was not written or already recycled"
+        p = int(op["parent_clv_index"])
+        assert tips <= p < tips + slots
+        assert int(op["parent_scaler_index"]) == p - tips
+        for c in (int(op["child1_clv_index"]), int(op["child2_clv_index"])):
+            assert c != p
+        holder[p] = "live"
+
+
+@pytest.mark.parametrize("tips,seed,caterpillar", [(5, 1, False), (64, 2, False), (1000, 3, False), (500, 4, True)])
+def test_recycled_operations_structure(lib, tips, seed, caterpillar):
+    t = T.Tree(lib, newick=random_newick(tips, seed, caterpillar))
+    ops, mi, bl, eclv, esc, used = t.operations_recycled(64)
+    assert used <= math.floor(math.log2(tips)) + 2
+    if caterpillar:
+        assert used <= 3
+    assert len(ops) == tips - 2 and len(mi) == 2 * tips - 3
+    _check_recycled(ops, tips, used)
+    # the same branches as the plain list, possibly in another order
+    _, mi0, bl0 = t.operations()
+    assert sorted(zip(mi.tolist(), bl.tolist())) == sorted(zip(mi0.tolist(), bl0.tolist()))
+    # exactly `used` slots suffice, one fewer does not
+    ops2 = t.operations_recycled(used)[0]
+    assert ops2.tobytes() == ops.tobytes()
+    with pytest.raises(PllError):
+        t.operations_recycled(used - 1)
+    t.destroy()
+
+
+def test_recycled_operations_give_identical_likelihood_on_reference(lib, ref):
+    """The reference evaluates the plain list (its own pll_utree_create_operations) and the
+    recycled list of the same tree: identical log-likelihoods, bit for bit."""
+    tips, sites = 120, 300
+    t = T.Tree(lib, newick=random_newick(tips, 77))
+    rng = np.random.default_rng(5)
+    seqs = ["".join(rng.choice(list("ACGT-"), sites)) for _ in range(tips)]
+
+    def evaluate(clv_buffers, ops, mi, bl, edge):
+        part = ref.partition(tips=tips, clv_buffers=clv_buffers, states=4, sites=sites, rate_matrices=1,
+                             prob_matrices=2 * tips - 3, rate_cats=4, scale_buffers=clv_buffers,
+                             attributes=PLL_ATTRIB_ARCH_AVX2 | PLL_ATTRIB_PATTERN_TIP)
+        part.set_frequencies(0, [0.3, 0.2, 0.25, 0.25])
+        part.set_subst_params(0, [1.2, 3.1, 0.9, 1.1, 3.3, 1.0])
+        part.set_category_rates(ref.gamma_rates(0.5, 4))
+        for i, s in enumerate(seqs):
+            part.set_tip_states(i, s.encode())
+        pidx = np.zeros(4, np.uint32)
+        part.update_prob_matrices(pidx, mi, bl)
+        part.update_partials(ops)
+        lnl = part.edge_loglikelihood(edge[0], edge[1], edge[2], edge[3], edge[4], pidx)
+        part.destroy()
+        return lnl
+
+    r = t.root.contents
+    ops, mi, bl = t.operations(ref)
+    plain = evaluate(tips - 2, ops, mi, bl, (r.clv_index, r.scaler_index, r.back.contents.clv_index,
+                                            r.back.contents.scaler_index, r.pmatrix_index))
+    ops, mi, bl, eclv, esc, used = t.operations_recycled(16)
+    recycled = evaluate(used, ops, mi, bl, (eclv[0], esc[0], eclv[1], esc[1], r.pmatrix_index))
+    assert np.isfinite(plain) and plain == recycled
+    t.destroy()
