@@ -341,6 +341,13 @@ PLL_EXPORT int pll_compute_likelihood_derivatives(pll_partition_t * partition,
                                                   double * d_f,
                                                   double * dd_f);
 
+/* ---- ascertainment-bias correction (reference src/pll.c:1061-1116).  The partition must be
+ * created with PLL_ATTRIB_AB_FLAG or one of the PLL_ATTRIB_AB_* types: it then holds `states`
+ * extra per-state sites.  Not combinable with PLL_ATTRIB_RATE_SCALERS on this backend. ---- */
+PLL_EXPORT int pll_set_asc_bias_type(pll_partition_t * partition, int asc_bias_type);
+PLL_EXPORT void pll_set_asc_state_weights(pll_partition_t * partition,
+                                          const unsigned int * state_weights);
+
 /* ---- discrete Gamma rates (reference src/gamma.c:220-292) ---- */
 PLL_EXPORT int pll_compute_gamma_cats(double alpha,
                                       unsigned int categories,

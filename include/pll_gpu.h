@@ -117,6 +117,21 @@ PLL_EXPORT int plg_set_pmatrix(plg_context_t * ctx, unsigned int matrix_index,
 PLL_EXPORT int plg_get_pmatrix(plg_context_t * ctx, unsigned int matrix_index,
                                double * pmatrix);
 
+/* Ascertainment-bias storage (reference src/pll.c:492-495: `sites + states` allocated sites):
+ * CLV updates and sumtables always cover all allocated sites; the log-likelihood and
+ * derivative reductions cover the first `sites` of plg_set_active_sites (default: all).  The
+ * host layer reads the few trailing per-state sites back through the *_sites getters and
+ * applies the correction terms (reference src/likelihood.c:24-119,170-247,321-414,
+ * src/core_derivatives.c:654-727).  first_site / count are in sites; scaler ranges are
+ * count (x rate_cats with per-rate scalers) values. */
+PLL_EXPORT int plg_set_active_sites(plg_context_t * ctx, unsigned int sites);
+PLL_EXPORT int plg_get_clv_sites(plg_context_t * ctx, unsigned int clv_index, unsigned int first_site,
+                                 unsigned int count, double * out);
+PLL_EXPORT int plg_get_scaler_sites(plg_context_t * ctx, unsigned int scaler_index,
+                                    unsigned int first_site, unsigned int count, unsigned int * out);
+PLL_EXPORT int plg_get_sumtable_sites(plg_context_t * ctx, const void * key, unsigned int first_site,
+                                      unsigned int count, double * out);
+
 /* ---- the hot path ---------------------------------------------------------------- */
 
 /* replaces: pll_core_update_pmatrix and its _4x4_avx / _20x20_avx2 rungs

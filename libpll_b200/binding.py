@@ -22,6 +22,10 @@ import numpy as np
 PLL_SUCCESS = 1
 PLL_FAILURE = 0
 PLL_ATTRIB_ARCH_CPU = 0
+PLL_ATTRIB_AB_LEWIS = 1 << 5
+PLL_ATTRIB_AB_FELSENSTEIN = 2 << 5
+PLL_ATTRIB_AB_STAMATAKIS = 3 << 5
+PLL_ATTRIB_AB_FLAG = 1 << 8
 PLL_ATTRIB_ARCH_SSE = 1 << 0
 PLL_ATTRIB_ARCH_AVX = 1 << 1
 PLL_ATTRIB_ARCH_AVX2 = 1 << 2
@@ -154,6 +158,8 @@ _PLL_API = {
         C.c_int,
         [PART_P, C.c_int, C.c_int, C.c_double, c_uint_p, c_double_p, c_double_p, c_double_p],
     ),
+    "pll_set_asc_bias_type": (C.c_int, [PART_P, C.c_int]),
+    "pll_set_asc_state_weights": (None, [PART_P, c_uint_p]),
     "pll_compute_gamma_cats": (C.c_int, [C.c_double, C.c_uint, c_double_p, C.c_int]),
     "pll_compress_site_patterns": (c_uint_p, [C.POINTER(C.c_char_p), c_uint_p, C.c_int, C.POINTER(C.c_int)]),
     "pll_aligned_alloc": (C.c_void_p, [C.c_size_t, C.c_size_t]),
@@ -325,6 +331,14 @@ class Partition:
         assert w.size == self.p.sites
         self.lib.pll_set_pattern_weights(self.ptr, w.ctypes.data_as(c_uint_p))
 
+    def set_asc_bias_type(self, asc_bias_type: int):
+        self._check(self.lib.pll_set_asc_bias_type(self.ptr, asc_bias_type), "pll_set_asc_bias_type")
+
+    def set_asc_state_weights(self, w):
+        w = _as_uint(w)
+        assert w.size == self.p.states
+        self.lib.pll_set_asc_state_weights(self.ptr, w.ctypes.data_as(c_uint_p))
+
     def set_subst_params(self, idx: int, params):
         a = _as_f64(params)
         self.lib.pll_set_subst_params(self.ptr, idx, a.ctypes.data_as(c_double_p))
@@ -379,7 +393,8 @@ class Partition:
     def new_sumtable(self) -> np.ndarray:
         """Caller-allocated sumtable buffer as in reference examples/newton/newton.c:47-51.
         (Under the GPU backend only its address matters; see include/pll.h.)"""
-        n = self.p.sites * self.span
+        # ascertainment-bias storage adds `states` per-state sites (reference src/derivatives.c:56)
+        n = (self.p.sites + (self.p.states if self.p.asc_bias_alloc else 0)) * self.span
         raw = np.zeros(n + 8, dtype=np.float64)
         off = (-raw.ctypes.data // 8) % 4  # 32-byte alignment like pll_aligned_alloc
         buf = raw[off:off + n]

@@ -113,6 +113,7 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   PLG_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
   ctx->pattern_tip = (dims->attributes & PLL_ATTRIB_PATTERN_TIP) != 0;
   ctx->rate_scalers = (dims->attributes & PLL_ATTRIB_RATE_SCALERS) != 0;
+  ctx->active_sites = dims->sites;
   ctx->span = (size_t)dims->rate_cats * dims->states_padded;
   ctx->clv_stride = round_up((size_t)dims->sites * ctx->span, 32);
   ctx->scaler_len = ctx->rate_scalers ? (size_t)dims->sites * dims->rate_cats : dims->sites;
@@ -612,4 +613,47 @@ extern "C" int plg_mem_info(plg_context_t * ctx, size_t * free_bytes, size_t * t
   if (free_bytes) *free_bytes = f;
   if (total_bytes) *total_bytes = t;
   return PLG_OK;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* site ranges: what the ascertainment-bias epilogue of the host layer reads              */
+/* ------------------------------------------------------------------------------------ */
+extern "C" int plg_set_active_sites(plg_context_t * ctx, unsigned int sites)
+{
+  PLG_CHECK_CTX(ctx);
+  if (sites == 0 || sites > ctx->d.sites)
+  {
+    plg_set_error("plg_set_active_sites: %u out of range (1..%u)", sites, ctx->d.sites);
+    return PLG_E_INVALID;
+  }
+  ctx->active_sites = sites;
+  return PLG_OK;
+}
+
+extern "C" int plg_get_clv_sites(plg_context_t * ctx, unsigned int clv_index, unsigned int first_site,
+                                 unsigned int count, double * out)
+{
+  PLG_CHECK_CTX(ctx);
+  if (clv_index < ctx->clv_first || clv_index >= ctx->d.tips + ctx->d.clv_buffers ||
+      (size_t)first_site + count > ctx->d.sites || !out)
+  {
+    plg_set_error("plg_get_clv_sites: index out of range");
+    return PLG_E_INVALID;
+  }
+  return d2h(ctx, out, plg_clv_ptr(ctx, clv_index) + (size_t)first_site * ctx->span,
+             (size_t)count * ctx->span * sizeof(double));
+}
+
+extern "C" int plg_get_scaler_sites(plg_context_t * ctx, unsigned int scaler_index, unsigned int first_site,
+                                    unsigned int count, unsigned int * out)
+{
+  PLG_CHECK_CTX(ctx);
+  const size_t per = ctx->rate_scalers ? ctx->d.rate_cats : 1;
+  if (scaler_index >= ctx->d.scale_buffers || (size_t)first_site + count > ctx->d.sites || !out)
+  {
+    plg_set_error("plg_get_scaler_sites: index out of range");
+    return PLG_E_INVALID;
+  }
+  return d2h(ctx, out, plg_scaler_ptr(ctx, (int)scaler_index) + (size_t)first_site * per,
+             (size_t)count * per * sizeof(unsigned int));
 }

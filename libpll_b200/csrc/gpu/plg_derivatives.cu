@@ -621,7 +621,7 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
   if (!plg_fast_path(ctx))
     return plg_gen_derivatives(ctx, it->second, diagptable, rate_weights, prop_invar, freqs, d_f, dd_f);
   const unsigned int R = ctx->d.rate_cats, K = ctx->d.states;
-  const unsigned int nelem = ctx->d.sites * R;
+  const unsigned int nelem = ctx->active_sites * R;
   unsigned int nblocks = (nelem + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
   const unsigned int cap = (unsigned int)ctx->sm_count * 8u; /* persistent: 8 CTAs per SM */
   if (nblocks > cap) nblocks = cap;
@@ -692,5 +692,23 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
   ctx->stats.d2h_bytes += 2 * sizeof(double);
   *d_f = ctx->result_host[0];
   *dd_f = ctx->result_host[1];
+  return PLG_OK;
+}
+
+extern "C" int plg_get_sumtable_sites(plg_context_t * ctx, const void * key, unsigned int first_site,
+                                      unsigned int count, double * out)
+{
+  PLG_CHECK_CTX(ctx);
+  auto it = ctx->sumtables->find(key);
+  if (it == ctx->sumtables->end() || (size_t)first_site + count > ctx->d.sites || !out)
+  {
+    plg_set_error("plg_get_sumtable_sites: unknown sumtable or range out of bounds");
+    return PLG_E_INVALID;
+  }
+  const size_t bytes = (size_t)count * ctx->span * sizeof(double);
+  PLG_CUDA(cudaMemcpyAsync(out, it->second + (size_t)first_site * ctx->span, bytes, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.d2h_bytes += bytes;
   return PLG_OK;
 }

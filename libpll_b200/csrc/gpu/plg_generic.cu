@@ -327,7 +327,7 @@ int plg_gen_loglikelihood(plg_context * ctx, const GenLnl & g, const double * fr
                           const double * prop_invar, double * persite_lnl, double * logl_out)
 {
   const unsigned int R = ctx->d.rate_cats, Kp = ctx->d.states_padded;
-  const unsigned int nblocks = (ctx->d.sites + PLG_GEN_THREADS - 1) / PLG_GEN_THREADS;
+  const unsigned int nblocks = (ctx->active_sites + PLG_GEN_THREADS - 1) / PLG_GEN_THREADS;
   int rc = plg_ensure_partials(ctx, nblocks);
   if (rc) return rc;
   bool any_pinv = false;
@@ -338,7 +338,7 @@ int plg_gen_loglikelihood(plg_context * ctx, const GenLnl & g, const double * fr
     return PLG_E_INVALID;
   }
   if (persite_lnl && !ctx->persite_dev)
-    PLG_CUDA(cudaMalloc(&ctx->persite_dev, (size_t)ctx->d.sites * sizeof(double)));
+    PLG_CUDA(cudaMalloc(&ctx->persite_dev, (size_t)ctx->active_sites * sizeof(double)));
   std::vector<double> pinv(R, 0.0);
   if (prop_invar) pinv.assign(prop_invar, prop_invar + R);
   if (plg_stage_reserve(ctx, ((size_t)R * Kp + 2 * R) * 8 + 1024 + 4 * 256)) return PLG_E_CUDA;
@@ -357,7 +357,7 @@ int plg_gen_loglikelihood(plg_context * ctx, const GenLnl & g, const double * fr
   a.counter = ctx->counter;
   a.result = ctx->result_dev;
   a.log_threshold = log(PLL_SCALE_THRESHOLD);
-  a.sites = ctx->d.sites;
+  a.sites = ctx->active_sites;
   a.R = R;
   a.K = ctx->d.states;
   a.Kp = Kp;
@@ -367,10 +367,10 @@ int plg_gen_loglikelihood(plg_context * ctx, const GenLnl & g, const double * fr
   PLG_LAUNCH_CHECK(ctx);
   PLG_CUDA(cudaMemcpyAsync(ctx->result_host, ctx->result_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (persite_lnl)
-    PLG_CUDA(cudaMemcpyAsync(persite_lnl, ctx->persite_dev, (size_t)ctx->d.sites * sizeof(double),
+    PLG_CUDA(cudaMemcpyAsync(persite_lnl, ctx->persite_dev, (size_t)ctx->active_sites * sizeof(double),
                              cudaMemcpyDeviceToHost, ctx->stream));
   PLG_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->stats.d2h_bytes += sizeof(double) + (persite_lnl ? (size_t)ctx->d.sites * sizeof(double) : 0);
+  ctx->stats.d2h_bytes += sizeof(double) + (persite_lnl ? (size_t)ctx->active_sites * sizeof(double) : 0);
   *logl_out = ctx->result_host[0];
   return PLG_OK;
 }
@@ -500,7 +500,7 @@ int plg_gen_derivatives(plg_context * ctx, const double * sumtable, const double
                         double * d_f, double * dd_f)
 {
   const unsigned int R = ctx->d.rate_cats, K = ctx->d.states, Kp = ctx->d.states_padded;
-  const unsigned int nblocks = (ctx->d.sites + PLG_GEN_THREADS - 1) / PLG_GEN_THREADS;
+  const unsigned int nblocks = (ctx->active_sites + PLG_GEN_THREADS - 1) / PLG_GEN_THREADS;
   int rc = plg_ensure_partials(ctx, 2 * (size_t)nblocks);
   if (rc) return rc;
   bool any_pinv = false;
@@ -518,7 +518,7 @@ int plg_gen_derivatives(plg_context * ctx, const double * sumtable, const double
   if (!d_diag || !d_rw || !d_pinv || !d_freqs) return PLG_E_CUDA;
   k_gen_derivatives<<<nblocks, PLG_GEN_THREADS, 0, ctx->stream>>>(
       sumtable, d_diag, d_rw, d_pinv, d_freqs, ctx->weights, ctx->has_invariant ? ctx->invariant : NULL,
-      ctx->d.sites, R, K, Kp, ctx->partials, ctx->counter, ctx->result_dev);
+      ctx->active_sites, R, K, Kp, ctx->partials, ctx->counter, ctx->result_dev);
   PLG_LAUNCH_CHECK(ctx);
   PLG_CUDA(cudaMemcpyAsync(ctx->result_host, ctx->result_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost,
                            ctx->stream));

@@ -76,6 +76,7 @@ struct plg_context
 
   bool pattern_tip;
   bool rate_scalers;
+  unsigned int active_sites; /* leading sites the lnL / derivative reductions cover */
 
   size_t span;          /* rate_cats * states_padded (doubles per site of a CLV)          */
   size_t clv_stride;    /* doubles between consecutive CLV slots                          */

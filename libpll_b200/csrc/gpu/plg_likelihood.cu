@@ -445,12 +445,12 @@ static int fill_params(plg_context * ctx, const double * freqs, const double * r
 
 static int common_args(plg_context * ctx, LnlArgs & a, double * persite_lnl, unsigned int * nblocks)
 {
-  const unsigned int nelem = ctx->d.sites * ctx->d.rate_cats;
+  const unsigned int nelem = ctx->active_sites * ctx->d.rate_cats;
   *nblocks = (nelem + PLG_LNL_THREADS - 1) / PLG_LNL_THREADS;
   int rc = plg_ensure_partials(ctx, *nblocks);
   if (rc) return rc;
   if (persite_lnl && !ctx->persite_dev)
-    PLG_CUDA(cudaMalloc(&ctx->persite_dev, (size_t)ctx->d.sites * sizeof(double)));
+    PLG_CUDA(cudaMalloc(&ctx->persite_dev, (size_t)ctx->active_sites * sizeof(double)));
   a.weights = ctx->weights;
   a.invariant = ctx->invariant;
   a.persite = persite_lnl ? ctx->persite_dev : NULL;
@@ -469,9 +469,9 @@ static int fetch_result(plg_context * ctx, double * persite_lnl, double * logl_o
   ctx->stats.d2h_bytes += sizeof(double);
   if (persite_lnl)
   {
-    PLG_CUDA(cudaMemcpyAsync(persite_lnl, ctx->persite_dev, (size_t)ctx->d.sites * sizeof(double),
+    PLG_CUDA(cudaMemcpyAsync(persite_lnl, ctx->persite_dev, (size_t)ctx->active_sites * sizeof(double),
                              cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->stats.d2h_bytes += (size_t)ctx->d.sites * sizeof(double);
+    ctx->stats.d2h_bytes += (size_t)ctx->active_sites * sizeof(double);
   }
   PLG_CUDA(cudaStreamSynchronize(ctx->stream));
   *logl_out = ctx->result_host[0];

@@ -113,8 +113,7 @@ PLL_EXPORT int pll_compute_likelihood_derivatives(pll_partition_t * partition,
   pll_partition_t * p = &g->pub;
   const unsigned int R = p->rate_cats, K = p->states, Kp = p->states_padded;
   unsigned int i, j;
-  (void)parent_scaler_index; /* site scalers cancel in L'/L; the reference only needs them */
-  (void)child_scaler_index;  /* for the ascertainment-bias terms                           */
+  /* site scalers cancel in L'/L; only the ascertainment-bias terms below use them */
 
   double * buf = (double *)calloc((size_t)R * K * 4 + (size_t)R * Kp + 2 * R, sizeof(double));
   if (!buf) return pll_fail(PLL_ERROR_MEM_ALLOC, "Cannot allocate memory for diagptable");
@@ -139,8 +138,18 @@ PLL_EXPORT int pll_compute_likelihood_derivatives(pll_partition_t * partition,
     }
   }
 
-  int rc = plg_likelihood_derivatives(g->ctx, sumtable, diagp, p->rate_weights, pinv, freqs,
-                                      d_f, dd_f);
+  /* ascertainment bias (reference src/core_derivatives.c:536-545, 654-727): Stamatakis simply
+   * extends the weighted sum over the per-state sites; Lewis / Felsenstein add a term built
+   * from the per-state site likelihoods */
+  const int ab = (int)(p->attributes & PLL_ATTRIB_AB_MASK);
+  int rc = PLG_OK;
+  if (ab == PLL_ATTRIB_AB_STAMATAKIS) rc = plg_set_active_sites(g->ctx, p->sites + K);
+  if (!rc)
+    rc = plg_likelihood_derivatives(g->ctx, sumtable, diagp, p->rate_weights, pinv, freqs, d_f, dd_f);
+  if (ab == PLL_ATTRIB_AB_STAMATAKIS) plg_set_active_sites(g->ctx, p->sites);
+  int ok = rc ? pllg_fail(rc, "pll_compute_likelihood_derivatives") : PLL_SUCCESS;
+  if (ok && ab && ab != PLL_ATTRIB_AB_STAMATAKIS)
+    ok = pllg_asc_derivatives(g, parent_scaler_index, child_scaler_index, diagp, sumtable, d_f, dd_f);
   free(buf);
-  return rc ? pllg_fail(rc, "pll_compute_likelihood_derivatives") : PLL_SUCCESS;
+  return ok;
 }

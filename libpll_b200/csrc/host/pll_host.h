@@ -33,6 +33,16 @@ static inline pllg_partition_t * pllg_from(const pll_partition_t * p)
   return (g && g->magic == PLLG_MAGIC) ? g : NULL;
 }
 
+/* ascertainment-bias epilogues (pll_ascbias.c) */
+double pllg_asc_root(pllg_partition_t * g, unsigned int clv_index, int scaler_index,
+                     const unsigned int * freqs_indices);
+double pllg_asc_edge(pllg_partition_t * g, unsigned int parent_clv_index, int parent_scaler_index,
+                     unsigned int child_clv_index, int child_scaler_index, unsigned int matrix_index,
+                     const unsigned int * freqs_indices);
+int pllg_asc_derivatives(pllg_partition_t * g, int parent_scaler_index, int child_scaler_index,
+                         const double * diagptable, const double * sumtable_key, double * d_f,
+                         double * dd_f);
+
 /* sets pll_errno / pll_errmsg from a PLG_E_* code + plg_last_error(); returns PLL_FAILURE */
 int pllg_fail(int plg_rc, const char * where);
 /* sets pll_errno / pll_errmsg from a format; returns PLL_FAILURE */

@@ -69,6 +69,8 @@ PLL_EXPORT double pll_compute_root_loglikelihood(pll_partition_t * partition,
     pllg_fail(rc, "pll_compute_root_loglikelihood");
     return -INFINITY;
   }
+  if (g->pub.attributes & PLL_ATTRIB_AB_MASK)
+    logl += pllg_asc_root(g, clv_index, scaler_index, freqs_indices);
   return logl;
 }
 
@@ -104,5 +106,8 @@ PLL_EXPORT double pll_compute_edge_loglikelihood(pll_partition_t * partition,
     pllg_fail(rc, "pll_compute_edge_loglikelihood");
     return -INFINITY;
   }
+  if (g->pub.attributes & PLL_ATTRIB_AB_MASK)
+    logl += pllg_asc_edge(g, parent_clv_index, parent_scaler_index, child_clv_index, child_scaler_index,
+                          matrix_index, freqs_indices);
   return logl;
 }

@@ -328,7 +328,7 @@ PLL_EXPORT int pll_update_invariant_sites(pll_partition_t * partition)
   pllg_partition_t * g = pllg_from(partition);
   if (!g) return pll_fail(PLL_ERROR_PARAM_INVALID, "Not a GPU partition.");
   pll_partition_t * p = &g->pub;
-  if (!p->invariant && !(p->invariant = (int *)malloc((size_t)p->sites * sizeof(int))))
+  if (!p->invariant && !(p->invariant = (int *)malloc((size_t)g->sites_alloc * sizeof(int))))
     return pll_fail(PLL_ERROR_MEM_ALLOC, "Cannot allocate charmap for invariant sites array.");
   int rc = plg_update_invariant(g->ctx, p->invariant);
   return rc ? pllg_fail(rc, "pll_update_invariant_sites") : PLL_SUCCESS;
@@ -368,7 +368,7 @@ PLL_EXPORT unsigned int pll_count_invariant_sites(pll_partition_t * partition,
   if (!inv)
   {
     pllg_partition_t * g = pllg_from(partition);
-    if (!g || !(tmp = (int *)malloc((size_t)p->sites * sizeof(int)))) return 0;
+    if (!g || !(tmp = (int *)malloc((size_t)g->sites_alloc * sizeof(int)))) return 0;
     if (plg_update_invariant(g->ctx, tmp))
     {
       free(tmp);

@@ -148,10 +148,12 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips,
     pll_fail(PLL_ERROR_PARAM_INVALID, "Multiple architecture flags specified.");
     return NULL;
   }
-  if (attributes & (PLL_ATTRIB_AB_MASK | PLL_ATTRIB_AB_FLAG))
+  if ((attributes & (PLL_ATTRIB_AB_MASK | PLL_ATTRIB_AB_FLAG)) && (attributes & PLL_ATTRIB_RATE_SCALERS))
   {
+    /* the reference indexes the scalers of the per-state sites per SITE (src/likelihood.c:91,
+     * src/core_derivatives.c:684-685), which is meaningless for per-rate arrays */
     pll_fail(PLL_ERROR_GPU_UNSUPPORTED,
-             "Ascertainment-bias correction is not implemented by the GPU backend yet.");
+             "Ascertainment-bias correction cannot be combined with per-rate scalers.");
     return NULL;
   }
   if (rate_matrices == 0 || rate_cats == 0 || states == 0 || sites == 0)
@@ -183,8 +185,9 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips,
   /* 256-bit device accesses want a multiple of 4 doubles per (site, rate): same padding rule
    * as the AVX layouts (reference src/pll.c:440-453) */
   p->states_padded = (states + 3) & 0xFFFFFFFCu;
-  p->asc_bias_alloc = 0;
-  g->sites_alloc = sites;
+  /* ascertainment-bias storage: `states` extra sites (reference src/pll.c:492-495) */
+  p->asc_bias_alloc = (attributes & (PLL_ATTRIB_AB_MASK | PLL_ATTRIB_AB_FLAG)) != 0;
+  g->sites_alloc = p->asc_bias_alloc ? sites + states : sites;
   const unsigned int Kp = p->states_padded;
 
   /* ---- device state ---- */
@@ -252,6 +255,19 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips,
   }
   for (i = 0; i < rate_cats; ++i) p->rate_weights[i] = 1.0 / rate_cats;
   for (i = 0; i < sites; ++i) p->pattern_weights[i] = 1;
+  for (i = sites; i < g->sites_alloc; ++i) p->pattern_weights[i] = 0;
+  if (p->asc_bias_alloc)
+  {
+    /* reductions cover the real sites; the per-state sites only feed the correction terms */
+    rc = plg_set_active_sites(g->ctx, sites);
+    if (!rc) rc = plg_set_pattern_weights(g->ctx, p->pattern_weights);
+    if (rc)
+    {
+      pllg_fail(rc, "pll_partition_create");
+      free_host(g);
+      return NULL;
+    }
+  }
   return p;
 }
 
@@ -328,6 +344,17 @@ static int merge_charmap(pll_partition_t * p, const unsigned int * map)
   return PLL_SUCCESS;
 }
 
+/* ascertainment-bias storage of a tip CLV: dummy site j is the unit vector of state j in every
+ * rate category (reference src/pll.c:942-961, 1028-1043); `clv` is zero-initialised */
+static void fill_asc_sites(const pllg_partition_t * g, double * clv)
+{
+  const pll_partition_t * p = &g->pub;
+  const size_t span = (size_t)p->rate_cats * p->states_padded;
+  for (unsigned int j = 0; j < g->sites_alloc - p->sites; ++j)
+    for (unsigned int r = 0; r < p->rate_cats; ++r)
+      clv[(size_t)(p->sites + j) * span + (size_t)r * p->states_padded + j] = 1.0;
+}
+
 static int illegal_state(char c)
 {
   return pll_fail(PLL_ERROR_TIPDATA_ILLEGALSTATE, "Illegal state code in tip \"%c\"", c);
@@ -362,6 +389,26 @@ PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition,
       g->tip_stage[i] = (p->states == 4) ? (unsigned char)c
                                          : p->charmap[(unsigned char)sequence[i]];
     }
+    /* ascertainment-bias storage: dummy site j shows the pure state j (reference
+     * src/pll.c:847-856).  Alphabets other than DNA store charmap codes, so the code whose
+     * state set is exactly {j} is looked up; the reference stores an ASCII character there
+     * (src/pll.c:885-903), which indexes past its lookup tables - not reproduced. */
+    for (j = 0; j < g->sites_alloc - p->sites; ++j)
+    {
+      if (p->states == 4)
+        g->tip_stage[p->sites + j] = (unsigned char)(1u << j);
+      else
+      {
+        unsigned int code;
+        for (code = 0; code < p->maxstates; ++code)
+          if (p->tipmap[code] == (1u << j)) break;
+        if (code == p->maxstates)
+          return pll_fail(PLL_ERROR_AB_NOSUPPORT,
+                          "The character map has no symbol for state %u alone (needed for ascertainment "
+                          "bias correction with PLL_ATTRIB_PATTERN_TIP).", j);
+        g->tip_stage[p->sites + j] = (unsigned char)code;
+      }
+    }
     if ((rc = plg_set_tipmap(g->ctx, p->tipmap, p->states == 4 ? 16u : p->maxstates)))
       return pllg_fail(rc, "pll_set_tip_states");
     if ((rc = plg_set_tipchars(g->ctx, tip_index, g->tip_stage)))
@@ -373,8 +420,9 @@ PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition,
 
   /* tips as full CLVs: 0/1 entries replicated over the rate categories */
   const size_t span = (size_t)p->rate_cats * p->states_padded;
-  double * clv = (double *)calloc((size_t)p->sites * span, sizeof(double));
+  double * clv = (double *)calloc((size_t)g->sites_alloc * span, sizeof(double));
   if (!clv) return pll_fail(PLL_ERROR_MEM_ALLOC, "Cannot allocate a host tip CLV.");
+  fill_asc_sites(g, clv);
   for (i = 0; i < p->sites; ++i)
   {
     unsigned int c = map[(unsigned char)sequence[i]];
@@ -410,8 +458,9 @@ PLL_EXPORT int pll_set_tip_clv(pll_partition_t * partition,
   if (tip_index >= p->tips) return pll_fail(PLL_ERROR_PARAM_INVALID, "Invalid tip index %u", tip_index);
 
   const size_t span = (size_t)p->rate_cats * p->states_padded;
-  double * full = (double *)calloc((size_t)p->sites * span, sizeof(double));
+  double * full = (double *)calloc((size_t)g->sites_alloc * span, sizeof(double));
   if (!full) return pll_fail(PLL_ERROR_MEM_ALLOC, "Cannot allocate a host tip CLV.");
+  fill_asc_sites(g, full);
   for (i = 0; i < p->sites; ++i)
   {
     for (j = 0; j < p->rate_cats; ++j)
