@@ -191,8 +191,10 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   PLG_CREATE_CUDA(cudaMalloc(&ctx->stage_dev, ctx->stage_size));
   PLG_CREATE_CUDA(cudaMalloc(&ctx->counter, 64 * sizeof(unsigned int)));
   PLG_CREATE_CUDA(cudaMemsetAsync(ctx->counter, 0, 64 * sizeof(unsigned int), ctx->stream));
-  PLG_CREATE_CUDA(cudaMalloc(&ctx->result_dev, 8 * sizeof(double)));
-  PLG_CREATE_CUDA(cudaHostAlloc(&ctx->result_host, 8 * sizeof(double), cudaHostAllocDefault));
+  /* scalar results (lnL, d_f, dd_f) are written by the last block straight into mapped pinned
+   * host memory: a value-returning call is launch + stream synchronise, no D2H copy */
+  PLG_CREATE_CUDA(cudaHostAlloc(&ctx->result_host, 8 * sizeof(double), cudaHostAllocMapped));
+  PLG_CREATE_CUDA(cudaHostGetDevicePointer((void **)&ctx->result_dev, ctx->result_host, 0));
 
   /* pattern weights default to 1 (reference src/pll.c:784) */
   {
@@ -238,7 +240,6 @@ extern "C" void plg_destroy(plg_context_t * ctx)
   cudaFree(ctx->tables);
   cudaFree(ctx->partials);
   cudaFree(ctx->counter);
-  cudaFree(ctx->result_dev);
   cudaFree(ctx->persite_dev);
   cudaFree(ctx->lnl_table);
   cudaFree(ctx->flush_buf);

@@ -66,73 +66,123 @@ __device__ __forceinline__ double rate_residual(bool valid, unsigned int e, cons
 /* ------------------------------------------------------------------------------------ */
 /* DNA sumtables                                                                         */
 /* ------------------------------------------------------------------------------------ */
+/* Each thread owns PLG_SUM_ITEMS elements (site, rate) of one rate category, 256 apart, and
+ * keeps that category's 4x4 left / right matrices in registers: all streaming loads of the
+ * thread are issued before the arithmetic. */
+#define PLG_SUM_ITEMS 4
+#define PLG_SUM_ITEMS_II 2
+
 template <int R>
-__global__ void __launch_bounds__(PLG_DER_THREADS) k_sumtable_ii_dna(const SumArgs a)
+__global__ void __launch_bounds__(PLG_DER_THREADS, 2) k_sumtable_ii_dna(const SumArgs a)
 {
   const unsigned int k = threadIdx.x & (R - 1);
-  const unsigned int e = blockIdx.x * PLG_DER_THREADS + threadIdx.x;
-  const bool valid = e < a.nelem;
-  const double f = rate_residual<R>(valid, e, a);
-  if (!valid) return;
-  const d4 p = ld_stream(a.clvp + (size_t)e * 4);
-  const d4 c = ld_stream(a.clvc + (size_t)e * 4);
-  const double * W = a.left + k * 16;
-  const double * V = a.right + k * 16;
-  d4 s;
-  /* left_j = (W_j . p), right_j = (V_j . c), both unfused with (a0+a1)+(a2+a3)
-   * reference src/core_derivatives_avx.c:131-185 */
-  s.x = __dmul_rn(dot4_unfused(W[0], W[1], W[2], W[3], p), dot4_unfused(V[0], V[1], V[2], V[3], c));
-  s.y = __dmul_rn(dot4_unfused(W[4], W[5], W[6], W[7], p), dot4_unfused(V[4], V[5], V[6], V[7], c));
-  s.z = __dmul_rn(dot4_unfused(W[8], W[9], W[10], W[11], p), dot4_unfused(V[8], V[9], V[10], V[11], c));
-  s.w = __dmul_rn(dot4_unfused(W[12], W[13], W[14], W[15], p), dot4_unfused(V[12], V[13], V[14], V[15], c));
-  if (f != 1.0)
+  const unsigned int base = blockIdx.x * (PLG_DER_THREADS * PLG_SUM_ITEMS_II) + threadIdx.x;
+  double W[16], V[16];
+#pragma unroll
+  for (int i = 0; i < 16; i += 4)
   {
-    s.x = __dmul_rn(s.x, f);
-    s.y = __dmul_rn(s.y, f);
-    s.z = __dmul_rn(s.z, f);
-    s.w = __dmul_rn(s.w, f);
+    const d4 w = *reinterpret_cast<const d4 *>(a.left + k * 16 + i);
+    const d4 v = *reinterpret_cast<const d4 *>(a.right + k * 16 + i);
+    W[i] = w.x; W[i + 1] = w.y; W[i + 2] = w.z; W[i + 3] = w.w;
+    V[i] = v.x; V[i + 1] = v.y; V[i + 2] = v.z; V[i + 3] = v.w;
   }
-  *reinterpret_cast<d4 *>(a.sumtable + (size_t)e * 4) = s;
+  d4 p[PLG_SUM_ITEMS_II], c[PLG_SUM_ITEMS_II];
+#pragma unroll
+  for (int u = 0; u < PLG_SUM_ITEMS_II; ++u)
+  {
+    const unsigned int e = base + u * PLG_DER_THREADS;
+    if (e < a.nelem)
+    {
+      p[u] = ld_stream(a.clvp + (size_t)e * 4);
+      c[u] = ld_stream(a.clvc + (size_t)e * 4);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < PLG_SUM_ITEMS_II; ++u)
+  {
+    const unsigned int e = base + u * PLG_DER_THREADS;
+    const bool valid = e < a.nelem; /* warp-uniform up to the last warp; shuffles inside */
+    const double f = rate_residual<R>(valid, e, a);
+    if (!valid) continue;
+    d4 s;
+    /* left_j = (W_j . p), right_j = (V_j . c), both unfused with (a0+a1)+(a2+a3)
+     * reference src/core_derivatives_avx.c:131-185 */
+    s.x = __dmul_rn(dot4_unfused(W[0], W[1], W[2], W[3], p[u]), dot4_unfused(V[0], V[1], V[2], V[3], c[u]));
+    s.y = __dmul_rn(dot4_unfused(W[4], W[5], W[6], W[7], p[u]), dot4_unfused(V[4], V[5], V[6], V[7], c[u]));
+    s.z = __dmul_rn(dot4_unfused(W[8], W[9], W[10], W[11], p[u]), dot4_unfused(V[8], V[9], V[10], V[11], c[u]));
+    s.w = __dmul_rn(dot4_unfused(W[12], W[13], W[14], W[15], p[u]), dot4_unfused(V[12], V[13], V[14], V[15], c[u]));
+    if (f != 1.0)
+    {
+      s.x = __dmul_rn(s.x, f);
+      s.y = __dmul_rn(s.y, f);
+      s.z = __dmul_rn(s.z, f);
+      s.w = __dmul_rn(s.w, f);
+    }
+    st_stream(a.sumtable + (size_t)e * 4, s);
+  }
 }
 
 template <int R>
 __global__ void __launch_bounds__(PLG_DER_THREADS) k_sumtable_ti_dna(const SumArgs a)
 {
   const unsigned int k = threadIdx.x & (R - 1);
-  const unsigned int e = blockIdx.x * PLG_DER_THREADS + threadIdx.x;
-  const bool valid = e < a.nelem;
-  const double f = rate_residual<R>(valid, e, a);
-  if (!valid) return;
-  const d4 c = ld_stream(a.clvp + (size_t)e * 4);
-  const unsigned int code = __ldg(a.tip + e / R);
-  const double * L = a.left + ((size_t)code * R + k) * 4;
-  const double * V = a.right + k * 16;
-  /* right_j accumulates sequentially over the child states (reference
-   * src/core_derivatives_avx.c:611-620: broadcast clvc[k] times column k of V^T) */
-  double r[4];
+  const unsigned int base = blockIdx.x * (PLG_DER_THREADS * PLG_SUM_ITEMS) + threadIdx.x;
+  double V[16];
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int i = 0; i < 16; i += 4)
   {
-    double acc = 0.0;
-    acc = __dadd_rn(acc, __dmul_rn(V[j * 4 + 0], c.x));
-    acc = __dadd_rn(acc, __dmul_rn(V[j * 4 + 1], c.y));
-    acc = __dadd_rn(acc, __dmul_rn(V[j * 4 + 2], c.z));
-    acc = __dadd_rn(acc, __dmul_rn(V[j * 4 + 3], c.w));
-    r[j] = acc;
+    const d4 v = *reinterpret_cast<const d4 *>(a.right + k * 16 + i);
+    V[i] = v.x; V[i + 1] = v.y; V[i + 2] = v.z; V[i + 3] = v.w;
   }
-  d4 s;
-  s.x = __dmul_rn(L[0], r[0]);
-  s.y = __dmul_rn(L[1], r[1]);
-  s.z = __dmul_rn(L[2], r[2]);
-  s.w = __dmul_rn(L[3], r[3]);
-  if (f != 1.0)
+  d4 cl[PLG_SUM_ITEMS];
+  unsigned int code[PLG_SUM_ITEMS];
+#pragma unroll
+  for (int u = 0; u < PLG_SUM_ITEMS; ++u)
   {
-    s.x = __dmul_rn(s.x, f);
-    s.y = __dmul_rn(s.y, f);
-    s.z = __dmul_rn(s.z, f);
-    s.w = __dmul_rn(s.w, f);
+    const unsigned int e = base + u * PLG_DER_THREADS;
+    code[u] = 0;
+    if (e < a.nelem)
+    {
+      cl[u] = ld_stream(a.clvp + (size_t)e * 4);
+      code[u] = __ldg(a.tip + e / R);
+    }
   }
-  *reinterpret_cast<d4 *>(a.sumtable + (size_t)e * 4) = s;
+#pragma unroll
+  for (int u = 0; u < PLG_SUM_ITEMS; ++u)
+  {
+    const unsigned int e = base + u * PLG_DER_THREADS;
+    const bool valid = e < a.nelem;
+    const double f = rate_residual<R>(valid, e, a);
+    if (!valid) continue;
+    const d4 c = cl[u];
+    const d4 L = *reinterpret_cast<const d4 *>(a.left + ((size_t)code[u] * R + k) * 4);
+    /* right_j accumulates sequentially over the child states (reference
+     * src/core_derivatives_avx.c:611-620: broadcast clvc[k] times column k of V^T) */
+    double r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+      double acc = 0.0;
+      acc = __dadd_rn(acc, __dmul_rn(V[j * 4 + 0], c.x));
+      acc = __dadd_rn(acc, __dmul_rn(V[j * 4 + 1], c.y));
+      acc = __dadd_rn(acc, __dmul_rn(V[j * 4 + 2], c.z));
+      acc = __dadd_rn(acc, __dmul_rn(V[j * 4 + 3], c.w));
+      r[j] = acc;
+    }
+    d4 s;
+    s.x = __dmul_rn(L.x, r[0]);
+    s.y = __dmul_rn(L.y, r[1]);
+    s.z = __dmul_rn(L.z, r[2]);
+    s.w = __dmul_rn(L.w, r[3]);
+    if (f != 1.0)
+    {
+      s.x = __dmul_rn(s.x, f);
+      s.y = __dmul_rn(s.y, f);
+      s.z = __dmul_rn(s.z, f);
+      s.w = __dmul_rn(s.w, f);
+    }
+    st_stream(a.sumtable + (size_t)e * 4, s);
+  }
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -268,15 +318,19 @@ struct DerArgs
   unsigned int nelem;
 };
 
-/* Persistent: a few CTAs per SM walk the (site, rate) elements with a grid stride, every
- * thread keeping its running d_f / dd_f in registers; one deterministic block tree at the
- * end and a last-block final sum (fixed grid => bit-reproducible).  A Newton iteration is
- * latency-bound (132 B per pattern), so the kernel is a single launch with no atomics on
- * doubles and two loads in flight per thread. */
+/* Persistent: as many CTAs as are resident walk the (site, rate) elements with a grid stride,
+ * every thread keeping its running d_f / dd_f in registers; one deterministic block tree at
+ * the end and a last-block final sum (fixed grid => bit-reproducible).  A Newton iteration
+ * moves only 132 B per pattern, so latency decides: each trip issues the streaming loads of
+ * U elements (and of their pattern weights / invariant indices) before any arithmetic. */
+template <int K> struct DerUnroll { static constexpr int U = (K == 4) ? 4 : 1; };
+
 template <int R, int K>
-__global__ void __launch_bounds__(PLG_DER_THREADS)
+__global__ void __launch_bounds__(PLG_DER_THREADS, 2)
 k_derivatives(const DerArgs a, const __grid_constant__ DerParams P)
 {
+  constexpr int U = DerUnroll<K>::U;
+  constexpr int SV = (K == 4) ? 4 : 20;
   const unsigned int lane = threadIdx.x & 31u;
   const unsigned int k = lane & (R - 1);
   const unsigned int gbase = lane & ~(unsigned int)(R - 1);
@@ -296,9 +350,61 @@ k_derivatives(const DerArgs a, const __grid_constant__ DerParams P)
   /* all lanes of a warp run the same number of iterations (shuffles inside) */
   const unsigned int first = blockIdx.x * PLG_DER_THREADS + threadIdx.x;
   const unsigned int warp_first = first - lane;
-  for (unsigned int e0 = warp_first; e0 < a.nelem; e0 += stride)
+  /* software pipeline: the loads of trip t+1 are in flight while trip t is being reduced */
+  double nsv[U][SV];
+  unsigned int nwgt[U];
+  int ninvs[U];
+  auto issue_loads = [&](unsigned int e00)
   {
-    const unsigned int e = e0 + lane;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const unsigned int e = e00 + u * stride + lane;
+      nwgt[u] = 0;
+      ninvs[u] = -1;
+      if (e < a.nelem)
+      {
+        if (K == 4)
+        {
+          const d4 s = ld_stream(a.sumtable + (size_t)e * 4);
+          nsv[u][0] = s.x; nsv[u][1] = s.y; nsv[u][2] = s.z; nsv[u][3] = s.w;
+        }
+        else
+        {
+#pragma unroll
+          for (int b = 0; b < 5; ++b)
+          {
+            const d4 s = ld_stream(a.sumtable + (size_t)e * 20 + 4 * b);
+            nsv[u][4 * b] = s.x; nsv[u][4 * b + 1] = s.y; nsv[u][4 * b + 2] = s.z; nsv[u][4 * b + 3] = s.w;
+          }
+        }
+        if (k == 0)
+        {
+          nwgt[u] = __ldg(a.weights + e / R);
+          if (P.use_pinv && a.invariant) ninvs[u] = __ldg(a.invariant + e / R);
+        }
+      }
+    }
+  };
+  if (warp_first < a.nelem) issue_loads(warp_first);
+  for (unsigned int e00 = warp_first; e00 < a.nelem; e00 += stride * U)
+  {
+    double sv[U][SV];
+    unsigned int wgt[U];
+    int invs[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      wgt[u] = nwgt[u];
+      invs[u] = ninvs[u];
+#pragma unroll
+      for (int j = 0; j < SV; ++j) sv[u][j] = nsv[u][j];
+    }
+    if (e00 + stride * U < a.nelem) issue_loads(e00 + stride * U);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+    const unsigned int e = e00 + u * stride + lane;
     const bool valid = e < a.nelem;
     double c0 = 0.0, c1 = 0.0, c2 = 0.0;
     if (valid)
@@ -307,34 +413,30 @@ k_derivatives(const DerArgs a, const __grid_constant__ DerParams P)
       {
         /* lanes (L, L', L'') accumulate fma(sum_j, diagp_j, acc) over the 4 states in order
          * reference src/core_derivatives_avx2.c:634-655 */
-        const d4 s = ld_stream(a.sumtable + (size_t)e * 4);
-        const double sv[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j)
         {
-          c0 = __fma_rn(sv[j], dg[j * 3 + 0], c0);
-          c1 = __fma_rn(sv[j], dg[j * 3 + 1], c1);
-          c2 = __fma_rn(sv[j], dg[j * 3 + 2], c2);
+          c0 = __fma_rn(sv[u][j], dg[j * 3 + 0], c0);
+          c1 = __fma_rn(sv[u][j], dg[j * 3 + 1], c1);
+          c2 = __fma_rn(sv[u][j], dg[j * 3 + 2], c2);
         }
       }
       else
       {
         /* blocked: first block by mul, the other four by fma, then hadd
          * reference src/core_derivatives_avx2.c:656-702 */
-        double s[20];
-        load20d(a.sumtable + (size_t)e * 20, s);
         const double * d = a.diagp + k * 60;
         double acc[3][4];
 #pragma unroll
         for (int x = 0; x < 3; ++x)
         {
 #pragma unroll
-          for (int l = 0; l < 4; ++l) acc[x][l] = __dmul_rn(s[l], __ldg(d + x * 20 + l));
+          for (int l = 0; l < 4; ++l) acc[x][l] = __dmul_rn(sv[u][l], __ldg(d + x * 20 + l));
 #pragma unroll
           for (int b = 1; b < 5; ++b)
 #pragma unroll
             for (int l = 0; l < 4; ++l)
-              acc[x][l] = __fma_rn(s[4 * b + l], __ldg(d + x * 20 + 4 * b + l), acc[x][l]);
+              acc[x][l] = __fma_rn(sv[u][4 * b + l], __ldg(d + x * 20 + 4 * b + l), acc[x][l]);
         }
         c0 = hsum4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
         c1 = hsum4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
@@ -343,8 +445,7 @@ k_derivatives(const DerArgs a, const __grid_constant__ DerParams P)
     }
 
     /* combine the rates of a site in order (reference src/core_derivatives_avx2.c:704-729) */
-    int inv = -1;
-    if (P.use_pinv && valid && k == 0 && a.invariant) inv = a.invariant[e / R];
+    const int inv = invs[u];
     double l0 = 0.0, l1 = 0.0, l2 = 0.0;
 #pragma unroll
     for (int kk = 0; kk < R; ++kk)
@@ -383,9 +484,10 @@ k_derivatives(const DerArgs a, const __grid_constant__ DerParams P)
       const double recip = __ddiv_rn(1.0, l0);
       const double d1 = __dmul_rn(l1, recip);
       const double d2 = __dsub_rn(__dmul_rn(d1, d1), __dmul_rn(l2, recip));
-      const double w = (double)a.weights[e / R];
+      const double w = (double)wgt[u];
       df = __dsub_rn(df, __dmul_rn(d1, w));
       ddf = __dadd_rn(ddf, __dmul_rn(d2, w));
+    }
     }
   }
 
@@ -425,6 +527,159 @@ k_derivatives(const DerArgs a, const __grid_constant__ DerParams P)
       *a.counter = 0u;
     }
   }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* DNA derivatives: one thread per pattern                                               */
+/* ------------------------------------------------------------------------------------ */
+/* The (site, rate)-per-thread mapping above spends most of its instructions on shuffles and
+ * predication (measured: issue-bound at 2.7 TB/s).  For 4 states a whole pattern is only
+ * R x 32 bytes, so one thread takes a pattern: R 256-bit loads, 12 R FMAs against diagptable
+ * entries that are immediate constant-bank operands (kernel parameter), one division.  Same
+ * operation order as above / the reference (src/core_derivatives_avx2.c:634-766). */
+struct DerDnaParams
+{
+  double diag[PLG_MAX_RATES * 12]; /* [rate][state][3] */
+  double invar_lk[PLG_MAX_RATES * 4];
+  double rate_weights[PLG_MAX_RATES];
+  double prop_invar[PLG_MAX_RATES];
+  int use_pinv;
+  int eq_weights;
+};
+
+#ifndef PLG_DERDNA_U
+#define PLG_DERDNA_U 1
+#endif
+#ifndef PLG_DERDNA_MINB
+#define PLG_DERDNA_MINB 2
+#endif
+template <int R>
+__global__ void __launch_bounds__(PLG_DER_THREADS, (R <= 4) ? PLG_DERDNA_MINB : 1)
+k_derivatives_dna(const DerArgs a, const __grid_constant__ DerDnaParams P)
+{
+  constexpr int U = (R <= 4) ? PLG_DERDNA_U : 1;
+  const unsigned int sites = a.nelem / R;
+  const unsigned int stride = gridDim.x * PLG_DER_THREADS;
+  double df = 0.0, ddf = 0.0;
+  for (unsigned int n0 = blockIdx.x * PLG_DER_THREADS + threadIdx.x; n0 < sites; n0 += stride * U)
+  {
+    d4 sv[U][R];
+    unsigned int wgt[U];
+    int inv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const unsigned int n = n0 + u * stride;
+      wgt[u] = 0;
+      inv[u] = -1;
+      if (n < sites)
+      {
+#pragma unroll
+        for (int r = 0; r < R; ++r) sv[u][r] = ld_stream(a.sumtable + ((size_t)n * R + r) * 4);
+        wgt[u] = __ldg(a.weights + n);
+        if (P.use_pinv && a.invariant) inv[u] = __ldg(a.invariant + n);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      if (n0 + u * stride >= sites) continue;
+      double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+      {
+        const double s[4] = {sv[u][r].x, sv[u][r].y, sv[u][r].z, sv[u][r].w};
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+          v0 = __fma_rn(s[j], P.diag[r * 12 + j * 3 + 0], v0);
+          v1 = __fma_rn(s[j], P.diag[r * 12 + j * 3 + 1], v1);
+          v2 = __fma_rn(s[j], P.diag[r * 12 + j * 3 + 2], v2);
+        }
+        if (P.use_pinv && P.prop_invar[r] > 0.0)
+        {
+          const double q = __dsub_rn(1.0, P.prop_invar[r]);
+          v0 = __dmul_rn(v0, q);
+          v1 = __dmul_rn(v1, q);
+          v2 = __dmul_rn(v2, q);
+          if (inv[u] != -1) v0 = __dadd_rn(v0, P.invar_lk[r * 4 + inv[u]]);
+        }
+        if (P.eq_weights)
+        {
+          l0 = __dadd_rn(l0, v0);
+          l1 = __dadd_rn(l1, v1);
+          l2 = __dadd_rn(l2, v2);
+        }
+        else
+        {
+          l0 = __fma_rn(v0, P.rate_weights[r], l0);
+          l1 = __fma_rn(v1, P.rate_weights[r], l1);
+          l2 = __fma_rn(v2, P.rate_weights[r], l2);
+        }
+      }
+      const double recip = __ddiv_rn(1.0, l0);
+      const double d1 = __dmul_rn(l1, recip);
+      const double d2 = __dsub_rn(__dmul_rn(d1, d1), __dmul_rn(l2, recip));
+      const double w = (double)wgt[u];
+      df = __dsub_rn(df, __dmul_rn(d1, w));
+      ddf = __dadd_rn(ddf, __dmul_rn(d2, w));
+    }
+  }
+
+  __shared__ double red[PLG_DER_THREADS / 32];
+  __shared__ bool is_last;
+  const double s1 = block_sum<PLG_DER_THREADS>(df, red);
+  const double s2 = block_sum<PLG_DER_THREADS>(ddf, red);
+  if (threadIdx.x == 0)
+  {
+    a.partials[2 * blockIdx.x + 0] = s1;
+    a.partials[2 * blockIdx.x + 1] = s2;
+    __threadfence();
+    is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last)
+  {
+    __threadfence();
+    const unsigned int nb = gridDim.x;
+    const unsigned int per = (nb + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
+    const unsigned int lo = threadIdx.x * per;
+    const unsigned int hi = (lo + per < nb) ? lo + per : nb;
+    double t1 = 0.0, t2 = 0.0;
+    for (unsigned int b = lo; b < hi; ++b)
+    {
+      t1 = __dadd_rn(t1, __ldcg(a.partials + 2 * b));
+      t2 = __dadd_rn(t2, __ldcg(a.partials + 2 * b + 1));
+    }
+    const double r1 = block_sum<PLG_DER_THREADS>(t1, red);
+    const double r2 = block_sum<PLG_DER_THREADS>(t2, red);
+    if (threadIdx.x == 0)
+    {
+      a.result[0] = r1;
+      a.result[1] = r2;
+      *a.counter = 0u;
+    }
+  }
+}
+
+template <int R>
+static int launch_derivatives_dna(plg_context * ctx, const DerArgs & a, const DerDnaParams & P)
+{
+  /* one resident wave: the grid is fixed for a given device, so results are reproducible */
+  static int per_sm = 0;
+  if (!per_sm)
+    PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_derivatives_dna<R>, PLG_DER_THREADS, 0));
+  const unsigned int sites = a.nelem / R;
+  unsigned int nblocks = (sites + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
+  const unsigned int cap = (unsigned int)(ctx->sm_count * (per_sm > 0 ? per_sm : 1));
+  if (nblocks > cap) nblocks = cap;
+  int rc = plg_ensure_partials(ctx, 2 * (size_t)nblocks);
+  if (rc) return rc;
+  DerArgs b = a;
+  b.partials = ctx->partials;
+  k_derivatives_dna<R><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(b, P);
+  return PLG_OK;
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -514,6 +769,8 @@ extern "C" int plg_update_sumtable(plg_context_t * ctx, unsigned int parent_clv_
   }
   const unsigned int nelem = ctx->d.sites * R;
   const unsigned int nblocks = (nelem + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
+  const unsigned int nblocks_dna =
+      (nelem + PLG_DER_THREADS * PLG_SUM_ITEMS - 1) / (PLG_DER_THREADS * PLG_SUM_ITEMS);
 
   SumArgs a;
   memset(&a, 0, sizeof(a));
@@ -526,10 +783,43 @@ extern "C" int plg_update_sumtable(plg_context_t * ctx, unsigned int parent_clv_
   const bool ti = ptip || ctip;
   const size_t codes = (K == 4) ? 16u : ctx->maxstates;
   const size_t left_bytes = ti ? codes * R * K * sizeof(double) : mat_bytes;
-  if (plg_stage_reserve(ctx, mat_bytes + left_bytes + 1024)) return PLG_E_CUDA;
+  if (plg_stage_reserve(ctx, mat_bytes + left_bytes + 2048)) return PLG_E_CUDA;
   a.right = (const double *)plg_stage(ctx, eigenvecs, mat_bytes);
   a.left = (const double *)plg_stage(ctx, left_table, left_bytes);
   if (!a.right || !a.left) return PLG_E_CUDA;
+
+  /* Without per-rate residuals the table is one CLV-update-shaped operation: DNA inner-inner
+   * is bit-identical to the streaming kernel's arithmetic; 20 states go to the tensor-core
+   * kernels (unless the bit-exact vector path was asked for).  The DNA tip-inner table keeps
+   * its own kernel: the reference sums the child states sequentially there. */
+  if (!ctx->rate_scalers && ((K == 4 && !ti) || (K == 20 && !ctx->aa_exact)))
+  {
+    DevOp op;
+    memset(&op, 0, sizeof(op));
+    op.parent = a.sumtable;
+    if (ti)
+    {
+      op.right = plg_clv_ptr(ctx, ptip ? child_clv_index : parent_clv_index);
+      op.ltip = plg_tip_ptr(ctx, ptip ? parent_clv_index : child_clv_index);
+    }
+    else
+    {
+      op.left = plg_clv_ptr(ctx, parent_clv_index);
+      op.right = plg_clv_ptr(ctx, child_clv_index);
+    }
+    op.lmat = a.left;
+    op.rmat = a.right;
+    rc = plg_launch_single_op(ctx, ti ? PLG_KIND_TI : PLG_KIND_II, op);
+    if (rc) return rc;
+    if (host_copy)
+    {
+      const size_t bytes = (size_t)ctx->d.sites * ctx->span * sizeof(double);
+      PLG_CUDA(cudaMemcpyAsync(host_copy, a.sumtable, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+      ctx->stats.d2h_bytes += bytes;
+    }
+    return PLG_OK;
+  }
 
   if (ti)
   {
@@ -540,7 +830,7 @@ extern "C" int plg_update_sumtable(plg_context_t * ctx, unsigned int parent_clv_
     a.pscale = plg_scaler_ptr(ctx, ptip ? child_scaler_index : parent_scaler_index);
     if (K == 4)
     {
-      PLG_DISPATCH_R(R, (k_sumtable_ti_dna<RR><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(a)));
+      PLG_DISPATCH_R(R, (k_sumtable_ti_dna<RR><<<nblocks_dna, PLG_DER_THREADS, 0, ctx->stream>>>(a)));
     }
     else
     {
@@ -565,7 +855,9 @@ extern "C" int plg_update_sumtable(plg_context_t * ctx, unsigned int parent_clv_
     a.cscale = plg_scaler_ptr(ctx, child_scaler_index);
     if (K == 4)
     {
-      PLG_DISPATCH_R(R, (k_sumtable_ii_dna<RR><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(a)));
+      const unsigned int nblocks_ii =
+          (nelem + PLG_DER_THREADS * PLG_SUM_ITEMS_II - 1) / (PLG_DER_THREADS * PLG_SUM_ITEMS_II);
+      PLG_DISPATCH_R(R, (k_sumtable_ii_dna<RR><<<nblocks_ii, PLG_DER_THREADS, 0, ctx->stream>>>(a)));
     }
     else
     {
@@ -623,7 +915,8 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
   const unsigned int R = ctx->d.rate_cats, K = ctx->d.states;
   const unsigned int nelem = ctx->active_sites * R;
   unsigned int nblocks = (nelem + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
-  const unsigned int cap = (unsigned int)ctx->sm_count * 8u; /* persistent: 8 CTAs per SM */
+  /* persistent: exactly the CTAs that are resident at once (one wave) */
+  const unsigned int cap = (unsigned int)ctx->sm_count * 2u;
   if (nblocks > cap) nblocks = cap;
   int rc = plg_ensure_partials(ctx, 2 * (size_t)nblocks);
   if (rc) return rc;
@@ -647,8 +940,43 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
     return PLG_E_INVALID;
   }
 
-  /* device layout of diagp: DNA keeps [R][state][4]; 20 states is transposed to
-   * [R][3][20] exactly like the reference's t_diagp (src/core_derivatives_avx2.c:598-609) */
+  if (K == 4)
+  {
+    /* everything the kernel needs besides the sumtable travels as kernel parameters */
+    DerDnaParams D;
+    memset(&D, 0, sizeof(D));
+    D.use_pinv = P.use_pinv;
+    D.eq_weights = P.eq_weights;
+    for (unsigned int i = 0; i < R; ++i)
+    {
+      D.rate_weights[i] = P.rate_weights[i];
+      D.prop_invar[i] = P.prop_invar[i];
+      for (unsigned int j = 0; j < 4; ++j)
+      {
+        D.invar_lk[i * 4 + j] = P.invar_lk[i * 4 + j];
+        for (unsigned int x = 0; x < 3; ++x) D.diag[i * 12 + j * 3 + x] = diagptable[(size_t)i * 16 + j * 4 + x];
+      }
+    }
+    DerArgs da;
+    da.sumtable = it->second;
+    da.diagp = NULL;
+    da.weights = ctx->weights;
+    da.invariant = ctx->has_invariant ? ctx->invariant : NULL;
+    da.partials = ctx->partials;
+    da.counter = ctx->counter;
+    da.result = ctx->result_dev;
+    da.nelem = nelem;
+    PLG_DISPATCH_R(R, { int lrc = launch_derivatives_dna<RR>(ctx, da, D); if (lrc) return lrc; });
+    PLG_LAUNCH_CHECK(ctx);
+    PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += 2 * sizeof(double);
+    *d_f = ctx->result_host[0];
+    *dd_f = ctx->result_host[1];
+    return PLG_OK;
+  }
+
+  /* device layout of diagp: 20 states is transposed to [R][3][20] exactly like the
+   * reference's t_diagp (src/core_derivatives_avx2.c:598-609) */
   double diag_host[PLG_MAX_RATES * 80];
   size_t diag_len;
   if (K == 4)
@@ -686,8 +1014,6 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
   }
   PLG_LAUNCH_CHECK(ctx);
 
-  PLG_CUDA(cudaMemcpyAsync(ctx->result_host, ctx->result_dev, 2 * sizeof(double),
-                           cudaMemcpyDeviceToHost, ctx->stream));
   PLG_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->stats.d2h_bytes += 2 * sizeof(double);
   *d_f = ctx->result_host[0];

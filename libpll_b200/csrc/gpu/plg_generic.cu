@@ -365,7 +365,6 @@ int plg_gen_loglikelihood(plg_context * ctx, const GenLnl & g, const double * fr
   a.use_map = ctx->d.states != 4;
   k_gen_lnl<<<nblocks, PLG_GEN_THREADS, 0, ctx->stream>>>(a);
   PLG_LAUNCH_CHECK(ctx);
-  PLG_CUDA(cudaMemcpyAsync(ctx->result_host, ctx->result_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (persite_lnl)
     PLG_CUDA(cudaMemcpyAsync(persite_lnl, ctx->persite_dev, (size_t)ctx->active_sites * sizeof(double),
                              cudaMemcpyDeviceToHost, ctx->stream));
@@ -520,8 +519,6 @@ int plg_gen_derivatives(plg_context * ctx, const double * sumtable, const double
       sumtable, d_diag, d_rw, d_pinv, d_freqs, ctx->weights, ctx->has_invariant ? ctx->invariant : NULL,
       ctx->active_sites, R, K, Kp, ctx->partials, ctx->counter, ctx->result_dev);
   PLG_LAUNCH_CHECK(ctx);
-  PLG_CUDA(cudaMemcpyAsync(ctx->result_host, ctx->result_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost,
-                           ctx->stream));
   PLG_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->stats.d2h_bytes += 2 * sizeof(double);
   *d_f = ctx->result_host[0];

@@ -110,7 +110,7 @@ struct plg_context
   double * partials;
   size_t partials_cap; /* doubles */
   unsigned int * counter; /* "last block done" ticket */
-  double * result_dev;    /* 4 doubles */
+  double * result_dev;    /* device alias of result_host (mapped) */
   double * result_host;   /* pinned, 4 doubles */
   double * persite_dev;   /* sites doubles, allocated on first use */
   double * lnl_table;     /* pi-weighted tip lookup of the edge-lnL tip-inner kernels */
@@ -161,6 +161,9 @@ struct TipmapArg
 {
   unsigned int map[PLL_ASCII_SIZE];
 };
+
+/* one operation-shaped launch on the specialised kernels (plg_partials.cu) */
+int plg_launch_single_op(plg_context * ctx, int kind, const DevOp & op);
 
 /* the generic (any state count / any number of rate categories) device path, plg_generic.cu */
 static inline bool plg_is_pow2(unsigned int v) { return v && !(v & (v - 1)); }

@@ -464,8 +464,6 @@ static int common_args(plg_context * ctx, LnlArgs & a, double * persite_lnl, uns
 
 static int fetch_result(plg_context * ctx, double * persite_lnl, double * logl_out)
 {
-  PLG_CUDA(cudaMemcpyAsync(ctx->result_host, ctx->result_dev, sizeof(double),
-                           cudaMemcpyDeviceToHost, ctx->stream));
   ctx->stats.d2h_bytes += sizeof(double);
   if (persite_lnl)
   {

@@ -1504,6 +1504,43 @@ static uint64_t fnv1a(const void * data, size_t bytes)
   return h;
 }
 
+/* One CLV-update-shaped operation outside an operations list: out = (L . a) o (R . b) per
+ * (site, rate), no scaling.  The sumtable of an inner-inner edge has exactly this shape
+ * (L = pi-weighted inverse eigenvectors, R = eigenvectors; reference
+ * src/core_derivatives_avx.c:131-185, src/core_derivatives_avx2.c:158-258), and that of a
+ * tip-inner edge the tip-inner shape, so plg_update_sumtable reuses the streaming / tensor-core
+ * kernels through this entry.  `op` holds device pointers. */
+int plg_launch_single_op(plg_context * ctx, int kind, const DevOp & op)
+{
+  const unsigned int R = ctx->d.rate_cats;
+  int rc = PLG_OK;
+  switch (R)
+  {
+    case 1: rc = set_smem_limits<1>(); break;
+    case 2: rc = set_smem_limits<2>(); break;
+    case 4: rc = set_smem_limits<4>(); break;
+    case 8: rc = set_smem_limits<8>(); break;
+    case 16: rc = set_smem_limits<16>(); break;
+    default: plg_set_error("rate_cats=%u unsupported", R); return PLG_E_UNSUPPORTED;
+  }
+  if (rc) return rc;
+  const DevOp * dev = (const DevOp *)plg_stage(ctx, &op, sizeof(DevOp));
+  if (!dev) return PLG_E_CUDA;
+  Group g{kind, 0, 0, 1, 0};
+  const unsigned int nelem = ctx->d.sites * R;
+  switch (R)
+  {
+    case 1: launch_group<1>(ctx, g, dev, nelem); break;
+    case 2: launch_group<2>(ctx, g, dev, nelem); break;
+    case 4: launch_group<4>(ctx, g, dev, nelem); break;
+    case 8: launch_group<8>(ctx, g, dev, nelem); break;
+    default: launch_group<16>(ctx, g, dev, nelem); break;
+  }
+  PLG_LAUNCH_CHECK(ctx);
+  ctx->stats.kernel_launches++;
+  return PLG_OK;
+}
+
 extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * operations,
                                    unsigned int count)
 {
