@@ -178,30 +178,147 @@ __device__ __forceinline__ void finish_sum(double v, const LnlArgs & a)
 /* ------------------------------------------------------------------------------------ */
 /* DNA kernels                                                                           */
 /* ------------------------------------------------------------------------------------ */
-template <int R>
-__global__ void __launch_bounds__(PLG_LNL_THREADS)
-k_edge_lnl_ii_dna(const LnlArgs a, const __grid_constant__ LnlParams P)
+/* One thread per pattern (a DNA pattern is only R x 32 bytes per CLV): all R rate terms, the
+ * scaler bookkeeping and the single log of a pattern stay in one thread - no shuffles, no
+ * idle lanes around the log.  Persistent grid of one resident wave; per-thread running sum,
+ * one block tree at the end.  MODE 0: edge, both ends inner; 1: edge with a pattern tip;
+ * 2: root.  Arithmetic order per rate as the reference's 4x4 AVX kernels:
+ *   edge ii  src/core_likelihood_avx.c:1166-1217   (P_row . c) * pi * p, then (t0+t1)+(t2+t3)
+ *   edge ti  src/core_likelihood_avx.c:296-300,330-345   (pi * masked row sum) * p
+ *   root     src/core_likelihood_avx.c:145-156 */
+template <int R, int MODE>
+__global__ void __launch_bounds__(PLG_LNL_THREADS, 2)
+k_lnl_dna(const LnlArgs a, const __grid_constant__ LnlParams P)
 {
-  const unsigned int k = threadIdx.x & (R - 1);
-  const unsigned int e = blockIdx.x * PLG_LNL_THREADS + threadIdx.x;
-  const bool valid = e < a.nelem;
-  double term_r = 0.0;
-  if (valid)
+  constexpr int RC = (R < 4) ? R : 4; /* rates whose loads are issued together */
+  __shared__ __align__(32) double Ms[(MODE == 2) ? 4 : ((MODE == 0) ? R * 16 : 16 * R * 4)];
+  if (MODE == 0)
+    for (unsigned int t = threadIdx.x; t < R * 16; t += PLG_LNL_THREADS) Ms[t] = __ldg(a.pmat + t);
+  if (MODE == 1)
+    for (unsigned int t = threadIdx.x; t < 16 * R * 4; t += PLG_LNL_THREADS) Ms[t] = __ldg(a.pmat + t);
+  __syncthreads();
+
+  const unsigned int sites = a.nelem / R;
+  const unsigned int stride = gridDim.x * PLG_LNL_THREADS;
+  double sum = 0.0;
+  for (unsigned int n = blockIdx.x * PLG_LNL_THREADS + threadIdx.x; n < sites; n += stride)
   {
-    const d4 p = ld_stream(a.clvp + (size_t)e * 4);
-    const d4 c = ld_stream(a.clvc + (size_t)e * 4);
-    const double * M = a.pmat + k * 16;
-    const double * f = P.freqs + k * 4;
-    /* (P_row . c), times pi, times clvp; then (t0+t1)+(t2+t3)
-     * reference src/core_likelihood_avx.c:1166-1217 */
-    const double t0 = __dmul_rn(__dmul_rn(f[0], dot4_unfused(__ldg(M + 0), __ldg(M + 1), __ldg(M + 2), __ldg(M + 3), c)), p.x);
-    const double t1 = __dmul_rn(__dmul_rn(f[1], dot4_unfused(__ldg(M + 4), __ldg(M + 5), __ldg(M + 6), __ldg(M + 7), c)), p.y);
-    const double t2 = __dmul_rn(__dmul_rn(f[2], dot4_unfused(__ldg(M + 8), __ldg(M + 9), __ldg(M + 10), __ldg(M + 11), c)), p.z);
-    const double t3 = __dmul_rn(__dmul_rn(f[3], dot4_unfused(__ldg(M + 12), __ldg(M + 13), __ldg(M + 14), __ldg(M + 15), c)), p.w);
-    term_r = hsum4(t0, t1, t2, t3);
+    const unsigned int weight = __ldg(a.weights + n);
+    const int inv = P.any_pinv ? __ldg(a.invariant + n) : -1;
+    unsigned int code = 0;
+    if (MODE == 1) code = __ldg(a.tip + n);
+
+    /* scaler counts: per-site sum, or per-rate with the site scaler = min over rates and
+     * capped residuals (reference src/core_likelihood_avx.c:1136-1154,1219-1223) */
+    unsigned int site_scalings = 0;
+    unsigned int resid[R];
+    if (a.per_rate_scaling)
+    {
+      unsigned int mn = 0xffffffffu;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+      {
+        unsigned int rs = 0;
+        if (a.pscale) rs += __ldg(a.pscale + (size_t)n * R + r);
+        if (a.cscale) rs += __ldg(a.cscale + (size_t)n * R + r);
+        resid[r] = rs;
+        mn = rs < mn ? rs : mn;
+      }
+      site_scalings = mn;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+      {
+        const unsigned int d = resid[r] - mn;
+        resid[r] = d > PLL_SCALE_RATE_MAXDIFF ? PLL_SCALE_RATE_MAXDIFF : d;
+      }
+    }
+    else
+    {
+      if (a.pscale) site_scalings += __ldg(a.pscale + n);
+      if (a.cscale) site_scalings += __ldg(a.cscale + n);
+    }
+
+    double term = 0.0;
+#pragma unroll
+    for (int r0 = 0; r0 < R; r0 += RC)
+    {
+      d4 p[RC], c[RC];
+#pragma unroll
+      for (int q = 0; q < RC; ++q)
+      {
+        p[q] = ld_stream(a.clvp + ((size_t)n * R + r0 + q) * 4);
+        if (MODE == 0) c[q] = ld_stream(a.clvc + ((size_t)n * R + r0 + q) * 4);
+      }
+#pragma unroll
+      for (int q = 0; q < RC; ++q)
+      {
+        const int r = r0 + q;
+        const double * f = P.freqs + r * 4;
+        double v;
+        if (MODE == 0)
+        {
+          const double * M = Ms + r * 16;
+          const double t0 = __dmul_rn(__dmul_rn(f[0], dot4_unfused(M[0], M[1], M[2], M[3], c[q])), p[q].x);
+          const double t1 = __dmul_rn(__dmul_rn(f[1], dot4_unfused(M[4], M[5], M[6], M[7], c[q])), p[q].y);
+          const double t2 = __dmul_rn(__dmul_rn(f[2], dot4_unfused(M[8], M[9], M[10], M[11], c[q])), p[q].z);
+          const double t3 = __dmul_rn(__dmul_rn(f[3], dot4_unfused(M[12], M[13], M[14], M[15], c[q])), p[q].w);
+          v = hsum4(t0, t1, t2, t3);
+        }
+        else if (MODE == 1)
+        {
+          const d4 l = *reinterpret_cast<const d4 *>(Ms + ((size_t)code * R + r) * 4);
+          v = hsum4(__dmul_rn(l.x, p[q].x), __dmul_rn(l.y, p[q].y), __dmul_rn(l.z, p[q].z), __dmul_rn(l.w, p[q].w));
+        }
+        else
+          v = hsum4(__dmul_rn(f[0], p[q].x), __dmul_rn(f[1], p[q].y), __dmul_rn(f[2], p[q].z), __dmul_rn(f[3], p[q].w));
+
+        if (a.per_rate_scaling && resid[r] > 0)
+        {
+          double sc = 1.0;
+          for (unsigned int i = 0; i < resid[r]; ++i) sc = __dmul_rn(sc, PLG_SCALE_THRESHOLD);
+          v = __dmul_rn(v, sc);
+        }
+        /* the edge kernels add a rate's term only if it is positive (reference
+         * src/core_likelihood_avx.c:1225); the root kernel adds it unconditionally */
+        if (MODE == 2 || v > 0.0)
+        {
+          const double pinv = P.prop_invar[r];
+          if (pinv > 0.0)
+          {
+            /* the tip-inner kernel reads the invariant frequency from the LAST rate's vector
+             * (reference src/core_likelihood_avx.c:274,370-371) */
+            const int fr = (MODE == 1) ? (R - 1) : r;
+            const double inv_lk = (inv == -1) ? 0.0 : P.freqs[fr * 4 + inv];
+            const double mix = __dadd_rn(__dmul_rn(v, __dsub_rn(1.0, pinv)), __dmul_rn(inv_lk, pinv));
+            term = __dadd_rn(term, __dmul_rn(P.rate_weights[r], mix));
+          }
+          else
+            term = __dadd_rn(term, __dmul_rn(v, P.rate_weights[r]));
+        }
+      }
+    }
+    double site_lk = log(term);
+    if (site_scalings) site_lk = __dadd_rn(site_lk, __dmul_rn((double)site_scalings, P.log_threshold));
+    site_lk = __dmul_rn(site_lk, (double)weight);
+    if (a.persite) a.persite[n] = site_lk;
+    sum = __dadd_rn(sum, site_lk);
   }
-  const double site_lk = site_epilogue<R, 4, true, false>(term_r, valid, e, a, P);
-  finish_sum<PLG_LNL_THREADS>(site_lk, a);
+  finish_sum<PLG_LNL_THREADS>(sum, a);
+}
+
+template <int R, int MODE>
+static int launch_lnl_dna(plg_context * ctx, LnlArgs & a, const LnlParams & P)
+{
+  /* one resident wave; the grid depends only on the device => reproducible sums */
+  static int per_sm = 0;
+  if (!per_sm)
+    PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lnl_dna<R, MODE>, PLG_LNL_THREADS, 0));
+  const unsigned int sites = a.nelem / R;
+  unsigned int nblocks = (sites + PLG_LNL_THREADS - 1) / PLG_LNL_THREADS;
+  const unsigned int cap = (unsigned int)(ctx->sm_count * (per_sm > 0 ? per_sm : 1));
+  if (nblocks > cap) nblocks = cap;
+  k_lnl_dna<R, MODE><<<nblocks, PLG_LNL_THREADS, 0, ctx->stream>>>(a, P);
+  return PLG_OK;
 }
 
 /* lookup[code][rate][i] = pi_i * (masked row sum of P_rate[i][:])
@@ -222,49 +339,6 @@ __global__ void k_edge_ti_table_dna(const double * __restrict__ pmat, double * _
     const double a3 = (code & 8u) ? row[3] : 0.0;
     out[t] = __dmul_rn(P.freqs[k * 4 + i], hsum4(a0, a1, a2, a3));
   }
-}
-
-template <int R>
-__global__ void __launch_bounds__(PLG_LNL_THREADS)
-k_edge_lnl_ti_dna(const LnlArgs a, const __grid_constant__ LnlParams P)
-{
-  __shared__ d4 tab[16 * R];
-  for (unsigned int t = threadIdx.x; t < 16 * R; t += PLG_LNL_THREADS)
-    tab[t] = *reinterpret_cast<const d4 *>(a.pmat + (size_t)t * 4);
-  __syncthreads();
-
-  const unsigned int k = threadIdx.x & (R - 1);
-  const unsigned int e = blockIdx.x * PLG_LNL_THREADS + threadIdx.x;
-  const bool valid = e < a.nelem;
-  double term_r = 0.0;
-  if (valid)
-  {
-    const d4 p = ld_stream(a.clvp + (size_t)e * 4);
-    const unsigned int code = __ldg(a.tip + e / R);
-    const d4 l = tab[code * R + k];
-    term_r = hsum4(__dmul_rn(l.x, p.x), __dmul_rn(l.y, p.y), __dmul_rn(l.z, p.z), __dmul_rn(l.w, p.w));
-  }
-  const double site_lk = site_epilogue<R, 4, true, true>(term_r, valid, e, a, P);
-  finish_sum<PLG_LNL_THREADS>(site_lk, a);
-}
-
-template <int R>
-__global__ void __launch_bounds__(PLG_LNL_THREADS)
-k_root_lnl_dna(const LnlArgs a, const __grid_constant__ LnlParams P)
-{
-  const unsigned int k = threadIdx.x & (R - 1);
-  const unsigned int e = blockIdx.x * PLG_LNL_THREADS + threadIdx.x;
-  const bool valid = e < a.nelem;
-  double term_r = 0.0;
-  if (valid)
-  {
-    const d4 c = ld_stream(a.clvp + (size_t)e * 4);
-    const double * f = P.freqs + k * 4;
-    /* hadd form: (f0 c0 + f1 c1) + (f2 c2 + f3 c3), reference src/core_likelihood_avx.c:145-156 */
-    term_r = hsum4(__dmul_rn(f[0], c.x), __dmul_rn(f[1], c.y), __dmul_rn(f[2], c.z), __dmul_rn(f[3], c.w));
-  }
-  const double site_lk = site_epilogue<R, 4, false, false>(term_r, valid, e, a, P);
-  finish_sum<PLG_LNL_THREADS>(site_lk, a);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -569,7 +643,7 @@ extern "C" int plg_edge_loglikelihood(plg_context_t * ctx, unsigned int parent_c
     {
       k_edge_ti_table_dna<<<1, 256, 0, ctx->stream>>>(plg_pmat_ptr(ctx, matrix_index), scratch, R, P);
       PLG_LAUNCH_CHECK(ctx);
-      PLG_DISPATCH_R(R, (k_edge_lnl_ti_dna<RR><<<nblocks, PLG_LNL_THREADS, 0, ctx->stream>>>(a, P)));
+      PLG_DISPATCH_R(R, { int lrc = launch_lnl_dna<RR, 1>(ctx, a, P); if (lrc) return lrc; });
     }
     else
     {
@@ -591,7 +665,7 @@ extern "C" int plg_edge_loglikelihood(plg_context_t * ctx, unsigned int parent_c
     a.cscale = plg_scaler_ptr(ctx, child_scaler_index);
     if (K == 4)
     {
-      PLG_DISPATCH_R(R, (k_edge_lnl_ii_dna<RR><<<nblocks, PLG_LNL_THREADS, 0, ctx->stream>>>(a, P)));
+      PLG_DISPATCH_R(R, { int lrc = launch_lnl_dna<RR, 0>(ctx, a, P); if (lrc) return lrc; });
     }
     else
     {
@@ -649,7 +723,7 @@ extern "C" int plg_root_loglikelihood(plg_context_t * ctx, unsigned int clv_inde
   const unsigned int R = ctx->d.rate_cats;
   if (ctx->d.states == 4)
   {
-    PLG_DISPATCH_R(R, (k_root_lnl_dna<RR><<<nblocks, PLG_LNL_THREADS, 0, ctx->stream>>>(a, P)));
+    PLG_DISPATCH_R(R, { int lrc = launch_lnl_dna<RR, 2>(ctx, a, P); if (lrc) return lrc; });
   }
   else
   {
