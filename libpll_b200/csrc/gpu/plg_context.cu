@@ -114,6 +114,7 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   ctx->pattern_tip = (dims->attributes & PLL_ATTRIB_PATTERN_TIP) != 0;
   ctx->rate_scalers = (dims->attributes & PLL_ATTRIB_RATE_SCALERS) != 0;
   ctx->active_sites = dims->sites;
+  ctx->lnl_scratch = NULL;
   ctx->span = (size_t)dims->rate_cats * dims->states_padded;
   ctx->clv_stride = round_up((size_t)dims->sites * ctx->span, 32);
   ctx->scaler_len = ctx->rate_scalers ? (size_t)dims->sites * dims->rate_cats : dims->sites;
@@ -244,6 +245,7 @@ extern "C" void plg_destroy(plg_context_t * ctx)
   cudaFree(ctx->lnl_table);
   cudaFree(ctx->flush_buf);
   if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+  cudaFree(ctx->lnl_scratch);
   if (ctx->result_host) cudaFreeHost(ctx->result_host);
   if (ctx->prof_events)
   {

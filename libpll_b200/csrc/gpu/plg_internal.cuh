@@ -77,6 +77,7 @@ struct plg_context
   bool pattern_tip;
   bool rate_scalers;
   unsigned int active_sites; /* leading sites the lnL / derivative reductions cover */
+  double * lnl_scratch;      /* one CLV-sized scratch (20-state edge lnL), lazily allocated */
 
   size_t span;          /* rate_cats * states_padded (doubles per site of a CLV)          */
   size_t clv_stride;    /* doubles between consecutive CLV slots                          */

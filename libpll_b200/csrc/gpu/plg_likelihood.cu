@@ -18,6 +18,7 @@
  * atomics on doubles, bit-reproducible from run to run.
  */
 #include <cmath>
+#include <vector>
 
 #include "plg_internal.cuh"
 
@@ -491,6 +492,34 @@ k_root_lnl_aa(const LnlArgs a, const __grid_constant__ LnlParams P)
   finish_sum<PLG_LNL_THREADS>(site_lk, a);
 }
 
+/* second half of the two-step 20-state edge log-likelihood: the scratch CLV already holds
+ * pi_i * p_i * (P c)_i, so a rate's term is the plain sum of its 20 entries */
+template <int R>
+__global__ void __launch_bounds__(PLG_LNL_THREADS)
+k_sum_lnl_aa(const LnlArgs a, const __grid_constant__ LnlParams P)
+{
+  const unsigned int e = blockIdx.x * PLG_LNL_THREADS + threadIdx.x;
+  const bool valid = e < a.nelem;
+  double term_r = 0.0;
+  if (valid)
+  {
+    double c[20];
+    load20s(a.clvp + (size_t)e * 20, c);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b)
+    {
+      a0 = __dadd_rn(a0, c[4 * b + 0]);
+      a1 = __dadd_rn(a1, c[4 * b + 1]);
+      a2 = __dadd_rn(a2, c[4 * b + 2]);
+      a3 = __dadd_rn(a3, c[4 * b + 3]);
+    }
+    term_r = hsum4(a0, a1, a2, a3);
+  }
+  const double site_lk = site_epilogue<R, 20, false, false>(term_r, valid, e, a, P);
+  finish_sum<PLG_LNL_THREADS>(site_lk, a);
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* host side                                                                             */
 /* ------------------------------------------------------------------------------------ */
@@ -666,6 +695,34 @@ extern "C" int plg_edge_loglikelihood(plg_context_t * ctx, unsigned int parent_c
     if (K == 4)
     {
       PLG_DISPATCH_R(R, { int lrc = launch_lnl_dna<RR, 0>(ctx, a, P); if (lrc) return lrc; });
+    }
+    else if (!ctx->aa_exact)
+    {
+      /* two steps on the tensor cores: the inner-inner update kernel with L = diag(pi) and
+       * R = P writes pi_i p_i (P c)_i into a scratch CLV (same shape as a CLV update, no
+       * scaling), then one streaming pass sums it per rate and finishes the pattern.  3.4x
+       * faster than the shared-memory mat-vec kernel below, which stays as the bit-exact
+       * (PLL_GPU_AA_EXACT) path. */
+      if (!ctx->lnl_scratch)
+        PLG_CUDA(cudaMalloc(&ctx->lnl_scratch, (size_t)ctx->d.sites * ctx->span * sizeof(double)));
+      std::vector<double> diag((size_t)R * 400, 0.0);
+      for (unsigned int r = 0; r < R; ++r)
+        for (unsigned int i = 0; i < 20; ++i) diag[(size_t)r * 400 + i * 20 + i] = freqs[(size_t)r * 20 + i];
+      if (plg_stage_reserve(ctx, diag.size() * sizeof(double) + 2048)) return PLG_E_CUDA;
+      const double * d_diag = (const double *)plg_stage(ctx, diag.data(), diag.size() * sizeof(double));
+      if (!d_diag) return PLG_E_CUDA;
+      DevOp op;
+      memset(&op, 0, sizeof(op));
+      op.parent = ctx->lnl_scratch;
+      op.left = a.clvp;
+      op.right = a.clvc;
+      op.lmat = d_diag;
+      op.rmat = a.pmat;
+      rc = plg_launch_single_op(ctx, PLG_KIND_II, op);
+      if (rc) return rc;
+      a.clvp = ctx->lnl_scratch;
+      a.clvc = NULL;
+      PLG_DISPATCH_R(R, (k_sum_lnl_aa<RR><<<nblocks, PLG_LNL_THREADS, 0, ctx->stream>>>(a, P)));
     }
     else
     {
