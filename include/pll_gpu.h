@@ -236,7 +236,27 @@ PLL_EXPORT int plg_flush_l2(plg_context_t * ctx);
 /* Free / total device memory in bytes. */
 PLL_EXPORT int plg_mem_info(plg_context_t * ctx, size_t * free_bytes, size_t * total_bytes);
 
+/* Site-pattern compression on the device; replaces the sort / unique core of
+ * pll_compress_site_patterns (reference src/compress.c:33-81,202-280).  rows[t] are `taxa` host
+ * buffers of `length` characters; they are overwritten with the unique columns in the
+ * reference's sorted order (first *unique_out characters of every row), decoded through
+ * inverse_table; weights_out (room for `length` entries) receives the multiplicities.
+ * code_table / inverse_table are the 256-entry byte tables the reference derives from the state
+ * map (src/compress.c:83-108,161-175).  No partition is involved; device < 0 = current. */
+PLL_EXPORT int plg_compress_patterns(int device, unsigned char * const * rows, unsigned int taxa,
+                                     size_t length, const unsigned char * code_table,
+                                     const unsigned char * inverse_table, unsigned int * weights_out,
+                                     size_t * unique_out);
+
 /* ================= pll_gpu_*: extensions on a GPU partition ========================== */
+
+/* pll_compress_site_patterns (reference src/compress.c:138-286) computed on the device: same
+ * arguments, same outputs (compressed 0-terminated sequences in sorted column order, malloc'ed
+ * weights, *length updated). */
+PLL_EXPORT unsigned int * pll_gpu_compress_site_patterns(char ** sequence,
+                                                         const unsigned int * map,
+                                                         int count,
+                                                         int * length);
 
 /* Device used by subsequent pll_partition_create(PLL_ATTRIB_ARCH_GPU) calls of this thread;
  * default: $PLL_GPU_DEVICE if set, else $LOCAL_RANK if set, else the current CUDA device. */

@@ -168,6 +168,7 @@ _PLL_API = {
 
 # extensions only this repository's library has (include/pll_gpu.h)
 _GPU_API = {
+    "pll_gpu_compress_site_patterns": (c_uint_p, [C.POINTER(C.c_char_p), c_uint_p, C.c_int, C.POINTER(C.c_int)]),
     "pll_gpu_set_device": (C.c_int, [C.c_int]),
     "pll_gpu_device_count": (C.c_int, []),
     "pll_gpu_context": (C.c_void_p, [PART_P]),

@@ -72,20 +72,10 @@ static int same_column(const columns_t * c, unsigned int a, unsigned int b)
                 (const char *)c->data + (size_t)b * c->stride) == 0;
 }
 
-PLL_EXPORT unsigned int * pll_compress_site_patterns(char ** sequence,
-                                                     const unsigned int * map,
-                                                     int count,
-                                                     int * length)
+/* code table (state map squeezed into a byte) and its inverse, as the reference builds them */
+static void build_tables(const unsigned int * map, unsigned char * charmap, unsigned char * inv_charmap)
 {
-  unsigned char charmap[PLL_ASCII_SIZE];
-  unsigned char inv_charmap[PLL_ASCII_SIZE];
   unsigned int i, maxcode = 0;
-  int j;
-
-  if (!count || !map || map[0]) return NULL;
-  const size_t len = (size_t)*length;
-  if (!len) return NULL;
-
   /* states that do not fit a byte are renumbered 1..k in order of first appearance
    * (reference src/compress.c:83-108, 161-169) */
   for (i = 0; i < PLL_ASCII_SIZE; ++i)
@@ -95,7 +85,7 @@ PLL_EXPORT unsigned int * pll_compress_site_patterns(char ** sequence,
     unsigned char k = 1;
     unsigned int seen[PLL_ASCII_SIZE];
     unsigned int nseen = 0, s;
-    memset(charmap, 0, sizeof(charmap));
+    memset(charmap, 0, PLL_ASCII_SIZE);
     for (i = 0; i < PLL_ASCII_SIZE; ++i)
     {
       if (!map[i]) continue;
@@ -113,9 +103,26 @@ PLL_EXPORT unsigned int * pll_compress_site_patterns(char ** sequence,
   else
     for (i = 0; i < PLL_ASCII_SIZE; ++i) charmap[i] = (unsigned char)map[i];
 
-  memset(inv_charmap, 0, sizeof(inv_charmap));
+  memset(inv_charmap, 0, PLL_ASCII_SIZE);
   for (i = 0; i < PLL_ASCII_SIZE; ++i)
     if (map[i]) inv_charmap[charmap[i]] = (unsigned char)i;
+}
+
+PLL_EXPORT unsigned int * pll_compress_site_patterns(char ** sequence,
+                                                     const unsigned int * map,
+                                                     int count,
+                                                     int * length)
+{
+  unsigned char charmap[PLL_ASCII_SIZE];
+  unsigned char inv_charmap[PLL_ASCII_SIZE];
+  unsigned int i;
+  int j;
+
+  if (!count || !map || map[0]) return NULL;
+  const size_t len = (size_t)*length;
+  if (!len) return NULL;
+
+  build_tables(map, charmap, inv_charmap);
 
   const size_t stride = (size_t)count + 1;
   signed char * data = (signed char *)malloc(len * stride);
@@ -163,6 +170,40 @@ PLL_EXPORT unsigned int * pll_compress_site_patterns(char ** sequence,
 
   free(data);
   free(idx);
+  unsigned int * shrunk = (unsigned int *)realloc(weight, unique * sizeof(unsigned int));
+  *length = (int)unique;
+  return shrunk ? shrunk : weight;
+}
+
+/* NEW: the same function on the device (gpu/plg_compress.cu).  Identical output - unique columns
+ * in the reference's sorted order, decoded through the inverse map, 0-terminated rows, weights
+ * in a malloc'ed array the caller frees - for alignments where the host sort is the set-up
+ * bottleneck (10 M columns). */
+PLL_EXPORT unsigned int * pll_gpu_compress_site_patterns(char ** sequence,
+                                                         const unsigned int * map,
+                                                         int count,
+                                                         int * length)
+{
+  unsigned char charmap[PLL_ASCII_SIZE];
+  unsigned char inv_charmap[PLL_ASCII_SIZE];
+  if (!count || !map || map[0] || !length || *length <= 0) return NULL;
+  build_tables(map, charmap, inv_charmap);
+  unsigned int * weight = (unsigned int *)malloc((size_t)*length * sizeof(unsigned int));
+  if (!weight)
+  {
+    pll_fail(PLL_ERROR_MEM_ALLOC, "Cannot allocate space for pattern weights.");
+    return NULL;
+  }
+  size_t unique = 0;
+  int rc = plg_compress_patterns(pll_gpu_current_device(), (unsigned char * const *)sequence, (unsigned int)count,
+                                 (size_t)*length, charmap, inv_charmap, weight, &unique);
+  if (rc)
+  {
+    free(weight);
+    pllg_fail(rc, "pll_gpu_compress_site_patterns");
+    return NULL;
+  }
+  for (int j = 0; j < count; ++j) sequence[j][unique] = 0;
   unsigned int * shrunk = (unsigned int *)realloc(weight, unique * sizeof(unsigned int));
   *length = (int)unique;
   return shrunk ? shrunk : weight;

@@ -33,6 +33,9 @@ static inline pllg_partition_t * pllg_from(const pll_partition_t * p)
   return (g && g->magic == PLLG_MAGIC) ? g : NULL;
 }
 
+/* device that pll_partition_create would use in this thread (-1 = current CUDA device) */
+int pll_gpu_current_device(void);
+
 /* ascertainment-bias epilogues (pll_ascbias.c) */
 double pllg_asc_root(pllg_partition_t * g, unsigned int clv_index, int scaler_index,
                      const unsigned int * freqs_indices);

@@ -77,6 +77,8 @@ static int pick_device(void)
   return -1; /* current CUDA device */
 }
 
+int pll_gpu_current_device(void) { return pick_device(); }
+
 /* ------------------------------------------------------------------------------------ */
 static void * zalloc_aligned(size_t bytes)
 {
