@@ -214,6 +214,31 @@ typedef struct pll_fasta
   long stripped[256];
 } pll_fasta_t;
 
+/* ---- multiple sequence alignment and the PHYLIP reader state (reference
+ * src/pll.h:271-278,295-308) ---- */
+typedef struct pll_msa_s
+{
+  int count;
+  int length;
+  char ** sequence;
+  char ** label;
+} pll_msa_t;
+
+typedef struct pll_phylip_s
+{
+  FILE * fp;
+  char * line;
+  size_t line_size;
+  size_t line_maxsize;
+  char buffer[PLL_LINEALLOC];
+  const unsigned int * chrstatus;
+  long no;
+  long filesize;
+  long lineno;
+  long stripped_count;
+  long stripped[256];
+} pll_phylip_t;
+
 /* ---- thread-local error channel (reference src/pll.h:470-471, src/pll.c:24-25) ---- */
 PLL_EXPORT extern __thread int pll_errno;
 PLL_EXPORT extern __thread char pll_errmsg[200];
@@ -368,6 +393,15 @@ PLL_EXPORT void pll_fasta_close(pll_fasta_t * fd);
 PLL_EXPORT long pll_fasta_getfilesize(const pll_fasta_t * fd);
 PLL_EXPORT long pll_fasta_getfilepos(pll_fasta_t * fd);
 PLL_EXPORT int pll_fasta_rewind(pll_fasta_t * fd);
+
+/* ---- PHYLIP reader, sequential and interleaved (reference src/phylip.c:249-730, prototypes
+ * src/pll.h:768-779) ---- */
+PLL_EXPORT void pll_msa_destroy(pll_msa_t * msa);
+PLL_EXPORT pll_phylip_t * pll_phylip_open(const char * filename, const unsigned int * map);
+PLL_EXPORT int pll_phylip_rewind(pll_phylip_t * fd);
+PLL_EXPORT void pll_phylip_close(pll_phylip_t * fd);
+PLL_EXPORT pll_msa_t * pll_phylip_parse_interleaved(pll_phylip_t * fd);
+PLL_EXPORT pll_msa_t * pll_phylip_parse_sequential(pll_phylip_t * fd);
 
 /* ---- unrooted trees: Newick reader, traversal, traversal -> operations
  * (reference src/parse_utree.y:71-524, src/utree.c:217-442, prototypes src/pll.h:702-760).

@@ -65,6 +65,20 @@ _TREE_API = {
     "pll_fasta_close": (None, [C.c_void_p]),
 }
 
+class Msa(C.Structure):
+    _fields_ = [("count", C.c_int), ("length", C.c_int), ("sequence", C.POINTER(C.c_char_p)),
+                ("label", C.POINTER(C.c_char_p))]
+
+
+_TREE_API.update({
+    "pll_phylip_open": (C.c_void_p, [C.c_char_p, C.POINTER(C.c_uint)]),
+    "pll_phylip_close": (None, [C.c_void_p]),
+    "pll_phylip_rewind": (C.c_int, [C.c_void_p]),
+    "pll_phylip_parse_sequential": (C.POINTER(Msa), [C.c_void_p]),
+    "pll_phylip_parse_interleaved": (C.POINTER(Msa), [C.c_void_p]),
+    "pll_msa_destroy": (None, [C.POINTER(Msa)]),
+})
+
 _libc = C.CDLL(None)
 _libc.free.argtypes = [C.c_void_p]
 
@@ -199,4 +213,30 @@ def read_fasta(lib: PllLibrary, path: str, status_table=None):
         _libc.free(seq)
     err = lib.errno()
     lib.pll_fasta_close(fd)
+    return out, err
+
+
+def read_phylip(lib: PllLibrary, path: str, interleaved: bool = False, twice: bool = False):
+    """([(label, sequence)], errno) read by `lib`'s PHYLIP reader; ([], errno) if it rejects the
+    file.  `twice` parses, rewinds and parses again (exercises pll_phylip_rewind)."""
+    bind(lib)
+    table = (C.c_uint * 256).in_dll(lib.dll, "pll_map_phylip")
+    C.c_int.in_dll(lib.dll, "pll_errno").value = 0
+    fd = lib.pll_phylip_open(path.encode(), table)
+    if not fd:
+        return [], lib.errno()
+    parse = lib.pll_phylip_parse_interleaved if interleaved else lib.pll_phylip_parse_sequential
+    msa = parse(fd)
+    if twice and msa:
+        lib.pll_msa_destroy(msa)
+        assert lib.pll_phylip_rewind(fd)
+        msa = parse(fd)
+    out = []
+    if msa:
+        m = msa.contents
+        out = [(m.label[i].decode(), m.sequence[i].decode()) for i in range(m.count)]
+        assert all(len(s) == m.length for _, s in out)
+        lib.pll_msa_destroy(msa)
+    err = lib.errno()
+    lib.pll_phylip_close(fd)
     return out, err

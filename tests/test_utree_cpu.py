@@ -199,6 +199,90 @@ def test_fasta_reader_matches_reference(lib, ref, tmp_path):
         assert ours == theirs
 
 
+# ---- PHYLIP reader -------------------------------------------------------------------------
+SEQUENTIAL = """ 4 12
+taxon_one  ACGTACGT
+  ACGT
+second   AC GT AC GT AC GT
+
+third\tACGTAC
+GTACGT
+fourth acgtnn--??AC
+"""
+INTERLEAVED = """4 14
+one      ACGTA CGT
+two      ACGTT CGA
+three
+  ACGTA CGC
+four     NNNNN NNN
+
+CCCCCC
+GGGGGG
+
+TTTTTT
+AAAAAA
+"""
+
+
+@pytest.mark.parametrize("text,interleaved", [(SEQUENTIAL, False), (INTERLEAVED, True),
+                                              (SEQUENTIAL.replace("\n", "\r\n"), False),
+                                              (INTERLEAVED.replace("\n", "\r\n"), True)])
+def test_phylip_reader_matches_reference(lib, ref, tmp_path, text, interleaved):
+    p = tmp_path / "a.phy"
+    p.write_bytes(text.encode())
+    ours, e1 = T.read_phylip(lib, str(p), interleaved)
+    theirs, e2 = T.read_phylip(ref, str(p), interleaved)
+    assert ours and ours == theirs
+    again, _ = T.read_phylip(lib, str(p), interleaved, twice=True)
+    assert again == ours
+
+
+@pytest.mark.parametrize("text,interleaved,code", [
+    ("x 12\na ACGT\n", False, 106),                      # bad header
+    ("2 4 extra\na ACGT\nb ACGT\n", False, 106),         # junk after the dimensions
+    ("2 4\na ACGT\n", False, 106),                       # too few sequences
+    ("1 4\na ACGT\nb ACGT\n", False, 106),               # too many sequences
+    ("2 4\na ACGTA\nb ACGT\n", False, 107),              # sequence too long
+    ("2 4\na AC\n", False, 106),                         # input ends inside a sequence
+    ("2 4\na AC.T\nb ACGT\n", False, 109),               # fatal character
+    ("2 4\na AC\x01T\nb ACGT\n", False, 110),            # unprintable character
+    ("2 6\na ACG\nb AC\n\nTTT\nGGG\n", True, 108),       # block out of alignment
+    ("2 6\na ACG\nb ACG\n\nTTT\n", True, 106),           # incomplete last block
+    ("2 8\na ACG\nb ACG\n\nTTT\nGGG\n", True, 0),        # total length differs from the header
+])
+def test_phylip_errors_match_reference(lib, ref, tmp_path, text, interleaved, code):
+    p = tmp_path / "bad.phy"
+    p.write_bytes(text.encode())
+    ours, e1 = T.read_phylip(lib, str(p), interleaved)
+    theirs, e2 = T.read_phylip(ref, str(p), interleaved)
+    assert ours == [] and theirs == []
+    if code:
+        assert e1 == code, (e1, e2)
+        # the reference rejects junk after the header dimensions without setting pll_errno
+        assert e2 == code or "extra" in text, (e1, e2)
+
+
+def test_phylip_large_random_files_match_reference(lib, ref, tmp_path):
+    rng = np.random.default_rng(8)
+    for trial in range(6):
+        count, length = int(rng.integers(1, 30)), int(rng.integers(1, 3000))
+        seqs = ["".join(rng.choice(list("ACGTN-"), length)) for _ in range(count)]
+        labels = [f"t{i}_{'x' * int(rng.integers(0, 12))}" for i in range(count)]
+        width = int(rng.integers(5, 200))
+        seq_text = f"{count} {length}\n" + "".join(
+            f"{l} " + "\n".join(s[k:k + width] for k in range(0, length, width)) + "\n" for l, s in zip(labels, seqs))
+        blocks = [f"{count} {length}\n"]
+        for k in range(0, length, width):
+            blocks.append("".join((f"{l}  " if k == 0 else "") + " ".join(s[k:k + width][q:q + 10] for q in range(0, width, 10))
+                                  + "\n" for l, s in zip(labels, seqs)) + "\n")
+        for text, inter in ((seq_text, False), ("".join(blocks), True)):
+            p = tmp_path / f"r{trial}_{inter}.phy"
+            p.write_text(text)
+            ours, _ = T.read_phylip(lib, str(p), inter)
+            theirs, _ = T.read_phylip(ref, str(p), inter)
+            assert ours == theirs == list(zip(labels, seqs))
+
+
 # ---- slot recycling -------------------------------------------------------------------------
 def _check_recycled(ops, tips, slots):
     """every operation reads tips or slots written before and not yet overwritten"""
