@@ -115,6 +115,8 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   ctx->rate_scalers = (dims->attributes & PLL_ATTRIB_RATE_SCALERS) != 0;
   ctx->active_sites = dims->sites;
   ctx->lnl_scratch = NULL;
+  ctx->fused_records = NULL;
+  ctx->fused_records_cap = 0;
   ctx->span = (size_t)dims->rate_cats * dims->states_padded;
   ctx->clv_stride = round_up((size_t)dims->sites * ctx->span, 32);
   ctx->scaler_len = ctx->rate_scalers ? (size_t)dims->sites * dims->rate_cats : dims->sites;
@@ -137,6 +139,14 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   ctx->use_graphs = g ? atoi(g) : 1;
   const char * ex = getenv("PLL_GPU_AA_EXACT");
   ctx->aa_exact = (ex && *ex && *ex != '0') ? 1 : 0;
+  {
+    const char * fu = getenv("PLL_GPU_FUSED");
+    const char * fs = getenv("PLL_GPU_FUSED_SLOTS");
+    ctx->use_fused = fu ? atoi(fu) : 1;
+    ctx->fused_slots = fs ? (unsigned int)atoi(fs) : 4u;
+    if (ctx->fused_slots < 1) ctx->fused_slots = 1;
+    if (ctx->fused_slots > 4) ctx->fused_slots = 4; /* shared-memory budget of plg_traverse.cu */
+  }
   ctx->flush_buf = NULL; ctx->flush_bytes = 0;
   ctx->stream = NULL; ctx->ev_start = NULL; ctx->ev_stop = NULL;
   ctx->profiling = 0;
@@ -246,6 +256,7 @@ extern "C" void plg_destroy(plg_context_t * ctx)
   cudaFree(ctx->flush_buf);
   if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
   cudaFree(ctx->lnl_scratch);
+  cudaFree(ctx->fused_records);
   if (ctx->result_host) cudaFreeHost(ctx->result_host);
   if (ctx->prof_events)
   {

@@ -78,6 +78,10 @@ struct plg_context
   bool rate_scalers;
   unsigned int active_sites; /* leading sites the lnL / derivative reductions cover */
   double * lnl_scratch;      /* one CLV-sized scratch (20-state edge lnL), lazily allocated */
+  int use_fused;             /* DNA: whole operations list in one kernel (PLL_GPU_FUSED, default 1) */
+  unsigned int fused_slots;  /* tiles a warp keeps in shared memory (PLL_GPU_FUSED_SLOTS, default 4) */
+  unsigned char * fused_records; /* packed operation records of the non-graph path */
+  size_t fused_records_cap;
 
   size_t span;          /* rate_cats * states_padded (doubles per site of a CLV)          */
   size_t clv_stride;    /* doubles between consecutive CLV slots                          */
@@ -162,6 +166,26 @@ struct TipmapArg
 {
   unsigned int map[PLL_ASCII_SIZE];
 };
+
+/* an operation of the fused traversal (plg_traverse.cu): where the children's tiles live
+ * (shared-memory slot of the warp, or -1 = HBM) and where the result tile is kept */
+struct FusedOp /* 128 bytes: it travels by TMA bulk copy */
+{
+  DevOp op;
+  int kind;
+  int scale_mode;
+  int lslot, rslot, pslot;
+  unsigned int lbytes, rbytes; /* bytes of the packed left / right block this operation reads */
+  int pad;
+  const double * lsrc;         /* P-matrix set of the left / right child (tip or inner) */
+  const double * rsrc;
+};
+/* bytes of one packed operation record: descriptor + left block + right block, each block a
+ * bank-conflict-padded P-matrix set ([rate] x 18 doubles) or tip table ([16 codes] x (4R+2)) */
+static inline size_t plg_fused_block_bytes(unsigned int R) { return (size_t)16 * (R * 4 + 2) * sizeof(double); }
+static inline size_t plg_fused_record_bytes(unsigned int R) { return 128 + 2 * plg_fused_block_bytes(R); }
+int plg_launch_fused(plg_context * ctx, const FusedOp * dev_ops, unsigned char * dev_records, unsigned int n_ops,
+                     unsigned int nslot);
 
 /* one operation-shaped launch on the specialised kernels (plg_partials.cu) */
 int plg_launch_single_op(plg_context * ctx, int kind, const DevOp & op);

@@ -1129,6 +1129,8 @@ struct Plan
   std::vector<DevOp> ops;      /* sorted by (level, kind, scale_mode) */
   std::vector<TableJob> jobs;  /* tip lookup tables to build first */
   std::vector<Group> groups;
+  std::vector<FusedOp> fused;  /* DNA: the same list for the single-kernel traversal */
+  unsigned int fused_hits, fused_misses;
   unsigned long long levels;
   unsigned long long algorithmic_bytes;
   size_t table_doubles;
@@ -1153,11 +1155,14 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
     int level, kind, scale_mode;
     unsigned long long bytes;
     DevOp op;
+    const double * src_l; /* P-matrix sets behind the left / right term (fused path) */
+    const double * src_r;
   };
   std::vector<Item> items(count);
   size_t n_tables = 0;
   int max_level = -1;
   plan.algorithmic_bytes = 0;
+  bool recycled = false; /* some CLV / scaler slot is written after an earlier read or write */
 
   const size_t span_bytes = ctx->span * sizeof(double);
   const size_t scaler_unit = ctx->rate_scalers ? 4u * R : 4u;
@@ -1189,10 +1194,12 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
     /* parent slot: WAW and WAR */
     after(clv_w[o.parent_clv_index]);
     after(clv_r[o.parent_clv_index]);
+    if (clv_w[o.parent_clv_index] >= 0 || clv_r[o.parent_clv_index] >= 0) recycled = true;
     if (it.op.pscale)
     {
       after(sc_w[o.parent_scaler_index]);
       after(sc_r[o.parent_scaler_index]);
+      if (sc_w[o.parent_scaler_index] >= 0 || sc_r[o.parent_scaler_index] >= 0) recycled = true;
     }
 
     int read_clv[2] = {-1, -1}, read_sc[2] = {-1, -1};
@@ -1203,6 +1210,8 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
       it.op.right = plg_clv_ptr(ctx, o.child2_clv_index);
       it.op.lmat = plg_pmat_ptr(ctx, o.child1_matrix_index);
       it.op.rmat = plg_pmat_ptr(ctx, o.child2_matrix_index);
+      it.src_l = it.op.lmat;
+      it.src_r = it.op.rmat;
       read_clv[0] = (int)o.child1_clv_index;
       read_clv[1] = (int)o.child2_clv_index;
       if (it.op.pscale)
@@ -1231,6 +1240,8 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
       it.op.lmat = (const double *)(uintptr_t)(n_tables * table_len); /* offset, fixed up below */
       plan.jobs.push_back(TableJob{plg_pmat_ptr(ctx, tip_mat), (double *)(uintptr_t)(n_tables * table_len)});
       ++n_tables;
+      it.src_l = plg_pmat_ptr(ctx, tip_mat);
+      it.src_r = it.op.rmat;
       read_clv[0] = (int)inner;
       if (it.op.pscale)
       {
@@ -1249,6 +1260,8 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
       it.op.rmat = (const double *)(uintptr_t)(n_tables * table_len);
       plan.jobs.push_back(TableJob{plg_pmat_ptr(ctx, o.child2_matrix_index), (double *)(uintptr_t)(n_tables * table_len)});
       ++n_tables;
+      it.src_l = plg_pmat_ptr(ctx, o.child1_matrix_index);
+      it.src_r = plg_pmat_ptr(ctx, o.child2_matrix_index);
       bytes += 2;
     }
     if (it.op.pscale) bytes += scaler_unit;
@@ -1298,6 +1311,122 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
     if (new_group) plan.groups.push_back(Group{it.kind, it.scale_mode, i, 0, 0});
     plan.groups.back().count++;
     plan.groups.back().bytes += it.bytes;
+  }
+
+  /* ---- the single-kernel traversal (plg_traverse.cu): execution order + tile cache ---- */
+  plan.fused.clear();
+  plan.fused_hits = plan.fused_misses = 0;
+  if (ctx->use_fused && K == 4 && R <= 4 && plg_fast_path(ctx) && count >= 2)
+  {
+    /* Execution order.  A list without slot recycling is a forest: walk it depth-first, the
+     * larger subtree first, so that few results are waiting for their parent at any time.
+     * A list that recycles slots is executed as given (its order is part of its meaning). */
+    std::vector<unsigned int> exec;
+    exec.reserve(count);
+    if (recycled)
+      for (unsigned int i = 0; i < count; ++i) exec.push_back(i);
+    else
+    {
+      std::vector<int> producer(n_clv, -1), kid0(count, -1), kid1(count, -1);
+      std::vector<unsigned int> size(count, 1);
+      std::vector<char> consumed(count, 0);
+      for (unsigned int i = 0; i < count; ++i) producer[operations[i].parent_clv_index] = (int)i;
+      for (unsigned int i = 0; i < count; ++i)
+      {
+        /* children are produced EARLIER in the list (it is a valid sequential program) */
+        const int a = producer[operations[i].child1_clv_index], b = producer[operations[i].child2_clv_index];
+        if (a >= 0 && (unsigned int)a < i && !plg_is_tip(ctx, operations[i].child1_clv_index)) kid0[i] = a;
+        if (b >= 0 && (unsigned int)b < i && !plg_is_tip(ctx, operations[i].child2_clv_index)) kid1[i] = b;
+        size[i] = 1 + (kid0[i] >= 0 ? size[kid0[i]] : 0) + (kid1[i] >= 0 ? size[kid1[i]] : 0);
+        if (kid0[i] >= 0) consumed[kid0[i]] = 1;
+        if (kid1[i] >= 0) consumed[kid1[i]] = 1;
+      }
+      std::vector<std::pair<unsigned int, int>> stack;
+      for (unsigned int root = 0; root < count; ++root)
+      {
+        if (consumed[root]) continue;
+        stack.push_back({root, 0});
+        while (!stack.empty())
+        {
+          auto [n, state] = stack.back();
+          stack.pop_back();
+          if (state == 1)
+          {
+            exec.push_back(n);
+            continue;
+          }
+          stack.push_back({n, 1});
+          int first = kid0[n], second = kid1[n];
+          if (second >= 0 && (first < 0 || size[second] > size[first])) std::swap(first, second);
+          if (second >= 0) stack.push_back({(unsigned int)second, 0});
+          if (first >= 0) stack.push_back({(unsigned int)first, 0}); /* popped next: runs first */
+        }
+      }
+      if (exec.size() != count) /* a CLV consumed twice or a cycle: fall back to the list order */
+      {
+        exec.clear();
+        for (unsigned int i = 0; i < count; ++i) exec.push_back(i);
+      }
+    }
+
+    /* Tile cache of a warp, simulated here: slot tags are (CLV address, scaler address). */
+    const unsigned int nslot = ctx->fused_slots;
+    std::vector<const double *> tag_clv(nslot, nullptr);
+    std::vector<const unsigned int *> tag_sc(nslot, nullptr);
+    std::vector<unsigned long long> born(nslot, 0);
+    unsigned long long clock = 0;
+    auto lookup = [&](const double * clv, const unsigned int * sc) -> int {
+      if (!clv) return -1;
+      for (unsigned int q = 0; q < nslot; ++q)
+        if (tag_clv[q] == clv && (!sc || tag_sc[q] == sc))
+        {
+          tag_clv[q] = nullptr; /* consumed: the slot is free again (also for this op's result) */
+          tag_sc[q] = nullptr;
+          return (int)q;
+        }
+      return -1;
+    };
+    plan.fused.resize(count);
+    for (unsigned int x = 0; x < count; ++x)
+    {
+      const Item & it = items[exec[x]];
+      FusedOp & f = plan.fused[x];
+      memset(&f, 0, sizeof(f));
+      f.op = it.op;
+      f.kind = it.kind;
+      f.scale_mode = it.scale_mode;
+      {
+        const unsigned int mat_bytes = R * 18u * 8u, table_bytes = (unsigned int)plg_fused_block_bytes(R);
+        f.lbytes = (it.kind == PLG_KIND_II) ? mat_bytes : table_bytes;
+        f.rbytes = (it.kind == PLG_KIND_TT) ? table_bytes : mat_bytes;
+        f.lsrc = it.src_l;
+        f.rsrc = it.src_r;
+      }
+      f.lslot = (it.kind == PLG_KIND_II) ? lookup(it.op.left, it.op.lscale) : -1;
+      f.rslot = (it.kind != PLG_KIND_TT) ? lookup(it.op.right, it.op.rscale) : -1;
+      if (it.kind == PLG_KIND_II) (f.lslot >= 0 ? plan.fused_hits : plan.fused_misses)++;
+      if (it.kind != PLG_KIND_TT) (f.rslot >= 0 ? plan.fused_hits : plan.fused_misses)++;
+      /* stale copies of what this operation overwrites */
+      for (unsigned int q = 0; q < nslot; ++q)
+        if (tag_clv[q] == it.op.parent || (it.op.pscale && tag_sc[q] == it.op.pscale))
+        {
+          tag_clv[q] = nullptr;
+          tag_sc[q] = nullptr;
+        }
+      int dst = -1;
+      for (unsigned int q = 0; q < nslot && dst < 0; ++q)
+        if (!tag_clv[q]) dst = (int)q;
+      if (dst < 0)
+      {
+        dst = 0; /* full: drop the oldest waiting tile (it is in HBM anyway) */
+        for (unsigned int q = 1; q < nslot; ++q)
+          if (born[q] < born[dst]) dst = (int)q;
+      }
+      f.pslot = dst;
+      tag_clv[dst] = it.op.parent;
+      tag_sc[dst] = it.op.pscale;
+      born[dst] = ++clock;
+    }
   }
   return PLG_OK;
 }
@@ -1408,15 +1537,17 @@ static int set_smem_limits()
   return PLG_OK;
 }
 
-static int enqueue_plan(plg_context * ctx, const Plan & plan, const DevOp * dev_ops,
-                        const TableJob * dev_jobs, unsigned long long * kernels)
+static int enqueue_plan(plg_context * ctx, const Plan & plan, const void * dev_payload,
+                        const TableJob * dev_jobs, unsigned long long * kernels, bool fused,
+                        unsigned char * dev_records)
 {
+  const DevOp * dev_ops = (const DevOp *)dev_payload;
   const unsigned int R = ctx->d.rate_cats;
   const unsigned int nelem = ctx->d.sites * R;
   unsigned long long launched = 0;
 
   const bool fast = plg_fast_path(ctx);
-  if (!plan.jobs.empty())
+  if (!plan.jobs.empty() && !fused)
   {
     if (!fast)
     {
@@ -1433,6 +1564,21 @@ static int enqueue_plan(plg_context * ctx, const Plan & plan, const DevOp * dev_
                                                                                 ctx->maxstates, tm);
     }
     ++launched;
+  }
+  if (fused)
+  {
+    /* the whole list in one kernel (plg_traverse.cu) */
+    int frc = plg_launch_fused(ctx, (const FusedOp *)dev_payload, dev_records, (unsigned int)plan.fused.size(),
+                               ctx->fused_slots);
+    if (frc) return frc;
+    cudaError_t ferr = cudaGetLastError();
+    if (ferr != cudaSuccess)
+    {
+      plg_set_error("plg_update_partials: kernel launch failed: %s", cudaGetErrorString(ferr));
+      return PLG_E_CUDA;
+    }
+    *kernels = launched + 2; /* pack + traverse */
+    return PLG_OK;
   }
   const bool prof = ctx->profiling != 0;
   if (prof)
@@ -1617,7 +1763,14 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
     }
   }
 
-  const size_t ops_bytes = plan.ops.size() * sizeof(DevOp);
+  const bool fused = !plan.fused.empty() && !ctx->profiling;
+  for (FusedOp & f : plan.fused)
+  {
+    if (f.kind != PLG_KIND_II) f.op.lmat = ctx->tables + (uintptr_t)f.op.lmat;
+    if (f.kind == PLG_KIND_TT) f.op.rmat = ctx->tables + (uintptr_t)f.op.rmat;
+  }
+  const void * ops_src = fused ? (const void *)plan.fused.data() : (const void *)plan.ops.data();
+  const size_t ops_bytes = fused ? plan.fused.size() * sizeof(FusedOp) : plan.ops.size() * sizeof(DevOp);
   const size_t jobs_bytes = plan.jobs.size() * sizeof(TableJob);
   const size_t ops_bytes_al = (ops_bytes + 255) / 256 * 256;
   unsigned long long kernels = 0;
@@ -1626,8 +1779,10 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
   {
     /* descriptors get a stable home, then the whole list is captured once */
     void * dev = NULL;
-    PLG_CUDA(cudaMalloc(&dev, ops_bytes_al + jobs_bytes + 256));
-    PLG_CUDA(cudaMemcpyAsync(dev, plan.ops.data(), ops_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t rec_bytes = fused ? plan.fused.size() * plg_fused_record_bytes(ctx->d.rate_cats) : 0;
+    const size_t jobs_bytes_al = (jobs_bytes + 255) / 256 * 256;
+    PLG_CUDA(cudaMalloc(&dev, ops_bytes_al + jobs_bytes_al + rec_bytes + 256));
+    PLG_CUDA(cudaMemcpyAsync(dev, ops_src, ops_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (jobs_bytes)
       PLG_CUDA(cudaMemcpyAsync((char *)dev + ops_bytes_al, plan.jobs.data(), jobs_bytes,
                                cudaMemcpyHostToDevice, ctx->stream));
@@ -1636,8 +1791,8 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
 
     cudaGraph_t graph = NULL;
     PLG_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    rc = enqueue_plan(ctx, plan, (const DevOp *)dev, (const TableJob *)((char *)dev + ops_bytes_al),
-                      &kernels);
+    rc = enqueue_plan(ctx, plan, dev, (const TableJob *)((char *)dev + ops_bytes_al), &kernels, fused,
+                      (unsigned char *)dev + ops_bytes_al + jobs_bytes_al);
     cudaError_t cerr = cudaStreamEndCapture(ctx->stream, &graph);
     if (rc || cerr != cudaSuccess)
     {
@@ -1682,7 +1837,7 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
   else
   {
     if (plg_stage_reserve(ctx, ops_bytes + jobs_bytes + 1024)) return PLG_E_CUDA;
-    const DevOp * dev_ops = (const DevOp *)plg_stage(ctx, plan.ops.data(), ops_bytes);
+    const void * dev_ops = plg_stage(ctx, ops_src, ops_bytes);
     if (!dev_ops) return PLG_E_CUDA;
     const TableJob * dev_jobs = NULL;
     if (jobs_bytes)
@@ -1690,7 +1845,22 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
       dev_jobs = (const TableJob *)plg_stage(ctx, plan.jobs.data(), jobs_bytes);
       if (!dev_jobs) return PLG_E_CUDA;
     }
-    rc = enqueue_plan(ctx, plan, dev_ops, dev_jobs, &kernels);
+    unsigned char * records = NULL;
+    if (fused)
+    {
+      const size_t need = plan.fused.size() * plg_fused_record_bytes(ctx->d.rate_cats);
+      if (need > ctx->fused_records_cap)
+      {
+        PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->fused_records);
+        ctx->fused_records = NULL;
+        ctx->fused_records_cap = 0;
+        PLG_CUDA(cudaMalloc(&ctx->fused_records, need));
+        ctx->fused_records_cap = need;
+      }
+      records = ctx->fused_records;
+    }
+    rc = enqueue_plan(ctx, plan, dev_ops, dev_jobs, &kernels, fused, records);
     if (rc) return rc;
   }
   ctx->stats.kernel_launches += kernels;
