@@ -314,6 +314,17 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     e2e_value = n_ops * S_gpu * world / e2e_s
 
     # ---- leg C: roofline of the dominant kernel, CUDA events per launch ------------------
+    # (1) the traversal as the library runs it: by default ONE kernel walks the whole list
+    #     (k_traverse_dna, libpll_b200/csrc/gpu/plg_traverse.cu); timed alone, on its stream
+    part.reset_stats()
+    part.timer_start()
+    for _ in range(3):
+        part.update_partials(w.ops)
+    trav_ms = allreduce_max(part.timer_stop()) / 3
+    trav_stats = part.stats()
+    fused = trav_stats["kernel_launches"] <= 3 * 3  # pack + traverse (+ nothing else) per call
+    alg_bytes = trav_stats["algorithmic_bytes"] / 3
+    # (2) the level-by-level kernels (one launch per dependency level and kind), per-kind times
     part.set_profiling(True)
     part.reset_stats()
     for _ in range(3):
@@ -339,26 +350,47 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    achieved = prof["kind_bytes"][dom] / max(prof["kind_ns"][dom], 1)
-    roofline = {
-        "bound": "hbm", "kernel": f"{KERNEL_NAMES[dom]} ({kinds[dom]})", "achieved": achieved,
-        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-        "traffic": None,
-        "algorithmic_bytes_per_launch": prof["kind_bytes"][dom] / max(prof["kind_launches"][dom], 1),
-        "avg_launch_ms": prof["kind_ns"][dom] / max(prof["kind_launches"][dom], 1) * 1e-6,
-        "whole_traversal_GBps": stats["algorithmic_bytes"] / args.steps / (ms_per_step * 1e-3) / 1e9,
-        "whole_traversal_frac_of_8TBps_nominal": stats["algorithmic_bytes"] / args.steps / (ms_per_step * 1e-3) / 8e12,
-        "by_kind": shares,
-    }
-    # DRAM traffic per launch: ratio (dram bytes / algorithmic byte) of this kernel from the
-    # committed `ncu` capture (profiles/traffic.json) times this launch's algorithmic bytes
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        ratio = traffic[kinds[dom]]["dram_bytes_per_algorithmic_byte"]
-        roofline["traffic"] = ratio * roofline["algorithmic_bytes_per_launch"]
-        roofline["traffic_source"] = traffic[kinds[dom]]["source"]
     except Exception:
-        pass
+        traffic = {}
+    level_achieved = prof["kind_bytes"][dom] / max(prof["kind_ns"][dom], 1)
+    level_path = {
+        "kernel": f"{KERNEL_NAMES[dom]} ({kinds[dom]})", "achieved": level_achieved, "frac": level_achieved / peak,
+        "algorithmic_bytes_per_launch": prof["kind_bytes"][dom] / max(prof["kind_launches"][dom], 1),
+        "avg_launch_ms": prof["kind_ns"][dom] / max(prof["kind_launches"][dom], 1) * 1e-6,
+        "traversal_ms": tot_ns / 3 * 1e-6, "by_kind": shares,
+    }
+    if fused:
+        achieved = alg_bytes / (trav_ms * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm", "kernel": "k_traverse_dna (the whole operations list in one launch)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+            "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": trav_ms,
+            "note": "algorithmic bytes count every child CLV read (SURVEY 8d); the kernel keeps freshly produced "
+                    "tiles in shared memory until their parent consumes them, so its DRAM traffic is about half "
+                    "of that and frac can exceed 1; dram_GBps = traffic / launch time is the HBM-level figure",
+        }
+        t = traffic.get("fused")
+        if t:
+            roofline["traffic"] = t["dram_bytes_per_algorithmic_byte"] * alg_bytes
+            roofline["traffic_source"] = t["source"]
+            roofline["dram_GBps"] = roofline["traffic"] / (trav_ms * 1e-3) / 1e9
+            roofline["dram_frac_of_peak"] = roofline["dram_GBps"] / peak
+        roofline["level_by_level_path"] = level_path
+    else:
+        roofline = {
+            "bound": "hbm", "kernel": level_path["kernel"], "achieved": level_achieved,
+            "peak": peak, "unit": "GB/s", "frac": level_achieved / peak, "peak_source": peak_src,
+            "traffic": None, "algorithmic_bytes_per_launch": level_path["algorithmic_bytes_per_launch"],
+            "avg_launch_ms": level_path["avg_launch_ms"], "by_kind": shares,
+        }
+        t = traffic.get(kinds[dom])
+        if t:
+            roofline["traffic"] = t["dram_bytes_per_algorithmic_byte"] * roofline["algorithmic_bytes_per_launch"]
+            roofline["traffic_source"] = t["source"]
+    roofline["whole_traversal_GBps"] = stats["algorithmic_bytes"] / args.steps / (ms_per_step * 1e-3) / 1e9
+    roofline["whole_traversal_frac_of_8TBps_nominal"] = roofline["whole_traversal_GBps"] * 1e9 / 8e12
 
     part.destroy()
 

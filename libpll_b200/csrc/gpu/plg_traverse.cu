@@ -226,12 +226,15 @@ __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> 
   if (KIND == PLG_KIND_II) load_matrix(st.L + k * FusedStage<R>::MPITCH, Lm);
   if (KIND != PLG_KIND_TT) load_matrix(st.Rr + k * FusedStage<R>::MPITCH, Rm);
 
+  /* phase 1: the products of all EPT elements (independent chains the scheduler can overlap) */
+  d4 p[EPT];
+  unsigned int sc[EPT];
 #pragma unroll
   for (int j = 0; j < EPT; ++j)
   {
     const unsigned int e = e0 + j * 32;
     const bool valid = FULL || e < nelem;
-    unsigned int sc = 0;
+    sc[j] = 0;
     d4 a, b;
     if (KIND == PLG_KIND_II)
     {
@@ -239,13 +242,13 @@ __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> 
       if (lslot >= 0)
       {
         x = cache.load(lslot, j, lane);
-        if (MODE != 0 && lscale) sc += cache.scaler(lslot, j, lane);
+        if (MODE != 0 && lscale) sc[j] += cache.scaler(lslot, j, lane);
       }
       else
       {
         /* not in the tile cache (rare): from HBM */
         x = valid ? ld_stream(st.desc.op.left + (size_t)e * 4) : d4{0.0, 0.0, 0.0, 0.0};
-        if (MODE != 0 && lscale && valid) sc += __ldg(lscale + (MODE == 2 ? e : e / R));
+        if (MODE != 0 && lscale && valid) sc[j] += __ldg(lscale + (MODE == 2 ? e : e / R));
       }
       a = fmatvec(Lm, x);
     }
@@ -259,22 +262,30 @@ __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> 
       if (rslot >= 0)
       {
         y = cache.load(rslot, j, lane);
-        if (MODE != 0 && rscale) sc += cache.scaler(rslot, j, lane);
+        if (MODE != 0 && rscale) sc[j] += cache.scaler(rslot, j, lane);
       }
       else
       {
         y = valid ? ld_stream(st.desc.op.right + (size_t)e * 4) : d4{0.0, 0.0, 0.0, 0.0};
-        if (MODE != 0 && rscale && valid) sc += __ldg(rscale + (MODE == 2 ? e : e / R));
+        if (MODE != 0 && rscale && valid) sc[j] += __ldg(rscale + (MODE == 2 ? e : e / R));
       }
       b = fmatvec(Rm, y);
     }
-    d4 p = fmul4(a, b);
-    /* tip-tip never rescales and zeroes the scaler (reference src/core_partials_avx.c:113-116) */
-    const unsigned int sv = (KIND == PLG_KIND_TT) ? 0u : finish_element<R, MODE>(p, valid, sc, gshift, full_mask);
-    cache.store(pslot, j, lane, p, sv);
+    p[j] = fmul4(a, b);
+  }
+  /* phase 2: rescaling votes (tip-tip never rescales and zeroes the scaler, reference
+   * src/core_partials_avx.c:113-116), then the write-back */
+#pragma unroll
+  for (int j = 0; j < EPT; ++j)
+  {
+    const unsigned int e = e0 + j * 32;
+    const bool valid = FULL || e < nelem;
+    const unsigned int sv =
+        (KIND == PLG_KIND_TT) ? 0u : finish_element<R, MODE>(p[j], valid, sc[j], gshift, full_mask);
+    cache.store(pslot, j, lane, p[j], sv);
     if (valid)
     {
-      st_stream(parent + j * 128, p);
+      st_stream(parent + j * 128, p[j]);
       if (MODE == 2) pscale[e] = sv;
       else if (MODE == 1 && k == 0) pscale[e / R] = sv;
     }
