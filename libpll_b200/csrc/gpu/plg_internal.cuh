@@ -79,7 +79,7 @@ struct plg_context
   unsigned int active_sites; /* leading sites the lnL / derivative reductions cover */
   double * lnl_scratch;      /* one CLV-sized scratch (20-state edge lnL), lazily allocated */
   int use_fused;             /* DNA: whole operations list in one kernel (PLL_GPU_FUSED, default 1) */
-  unsigned int fused_slots;  /* tiles a warp keeps in shared memory (PLL_GPU_FUSED_SLOTS, default 4) */
+  unsigned int fused_slots;  /* tiles a warp keeps in shared memory (PLL_GPU_FUSED_SLOTS, default 3) */
   unsigned char * fused_records; /* packed operation records of the non-graph path */
   size_t fused_records_cap;
 

@@ -1386,6 +1386,21 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
         }
       return -1;
     };
+    /* Register forwarding: in depth-first order the child finished LAST is the operation right
+     * before its parent (always so for the inner child of a tip-inner operation and for one
+     * child of an inner-inner operation); the kernel hands that tile over in registers
+     * (slot -2), it never enters the shared-memory cache. */
+    std::vector<signed char> forward(count, 0); /* 1: left child is the previous result, 2: right */
+    for (unsigned int x = 1; x < count; ++x)
+    {
+      const Item & it = items[exec[x]];
+      const Item & pv = items[exec[x - 1]];
+      if (it.kind == PLG_KIND_II && it.op.left == pv.op.parent && (!it.op.lscale || it.op.lscale == pv.op.pscale))
+        forward[x] = 1;
+      else if (it.kind != PLG_KIND_TT && it.op.right == pv.op.parent &&
+               (!it.op.rscale || it.op.rscale == pv.op.pscale))
+        forward[x] = 2;
+    }
     plan.fused.resize(count);
     for (unsigned int x = 0; x < count; ++x)
     {
@@ -1402,10 +1417,10 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
         f.lsrc = it.src_l;
         f.rsrc = it.src_r;
       }
-      f.lslot = (it.kind == PLG_KIND_II) ? lookup(it.op.left, it.op.lscale) : -1;
-      f.rslot = (it.kind != PLG_KIND_TT) ? lookup(it.op.right, it.op.rscale) : -1;
-      if (it.kind == PLG_KIND_II) (f.lslot >= 0 ? plan.fused_hits : plan.fused_misses)++;
-      if (it.kind != PLG_KIND_TT) (f.rslot >= 0 ? plan.fused_hits : plan.fused_misses)++;
+      f.lslot = (forward[x] == 1) ? -2 : ((it.kind == PLG_KIND_II) ? lookup(it.op.left, it.op.lscale) : -1);
+      f.rslot = (forward[x] == 2) ? -2 : ((it.kind != PLG_KIND_TT) ? lookup(it.op.right, it.op.rscale) : -1);
+      if (it.kind == PLG_KIND_II) (f.lslot != -1 ? plan.fused_hits : plan.fused_misses)++;
+      if (it.kind != PLG_KIND_TT) (f.rslot != -1 ? plan.fused_hits : plan.fused_misses)++;
       /* stale copies of what this operation overwrites */
       for (unsigned int q = 0; q < nslot; ++q)
         if (tag_clv[q] == it.op.parent || (it.op.pscale && tag_sc[q] == it.op.pscale))
@@ -1413,6 +1428,11 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
           tag_clv[q] = nullptr;
           tag_sc[q] = nullptr;
         }
+      if (x + 1 < count && forward[x + 1])
+      {
+        f.pslot = -1; /* handed to the next operation in registers */
+        continue;
+      }
       int dst = -1;
       for (unsigned int q = 0; q < nslot && dst < 0; ++q)
         if (!tag_clv[q]) dst = (int)q;

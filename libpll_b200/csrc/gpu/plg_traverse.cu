@@ -31,7 +31,7 @@
 #define PLG_FUSED_EPT 4
 #endif
 #ifndef PLG_FUSED_WARPS
-#define PLG_FUSED_WARPS 10
+#define PLG_FUSED_WARPS 11 /* + 1 producer warp = 12: registers are allocated per 4 warps */
 #endif
 
 __device__ __forceinline__ d4 ld_cached(const double * p)
@@ -208,72 +208,126 @@ __device__ __forceinline__ void load_matrix(const double * M, d4 (&out)[4])
   for (int r = 0; r < 4; ++r) out[r] = lds_d4(M + r * 4);
 }
 
-/* One operation on the EPT elements of this lane.  KIND, MODE (scaling) and FULL (no element of
- * the tile is past the end) are compile-time: the three kinds share nothing but the write-back. */
-template <int R, int EPT, int KIND, int MODE, bool FULL>
+/* child term of one element: handed over in registers by the previous operation (slot -2), from
+ * the warp's tile cache (slot >= 0), or - rare - from HBM (slot -1) */
+template <int R, int EPT, int MODE, bool FULL>
+__device__ __forceinline__ d4 child_term(const WarpCache<EPT> & cache, int slot, int j, unsigned int lane,
+                                         const double * clv, const unsigned int * scaler, unsigned int e,
+                                         unsigned int nelem, const d4 & prev, unsigned int prev_sc,
+                                         unsigned int & sc)
+{
+  if (slot == -2)
+  {
+    if (MODE != 0 && scaler) sc += prev_sc;
+    return prev;
+  }
+  if (slot >= 0)
+  {
+    if (MODE != 0 && scaler) sc += cache.scaler(slot, j, lane);
+    return cache.load(slot, j, lane);
+  }
+  const bool valid = FULL || e < nelem;
+  if (MODE != 0 && scaler && valid) sc += __ldg(scaler + (MODE == 2 ? e : e / R));
+  return valid ? ld_stream(clv + (size_t)e * 4) : d4{0.0, 0.0, 0.0, 0.0};
+}
+
+/* One operation on the EPT elements of this lane.  KIND, MODE (scaling), FULL (no element of the
+ * tile is past the end) and RIGHT_FIRST are compile-time.  `p` / `psc` hold the result tile of
+ * the previous operation on entry and this operation's on exit; a child handed over that way is
+ * transformed IN PLACE, so its side is evaluated first (the product of the two sides commutes
+ * bit for bit).  One matrix is resident in registers at a time. */
+template <int R, int EPT, int KIND, int MODE, bool FULL, bool RIGHT_FIRST>
 __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> & cache, unsigned int lane,
                                        unsigned int k, unsigned int e0, unsigned int nelem,
                                        const unsigned int (&lcode)[EPT], const unsigned int (&rcode)[EPT],
-                                       unsigned int gshift, unsigned int full_mask)
+                                       unsigned int gshift, unsigned int full_mask, d4 (&p)[EPT],
+                                       unsigned int (&psc)[EPT])
 {
   const int lslot = st.desc.lslot, rslot = st.desc.rslot, pslot = st.desc.pslot;
   const unsigned int * lscale = st.desc.op.lscale;
   const unsigned int * rscale = st.desc.op.rscale;
   double * parent = st.desc.op.parent + (size_t)e0 * 4;
   unsigned int * pscale = st.desc.op.pscale;
-
-  d4 Lm[4], Rm[4];
-  if (KIND == PLG_KIND_II) load_matrix(st.L + k * FusedStage<R>::MPITCH, Lm);
-  if (KIND != PLG_KIND_TT) load_matrix(st.Rr + k * FusedStage<R>::MPITCH, Rm);
-
-  /* phase 1: the products of all EPT elements (independent chains the scheduler can overlap) */
-  d4 p[EPT];
   unsigned int sc[EPT];
-#pragma unroll
-  for (int j = 0; j < EPT; ++j)
+
+  if (KIND == PLG_KIND_TT)
   {
-    const unsigned int e = e0 + j * 32;
-    const bool valid = FULL || e < nelem;
-    sc[j] = 0;
-    d4 a, b;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j)
+    {
+      sc[j] = 0;
+      p[j] = fmul4(lds_d4(st.L + lcode[j] * FusedStage<R>::TPITCH + k * 4),
+                   lds_d4(st.Rr + rcode[j] * FusedStage<R>::TPITCH + k * 4));
+    }
+  }
+  else if (RIGHT_FIRST)
+  {
+    /* right child = previous result: p <- R.p, then times the left term */
+    {
+      d4 Rm[4];
+      load_matrix(st.Rr + k * FusedStage<R>::MPITCH, Rm);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j)
+      {
+        sc[j] = (MODE != 0 && rscale) ? psc[j] : 0u;
+        p[j] = fmatvec(Rm, p[j]);
+      }
+    }
     if (KIND == PLG_KIND_II)
     {
-      d4 x;
-      if (lslot >= 0)
+      d4 Lm[4];
+      load_matrix(st.L + k * FusedStage<R>::MPITCH, Lm);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j)
       {
-        x = cache.load(lslot, j, lane);
-        if (MODE != 0 && lscale) sc[j] += cache.scaler(lslot, j, lane);
+        const d4 x = child_term<R, EPT, MODE, FULL>(cache, lslot, j, lane, st.desc.op.left, lscale, e0 + j * 32,
+                                                    nelem, p[j], 0u, sc[j]);
+        p[j] = fmul4(fmatvec(Lm, x), p[j]);
       }
-      else
-      {
-        /* not in the tile cache (rare): from HBM */
-        x = valid ? ld_stream(st.desc.op.left + (size_t)e * 4) : d4{0.0, 0.0, 0.0, 0.0};
-        if (MODE != 0 && lscale && valid) sc[j] += __ldg(lscale + (MODE == 2 ? e : e / R));
-      }
-      a = fmatvec(Lm, x);
     }
-    else
-      a = lds_d4(st.L + lcode[j] * FusedStage<R>::TPITCH + k * 4);
-    if (KIND == PLG_KIND_TT)
-      b = lds_d4(st.Rr + rcode[j] * FusedStage<R>::TPITCH + k * 4);
     else
     {
-      d4 y;
-      if (rslot >= 0)
-      {
-        y = cache.load(rslot, j, lane);
-        if (MODE != 0 && rscale) sc[j] += cache.scaler(rslot, j, lane);
-      }
-      else
-      {
-        y = valid ? ld_stream(st.desc.op.right + (size_t)e * 4) : d4{0.0, 0.0, 0.0, 0.0};
-        if (MODE != 0 && rscale && valid) sc[j] += __ldg(rscale + (MODE == 2 ? e : e / R));
-      }
-      b = fmatvec(Rm, y);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) p[j] = fmul4(lds_d4(st.L + lcode[j] * FusedStage<R>::TPITCH + k * 4), p[j]);
     }
-    p[j] = fmul4(a, b);
   }
-  /* phase 2: rescaling votes (tip-tip never rescales and zeroes the scaler, reference
+  else
+  {
+    /* left term first (in place if the left child is the previous result), then the right */
+    if (KIND == PLG_KIND_II)
+    {
+      d4 Lm[4];
+      load_matrix(st.L + k * FusedStage<R>::MPITCH, Lm);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j)
+      {
+        sc[j] = 0;
+        const d4 x = child_term<R, EPT, MODE, FULL>(cache, lslot, j, lane, st.desc.op.left, lscale, e0 + j * 32,
+                                                    nelem, p[j], psc[j], sc[j]);
+        p[j] = fmatvec(Lm, x);
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j)
+      {
+        sc[j] = 0;
+        p[j] = lds_d4(st.L + lcode[j] * FusedStage<R>::TPITCH + k * 4);
+      }
+    }
+    d4 Rm[4];
+    load_matrix(st.Rr + k * FusedStage<R>::MPITCH, Rm);
+#pragma unroll
+    for (int j = 0; j < EPT; ++j)
+    {
+      /* rslot is never -2 here */
+      const d4 y = child_term<R, EPT, MODE, FULL>(cache, rslot, j, lane, st.desc.op.right, rscale, e0 + j * 32,
+                                                  nelem, p[j], 0u, sc[j]);
+      p[j] = fmul4(p[j], fmatvec(Rm, y));
+    }
+  }
+  /* rescaling votes (tip-tip never rescales and zeroes the scaler, reference
    * src/core_partials_avx.c:113-116), then the write-back */
 #pragma unroll
   for (int j = 0; j < EPT; ++j)
@@ -282,7 +336,8 @@ __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> 
     const bool valid = FULL || e < nelem;
     const unsigned int sv =
         (KIND == PLG_KIND_TT) ? 0u : finish_element<R, MODE>(p[j], valid, sc[j], gshift, full_mask);
-    cache.store(pslot, j, lane, p[j], sv);
+    if (pslot >= 0) cache.store(pslot, j, lane, p[j], sv);
+    psc[j] = sv;
     if (valid)
     {
       st_stream(parent + j * 128, p[j]);
@@ -296,10 +351,19 @@ template <int R, int EPT, bool FULL>
 __device__ __forceinline__ void dispatch_op(const FusedStage<R> & st, WarpCache<EPT> & cache, unsigned int lane,
                                             unsigned int k, unsigned int e0, unsigned int nelem,
                                             const unsigned int (&lcode)[EPT], const unsigned int (&rcode)[EPT],
-                                            unsigned int gshift, unsigned int full_mask)
+                                            unsigned int gshift, unsigned int full_mask, d4 (&prev)[EPT],
+                                            unsigned int (&prev_sc)[EPT])
 {
   const int kind = st.desc.kind, mode = st.desc.scale_mode;
-#define PLG_RUN(K_, M_) run_op<R, EPT, K_, M_, FULL>(st, cache, lane, k, e0, nelem, lcode, rcode, gshift, full_mask)
+#define PLG_RUN(K_, M_)                                                                                   \
+  do {                                                                                                    \
+    if (K_ != PLG_KIND_TT && st.desc.rslot == -2)                                                         \
+      run_op<R, EPT, K_, M_, FULL, true>(st, cache, lane, k, e0, nelem, lcode, rcode, gshift, full_mask,  \
+                                         prev, prev_sc);                                                  \
+    else                                                                                                  \
+      run_op<R, EPT, K_, M_, FULL, false>(st, cache, lane, k, e0, nelem, lcode, rcode, gshift, full_mask, \
+                                          prev, prev_sc);                                                 \
+  } while (0)
   if (kind == PLG_KIND_TT)
   {
     if (mode == 0) PLG_RUN(PLG_KIND_TT, 0);
@@ -426,6 +490,14 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
     }
   };
 
+  d4 prev[EPT];                /* result tile of the previous operation (register forwarding) */
+  unsigned int prev_sc[EPT];
+#pragma unroll
+  for (int j = 0; j < EPT; ++j)
+  {
+    prev[j] = d4{0.0, 0.0, 0.0, 0.0};
+    prev_sc[j] = 0;
+  }
   unsigned int it = 0;
   const unsigned int total_its = passes * n_ops;
   {
@@ -462,9 +534,9 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
       {
         const FusedStage<R> & st = stages[s];
         if (tile_full)
-          dispatch_op<R, EPT, true>(st, cache, lane, k, e0, nelem, lcode, rcode, gshift, full_mask);
+          dispatch_op<R, EPT, true>(st, cache, lane, k, e0, nelem, lcode, rcode, gshift, full_mask, prev, prev_sc);
         else
-          dispatch_op<R, EPT, false>(st, cache, lane, k, e0, nelem, lcode, rcode, gshift, full_mask);
+          dispatch_op<R, EPT, false>(st, cache, lane, k, e0, nelem, lcode, rcode, gshift, full_mask, prev, prev_sc);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
