@@ -109,6 +109,9 @@ struct WarpCache
 #ifndef PLG_FUSED_MINB
 #define PLG_FUSED_MINB 1
 #endif
+#ifndef PLG_FUSED_SLEEP
+#define PLG_FUSED_SLEEP 64
+#endif
 #ifndef PLG_FUSED_STAGES
 #define PLG_FUSED_STAGES 8
 #endif
@@ -450,7 +453,10 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
             q_lb[q] = nxt->desc.lbytes;
             q_rb[q] = nxt->desc.rbytes;
           }
-          if (it >= (unsigned int)S) mbar_wait(&empty[s], ((it / S) - 1) & 1u);
+          /* the producer is usually a ring ahead: wait politely, its spinning would take issue
+           * slots from the compute warps of its scheduler */
+          if (it >= (unsigned int)S)
+            while (!mbar_try_wait(&empty[s], ((it / S) - 1) & 1u)) __nanosleep(PLG_FUSED_SLEEP);
           mbar_arrive_expect_tx(&full[s], (unsigned int)sizeof(FusedOp) + lb + rb);
           /* descriptor and left block are adjacent in the record */
           bulk_g2s(&stages[s].desc, &src->desc, (unsigned int)sizeof(FusedOp) + lb, &full[s]);
