@@ -316,14 +316,17 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     # ---- leg C: roofline of the dominant kernel, CUDA events per launch ------------------
     # (1) the traversal as the library runs it: by default ONE kernel walks the whole list
     #     (k_traverse_dna, libpll_b200/csrc/gpu/plg_traverse.cu); timed alone, on its stream
+    n_trav = max(args.steps, 3)
+    for _ in range(2):
+        part.update_partials(w.ops)
     part.reset_stats()
     part.timer_start()
-    for _ in range(3):
+    for _ in range(n_trav):
         part.update_partials(w.ops)
-    trav_ms = allreduce_max(part.timer_stop()) / 3
+    trav_ms = allreduce_max(part.timer_stop()) / n_trav
     trav_stats = part.stats()
-    fused = trav_stats["kernel_launches"] <= 3 * 3  # pack + traverse (+ nothing else) per call
-    alg_bytes = trav_stats["algorithmic_bytes"] / 3
+    fused = trav_stats["kernel_launches"] <= 3 * n_trav  # pack + traverse (+ nothing else) per call
+    alg_bytes = trav_stats["algorithmic_bytes"] / n_trav
     # (2) the level-by-level kernels (one launch per dependency level and kind), per-kind times
     part.set_profiling(True)
     part.reset_stats()
