@@ -480,19 +480,24 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
    * path; they are fetched one operation ahead: while operation i is being computed, the
    * descriptor of i+1 (normally already in the ring) is peeked at and its codes requested. */
   unsigned int pre_l[EPT], pre_r[EPT];
-  auto prefetch_codes = [&](const FusedStage<R> & st, unsigned int e0n, bool haven)
+  /* site of element j of a tile: (e0 + 32 j) / R = e0 / R + j * (32 / R) for R | 32 */
+  constexpr unsigned int SITE_STEP = 32u / R;
+  auto prefetch_codes = [&](const FusedStage<R> & st, unsigned int e0n, bool haven, bool fulln)
   {
+    const int kind = st.desc.kind;
+    if (kind == PLG_KIND_II || !haven) return;
+    const unsigned char * lt = st.desc.op.ltip + e0n / R;
+    const unsigned char * rt = (kind == PLG_KIND_TT) ? st.desc.op.rtip + e0n / R : lt;
 #pragma unroll
     for (int j = 0; j < EPT; ++j)
     {
-      const unsigned int e = e0n + j * 32;
-      pre_l[j] = pre_r[j] = 0;
-      if (haven && e < nelem)
+      if (fulln || e0n + j * 32 < nelem)
       {
-        const unsigned int n = e / R;
-        if (st.desc.kind != PLG_KIND_II) pre_l[j] = __ldg(st.desc.op.ltip + n);
-        if (st.desc.kind == PLG_KIND_TT) pre_r[j] = __ldg(st.desc.op.rtip + n);
+        pre_l[j] = __ldg(lt + j * SITE_STEP);
+        if (kind == PLG_KIND_TT) pre_r[j] = __ldg(rt + j * SITE_STEP);
       }
+      else
+        pre_l[j] = pre_r[j] = 0;
     }
   };
 
@@ -503,13 +508,14 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
   {
     prev[j] = d4{0.0, 0.0, 0.0, 0.0};
     prev_sc[j] = 0;
+    pre_l[j] = pre_r[j] = 0;
   }
   unsigned int it = 0;
   const unsigned int total_its = passes * n_ops;
   {
     mbar_wait(&full[0], 0);
     const unsigned int tile0 = blockIdx.x * NW + warp;
-    prefetch_codes(stages[0], tile0 * TILE + lane, tile0 < ntiles);
+    prefetch_codes(stages[0], tile0 * TILE + lane, tile0 < ntiles, (tile0 + 1) * TILE <= nelem);
   }
   for (unsigned int pass = 0; pass < passes; ++pass)
   {
@@ -517,10 +523,11 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
     const bool have = tile < ntiles;
     const unsigned int e0 = tile * TILE + lane;
     const bool tile_full = (tile + 1) * TILE <= nelem;
+    const unsigned int tile_next = ((pass + 1) * gridDim.x + blockIdx.x) * NW + warp;
     for (unsigned int i = 0; i < n_ops; ++i, ++it)
     {
+      /* stage `it` is known to be full: it was waited for when its tip codes were requested */
       const int s = it % S;
-      mbar_wait(&full[s], (it / S) & 1u);
       unsigned int lcode[EPT], rcode[EPT];
 #pragma unroll
       for (int j = 0; j < EPT; ++j)
@@ -532,9 +539,10 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
       {
         const unsigned int itn = it + 1;
         mbar_wait(&full[itn % S], (itn / S) & 1u);
-        const bool wraps = (i + 1 == n_ops);
-        const unsigned int tilen = wraps ? ((pass + 1) * gridDim.x + blockIdx.x) * NW + warp : tile;
-        prefetch_codes(stages[itn % S], tilen * TILE + lane, tilen < ntiles);
+        if (i + 1 == n_ops)
+          prefetch_codes(stages[itn % S], tile_next * TILE + lane, tile_next < ntiles, (tile_next + 1) * TILE <= nelem);
+        else
+          prefetch_codes(stages[itn % S], e0, have, tile_full);
       }
       if (have)
       {
