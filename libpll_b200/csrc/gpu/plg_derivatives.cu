@@ -977,21 +977,12 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
 
   /* device layout of diagp: 20 states is transposed to [R][3][20] exactly like the
    * reference's t_diagp (src/core_derivatives_avx2.c:598-609) */
-  double diag_host[PLG_MAX_RATES * 80];
-  size_t diag_len;
-  if (K == 4)
-  {
-    diag_len = (size_t)R * 16;
-    memcpy(diag_host, diagptable, diag_len * sizeof(double));
-  }
-  else
-  {
-    diag_len = (size_t)R * 60;
-    for (unsigned int i = 0; i < R; ++i)
-      for (unsigned int j = 0; j < K; ++j)
-        for (unsigned int x = 0; x < 3; ++x)
-          diag_host[i * 60 + x * 20 + j] = diagptable[(size_t)i * K * 4 + j * 4 + x];
-  }
+  double diag_host[PLG_MAX_RATES * 60];
+  const size_t diag_len = (size_t)R * 60;
+  for (unsigned int i = 0; i < R; ++i)
+    for (unsigned int j = 0; j < K; ++j)
+      for (unsigned int x = 0; x < 3; ++x)
+        diag_host[i * 60 + x * 20 + j] = diagptable[(size_t)i * K * 4 + j * 4 + x];
 
   DerArgs a;
   a.sumtable = it->second;
@@ -1004,14 +995,7 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
   a.result = ctx->result_dev;
   a.nelem = nelem;
 
-  if (K == 4)
-  {
-    PLG_DISPATCH_R(R, (k_derivatives<RR, 4><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(a, P)));
-  }
-  else
-  {
-    PLG_DISPATCH_R(R, (k_derivatives<RR, 20><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(a, P)));
-  }
+  PLG_DISPATCH_R(R, (k_derivatives<RR, 20><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(a, P)));
   PLG_LAUNCH_CHECK(ctx);
 
   PLG_CUDA(cudaStreamSynchronize(ctx->stream));

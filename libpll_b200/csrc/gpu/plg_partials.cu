@@ -142,131 +142,6 @@ __device__ __forceinline__ d4 scale_up(const d4 & p)
 /* ------------------------------------------------------------------------------------ */
 #define PLG_DNA_THREADS 256
 
-__device__ __forceinline__ d4 matvec4_unfused(const double (&M)[16], const d4 & c)
-{
-  d4 y;
-  y.x = dot4_unfused(M[0], M[1], M[2], M[3], c);
-  y.y = dot4_unfused(M[4], M[5], M[6], M[7], c);
-  y.z = dot4_unfused(M[8], M[9], M[10], M[11], c);
-  y.w = dot4_unfused(M[12], M[13], M[14], M[15], c);
-  return y;
-}
-
-__device__ __forceinline__ d4 mul4(const d4 & a, const d4 & b)
-{
-  d4 r;
-  r.x = __dmul_rn(a.x, b.x);
-  r.y = __dmul_rn(a.y, b.y);
-  r.z = __dmul_rn(a.z, b.z);
-  r.w = __dmul_rn(a.w, b.w);
-  return r;
-}
-
-/* inner-inner: parent[n][k][i] = (sum_j L_k[i][j] l[n][k][j]) * (sum_j R_k[i][j] r[n][k][j])
- * reference src/core_partials_avx.c:412-528 */
-template <int R, int ITEMS>
-__global__ void __launch_bounds__(PLG_DNA_THREADS)
-k_partial_ii_dna(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mode)
-{
-  const DevOp op = ops[blockIdx.y];
-  const unsigned int k = threadIdx.x & (R - 1);
-
-  double L[16], Rm[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i)
-  {
-    L[i] = __ldg(op.lmat + k * 16 + i);
-    Rm[i] = __ldg(op.rmat + k * 16 + i);
-  }
-
-  const unsigned int base = blockIdx.x * (PLG_DNA_THREADS * ITEMS) + threadIdx.x;
-  d4 l[ITEMS], r[ITEMS];
-  bool valid[ITEMS];
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j)
-  {
-    const unsigned int e = base + j * PLG_DNA_THREADS;
-    valid[j] = e < nelem;
-    if (valid[j])
-    {
-      l[j] = ld_stream(op.left + (size_t)e * 4);
-      r[j] = ld_stream(op.right + (size_t)e * 4);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j)
-  {
-    const unsigned int e = base + j * PLG_DNA_THREADS;
-    d4 p;
-    bool below = false;
-    if (valid[j])
-    {
-      p = mul4(matvec4_unfused(L, l[j]), matvec4_unfused(Rm, r[j]));
-      below = all_below(p);
-    }
-    const bool scale = scale_decision<R>(valid[j], below, scale_mode, e, op);
-    if (valid[j])
-    {
-      if (scale) p = scale_up(p);
-      st_stream(op.parent + (size_t)e * 4, p);
-    }
-  }
-}
-
-/* tip-inner: parent[n][k][i] = table[tip[n]][k][i] * (sum_j R_k[i][j] r[n][k][j])
- * reference src/core_partials_avx.c:1006-1093 */
-template <int R, int ITEMS>
-__global__ void __launch_bounds__(PLG_DNA_THREADS)
-k_partial_ti_dna(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mode)
-{
-  const DevOp op = ops[blockIdx.y];
-  const unsigned int k = threadIdx.x & (R - 1);
-
-  __shared__ d4 tab[16 * R];
-  for (unsigned int t = threadIdx.x; t < 16 * R; t += PLG_DNA_THREADS)
-    tab[t] = *reinterpret_cast<const d4 *>(op.lmat + (size_t)t * 4);
-
-  double Rm[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) Rm[i] = __ldg(op.rmat + k * 16 + i);
-  __syncthreads();
-
-  const unsigned int base = blockIdx.x * (PLG_DNA_THREADS * ITEMS) + threadIdx.x;
-  d4 r[ITEMS];
-  unsigned int code[ITEMS];
-  bool valid[ITEMS];
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j)
-  {
-    const unsigned int e = base + j * PLG_DNA_THREADS;
-    valid[j] = e < nelem;
-    code[j] = 0;
-    if (valid[j])
-    {
-      r[j] = ld_stream(op.right + (size_t)e * 4);
-      code[j] = __ldg(op.ltip + e / R);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j)
-  {
-    const unsigned int e = base + j * PLG_DNA_THREADS;
-    d4 p;
-    bool below = false;
-    if (valid[j])
-    {
-      p = mul4(tab[code[j] * R + k], matvec4_unfused(Rm, r[j]));
-      below = all_below(p);
-    }
-    const bool scale = scale_decision<R>(valid[j], below, scale_mode, e, op);
-    if (valid[j])
-    {
-      if (scale) p = scale_up(p);
-      st_stream(op.parent + (size_t)e * 4, p);
-    }
-  }
-}
-
 /* tip-tip: parent[n][k][i] = tableL[l[n]][k][i] * tableR[r[n]][k][i]; never scales and
  * zeroes the parent scaler (reference src/core_partials_avx.c:581-618, :262-364: the
  * reference materialises the 16x16 product table, the products are the same numbers). */

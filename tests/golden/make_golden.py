@@ -170,6 +170,34 @@ for cats in (1, 2, 4):
                       "CEBCBBECAA--AB-C-AAE", "CEACBBECCA--AB-B-AAE"],
                 steps=steps, odd_block=dict(alpha=alpha, cats=cats, pinv=pinv)))
 
+# ---- ascertainment-bias correction: recipe of reference test/src/asc-bias.c:206-265 (no
+# correction, Lewis, Felsenstein, Stamatakis; lnL and derivatives) on the 00010 data - the test's
+# own alignment (testdata/2000.fas) is not shipped with the reference ---------------------------
+AB_LEWIS, AB_FELSENSTEIN, AB_STAMATAKIS, AB_FLAG = 1 << 5, 2 << 5, 3 << 5, 1 << 8
+asc_steps = [
+    dict(do="pmatrix", params=[0, 0, 0, 0], matrices=[0, 1, 2, 3], lengths=[0.1, 0.2, 1, 1]),
+    dict(do="partials", ops=[op(5, NONE, 0, 1, NONE, 1, 1, NONE), op(6, NONE, 5, 0, NONE, 2, 1, NONE),
+                             op(7, NONE, 3, 1, NONE, 4, 1, NONE)]),
+]
+for asc_type in (0, AB_LEWIS, AB_FELSENSTEIN, AB_STAMATAKIS):
+    asc_steps.append(dict(do="asc_type", value=asc_type))
+    if asc_type in (AB_FELSENSTEIN, AB_STAMATAKIS):
+        asc_steps.append(dict(do="asc_weights", value=[5, 7, 3, 9]))
+    asc_steps.append(dict(do="edge", args=[6, NONE, 7, NONE, 0], freqs_indices=[0, 0, 0, 0], tag=f"asc {asc_type} ii"))
+    asc_steps.append(dict(do="edge", args=[6, NONE, 2, NONE, 1], freqs_indices=[0, 0, 0, 0], tag=f"asc {asc_type} ti"))
+    asc_steps.append(dict(do="root", clv=6, scaler=NONE, freqs_indices=[0, 0, 0, 0], tag=f"asc {asc_type} root"))
+    asc_steps.append(dict(do="sumtable", key=f"ii{asc_type}", edge=[6, 7, NONE, NONE], params=[0, 0, 0, 0]))
+    asc_steps.append(dict(do="sumtable", key=f"ti{asc_type}", edge=[6, 2, NONE, NONE], params=[0, 0, 0, 0]))
+    for t in (0.0001, 0.01, 0.1, 1.0, 10.0):
+        asc_steps.append(dict(do="derivs", key=f"ii{asc_type}", t=t, params=[0, 0, 0, 0]))
+        asc_steps.append(dict(do="derivs", key=f"ti{asc_type}", t=t, params=[0, 0, 0, 0]))
+CASES.append(dict(
+    name="asc_bias_recipe", states=4, tips=5, clv_buffers=4, sites=12, rate_matrices=1, prob_matrices=7,
+    rate_cats=4, scale_buffers=0, alpha=0.5, extra_attributes=AB_FLAG, no_port=True,
+    freqs=[[0.3, 0.4, 0.1, 0.2]], subst=[[1, 2.5, 1, 1, 2.5, 1]],
+    seqs=["WAC-CTA-ATCT", "CCC-TTA-ATGT", "A-C-TAG-CTCT", "CTCTTAA-A-CG", "CAC-TCA-A-TG"],
+    steps=asc_steps))
+
 # test 00011 shares the step list of 00010
 CASES[1]["steps"] = [dict(s) for s in CASES[0]["steps"]]
 CASES[1]["printed"] = {"inner-inner": -227.371279, "tip-inner": -227.371279}

@@ -21,7 +21,7 @@ def execute(lib, case, attributes):
     part = lib.partition(tips=case["tips"], clv_buffers=case["clv_buffers"], states=case["states"],
                          sites=case["sites"], rate_matrices=case["rate_matrices"],
                          prob_matrices=case["prob_matrices"], rate_cats=case["rate_cats"],
-                         scale_buffers=case["scale_buffers"], attributes=attributes)
+                         scale_buffers=case["scale_buffers"], attributes=attributes | case.get("extra_attributes", 0))
     for i, (f, s) in enumerate(zip(case["freqs"], case["subst"])):
         part.set_frequencies(i, f)
         part.set_subst_params(i, s)
@@ -68,6 +68,10 @@ def _run_steps(part, case):
             ps = np.zeros(case["sites"])
             logl = part.root_loglikelihood(st["clv"], st["scaler"], st["freqs_indices"], persite=ps)
             out.append(dict(kind="root", tag=st.get("tag"), logl=logl, persite=ps.tolist()))
+        elif do == "asc_type":
+            part.set_asc_bias_type(st["value"])
+        elif do == "asc_weights":
+            part.set_asc_state_weights(st["value"])
         elif do == "pinv":
             part.update_invariant_sites_proportion(st["index"], st["value"])
         elif do == "sumtable":

@@ -281,6 +281,8 @@ def test_port_reproduces_golden_cases(case, variant):
     """oracle port (independent eigen / gamma set-up) vs the reference's recorded outputs."""
     from golden_runner import execute
 
+    if case.get("no_port"):
+        pytest.skip("ascertainment-bias cases are pinned on the reference itself (oracle/_ref), not on the port")
     attr = PLL_ATTRIB_ARCH_AVX2 | (PLL_ATTRIB_PATTERN_TIP if variant == "tv" else 0)
     got = execute(port.PortAsLibrary(), case, attr)
     compare_outputs(got, case["expect"][variant], 1e-10, f"{case['name']}[{variant}]")
