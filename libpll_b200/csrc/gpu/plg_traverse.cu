@@ -242,7 +242,7 @@ __device__ __forceinline__ d4 child_term(const WarpCache<EPT> & cache, int slot,
 template <int R, int EPT, int KIND, int MODE, bool FULL, bool RIGHT_FIRST>
 __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> & cache, unsigned int lane,
                                        unsigned int k, unsigned int e0, unsigned int nelem,
-                                       const unsigned int (&lcode)[EPT], const unsigned int (&rcode)[EPT],
+                                       const unsigned char * lcode, const unsigned char * rcode,
                                        unsigned int gshift, unsigned int full_mask, d4 (&p)[EPT],
                                        unsigned int (&psc)[EPT])
 {
@@ -259,8 +259,8 @@ __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> 
     for (int j = 0; j < EPT; ++j)
     {
       sc[j] = 0;
-      p[j] = fmul4(lds_d4(st.L + lcode[j] * FusedStage<R>::TPITCH + k * 4),
-                   lds_d4(st.Rr + rcode[j] * FusedStage<R>::TPITCH + k * 4));
+      p[j] = fmul4(lds_d4(st.L + lcode[j * (32 / R)] * FusedStage<R>::TPITCH + k * 4),
+                   lds_d4(st.Rr + rcode[j * (32 / R)] * FusedStage<R>::TPITCH + k * 4));
     }
   }
   else if (RIGHT_FIRST)
@@ -291,7 +291,7 @@ __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> 
     else
     {
 #pragma unroll
-      for (int j = 0; j < EPT; ++j) p[j] = fmul4(lds_d4(st.L + lcode[j] * FusedStage<R>::TPITCH + k * 4), p[j]);
+      for (int j = 0; j < EPT; ++j) p[j] = fmul4(lds_d4(st.L + lcode[j * (32 / R)] * FusedStage<R>::TPITCH + k * 4), p[j]);
     }
   }
   else
@@ -316,7 +316,7 @@ __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> 
       for (int j = 0; j < EPT; ++j)
       {
         sc[j] = 0;
-        p[j] = lds_d4(st.L + lcode[j] * FusedStage<R>::TPITCH + k * 4);
+        p[j] = lds_d4(st.L + lcode[j * (32 / R)] * FusedStage<R>::TPITCH + k * 4);
       }
     }
     d4 Rm[4];
@@ -353,7 +353,7 @@ __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> 
 template <int R, int EPT, bool FULL>
 __device__ __forceinline__ void dispatch_op(const FusedStage<R> & st, WarpCache<EPT> & cache, unsigned int lane,
                                             unsigned int k, unsigned int e0, unsigned int nelem,
-                                            const unsigned int (&lcode)[EPT], const unsigned int (&rcode)[EPT],
+                                            const unsigned char * lcode, const unsigned char * rcode,
                                             unsigned int gshift, unsigned int full_mask, d4 (&prev)[EPT],
                                             unsigned int (&prev_sc)[EPT])
 {
@@ -476,29 +476,29 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
   const unsigned int full_mask = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
   const unsigned int gshift = lane & ~(unsigned int)(R - 1);
 
-  /* Tip characters are the one per-tile input that still comes from HBM / L2 on the critical
-   * path; they are fetched one operation ahead: while operation i is being computed, the
-   * descriptor of i+1 (normally already in the ring) is peeked at and its codes requested. */
-  unsigned int pre_l[EPT], pre_r[EPT];
-  /* site of element j of a tile: (e0 + 32 j) / R = e0 / R + j * (32 / R) for R | 32 */
-  constexpr unsigned int SITE_STEP = 32u / R;
-  auto prefetch_codes = [&](const FusedStage<R> & st, unsigned int e0n, bool haven, bool fulln)
+  /* Tip characters are the one per-tile input that still comes from HBM / L2.  A tile covers
+   * TILE / R consecutive sites, i.e. TILE / R consecutive bytes of a tip row (rows are padded to
+   * 256 bytes, a tile never straddles the padding): while operation i is computed, a few lanes
+   * copy the bytes operation i+1 needs into a double-buffered strip of shared memory with
+   * cp.async - no register holds them in the meantime. */
+  constexpr unsigned int TIP_BYTES = TILE / R;           /* per tip row and tile */
+  constexpr unsigned int TIP_LANES = TIP_BYTES / 4;      /* 4-byte cp.async each */
+  unsigned char * codes = cache_base + (size_t)NW * per_warp + (size_t)warp * (4 * TIP_BYTES);
+  auto prefetch_codes = [&](const FusedStage<R> & st, unsigned int tile_n, bool haven, unsigned int buf)
   {
     const int kind = st.desc.kind;
-    if (kind == PLG_KIND_II || !haven) return;
-    const unsigned char * lt = st.desc.op.ltip + e0n / R;
-    const unsigned char * rt = (kind == PLG_KIND_TT) ? st.desc.op.rtip + e0n / R : lt;
-#pragma unroll
-    for (int j = 0; j < EPT; ++j)
+    if (kind != PLG_KIND_II && haven)
     {
-      if (fulln || e0n + j * 32 < nelem)
+      const unsigned int chunks = ((kind == PLG_KIND_TT) ? 2u : 1u) * TIP_LANES;
+      for (unsigned int c = lane; c < chunks; c += 32)
       {
-        pre_l[j] = __ldg(lt + j * SITE_STEP);
-        if (kind == PLG_KIND_TT) pre_r[j] = __ldg(rt + j * SITE_STEP);
+        const unsigned int side = c / TIP_LANES, q = c % TIP_LANES;
+        const unsigned char * src = (side ? st.desc.op.rtip : st.desc.op.ltip) + (size_t)tile_n * TIP_BYTES + q * 4;
+        unsigned char * dst = codes + (buf * 2 + side) * TIP_BYTES + q * 4;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
       }
-      else
-        pre_l[j] = pre_r[j] = 0;
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
   d4 prev[EPT];                /* result tile of the previous operation (register forwarding) */
@@ -508,14 +508,13 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
   {
     prev[j] = d4{0.0, 0.0, 0.0, 0.0};
     prev_sc[j] = 0;
-    pre_l[j] = pre_r[j] = 0;
   }
   unsigned int it = 0;
   const unsigned int total_its = passes * n_ops;
   {
     mbar_wait(&full[0], 0);
     const unsigned int tile0 = blockIdx.x * NW + warp;
-    prefetch_codes(stages[0], tile0 * TILE + lane, tile0 < ntiles, (tile0 + 1) * TILE <= nelem);
+    prefetch_codes(stages[0], tile0, tile0 < ntiles, 0);
   }
   for (unsigned int pass = 0; pass < passes; ++pass)
   {
@@ -528,21 +527,19 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
     {
       /* stage `it` is known to be full: it was waited for when its tip codes were requested */
       const int s = it % S;
-      unsigned int lcode[EPT], rcode[EPT];
-#pragma unroll
-      for (int j = 0; j < EPT; ++j)
-      {
-        lcode[j] = pre_l[j];
-        rcode[j] = pre_r[j];
-      }
+      const unsigned int buf = it & 1u;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      const unsigned char * lcode = codes + (buf * 2 + 0) * TIP_BYTES + lane / R;
+      const unsigned char * rcode = codes + (buf * 2 + 1) * TIP_BYTES + lane / R;
       if (it + 1 < total_its)
       {
         const unsigned int itn = it + 1;
         mbar_wait(&full[itn % S], (itn / S) & 1u);
         if (i + 1 == n_ops)
-          prefetch_codes(stages[itn % S], tile_next * TILE + lane, tile_next < ntiles, (tile_next + 1) * TILE <= nelem);
+          prefetch_codes(stages[itn % S], tile_next, tile_next < ntiles, buf ^ 1u);
         else
-          prefetch_codes(stages[itn % S], e0, have, tile_full);
+          prefetch_codes(stages[itn % S], tile, have, buf ^ 1u);
       }
       if (have)
       {
@@ -566,7 +563,8 @@ static int launch_fused(plg_context * ctx, const FusedOp * dev_ops, unsigned cha
   constexpr int EPT = PLG_FUSED_EPT;
   static_assert(sizeof(FusedOp) == 128, "descriptor must be 128 bytes");
   const size_t smem = PLG_FUSED_STAGES * sizeof(FusedStage<R>) + 128 +
-                      (size_t)PLG_FUSED_WARPS * nslot * EPT * 32 * (32 + 4);
+                      (size_t)PLG_FUSED_WARPS * nslot * EPT * 32 * (32 + 4) +
+                      (size_t)PLG_FUSED_WARPS * 4 * (32 * EPT / R);
   static size_t configured = 0;
   if (smem > configured)
   {
