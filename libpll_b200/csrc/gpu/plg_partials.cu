@@ -1670,7 +1670,10 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
   const size_t ops_bytes_al = (ops_bytes + 255) / 256 * 256;
   unsigned long long kernels = 0;
 
-  if (try_graph && ctx->graphs->size() < 64)
+  /* a cached graph owns its descriptors (and, fused path, its packed records: 4.7 KB per
+   * operation); very long lists are not worth pinning that much memory per distinct list */
+  const bool graph_fits = plan.fused.size() * plg_fused_record_bytes(ctx->d.rate_cats) <= ((size_t)64 << 20);
+  if (try_graph && graph_fits && ctx->graphs->size() < 64)
   {
     /* descriptors get a stable home, then the whole list is captured once */
     void * dev = NULL;
