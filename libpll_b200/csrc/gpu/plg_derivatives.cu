@@ -318,217 +318,6 @@ struct DerArgs
   unsigned int nelem;
 };
 
-/* Persistent: as many CTAs as are resident walk the (site, rate) elements with a grid stride,
- * every thread keeping its running d_f / dd_f in registers; one deterministic block tree at
- * the end and a last-block final sum (fixed grid => bit-reproducible).  A Newton iteration
- * moves only 132 B per pattern, so latency decides: each trip issues the streaming loads of
- * U elements (and of their pattern weights / invariant indices) before any arithmetic. */
-template <int K> struct DerUnroll { static constexpr int U = (K == 4) ? 4 : 1; };
-
-template <int R, int K>
-__global__ void __launch_bounds__(PLG_DER_THREADS, 2)
-k_derivatives(const DerArgs a, const __grid_constant__ DerParams P)
-{
-  constexpr int U = DerUnroll<K>::U;
-  constexpr int SV = (K == 4) ? 4 : 20;
-  const unsigned int lane = threadIdx.x & 31u;
-  const unsigned int k = lane & (R - 1);
-  const unsigned int gbase = lane & ~(unsigned int)(R - 1);
-  const unsigned int stride = gridDim.x * PLG_DER_THREADS;
-
-  /* this thread's rate: diagptable rows in registers (DNA) */
-  double dg[K == 4 ? 12 : 1];
-  if (K == 4)
-  {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int x = 0; x < 3; ++x) dg[j * 3 + x] = __ldg(a.diagp + k * 16 + j * 4 + x);
-  }
-
-  double df = 0.0, ddf = 0.0;
-  /* all lanes of a warp run the same number of iterations (shuffles inside) */
-  const unsigned int first = blockIdx.x * PLG_DER_THREADS + threadIdx.x;
-  const unsigned int warp_first = first - lane;
-  /* software pipeline: the loads of trip t+1 are in flight while trip t is being reduced */
-  double nsv[U][SV];
-  unsigned int nwgt[U];
-  int ninvs[U];
-  auto issue_loads = [&](unsigned int e00)
-  {
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-      const unsigned int e = e00 + u * stride + lane;
-      nwgt[u] = 0;
-      ninvs[u] = -1;
-      if (e < a.nelem)
-      {
-        if (K == 4)
-        {
-          const d4 s = ld_stream(a.sumtable + (size_t)e * 4);
-          nsv[u][0] = s.x; nsv[u][1] = s.y; nsv[u][2] = s.z; nsv[u][3] = s.w;
-        }
-        else
-        {
-#pragma unroll
-          for (int b = 0; b < 5; ++b)
-          {
-            const d4 s = ld_stream(a.sumtable + (size_t)e * 20 + 4 * b);
-            nsv[u][4 * b] = s.x; nsv[u][4 * b + 1] = s.y; nsv[u][4 * b + 2] = s.z; nsv[u][4 * b + 3] = s.w;
-          }
-        }
-        if (k == 0)
-        {
-          nwgt[u] = __ldg(a.weights + e / R);
-          if (P.use_pinv && a.invariant) ninvs[u] = __ldg(a.invariant + e / R);
-        }
-      }
-    }
-  };
-  if (warp_first < a.nelem) issue_loads(warp_first);
-  for (unsigned int e00 = warp_first; e00 < a.nelem; e00 += stride * U)
-  {
-    double sv[U][SV];
-    unsigned int wgt[U];
-    int invs[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-      wgt[u] = nwgt[u];
-      invs[u] = ninvs[u];
-#pragma unroll
-      for (int j = 0; j < SV; ++j) sv[u][j] = nsv[u][j];
-    }
-    if (e00 + stride * U < a.nelem) issue_loads(e00 + stride * U);
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-    const unsigned int e = e00 + u * stride + lane;
-    const bool valid = e < a.nelem;
-    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-    if (valid)
-    {
-      if (K == 4)
-      {
-        /* lanes (L, L', L'') accumulate fma(sum_j, diagp_j, acc) over the 4 states in order
-         * reference src/core_derivatives_avx2.c:634-655 */
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-        {
-          c0 = __fma_rn(sv[u][j], dg[j * 3 + 0], c0);
-          c1 = __fma_rn(sv[u][j], dg[j * 3 + 1], c1);
-          c2 = __fma_rn(sv[u][j], dg[j * 3 + 2], c2);
-        }
-      }
-      else
-      {
-        /* blocked: first block by mul, the other four by fma, then hadd
-         * reference src/core_derivatives_avx2.c:656-702 */
-        const double * d = a.diagp + k * 60;
-        double acc[3][4];
-#pragma unroll
-        for (int x = 0; x < 3; ++x)
-        {
-#pragma unroll
-          for (int l = 0; l < 4; ++l) acc[x][l] = __dmul_rn(sv[u][l], __ldg(d + x * 20 + l));
-#pragma unroll
-          for (int b = 1; b < 5; ++b)
-#pragma unroll
-            for (int l = 0; l < 4; ++l)
-              acc[x][l] = __fma_rn(sv[u][4 * b + l], __ldg(d + x * 20 + 4 * b + l), acc[x][l]);
-        }
-        c0 = hsum4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
-        c1 = hsum4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
-        c2 = hsum4(acc[2][0], acc[2][1], acc[2][2], acc[2][3]);
-      }
-    }
-
-    /* combine the rates of a site in order (reference src/core_derivatives_avx2.c:704-729) */
-    const int inv = invs[u];
-    double l0 = 0.0, l1 = 0.0, l2 = 0.0;
-#pragma unroll
-    for (int kk = 0; kk < R; ++kk)
-    {
-      double v0 = __shfl_sync(0xffffffffu, c0, gbase + kk);
-      double v1 = __shfl_sync(0xffffffffu, c1, gbase + kk);
-      double v2 = __shfl_sync(0xffffffffu, c2, gbase + kk);
-      if (k == 0)
-      {
-        if (P.use_pinv && P.prop_invar[kk] > 0.0)
-        {
-          const double q = __dsub_rn(1.0, P.prop_invar[kk]);
-          v0 = __dmul_rn(v0, q);
-          v1 = __dmul_rn(v1, q);
-          v2 = __dmul_rn(v2, q);
-          if (inv != -1) v0 = __dadd_rn(v0, P.invar_lk[kk * K + inv]);
-        }
-        if (P.eq_weights)
-        {
-          l0 = __dadd_rn(l0, v0);
-          l1 = __dadd_rn(l1, v1);
-          l2 = __dadd_rn(l2, v2);
-        }
-        else
-        {
-          const double w = P.rate_weights[kk];
-          l0 = __fma_rn(v0, w, l0);
-          l1 = __fma_rn(v1, w, l1);
-          l2 = __fma_rn(v2, w, l2);
-        }
-      }
-    }
-    if (valid && k == 0)
-    {
-      /* reference src/core_derivatives_avx2.c:746-766 */
-      const double recip = __ddiv_rn(1.0, l0);
-      const double d1 = __dmul_rn(l1, recip);
-      const double d2 = __dsub_rn(__dmul_rn(d1, d1), __dmul_rn(l2, recip));
-      const double w = (double)wgt[u];
-      df = __dsub_rn(df, __dmul_rn(d1, w));
-      ddf = __dadd_rn(ddf, __dmul_rn(d2, w));
-    }
-    }
-  }
-
-  __shared__ double red[PLG_DER_THREADS / 32];
-  __shared__ bool is_last;
-  const double s1 = block_sum<PLG_DER_THREADS>(df, red);
-  const double s2 = block_sum<PLG_DER_THREADS>(ddf, red);
-  if (threadIdx.x == 0)
-  {
-    a.partials[2 * blockIdx.x + 0] = s1;
-    a.partials[2 * blockIdx.x + 1] = s2;
-    __threadfence();
-    const unsigned int ticket = atomicAdd(a.counter, 1u);
-    is_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last)
-  {
-    __threadfence();
-    const unsigned int nb = gridDim.x;
-    const unsigned int per = (nb + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
-    const unsigned int lo = threadIdx.x * per;
-    unsigned int hi = lo + per;
-    if (hi > nb) hi = nb;
-    double t1 = 0.0, t2 = 0.0;
-    for (unsigned int b = lo; b < hi; ++b)
-    {
-      t1 = __dadd_rn(t1, __ldcg(a.partials + 2 * b));
-      t2 = __dadd_rn(t2, __ldcg(a.partials + 2 * b + 1));
-    }
-    const double r1 = block_sum<PLG_DER_THREADS>(t1, red);
-    const double r2 = block_sum<PLG_DER_THREADS>(t2, red);
-    if (threadIdx.x == 0)
-    {
-      a.result[0] = r1;
-      a.result[1] = r2;
-      *a.counter = 0u;
-    }
-  }
-}
-
 /* ------------------------------------------------------------------------------------ */
 /* DNA derivatives: one thread per pattern                                               */
 /* ------------------------------------------------------------------------------------ */
@@ -679,6 +468,131 @@ static int launch_derivatives_dna(plg_context * ctx, const DerArgs & a, const De
   DerArgs b = a;
   b.partials = ctx->partials;
   k_derivatives_dna<R><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(b, P);
+  return PLG_OK;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* 20-state derivatives: one thread per pattern                                          */
+/* ------------------------------------------------------------------------------------ */
+/* Same mapping as k_derivatives_dna; the transposed diagptable ([rate][3][20], reference
+ * src/core_derivatives_avx2.c:598-609) sits in shared memory, read as broadcast.  Per rate and
+ * per derivative order: first block by mul, the other four by fma, then the AVX horizontal sum
+ * (reference src/core_derivatives_avx2.c:656-702); rates combined in order (:704-729). */
+template <int R>
+__global__ void __launch_bounds__(PLG_DER_THREADS, 2)
+k_derivatives_aa(const DerArgs a, const __grid_constant__ DerParams P)
+{
+  __shared__ __align__(32) double sd[R * 60];
+  for (unsigned int t = threadIdx.x; t < R * 60; t += PLG_DER_THREADS) sd[t] = __ldg(a.diagp + t);
+  __syncthreads();
+  const unsigned int sites = a.nelem / R;
+  const unsigned int stride = gridDim.x * PLG_DER_THREADS;
+  double df = 0.0, ddf = 0.0;
+  for (unsigned int n = blockIdx.x * PLG_DER_THREADS + threadIdx.x; n < sites; n += stride)
+  {
+    const unsigned int wgt = __ldg(a.weights + n);
+    int inv = -1;
+    if (P.use_pinv && a.invariant) inv = __ldg(a.invariant + n);
+    double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+      double s[20];
+      load20d(a.sumtable + ((size_t)n * R + r) * 20, s);
+      double v[3];
+#pragma unroll
+      for (int x = 0; x < 3; ++x)
+      {
+        const double * d = sd + r * 60 + x * 20;
+        double acc[4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) acc[l] = __dmul_rn(s[l], d[l]);
+#pragma unroll
+        for (int b = 1; b < 5; ++b)
+#pragma unroll
+          for (int l = 0; l < 4; ++l) acc[l] = __fma_rn(s[4 * b + l], d[4 * b + l], acc[l]);
+        v[x] = hsum4(acc[0], acc[1], acc[2], acc[3]);
+      }
+      if (P.use_pinv && P.prop_invar[r] > 0.0)
+      {
+        const double q = __dsub_rn(1.0, P.prop_invar[r]);
+        v[0] = __dmul_rn(v[0], q);
+        v[1] = __dmul_rn(v[1], q);
+        v[2] = __dmul_rn(v[2], q);
+        if (inv != -1) v[0] = __dadd_rn(v[0], P.invar_lk[r * 20 + inv]);
+      }
+      if (P.eq_weights)
+      {
+        l0 = __dadd_rn(l0, v[0]);
+        l1 = __dadd_rn(l1, v[1]);
+        l2 = __dadd_rn(l2, v[2]);
+      }
+      else
+      {
+        l0 = __fma_rn(v[0], P.rate_weights[r], l0);
+        l1 = __fma_rn(v[1], P.rate_weights[r], l1);
+        l2 = __fma_rn(v[2], P.rate_weights[r], l2);
+      }
+    }
+    const double recip = __ddiv_rn(1.0, l0);
+    const double d1 = __dmul_rn(l1, recip);
+    const double d2 = __dsub_rn(__dmul_rn(d1, d1), __dmul_rn(l2, recip));
+    const double w = (double)wgt;
+    df = __dsub_rn(df, __dmul_rn(d1, w));
+    ddf = __dadd_rn(ddf, __dmul_rn(d2, w));
+  }
+
+  __shared__ double red[PLG_DER_THREADS / 32];
+  __shared__ bool is_last;
+  const double s1 = block_sum<PLG_DER_THREADS>(df, red);
+  const double s2 = block_sum<PLG_DER_THREADS>(ddf, red);
+  if (threadIdx.x == 0)
+  {
+    a.partials[2 * blockIdx.x + 0] = s1;
+    a.partials[2 * blockIdx.x + 1] = s2;
+    __threadfence();
+    is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last)
+  {
+    __threadfence();
+    const unsigned int nb = gridDim.x;
+    const unsigned int per = (nb + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
+    const unsigned int lo = threadIdx.x * per;
+    const unsigned int hi = (lo + per < nb) ? lo + per : nb;
+    double t1 = 0.0, t2 = 0.0;
+    for (unsigned int b = lo; b < hi; ++b)
+    {
+      t1 = __dadd_rn(t1, __ldcg(a.partials + 2 * b));
+      t2 = __dadd_rn(t2, __ldcg(a.partials + 2 * b + 1));
+    }
+    const double r1 = block_sum<PLG_DER_THREADS>(t1, red);
+    const double r2 = block_sum<PLG_DER_THREADS>(t2, red);
+    if (threadIdx.x == 0)
+    {
+      a.result[0] = r1;
+      a.result[1] = r2;
+      *a.counter = 0u;
+    }
+  }
+}
+
+template <int R>
+static int launch_derivatives_aa(plg_context * ctx, const DerArgs & a, const DerParams & P)
+{
+  static int per_sm = 0;
+  if (!per_sm)
+    PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_derivatives_aa<R>, PLG_DER_THREADS, 0));
+  const unsigned int sites = a.nelem / R;
+  unsigned int nblocks = (sites + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
+  const unsigned int cap = (unsigned int)(ctx->sm_count * (per_sm > 0 ? per_sm : 1));
+  if (nblocks > cap) nblocks = cap;
+  int rc = plg_ensure_partials(ctx, 2 * (size_t)nblocks);
+  if (rc) return rc;
+  DerArgs b = a;
+  b.partials = ctx->partials;
+  k_derivatives_aa<R><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(b, P);
   return PLG_OK;
 }
 
@@ -995,7 +909,7 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
   a.result = ctx->result_dev;
   a.nelem = nelem;
 
-  PLG_DISPATCH_R(R, (k_derivatives<RR, 20><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(a, P)));
+  PLG_DISPATCH_R(R, { int lrc = launch_derivatives_aa<RR>(ctx, a, P); if (lrc) return lrc; });
   PLG_LAUNCH_CHECK(ctx);
 
   PLG_CUDA(cudaStreamSynchronize(ctx->stream));

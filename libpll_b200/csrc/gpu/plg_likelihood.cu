@@ -431,93 +431,127 @@ __global__ void k_edge_ti_table_aa(const double * __restrict__ pmat, double * __
   }
 }
 
-template <int R>
-__global__ void __launch_bounds__(PLG_LNL_THREADS)
-k_edge_lnl_ti_aa(const LnlArgs a, const __grid_constant__ LnlParams P)
+/* 20 states, one thread per pattern (as k_lnl_dna): MODE 1 edge with a pattern tip (pi-weighted
+ * lookup table in a.pmat, [code][rate][20]), MODE 2 root (frequencies), MODE 3 plain sum of a
+ * scratch CLV that already holds pi_i p_i (P c)_i (second half of the two-step inner-inner edge).
+ * Per rate: four FMA lane accumulators over the five blocks of four states, then the AVX
+ * horizontal sum (reference src/core_likelihood_avx2.c:57-77, 266-286). */
+template <int R, int MODE>
+__global__ void __launch_bounds__(PLG_LNL_THREADS, 2)
+k_lnl_aa(const LnlArgs a, const __grid_constant__ LnlParams P)
 {
-  const unsigned int k = threadIdx.x & (R - 1);
-  const unsigned int e = blockIdx.x * PLG_LNL_THREADS + threadIdx.x;
-  const bool valid = e < a.nelem;
-  double term_r = 0.0;
-  if (valid)
+  const unsigned int sites = a.nelem / R;
+  const unsigned int stride = gridDim.x * PLG_LNL_THREADS;
+  double sum = 0.0;
+  for (unsigned int n = blockIdx.x * PLG_LNL_THREADS + threadIdx.x; n < sites; n += stride)
   {
-    double p[20];
-    load20s(a.clvp + (size_t)e * 20, p);
-    const unsigned int code = __ldg(a.tip + e / R);
-    const double * tab = a.pmat + ((size_t)code * R + k) * 20;
-    /* four FMA lane accumulators over the five blocks, then hadd
-     * reference src/core_likelihood_avx2.c:266-286 */
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-    for (int b = 0; b < 5; ++b)
+    const unsigned int weight = __ldg(a.weights + n);
+    const int inv = P.any_pinv ? __ldg(a.invariant + n) : -1;
+    unsigned int code = 0;
+    if (MODE == 1) code = __ldg(a.tip + n);
+
+    unsigned int site_scalings = 0;
+    unsigned int resid[R];
+    if (a.per_rate_scaling)
     {
-      const d4 l = *reinterpret_cast<const d4 *>(tab + 4 * b);
-      a0 = __fma_rn(l.x, p[4 * b + 0], a0);
-      a1 = __fma_rn(l.y, p[4 * b + 1], a1);
-      a2 = __fma_rn(l.z, p[4 * b + 2], a2);
-      a3 = __fma_rn(l.w, p[4 * b + 3], a3);
+      unsigned int mn = 0xffffffffu;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+      {
+        unsigned int rs = 0;
+        if (a.pscale) rs += __ldg(a.pscale + (size_t)n * R + r);
+        if (a.cscale) rs += __ldg(a.cscale + (size_t)n * R + r);
+        resid[r] = rs;
+        mn = rs < mn ? rs : mn;
+      }
+      site_scalings = mn;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+      {
+        const unsigned int d = resid[r] - mn;
+        resid[r] = d > PLL_SCALE_RATE_MAXDIFF ? PLL_SCALE_RATE_MAXDIFF : d;
+      }
     }
-    term_r = hsum4(a0, a1, a2, a3);
+    else
+    {
+      if (a.pscale) site_scalings += __ldg(a.pscale + n);
+      if (a.cscale) site_scalings += __ldg(a.cscale + n);
+    }
+
+    double term = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+      double c[20];
+      load20s(a.clvp + ((size_t)n * R + r) * 20, c);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      if (MODE == 3)
+      {
+#pragma unroll
+        for (int b = 0; b < 5; ++b)
+        {
+          a0 = __dadd_rn(a0, c[4 * b + 0]);
+          a1 = __dadd_rn(a1, c[4 * b + 1]);
+          a2 = __dadd_rn(a2, c[4 * b + 2]);
+          a3 = __dadd_rn(a3, c[4 * b + 3]);
+        }
+      }
+      else
+      {
+        const double * tab = a.pmat + ((size_t)code * R + r) * 20;
+#pragma unroll
+        for (int b = 0; b < 5; ++b)
+        {
+          d4 l;
+          if (MODE == 1)
+            l = *reinterpret_cast<const d4 *>(tab + 4 * b);
+          else
+            l = d4{P.freqs[r * 20 + 4 * b], P.freqs[r * 20 + 4 * b + 1], P.freqs[r * 20 + 4 * b + 2],
+                   P.freqs[r * 20 + 4 * b + 3]};
+          a0 = __fma_rn(l.x, c[4 * b + 0], a0);
+          a1 = __fma_rn(l.y, c[4 * b + 1], a1);
+          a2 = __fma_rn(l.z, c[4 * b + 2], a2);
+          a3 = __fma_rn(l.w, c[4 * b + 3], a3);
+        }
+      }
+      double v = hsum4(a0, a1, a2, a3);
+      if (a.per_rate_scaling && resid[r] > 0)
+      {
+        double sc = 1.0;
+        for (unsigned int i = 0; i < resid[r]; ++i) sc = __dmul_rn(sc, PLG_SCALE_THRESHOLD);
+        v = __dmul_rn(v, sc);
+      }
+      const double pinv = P.prop_invar[r];
+      if (pinv > 0.0)
+      {
+        const double inv_lk = (inv == -1) ? 0.0 : P.freqs[r * 20 + inv];
+        const double mix = __dadd_rn(__dmul_rn(v, __dsub_rn(1.0, pinv)), __dmul_rn(inv_lk, pinv));
+        term = __dadd_rn(term, __dmul_rn(P.rate_weights[r], mix));
+      }
+      else
+        term = __dadd_rn(term, __dmul_rn(v, P.rate_weights[r]));
+    }
+    double site_lk = log(term);
+    if (site_scalings) site_lk = __dadd_rn(site_lk, __dmul_rn((double)site_scalings, P.log_threshold));
+    site_lk = __dmul_rn(site_lk, (double)weight);
+    if (a.persite) a.persite[n] = site_lk;
+    sum = __dadd_rn(sum, site_lk);
   }
-  const double site_lk = site_epilogue<R, 20, false, false>(term_r, valid, e, a, P);
-  finish_sum<PLG_LNL_THREADS>(site_lk, a);
+  finish_sum<PLG_LNL_THREADS>(sum, a);
 }
 
-template <int R>
-__global__ void __launch_bounds__(PLG_LNL_THREADS)
-k_root_lnl_aa(const LnlArgs a, const __grid_constant__ LnlParams P)
+template <int R, int MODE>
+static int launch_lnl_aa(plg_context * ctx, LnlArgs & a, const LnlParams & P)
 {
-  const unsigned int k = threadIdx.x & (R - 1);
-  const unsigned int e = blockIdx.x * PLG_LNL_THREADS + threadIdx.x;
-  const bool valid = e < a.nelem;
-  double term_r = 0.0;
-  if (valid)
-  {
-    double c[20];
-    load20s(a.clvp + (size_t)e * 20, c);
-    const double * f = P.freqs + k * 20;
-    /* reference src/core_likelihood_avx2.c:57-77 */
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-    for (int b = 0; b < 5; ++b)
-    {
-      a0 = __fma_rn(f[4 * b + 0], c[4 * b + 0], a0);
-      a1 = __fma_rn(f[4 * b + 1], c[4 * b + 1], a1);
-      a2 = __fma_rn(f[4 * b + 2], c[4 * b + 2], a2);
-      a3 = __fma_rn(f[4 * b + 3], c[4 * b + 3], a3);
-    }
-    term_r = hsum4(a0, a1, a2, a3);
-  }
-  const double site_lk = site_epilogue<R, 20, false, false>(term_r, valid, e, a, P);
-  finish_sum<PLG_LNL_THREADS>(site_lk, a);
-}
-
-/* second half of the two-step 20-state edge log-likelihood: the scratch CLV already holds
- * pi_i * p_i * (P c)_i, so a rate's term is the plain sum of its 20 entries */
-template <int R>
-__global__ void __launch_bounds__(PLG_LNL_THREADS)
-k_sum_lnl_aa(const LnlArgs a, const __grid_constant__ LnlParams P)
-{
-  const unsigned int e = blockIdx.x * PLG_LNL_THREADS + threadIdx.x;
-  const bool valid = e < a.nelem;
-  double term_r = 0.0;
-  if (valid)
-  {
-    double c[20];
-    load20s(a.clvp + (size_t)e * 20, c);
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-    for (int b = 0; b < 5; ++b)
-    {
-      a0 = __dadd_rn(a0, c[4 * b + 0]);
-      a1 = __dadd_rn(a1, c[4 * b + 1]);
-      a2 = __dadd_rn(a2, c[4 * b + 2]);
-      a3 = __dadd_rn(a3, c[4 * b + 3]);
-    }
-    term_r = hsum4(a0, a1, a2, a3);
-  }
-  const double site_lk = site_epilogue<R, 20, false, false>(term_r, valid, e, a, P);
-  finish_sum<PLG_LNL_THREADS>(site_lk, a);
+  static int per_sm = 0;
+  if (!per_sm)
+    PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lnl_aa<R, MODE>, PLG_LNL_THREADS, 0));
+  const unsigned int sites = a.nelem / R;
+  unsigned int nblocks = (sites + PLG_LNL_THREADS - 1) / PLG_LNL_THREADS;
+  const unsigned int cap = (unsigned int)(ctx->sm_count * (per_sm > 0 ? per_sm : 1));
+  if (nblocks > cap) nblocks = cap;
+  k_lnl_aa<R, MODE><<<nblocks, PLG_LNL_THREADS, 0, ctx->stream>>>(a, P);
+  return PLG_OK;
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -681,7 +715,7 @@ extern "C" int plg_edge_loglikelihood(plg_context_t * ctx, unsigned int parent_c
       k_edge_ti_table_aa<<<8, 256, 0, ctx->stream>>>(plg_pmat_ptr(ctx, matrix_index), scratch, R,
                                                      ctx->maxstates, tm, P);
       PLG_LAUNCH_CHECK(ctx);
-      PLG_DISPATCH_R(R, (k_edge_lnl_ti_aa<RR><<<nblocks, PLG_LNL_THREADS, 0, ctx->stream>>>(a, P)));
+      PLG_DISPATCH_R(R, { int lrc = launch_lnl_aa<RR, 1>(ctx, a, P); if (lrc) return lrc; });
     }
     PLG_LAUNCH_CHECK(ctx);
   }
@@ -722,7 +756,7 @@ extern "C" int plg_edge_loglikelihood(plg_context_t * ctx, unsigned int parent_c
       if (rc) return rc;
       a.clvp = ctx->lnl_scratch;
       a.clvc = NULL;
-      PLG_DISPATCH_R(R, (k_sum_lnl_aa<RR><<<nblocks, PLG_LNL_THREADS, 0, ctx->stream>>>(a, P)));
+      PLG_DISPATCH_R(R, { int lrc = launch_lnl_aa<RR, 3>(ctx, a, P); if (lrc) return lrc; });
     }
     else
     {
@@ -784,7 +818,7 @@ extern "C" int plg_root_loglikelihood(plg_context_t * ctx, unsigned int clv_inde
   }
   else
   {
-    PLG_DISPATCH_R(R, (k_root_lnl_aa<RR><<<nblocks, PLG_LNL_THREADS, 0, ctx->stream>>>(a, P)));
+    PLG_DISPATCH_R(R, { int lrc = launch_lnl_aa<RR, 2>(ctx, a, P); if (lrc) return lrc; });
   }
   PLG_LAUNCH_CHECK(ctx);
   return fetch_result(ctx, persite_lnl, logl_out);
