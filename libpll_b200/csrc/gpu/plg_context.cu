@@ -135,6 +135,7 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   ctx->lnl_table = NULL; ctx->lnl_table_cap = 0;
   ctx->sumtables = new std::unordered_map<const void *, double *>();
   ctx->graphs = new std::unordered_map<uint64_t, plg_graph_entry *>();
+  ctx->seen_lists = new std::unordered_map<uint64_t, unsigned int>();
   const char * g = getenv("PLL_GPU_GRAPHS");
   ctx->use_graphs = g ? atoi(g) : 1;
   const char * ex = getenv("PLL_GPU_AA_EXACT");
@@ -235,6 +236,7 @@ extern "C" void plg_destroy(plg_context_t * ctx)
       delete kv.second;
     }
     delete ctx->graphs;
+    delete ctx->seen_lists;
   }
   if (ctx->sumtables)
   {

@@ -126,6 +126,7 @@ struct plg_context
 
   /* cached CUDA graphs of whole operation lists, keyed by a hash of the list */
   std::unordered_map<uint64_t, plg_graph_entry *> * graphs;
+  std::unordered_map<uint64_t, unsigned int> * seen_lists; /* hash -> times seen, lists not (yet) captured */
   int use_graphs;
   int aa_exact; /* 20 states: 1 = bit-exact vector-pipe kernels, 0 = DMMA tensor-core kernels */
 

@@ -1673,7 +1673,15 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
   /* a cached graph owns its descriptors (and, fused path, its packed records: 4.7 KB per
    * operation); very long lists are not worth pinning that much memory per distinct list */
   const bool graph_fits = plan.fused.size() * plg_fused_record_bytes(ctx->d.rate_cats) <= ((size_t)64 << 20);
-  if (try_graph && graph_fits && ctx->graphs->size() < 64)
+  /* capture on the SECOND sighting of a list: one-off lists (partial traversals during a tree
+   * search) do not pay for cudaGraphInstantiate */
+  bool capture = try_graph && graph_fits && ctx->graphs->size() < 64;
+  if (capture)
+  {
+    if (ctx->seen_lists->size() > 4096) ctx->seen_lists->clear();
+    capture = ++(*ctx->seen_lists)[key] >= 2;
+  }
+  if (capture)
   {
     /* descriptors get a stable home, then the whole list is captured once */
     void * dev = NULL;
