@@ -177,7 +177,7 @@ struct FusedOp /* 128 bytes: it travels by TMA bulk copy */
   int scale_mode;
   int lslot, rslot, pslot;
   unsigned int lbytes, rbytes; /* bytes of the packed left / right block this operation reads */
-  int pad;
+  int pad;                     /* 1: write the result through to HBM; 0: dead store (see build_plan) */
   const double * lsrc;         /* P-matrix set of the left / right child (tip or inner) */
   const double * rsrc;
 };

@@ -25,6 +25,8 @@
 #include <algorithm>
 #include <cmath>
 
+#include <unordered_map>
+
 #include "plg_internal.cuh"
 #include "plg_async.cuh"
 
@@ -1276,6 +1278,15 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
                (!it.op.rscale || it.op.rscale == pv.op.pscale))
         forward[x] = 2;
     }
+    /* Dead stores: with slot recycling a CLV / scaler buffer is overwritten several times within
+     * one list.  Only the LAST value of a buffer is observable after the call; an earlier one
+     * must reach HBM only if some operation of the list reads it from there (tile-cache miss).
+     * `pad` = 1 marks the operations whose result is written through. */
+    std::unordered_map<const void *, unsigned int> last_clv, last_sc;
+    auto need_hbm = [&](const void * buffer) {
+      auto w = last_clv.find(buffer);
+      if (w != last_clv.end()) plan.fused[w->second].pad = 1;
+    };
     plan.fused.resize(count);
     for (unsigned int x = 0; x < count; ++x)
     {
@@ -1296,6 +1307,10 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
       f.rslot = (forward[x] == 2) ? -2 : ((it.kind != PLG_KIND_TT) ? lookup(it.op.right, it.op.rscale) : -1);
       if (it.kind == PLG_KIND_II) (f.lslot != -1 ? plan.fused_hits : plan.fused_misses)++;
       if (it.kind != PLG_KIND_TT) (f.rslot != -1 ? plan.fused_hits : plan.fused_misses)++;
+      if (it.kind == PLG_KIND_II && f.lslot == -1) need_hbm(it.op.left);
+      if (it.kind != PLG_KIND_TT && f.rslot == -1) need_hbm(it.op.right);
+      last_clv[it.op.parent] = x;
+      if (it.op.pscale) last_sc[it.op.pscale] = x;
       /* stale copies of what this operation overwrites */
       for (unsigned int q = 0; q < nslot; ++q)
         if (tag_clv[q] == it.op.parent || (it.op.pscale && tag_sc[q] == it.op.pscale))
@@ -1322,6 +1337,8 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
       tag_sc[dst] = it.op.pscale;
       born[dst] = ++clock;
     }
+    for (const auto & kv : last_clv) plan.fused[kv.second].pad = 1;
+    for (const auto & kv : last_sc) plan.fused[kv.second].pad = 1;
   }
   return PLG_OK;
 }

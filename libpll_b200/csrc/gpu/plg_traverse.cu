@@ -251,6 +251,9 @@ __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> 
   const unsigned int * rscale = st.desc.op.rscale;
   double * parent = st.desc.op.parent + (size_t)e0 * 4;
   unsigned int * pscale = st.desc.op.pscale;
+  /* 0: a dead store - the buffer is overwritten later in this list and nobody reads this value
+   * from HBM (slot-recycling lists; see build_plan) */
+  const bool write_back = st.desc.pad != 0;
   unsigned int sc[EPT];
 
   if (KIND == PLG_KIND_TT)
@@ -341,7 +344,7 @@ __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> 
         (KIND == PLG_KIND_TT) ? 0u : finish_element<R, MODE>(p[j], valid, sc[j], gshift, full_mask);
     if (pslot >= 0) cache.store(pslot, j, lane, p[j], sv);
     psc[j] = sv;
-    if (valid)
+    if (valid && write_back)
     {
       st_stream(parent + j * 128, p[j]);
       if (MODE == 2) pscale[e] = sv;
