@@ -1193,7 +1193,7 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
   /* ---- the single-kernel traversal (plg_traverse.cu): execution order + tile cache ---- */
   plan.fused.clear();
   plan.fused_hits = plan.fused_misses = 0;
-  if (ctx->use_fused && K == 4 && R <= 4 && plg_fast_path(ctx) && count >= 2)
+  if (ctx->use_fused && K == 4 && plg_fast_path(ctx) && count >= 2)
   {
     /* Execution order.  A list without slot recycling is a forest: walk it depth-first, the
      * larger subtree first, so that few results are waiting for their parent at any time.

@@ -125,6 +125,9 @@ struct WarpCache
  * is either this operation's P-matrix set with rows of one rate 18 doubles apart, or a tip
  * table with the 16 codes (4R + 2) doubles apart: the 2-double pads rotate the shared-memory
  * banks so that the four rates of a site (matrix) and neighbouring codes (table) do not collide. */
+/* ring depth: the records of 8 / 16 rate categories are larger (8.8 / 17 KB), the ring shorter */
+__host__ __device__ constexpr int fused_stages(int R) { return R <= 4 ? PLG_FUSED_STAGES : 4; }
+
 template <int R>
 struct FusedStage
 {
@@ -397,7 +400,7 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
                unsigned int nslot)
 {
   using namespace plg_async;
-  constexpr int S = PLG_FUSED_STAGES;
+  constexpr int S = fused_stages(R);
   constexpr int NW = PLG_FUSED_WARPS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FusedStage<R> * stages = reinterpret_cast<FusedStage<R> *>(smem_raw);
@@ -565,7 +568,7 @@ static int launch_fused(plg_context * ctx, const FusedOp * dev_ops, unsigned cha
 {
   constexpr int EPT = PLG_FUSED_EPT;
   static_assert(sizeof(FusedOp) == 128, "descriptor must be 128 bytes");
-  const size_t smem = PLG_FUSED_STAGES * sizeof(FusedStage<R>) + 128 +
+  const size_t smem = fused_stages(R) * sizeof(FusedStage<R>) + 128 +
                       (size_t)PLG_FUSED_WARPS * nslot * EPT * 32 * (32 + 4) +
                       (size_t)PLG_FUSED_WARPS * 4 * (32 * EPT / R);
   static size_t configured = 0;

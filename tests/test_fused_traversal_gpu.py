@@ -2,7 +2,7 @@
 the level-by-level kernels (PLL_GPU_FUSED=0) on the same partitions: every CLV and every scaler
 array must be bit-identical, for plain and slot-recycling lists, per-site and per-rate scalers,
 with a tile cache of 1, 2 and 3 slots (1 slot forces many reads back from HBM), for alignment
-lengths that leave partial tiles, and for 1, 2 and 4 rate categories."""
+lengths that leave partial tiles, and for 1, 2, 4, 8 and 16 rate categories."""
 import numpy as np
 import pytest
 
@@ -30,7 +30,8 @@ def _run(gpu_lib, monkeypatch, w, attrs, fused, slots=3):
     return clvs, scalers, lnl, launches
 
 
-@pytest.mark.parametrize("tips,sites,cats", [(40, 1000, 4), (150, 4097, 4), (33, 777, 1), (64, 2050, 2)])
+@pytest.mark.parametrize("tips,sites,cats", [(40, 1000, 4), (150, 4097, 4), (33, 777, 1), (64, 2050, 2), (30, 1500, 8),
+                                             (25, 900, 16)])
 @pytest.mark.parametrize("rate_scalers", [False, True])
 @pytest.mark.parametrize("pattern_tip", [True, False])
 def test_fused_equals_level_by_level(gpu_lib, monkeypatch, tips, sites, cats, rate_scalers, pattern_tip):
