@@ -750,12 +750,12 @@ extern "C" int plg_update_sumtable(plg_context_t * ctx, unsigned int parent_clv_
     {
       const size_t smem = (size_t)R * 400 * sizeof(double);
       PLG_DISPATCH_R(R, {
-        static bool attr_done = false;
-        if (!attr_done)
+        static bool attr_done[PLG_MAX_DEVICES] = {}; /* a function attribute is per device */
+        if (!attr_done[ctx->device % PLG_MAX_DEVICES])
         {
           PLG_CUDA(cudaFuncSetAttribute(k_sumtable_ti_aa<RR>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          attr_done = true;
+          attr_done[ctx->device % PLG_MAX_DEVICES] = true;
         }
         k_sumtable_ti_aa<RR><<<nblocks, PLG_DER_THREADS, smem, ctx->stream>>>(a);
       });
@@ -777,12 +777,12 @@ extern "C" int plg_update_sumtable(plg_context_t * ctx, unsigned int parent_clv_
     {
       const size_t smem = (size_t)2 * R * 400 * sizeof(double);
       PLG_DISPATCH_R(R, {
-        static bool attr_done = false;
-        if (!attr_done)
+        static bool attr_done[PLG_MAX_DEVICES] = {}; /* a function attribute is per device */
+        if (!attr_done[ctx->device % PLG_MAX_DEVICES])
         {
           PLG_CUDA(cudaFuncSetAttribute(k_sumtable_ii_aa<RR>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          attr_done = true;
+          attr_done[ctx->device % PLG_MAX_DEVICES] = true;
         }
         k_sumtable_ii_aa<RR><<<nblocks, PLG_DER_THREADS, smem, ctx->stream>>>(a);
       });

@@ -140,6 +140,8 @@ struct plg_context
   plg_stats_t stats;
 };
 
+#define PLG_MAX_DEVICES 64
+
 /* ---- descriptors shared by the CLV-update kernels (plg_partials.cu, plg_generic.cu) ---- */
 enum { PLG_KIND_TT = 0, PLG_KIND_TI = 1, PLG_KIND_II = 2 };
 

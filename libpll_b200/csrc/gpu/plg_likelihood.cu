@@ -762,12 +762,12 @@ extern "C" int plg_edge_loglikelihood(plg_context_t * ctx, unsigned int parent_c
     {
       const size_t smem = (size_t)R * 400 * sizeof(double);
       PLG_DISPATCH_R(R, {
-        static bool attr_done = false;
-        if (!attr_done)
+        static bool attr_done[PLG_MAX_DEVICES] = {}; /* a function attribute is per device */
+        if (!attr_done[ctx->device % PLG_MAX_DEVICES])
         {
           PLG_CUDA(cudaFuncSetAttribute(k_edge_lnl_ii_aa<RR>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          attr_done = true;
+          attr_done[ctx->device % PLG_MAX_DEVICES] = true;
         }
         k_edge_lnl_ii_aa<RR><<<nblocks, PLG_LNL_THREADS, smem, ctx->stream>>>(a, P);
       });

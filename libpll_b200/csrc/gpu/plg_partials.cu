@@ -1424,8 +1424,10 @@ static int set_smem_limits()
 {
   /* opt in to > 48 KB of dynamic shared memory: the DNA streaming rings and the 20-state
    * kernels' P-matrix sets (2*R*3200 bytes) */
-  static bool done = false;
-  if (done) return PLG_OK;
+  static bool done[PLG_MAX_DEVICES] = {}; /* function attributes are per device */
+  int dev = 0;
+  PLG_CUDA(cudaGetDevice(&dev));
+  if (done[dev % PLG_MAX_DEVICES]) return PLG_OK;
   PLG_CUDA(cudaFuncSetAttribute(k_partial_stream_dna<R, PLG_KIND_II, PLG_II_STAGES, PLG_II_MINB>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(StreamSmem<R, PLG_KIND_II, PLG_II_STAGES>)));
@@ -1445,7 +1447,7 @@ static int set_smem_limits()
                                 2 * R * PLG_AA_MSTRIDE * (int)sizeof(double)));
   PLG_CUDA(cudaFuncSetAttribute(k_partial_ti_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 R * PLG_AA_MSTRIDE * (int)sizeof(double)));
-  done = true;
+  done[dev % PLG_MAX_DEVICES] = true;
   return PLG_OK;
 }
 

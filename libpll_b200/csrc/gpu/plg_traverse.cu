@@ -571,11 +571,11 @@ static int launch_fused(plg_context * ctx, const FusedOp * dev_ops, unsigned cha
   const size_t smem = fused_stages(R) * sizeof(FusedStage<R>) + 128 +
                       (size_t)PLG_FUSED_WARPS * nslot * EPT * 32 * (32 + 4) +
                       (size_t)PLG_FUSED_WARPS * 4 * (32 * EPT / R);
-  static size_t configured = 0;
-  if (smem > configured)
+  static size_t configured[PLG_MAX_DEVICES] = {}; /* function attributes are per device */
+  if (smem > configured[ctx->device % PLG_MAX_DEVICES])
   {
     PLG_CUDA(cudaFuncSetAttribute(k_traverse_dna<R, EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    configured[ctx->device % PLG_MAX_DEVICES] = smem;
   }
   int per_sm = 0;
   PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse_dna<R, EPT>,

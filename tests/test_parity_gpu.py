@@ -247,3 +247,26 @@ def test_full_width_properties(gpu_lib, ref_lib):
     pr.edge_loglikelihood(*args, persite=ps_ref)
     pr.destroy()
     np.testing.assert_allclose(persite[lo:hi], ps_ref, rtol=RTOL, atol=0)
+
+
+def test_two_devices_in_one_process(gpu_lib):
+    """Partitions on two different GPUs of one process (pll_gpu_set_device): per-device kernel
+    attributes (opt-in shared memory) must be set on both; same workload, same log-likelihood."""
+    if gpu_lib.pll_gpu_device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    results = []
+    for states, tips, sites in ((4, 40, 5000), (20, 12, 700)):
+        w = S.make_workload(tips, sites, states=states, seed=77)
+        per_device = []
+        for dev in (0, 1):
+            gpu_lib.pll_gpu_set_device(dev)
+            part, pidx = S.build_partition(gpu_lib, w, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP)
+            per_device.append(S.full_evaluation(part, w, pidx))
+            a, b = w.root_a, w.root_b
+            tab = part.new_sumtable()
+            part.update_sumtable(a, b, w.scaler_of(a), w.scaler_of(b), pidx, tab)
+            per_device.append(part.likelihood_derivatives(w.scaler_of(a), w.scaler_of(b), 0.1, pidx, tab))
+            part.destroy()
+        results.append(per_device)
+        assert per_device[0] == per_device[2] and per_device[1] == per_device[3], per_device
+    gpu_lib.pll_gpu_set_device(0)
