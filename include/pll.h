@@ -420,6 +420,10 @@ PLL_EXPORT int pll_utree_traverse(pll_unode_t * root,
                                   pll_unode_t ** outbuffer,
                                   unsigned int * trav_size);
 PLL_EXPORT int pll_utree_every(pll_utree_t * tree, int (*cb)(pll_unode_t *));
+PLL_EXPORT int pll_utree_every_const(const pll_utree_t * tree, int (*cb)(const pll_unode_t *));
+PLL_EXPORT int pll_utree_check_integrity(const pll_utree_t * tree);
+PLL_EXPORT pll_unode_t * pll_utree_graph_clone(const pll_unode_t * root);
+PLL_EXPORT pll_utree_t * pll_utree_clone(const pll_utree_t * tree);
 PLL_EXPORT void pll_utree_create_operations(pll_unode_t * const * trav_buffer,
                                             unsigned int trav_buffer_size,
                                             double * branches,

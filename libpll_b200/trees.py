@@ -59,6 +59,9 @@ _TREE_API = {
                                                        C.POINTER(C.c_uint), C.c_void_p, C.POINTER(C.c_uint),
                                                        C.POINTER(C.c_uint), C.POINTER(C.c_uint),
                                                        C.POINTER(C.c_int), C.POINTER(C.c_uint)]),
+    "pll_utree_check_integrity": (C.c_int, [UTREE_P]),
+    "pll_utree_clone": (UTREE_P, [UTREE_P]),
+    "pll_utree_graph_clone": (UNODE_P, [UNODE_P]),
     "pll_fasta_open": (C.c_void_p, [C.c_char_p, C.POINTER(C.c_uint)]),
     "pll_fasta_getnext": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_long),
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_long), C.POINTER(C.c_long)]),
@@ -186,6 +189,24 @@ class Tree:
         if not ok:
             raise PllError(f"[{lib.errno()}] {lib.errmsg()} (needs {used.value} slots)")
         return ops[:no.value], matrices[:nm.value], branches[:nm.value], list(eclv), list(esc), used.value
+
+    def clone(self, graph_lib: PllLibrary | None = None) -> "Tree":
+        """A deep copy.  With `graph_lib` the node graph is copied by THAT library's
+        pll_utree_graph_clone and wrapped by the owner's pll_utree_wraptree (the reference built
+        without bison has no wraptree); both libraries allocate with the same malloc."""
+        if graph_lib is None:
+            ptr = self.lib.pll_utree_clone(self.ptr)
+        else:
+            root = bind(graph_lib).pll_utree_graph_clone(self.root)
+            ptr = self.lib.pll_utree_wraptree(root, self.tips) if root else None
+        if not ptr:
+            raise PllError(self.lib.errmsg())
+        t = Tree.__new__(Tree)
+        t.lib, t.ptr, t.t = self.lib, ptr, ptr.contents
+        return t
+
+    def check_integrity(self, lib: PllLibrary | None = None) -> bool:
+        return bool(bind(lib or self.lib).pll_utree_check_integrity(self.ptr))
 
     def export_newick(self, lib: PllLibrary | None = None) -> str:
         lib = bind(lib or self.lib)

@@ -138,6 +138,26 @@ def test_export_parse_round_trip(lib):
     t2.destroy()
 
 
+def test_clone_and_integrity_match_reference(lib, ref):
+    t = T.Tree(lib, newick=random_newick(150, 31))
+    assert t.check_integrity(lib) and t.check_integrity(ref)
+    ours, theirs = t.clone(), t.clone(graph_lib=ref)
+    for c in (ours, theirs):
+        assert c.check_integrity(lib) and c.check_integrity(ref)
+    assert ours.records() == theirs.records() == t.records()
+    assert ours.export_newick() == t.export_newick()
+    o1, m1, b1 = ours.operations()
+    o0, m0, b0 = t.operations()
+    assert o1.tobytes() == o0.tobytes() and m1.tobytes() == m0.tobytes() and b1.tobytes() == b0.tobytes()
+    # a clone is independent of the original
+    t.node(0).contents.length = 123.0
+    assert ours.node(0).contents.length != 123.0
+    assert not t.check_integrity(lib) and not t.check_integrity(ref)  # the edge's two ends now disagree
+    ours.destroy()
+    theirs.destroy()
+    t.destroy()
+
+
 def test_deep_tree_needs_no_recursion(lib):
     """A 200 000-taxon caterpillar: the reference's recursive walks would need ~200 000 stack
     frames; the reader, template, traversal, operations and export here are all iterative."""
