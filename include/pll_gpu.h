@@ -153,8 +153,11 @@ PLL_EXPORT int plg_update_pmatrix(plg_context_t * ctx,
  * pll_core_create_lookup + pll_core_update_partial_tt / _ti / _ii with fill_parent_scaler and
  * the scaling-threshold rescale (reference src/partials.c:177-213,
  * src/core_partials.c:82-862, src/core_partials_avx.c, src/core_partials_avx2.c:568-803).
- * The whole list is levelised by data dependency (RAW/WAR/WAW on CLV and scaler slots) and
- * enqueued as one batch; results are identical to executing the list in array order. */
+ * The whole list is analysed for data dependencies (RAW/WAR/WAW on CLV and scaler slots) and
+ * enqueued as one batch: for 4 states ONE kernel walks the list tile by tile with the children
+ * held on chip (every CLV / scaler whose value is observable after the call is still written to
+ * HBM); otherwise one launch per dependency level and kind.  Repeated lists replay a CUDA graph.
+ * Results are identical to executing the list in array order. */
 PLL_EXPORT int plg_update_partials(plg_context_t * ctx,
                                    const pll_operation_t * operations,
                                    unsigned int count);
