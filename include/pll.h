@@ -253,9 +253,46 @@ PLL_EXPORT extern const unsigned int pll_map_aa[256];
 PLL_EXPORT extern const unsigned int pll_map_fasta[256];
 PLL_EXPORT extern const unsigned int pll_map_phylip[256];
 
-/* ---- empirical amino-acid models used by the BASELINE configs (reference src/maps.c) ---- */
+/* ---- empirical amino-acid models (reference src/pll.h:480-522, tables src/maps.c:172-1165):
+ * 190 exchangeabilities in pll_set_subst_params order + 20 frequencies each ---- */
+PLL_EXPORT extern const double pll_aa_rates_dayhoff[190];
 PLL_EXPORT extern const double pll_aa_rates_lg[190];
+PLL_EXPORT extern const double pll_aa_rates_dcmut[190];
+PLL_EXPORT extern const double pll_aa_rates_jtt[190];
+PLL_EXPORT extern const double pll_aa_rates_mtrev[190];
+PLL_EXPORT extern const double pll_aa_rates_wag[190];
+PLL_EXPORT extern const double pll_aa_rates_rtrev[190];
+PLL_EXPORT extern const double pll_aa_rates_cprev[190];
+PLL_EXPORT extern const double pll_aa_rates_vt[190];
+PLL_EXPORT extern const double pll_aa_rates_blosum62[190];
+PLL_EXPORT extern const double pll_aa_rates_mtmam[190];
+PLL_EXPORT extern const double pll_aa_rates_mtart[190];
+PLL_EXPORT extern const double pll_aa_rates_mtzoa[190];
+PLL_EXPORT extern const double pll_aa_rates_pmb[190];
+PLL_EXPORT extern const double pll_aa_rates_hivb[190];
+PLL_EXPORT extern const double pll_aa_rates_hivw[190];
+PLL_EXPORT extern const double pll_aa_rates_jttdcmut[190];
+PLL_EXPORT extern const double pll_aa_rates_flu[190];
+PLL_EXPORT extern const double pll_aa_rates_stmtrev[190];
+PLL_EXPORT extern const double pll_aa_freqs_dayhoff[20];
 PLL_EXPORT extern const double pll_aa_freqs_lg[20];
+PLL_EXPORT extern const double pll_aa_freqs_dcmut[20];
+PLL_EXPORT extern const double pll_aa_freqs_jtt[20];
+PLL_EXPORT extern const double pll_aa_freqs_mtrev[20];
+PLL_EXPORT extern const double pll_aa_freqs_wag[20];
+PLL_EXPORT extern const double pll_aa_freqs_rtrev[20];
+PLL_EXPORT extern const double pll_aa_freqs_cprev[20];
+PLL_EXPORT extern const double pll_aa_freqs_vt[20];
+PLL_EXPORT extern const double pll_aa_freqs_blosum62[20];
+PLL_EXPORT extern const double pll_aa_freqs_mtmam[20];
+PLL_EXPORT extern const double pll_aa_freqs_mtart[20];
+PLL_EXPORT extern const double pll_aa_freqs_mtzoa[20];
+PLL_EXPORT extern const double pll_aa_freqs_pmb[20];
+PLL_EXPORT extern const double pll_aa_freqs_hivb[20];
+PLL_EXPORT extern const double pll_aa_freqs_hivw[20];
+PLL_EXPORT extern const double pll_aa_freqs_jttdcmut[20];
+PLL_EXPORT extern const double pll_aa_freqs_flu[20];
+PLL_EXPORT extern const double pll_aa_freqs_stmtrev[20];
 PLL_EXPORT extern const double pll_aa_rates_lg4m[4][190];
 PLL_EXPORT extern const double pll_aa_freqs_lg4m[4][20];
 PLL_EXPORT extern const double pll_aa_rates_lg4x[4][190];

@@ -80,10 +80,13 @@ def test_maps_match_reference(gpu_lib, ref_lib):
 
 
 def test_aa_model_tables_match_reference(gpu_lib, ref_lib):
-    for name, shape in (("pll_aa_rates_lg", (190,)), ("pll_aa_freqs_lg", (20,)), ("pll_aa_rates_lg4m", (4, 190)),
-                        ("pll_aa_freqs_lg4m", (4, 20)), ("pll_aa_rates_lg4x", (4, 190)),
-                        ("pll_aa_freqs_lg4x", (4, 20))):
-        assert np.array_equal(gpu_lib.aa_table(name, shape), ref_lib.aa_table(name, shape)), name
+    single = ("dayhoff", "lg", "dcmut", "jtt", "mtrev", "wag", "rtrev", "cprev", "vt", "blosum62", "mtmam",
+              "mtart", "mtzoa", "pmb", "hivb", "hivw", "jttdcmut", "flu", "stmtrev")   # src/pll.h:480-522
+    tables = [(f"pll_aa_rates_{m}", (190,)) for m in single] + [(f"pll_aa_freqs_{m}", (20,)) for m in single]
+    tables += [("pll_aa_rates_lg4m", (4, 190)), ("pll_aa_freqs_lg4m", (4, 20)),
+               ("pll_aa_rates_lg4x", (4, 190)), ("pll_aa_freqs_lg4x", (4, 20))]
+    for name, shape in tables:
+        assert gpu_lib.aa_table(name, shape).tobytes() == ref_lib.aa_table(name, shape).tobytes(), name
 
 
 def test_gamma_rates_bit_identical_to_reference(gpu_lib, ref_lib):
