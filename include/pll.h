@@ -492,7 +492,8 @@ PLL_EXPORT int pll_utree_create_operations_recycled(pll_unode_t * root,
                                                     int * edge_scaler,
                                                     unsigned int * slots_used);
 
-/* ---- printing helpers (reference src/output.c:26-96); sync the needed mirrors first ---- */
+/* ---- printing helpers (reference src/output.c:26-96); they download the arrays they print
+ * from HBM into the host mirrors themselves ---- */
 PLL_EXPORT void pll_show_pmatrix(const pll_partition_t * partition,
                                  unsigned int index,
                                  unsigned int float_precision);

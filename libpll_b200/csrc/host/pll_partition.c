@@ -139,6 +139,17 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips,
 {
   unsigned int i;
 
+  /* PLL_GPU_FORCE=1: relink-only drop-in.  A program built against the reference's pll.h asks
+   * for PLL_ATTRIB_ARCH_CPU/SSE/AVX/AVX2 (it cannot know the new flag); with this switch its
+   * architecture bits are replaced by PLL_ATTRIB_ARCH_GPU, so unmodified callers - the
+   * reference's own test/src programs, see tests/test_reference_programs_gpu.py - run on the
+   * device.  Still no CPU path: without the switch such a request fails below. */
+  {
+    const char * force = getenv("PLL_GPU_FORCE");
+    if (force && *force && strcmp(force, "0") != 0)
+      attributes = (attributes & ~(unsigned int)PLL_ATTRIB_ARCH_MASK) | PLL_ATTRIB_ARCH_GPU;
+  }
+
   if (!(attributes & PLL_ATTRIB_ARCH_GPU))
   {
     pll_fail(PLL_ERROR_PARAM_INVALID,

@@ -1,0 +1,93 @@
+"""GPU: the reference's OWN known-answer programs run on the device, relink-only.
+
+`make -C oracle dropin` (part of `__graft_entry__.build()` whenever /root/reference is present)
+compiles the unmodified reference test sources - test/src/<name>.c with the reference's
+test/src/common.c and the reference's own pll.h - and links them against libpll_b200.so instead
+of -lpll.  The binaries and the expected text travel to the GPU box in the git-ignored
+oracle/_ref/dropin/ (nothing of the reference is copied into the repository):
+
+  oracle/_ref/dropin/<name>                 the program under test
+  oracle/_ref/dropin/expected/<name>.out    what the same program prints on the reference
+                                            library (AVX2 path); byte-identical to the
+                                            reference's fixture test/out/<name>.out
+
+The programs ask for PLL_ATTRIB_ARCH_CPU/AVX2 (they predate the GPU flag); PLL_GPU_FORCE=1 makes
+pll_partition_create replace the architecture bits by PLL_ATTRIB_ARCH_GPU.  Like the reference's
+test/runtest.py:265-347 every program runs under several attribute sets and must print the one
+fixture; unlike its byte-wise diff, numbers may differ by one unit in the last printed digit
+(device expm1/log/exp are 1-2 ulp from glibc's) and values at the cancellation floor of the
+derivatives (|x| <= 1e-10, e.g. -6.6613e-15) are compared absolutely.
+"""
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN = os.path.join(ROOT, "oracle", "_ref", "dropin")
+
+PROGRAMS = ["00010_NMDU_lkcalc", "00011_NMAU_lkcalc", "00012_NMOU_lkcalc", "00020_NMDR_lkcalc",
+            "00021_NMAR_lkcalc", "00022_NMOR_lkcalc", "00030_NMDU_gamma", "00032_NMOU_gamma",
+            "alpha-cats", "hky", "pmatrix", "derivatives", "derivatives-oddstates"]
+ATTRIBUTE_SETS = [(), ("tv",), ("tv", "avx2")]          # tokens of reference test/src/common.c:22-56
+
+NUMBER = re.compile(r"^([-+]?)(\d+)\.(\d+)(?:[eE]([-+]?\d+))?$")
+
+
+def tokens_agree(got: str, want: str) -> bool:
+    if got == want:
+        return True
+    g, w = NUMBER.match(got), NUMBER.match(want)
+    if not g or not w:
+        # "-0.000000" vs "0.000000" style sign of a rounded zero is the only non-numeric slack
+        return False
+    a, b = float(got), float(want)
+    exponent = int(w.group(4)) if w.group(4) else 0
+    last_place = 10.0 ** (exponent - len(w.group(3)))
+    return abs(a - b) <= 1.01 * last_place or abs(a - b) <= 1e-10
+
+
+def compare_text(got: str, want: str, what: str):
+    gl, wl = got.splitlines(), want.splitlines()
+    assert len(gl) == len(wl), f"{what}: {len(gl)} lines printed, {len(wl)} expected"
+    inexact = 0
+    for n, (x, y) in enumerate(zip(gl, wl), 1):
+        if x == y:
+            continue
+        xt, yt = x.split(), y.split()
+        assert len(xt) == len(yt), f"{what}:{n}: {x!r} != {y!r}"
+        for a, b in zip(xt, yt):
+            assert tokens_agree(a, b), f"{what}:{n}: {a} != {b}\n  got : {x}\n  want: {y}"
+        inexact += 1
+    return inexact, len(wl)
+
+
+@pytest.mark.parametrize("attrs", ATTRIBUTE_SETS, ids=lambda a: "+".join(a) or "default")
+@pytest.mark.parametrize("name", PROGRAMS)
+def test_reference_program_prints_its_fixture(name, attrs, capsys):
+    exe = os.path.join(DROPIN, name)
+    expected = os.path.join(DROPIN, "expected", name + ".out")
+    if not (os.path.exists(exe) and os.path.exists(expected)):
+        pytest.skip("oracle/_ref/dropin not built (needs /root/reference at build time)")
+    env = dict(os.environ, PLL_GPU_FORCE="1")
+    out = subprocess.run([exe, *attrs], capture_output=True, text=True, timeout=300, env=env, cwd=DROPIN)
+    if out.stdout == "Skip\n":           # the program itself declines this attribute set
+        pytest.skip(f"{name} skips {attrs}")   # (reference test/out/skip.out, runtest.py:339-345)
+    assert out.returncode == 0, (out.returncode, out.stderr[-2000:], out.stdout[-2000:])
+    inexact, total = compare_text(out.stdout, open(expected).read(), f"{name} {' '.join(attrs)}")
+    with capsys.disabled():
+        print(f"\n[{name} {' '.join(attrs) or '-'}] {total - inexact}/{total} lines byte-identical, "
+              f"{inexact} within one unit in the last printed digit")
+
+
+def test_without_the_switch_a_cpu_request_is_refused():
+    """No CPU path: the same binary without PLL_GPU_FORCE fails in pll_partition_create."""
+    exe = os.path.join(DROPIN, "00010_NMDU_lkcalc")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dropin not built")
+    env = {k: v for k, v in os.environ.items() if k != "PLL_GPU_FORCE"}
+    out = subprocess.run([exe, "tv", "avx2"], capture_output=True, text=True, timeout=60, env=env, cwd=DROPIN)
+    assert out.returncode != 0
+    assert "PLL_ATTRIB_ARCH_GPU only" in out.stdout + out.stderr
