@@ -266,7 +266,24 @@ PLL_EXPORT unsigned int * pll_gpu_compress_site_patterns(char ** sequence,
 PLL_EXPORT int pll_gpu_set_device(int device);
 PLL_EXPORT int pll_gpu_device_count(void);
 
-/* The device context behind a GPU partition (NULL if not a GPU partition). */
+/* Several GPUs behind ONE partition, in one process: partitions created by this thread after
+ * pll_gpu_set_devices(n) (n = 0 restores the default: $PLL_GPU_DEVICES, else 1) are cut into n contiguous pattern
+ * slices (64-pattern aligned; fewer if the alignment is that short), slice d living on device
+ * (first device + d) mod pll_gpu_device_count().  Every pll.h call fans out to all slices -
+ * setters and pll_update_partials only enqueue, so the devices run concurrently - and
+ * log-likelihoods / derivatives are the per-slice partial results added on the host in slice
+ * order (the only cross-device exchange on the path: reference src/core_likelihood_avx.c:1259
+ * `logl +=`, src/core_derivatives_avx2.c:756-765 are the only statements that couple sites).
+ * Nothing in the caller changes.  Not combinable with ascertainment-bias correction. */
+PLL_EXPORT int pll_gpu_set_devices(int count);
+/* Number of pattern slices of a partition (0 if not a GPU partition). */
+PLL_EXPORT int pll_gpu_partition_devices(const pll_partition_t * partition);
+/* Context of one slice and the pattern range it owns (NULL if out of range). */
+PLL_EXPORT plg_context_t * pll_gpu_context_of(const pll_partition_t * partition, unsigned int slice,
+                                              unsigned int * first_site, unsigned int * sites);
+
+/* The device context behind a GPU partition (NULL if not a GPU partition); with several
+ * pattern slices, the context of slice 0. */
 PLL_EXPORT plg_context_t * pll_gpu_context(const pll_partition_t * partition);
 
 /* Download one array into its host mirror (allocated on first use):

@@ -92,7 +92,7 @@ PLL_EXPORT int pll_update_sumtable(pll_partition_t * partition,
     }
   }
 
-  int rc = plg_update_sumtable(g->ctx, parent_clv_index, child_clv_index, parent_scaler_index,
+  int rc = pllg_dev_update_sumtable(g, parent_clv_index, child_clv_index, parent_scaler_index,
                                child_scaler_index, evecs, left, sumtable,
                                want_hostcopy() ? sumtable : NULL);
   free(evecs);
@@ -145,7 +145,7 @@ PLL_EXPORT int pll_compute_likelihood_derivatives(pll_partition_t * partition,
   int rc = PLG_OK;
   if (ab == PLL_ATTRIB_AB_STAMATAKIS) rc = plg_set_active_sites(g->ctx, p->sites + K);
   if (!rc)
-    rc = plg_likelihood_derivatives(g->ctx, sumtable, diagp, p->rate_weights, pinv, freqs, d_f, dd_f);
+    rc = pllg_dev_likelihood_derivatives(g, sumtable, diagp, p->rate_weights, pinv, freqs, d_f, dd_f);
   if (ab == PLL_ATTRIB_AB_STAMATAKIS) plg_set_active_sites(g->ctx, p->sites);
   int ok = rc ? pllg_fail(rc, "pll_compute_likelihood_derivatives") : PLL_SUCCESS;
   if (ok && ab && ab != PLL_ATTRIB_AB_STAMATAKIS)

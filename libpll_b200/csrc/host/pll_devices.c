@@ -1,0 +1,256 @@
+/*
+ * pll_devices.c - one pll_partition_t over several GPUs of one process.
+ *
+ * Site patterns are the independent unit of every kernel on the path (reference
+ * src/core_partials_avx.c:421-529, src/core_likelihood_avx.c:1166-1260 and
+ * src/core_derivatives_avx2.c:634-766 all loop `for n < sites` with no cross-site dependence;
+ * only `logl +=`, `d_f +=`, `dd_f +=` couple sites).  A partition created after
+ * pll_gpu_set_devices(n) (or with PLL_GPU_DEVICES=n in the environment) therefore owns n device
+ * contexts; context d holds the contiguous pattern slice [lo[d], lo[d+1]) of EVERY CLV, scale
+ * buffer, tip row, weight / invariant array and sumtable, while P-matrices, tip maps and the
+ * operations list are replicated (KBs; the P-matrix kernel simply runs on every device).
+ * Setters and pll_update_partials enqueue on every context's stream and return, so the devices
+ * work concurrently; log-likelihoods and derivatives are the sum of the per-device partial
+ * results, added on the host in device order (a 1- or 2-double "all-reduce": nothing else ever
+ * crosses between GPUs).  Slices are placed round-robin over the visible devices, so n may
+ * exceed the device count (the slicing logic is testable on one GPU).
+ *
+ * Every pllg_dev_* function has the signature of the plg_* function it fans out to, with the
+ * partition wrapper in place of the context; host arrays indexed by site are passed with the
+ * slice's offset.  With one device they reduce to the single plg_* call.
+ */
+#include "pll_host.h"
+
+static __thread int g_slices = 0; /* 0 = not set by pll_gpu_set_devices: look at the environment */
+
+PLL_EXPORT int pll_gpu_set_devices(int count)
+{
+  if (count < 0 || count > PLLG_MAX_DEVICES)
+    return pll_fail(PLL_ERROR_PARAM_INVALID, "pll_gpu_set_devices: count must be 0..%d", PLLG_MAX_DEVICES);
+  g_slices = count;
+  return PLL_SUCCESS;
+}
+
+int pll_gpu_current_slices(void)
+{
+  if (g_slices > 0) return g_slices;
+  const char * e = getenv("PLL_GPU_DEVICES");
+  if (e && *e)
+  {
+    int n = atoi(e);
+    if (n >= 1) return n > PLLG_MAX_DEVICES ? PLLG_MAX_DEVICES : n;
+  }
+  return 1;
+}
+
+PLL_EXPORT int pll_gpu_partition_devices(const pll_partition_t * partition)
+{
+  pllg_partition_t * g = pllg_from(partition);
+  return g ? (int)g->ndev : 0;
+}
+
+PLL_EXPORT plg_context_t * pll_gpu_context_of(const pll_partition_t * partition, unsigned int slice,
+                                              unsigned int * first_site, unsigned int * sites)
+{
+  pllg_partition_t * g = pllg_from(partition);
+  if (!g || slice >= g->ndev) return NULL;
+  if (first_site) *first_site = g->lo[slice];
+  if (sites) *sites = g->lo[slice + 1] - g->lo[slice];
+  return g->ctxs[slice];
+}
+
+/* Slice boundaries are multiples of 64 patterns (256-bit vector accesses, whole warp tiles). */
+int pllg_dev_create(pllg_partition_t * g, const plg_dims_t * dims, int first_device, int slices)
+{
+  const unsigned int total = dims->sites;
+  unsigned int per = (total + (unsigned int)slices - 1) / (unsigned int)slices;
+  per = (per + 63u) & ~63u;
+  unsigned int n = (total + per - 1) / per; /* slices that receive at least one pattern */
+  if (n < 1) n = 1;
+  int visible = plg_device_count();
+  if (visible < 1) visible = 1;
+
+  g->ndev = 0;
+  for (unsigned int d = 0; d < n; ++d)
+  {
+    plg_dims_t slice = *dims;
+    g->lo[d] = d * per;
+    g->lo[d + 1] = (d + 1) * per < total ? (d + 1) * per : total;
+    slice.sites = g->lo[d + 1] - g->lo[d];
+    int device = first_device;
+    if (n > 1) device = ((first_device < 0 ? 0 : first_device) + (int)d) % visible;
+    int rc = plg_create(&slice, device, &g->ctxs[d]);
+    if (rc)
+    {
+      g->ctxs[d] = NULL;
+      pllg_dev_destroy(g);
+      return rc;
+    }
+    g->ndev = d + 1;
+  }
+  g->ctx = g->ctxs[0];
+  return PLG_OK;
+}
+
+void pllg_dev_destroy(pllg_partition_t * g)
+{
+  for (unsigned int d = 0; d < g->ndev; ++d)
+    if (g->ctxs[d]) plg_destroy(g->ctxs[d]);
+  memset(g->ctxs, 0, sizeof(g->ctxs));
+  g->ndev = 0;
+  g->ctx = NULL;
+}
+
+#define FOR_EACH_DEVICE(call)                              \
+  do                                                       \
+  {                                                        \
+    for (unsigned int d = 0; d < g->ndev; ++d)             \
+    {                                                      \
+      plg_context_t * ctx = g->ctxs[d];                    \
+      const size_t lo = g->lo[d];                          \
+      (void)lo;                                            \
+      int rc_ = (call);                                    \
+      if (rc_) return rc_;                                 \
+    }                                                      \
+    return PLG_OK;                                         \
+  } while (0)
+
+/* doubles per pattern of a CLV / sumtable, scaler entries per pattern */
+static size_t clv_span(const pllg_partition_t * g)
+{
+  return (size_t)g->pub.rate_cats * g->pub.states_padded;
+}
+static size_t scaler_span(const pllg_partition_t * g)
+{
+  return (g->pub.attributes & PLL_ATTRIB_RATE_SCALERS) ? g->pub.rate_cats : 1u;
+}
+
+int pllg_dev_synchronize(pllg_partition_t * g) { FOR_EACH_DEVICE(plg_synchronize(ctx)); }
+
+int pllg_dev_set_tipmap(pllg_partition_t * g, const unsigned int * tipmap, unsigned int maxstates)
+{
+  FOR_EACH_DEVICE(plg_set_tipmap(ctx, tipmap, maxstates));
+}
+
+int pllg_dev_set_tipchars(pllg_partition_t * g, unsigned int tip_index, const unsigned char * chars)
+{
+  FOR_EACH_DEVICE(plg_set_tipchars(ctx, tip_index, chars + lo));
+}
+
+int pllg_dev_get_tipchars(pllg_partition_t * g, unsigned int tip_index, unsigned char * chars)
+{
+  FOR_EACH_DEVICE(plg_get_tipchars(ctx, tip_index, chars + lo));
+}
+
+int pllg_dev_set_clv(pllg_partition_t * g, unsigned int clv_index, const double * clv)
+{
+  const size_t span = clv_span(g);
+  FOR_EACH_DEVICE(plg_set_clv(ctx, clv_index, clv + lo * span));
+}
+
+int pllg_dev_get_clv(pllg_partition_t * g, unsigned int clv_index, double * clv)
+{
+  const size_t span = clv_span(g);
+  FOR_EACH_DEVICE(plg_get_clv(ctx, clv_index, clv + lo * span));
+}
+
+int pllg_dev_get_scaler(pllg_partition_t * g, unsigned int scaler_index, unsigned int * scaler)
+{
+  const size_t span = scaler_span(g);
+  FOR_EACH_DEVICE(plg_get_scaler(ctx, scaler_index, scaler + lo * span));
+}
+
+int pllg_dev_set_pattern_weights(pllg_partition_t * g, const unsigned int * weights)
+{
+  FOR_EACH_DEVICE(plg_set_pattern_weights(ctx, weights + lo));
+}
+
+int pllg_dev_update_invariant(pllg_partition_t * g, int * invariant_out)
+{
+  FOR_EACH_DEVICE(plg_update_invariant(ctx, invariant_out ? invariant_out + lo : NULL));
+}
+
+int pllg_dev_set_pmatrix(pllg_partition_t * g, unsigned int matrix_index, const double * pmatrix)
+{
+  FOR_EACH_DEVICE(plg_set_pmatrix(ctx, matrix_index, pmatrix));
+}
+
+int pllg_dev_update_pmatrix(pllg_partition_t * g, const unsigned int * matrix_indices,
+                            const double * branch_lengths, unsigned int count, const double * rates,
+                            const double * prop_invar, const double * eigenvals,
+                            const double * eigenvecs, const double * inv_eigenvecs)
+{
+  FOR_EACH_DEVICE(plg_update_pmatrix(ctx, matrix_indices, branch_lengths, count, rates, prop_invar,
+                                     eigenvals, eigenvecs, inv_eigenvecs));
+}
+
+int pllg_dev_update_partials(pllg_partition_t * g, const pll_operation_t * operations, unsigned int count)
+{
+  FOR_EACH_DEVICE(plg_update_partials(ctx, operations, count));
+}
+
+int pllg_dev_edge_loglikelihood(pllg_partition_t * g, unsigned int parent_clv_index,
+                                int parent_scaler_index, unsigned int child_clv_index,
+                                int child_scaler_index, unsigned int matrix_index, const double * freqs,
+                                const double * rate_weights, const double * prop_invar,
+                                double * persite_lnl, double * logl_out)
+{
+  double total = 0.0;
+  for (unsigned int d = 0; d < g->ndev; ++d)
+  {
+    double part = 0.0;
+    int rc = plg_edge_loglikelihood(g->ctxs[d], parent_clv_index, parent_scaler_index, child_clv_index,
+                                    child_scaler_index, matrix_index, freqs, rate_weights, prop_invar,
+                                    persite_lnl ? persite_lnl + g->lo[d] : NULL, &part);
+    if (rc) return rc;
+    total = d ? total + part : part;
+  }
+  *logl_out = total;
+  return PLG_OK;
+}
+
+int pllg_dev_root_loglikelihood(pllg_partition_t * g, unsigned int clv_index, int scaler_index,
+                                const double * freqs, const double * rate_weights,
+                                const double * prop_invar, double * persite_lnl, double * logl_out)
+{
+  double total = 0.0;
+  for (unsigned int d = 0; d < g->ndev; ++d)
+  {
+    double part = 0.0;
+    int rc = plg_root_loglikelihood(g->ctxs[d], clv_index, scaler_index, freqs, rate_weights, prop_invar,
+                                    persite_lnl ? persite_lnl + g->lo[d] : NULL, &part);
+    if (rc) return rc;
+    total = d ? total + part : part;
+  }
+  *logl_out = total;
+  return PLG_OK;
+}
+
+int pllg_dev_update_sumtable(pllg_partition_t * g, unsigned int parent_clv_index,
+                             unsigned int child_clv_index, int parent_scaler_index,
+                             int child_scaler_index, const double * eigenvecs,
+                             const double * left_terms, const void * key, double * host_copy)
+{
+  const size_t span = clv_span(g);
+  FOR_EACH_DEVICE(plg_update_sumtable(ctx, parent_clv_index, child_clv_index, parent_scaler_index,
+                                      child_scaler_index, eigenvecs, left_terms, key,
+                                      host_copy ? host_copy + lo * span : NULL));
+}
+
+int pllg_dev_likelihood_derivatives(pllg_partition_t * g, const void * key, const double * diagptable,
+                                    const double * rate_weights, const double * prop_invar,
+                                    const double * freqs, double * d_f, double * dd_f)
+{
+  double s1 = 0.0, s2 = 0.0;
+  for (unsigned int d = 0; d < g->ndev; ++d)
+  {
+    double a = 0.0, b = 0.0;
+    int rc = plg_likelihood_derivatives(g->ctxs[d], key, diagptable, rate_weights, prop_invar, freqs, &a, &b);
+    if (rc) return rc;
+    s1 = d ? s1 + a : a;
+    s2 = d ? s2 + b : b;
+  }
+  *d_f = s1;
+  *dd_f = s2;
+  return PLG_OK;
+}

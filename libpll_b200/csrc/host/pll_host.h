@@ -18,13 +18,19 @@
 
 #define PLLG_MAGIC 0x706c6c67u /* "pllg" */
 
+#define PLLG_MAX_DEVICES 16
+
 typedef struct pllg_partition
 {
   pll_partition_t pub; /* MUST be first */
   unsigned int magic;
-  plg_context_t * ctx;
+  plg_context_t * ctx;       /* = ctxs[0]; the only context unless pll_gpu_set_devices(n > 1) */
   unsigned int sites_alloc;  /* sites (+ states with ascertainment-bias storage) */
   unsigned char * tip_stage; /* sites_alloc bytes: encoding buffer for one tip   */
+  /* pattern slices over several devices (pll_devices.c): context d owns [lo[d], lo[d+1]) */
+  unsigned int ndev;
+  plg_context_t * ctxs[PLLG_MAX_DEVICES];
+  unsigned int lo[PLLG_MAX_DEVICES + 1];
 } pllg_partition_t;
 
 static inline pllg_partition_t * pllg_from(const pll_partition_t * p)
@@ -35,6 +41,45 @@ static inline pllg_partition_t * pllg_from(const pll_partition_t * p)
 
 /* device that pll_partition_create would use in this thread (-1 = current CUDA device) */
 int pll_gpu_current_device(void);
+
+/* number of pattern slices pll_partition_create would use in this thread (pll_devices.c) */
+int pll_gpu_current_slices(void);
+
+/* the plg_* device ABI fanned out over the partition's pattern slices (pll_devices.c): same
+ * arguments as the plg_* function of the same name, host arrays indexed by site are offset per
+ * slice, scalar results are summed in slice order */
+int pllg_dev_create(pllg_partition_t * g, const plg_dims_t * dims, int first_device, int slices);
+void pllg_dev_destroy(pllg_partition_t * g);
+int pllg_dev_synchronize(pllg_partition_t * g);
+int pllg_dev_set_tipmap(pllg_partition_t * g, const unsigned int * tipmap, unsigned int maxstates);
+int pllg_dev_set_tipchars(pllg_partition_t * g, unsigned int tip_index, const unsigned char * chars);
+int pllg_dev_get_tipchars(pllg_partition_t * g, unsigned int tip_index, unsigned char * chars);
+int pllg_dev_set_clv(pllg_partition_t * g, unsigned int clv_index, const double * clv);
+int pllg_dev_get_clv(pllg_partition_t * g, unsigned int clv_index, double * clv);
+int pllg_dev_get_scaler(pllg_partition_t * g, unsigned int scaler_index, unsigned int * scaler);
+int pllg_dev_set_pattern_weights(pllg_partition_t * g, const unsigned int * weights);
+int pllg_dev_update_invariant(pllg_partition_t * g, int * invariant_out);
+int pllg_dev_set_pmatrix(pllg_partition_t * g, unsigned int matrix_index, const double * pmatrix);
+int pllg_dev_update_pmatrix(pllg_partition_t * g, const unsigned int * matrix_indices,
+                            const double * branch_lengths, unsigned int count, const double * rates,
+                            const double * prop_invar, const double * eigenvals,
+                            const double * eigenvecs, const double * inv_eigenvecs);
+int pllg_dev_update_partials(pllg_partition_t * g, const pll_operation_t * operations, unsigned int count);
+int pllg_dev_edge_loglikelihood(pllg_partition_t * g, unsigned int parent_clv_index,
+                                int parent_scaler_index, unsigned int child_clv_index,
+                                int child_scaler_index, unsigned int matrix_index, const double * freqs,
+                                const double * rate_weights, const double * prop_invar,
+                                double * persite_lnl, double * logl_out);
+int pllg_dev_root_loglikelihood(pllg_partition_t * g, unsigned int clv_index, int scaler_index,
+                                const double * freqs, const double * rate_weights,
+                                const double * prop_invar, double * persite_lnl, double * logl_out);
+int pllg_dev_update_sumtable(pllg_partition_t * g, unsigned int parent_clv_index,
+                             unsigned int child_clv_index, int parent_scaler_index,
+                             int child_scaler_index, const double * eigenvecs,
+                             const double * left_terms, const void * key, double * host_copy);
+int pllg_dev_likelihood_derivatives(pllg_partition_t * g, const void * key, const double * diagptable,
+                                    const double * rate_weights, const double * prop_invar,
+                                    const double * freqs, double * d_f, double * dd_f);
 
 /* ascertainment-bias epilogues (pll_ascbias.c) */
 double pllg_asc_root(pllg_partition_t * g, unsigned int clv_index, int scaler_index,

@@ -19,7 +19,7 @@ PLL_EXPORT void pll_update_partials(pll_partition_t * partition,
     pll_fail(PLL_ERROR_PARAM_INVALID, "Not a GPU partition.");
     return;
   }
-  int rc = plg_update_partials(g->ctx, operations, count);
+  int rc = pllg_dev_update_partials(g, operations, count);
   if (rc) pllg_fail(rc, "pll_update_partials");
 }
 
@@ -61,7 +61,7 @@ PLL_EXPORT double pll_compute_root_loglikelihood(pll_partition_t * partition,
     return -INFINITY;
   }
   double logl = -INFINITY;
-  int rc = plg_root_loglikelihood(g->ctx, clv_index, scaler_index, freqs, g->pub.rate_weights,
+  int rc = pllg_dev_root_loglikelihood(g, clv_index, scaler_index, freqs, g->pub.rate_weights,
                                   pinv, persite_lnl, &logl);
   free(freqs);
   if (rc)
@@ -97,7 +97,7 @@ PLL_EXPORT double pll_compute_edge_loglikelihood(pll_partition_t * partition,
     return -INFINITY;
   }
   double logl = -INFINITY;
-  int rc = plg_edge_loglikelihood(g->ctx, parent_clv_index, parent_scaler_index, child_clv_index,
+  int rc = pllg_dev_edge_loglikelihood(g, parent_clv_index, parent_scaler_index, child_clv_index,
                                   child_scaler_index, matrix_index, freqs, g->pub.rate_weights,
                                   pinv, persite_lnl, &logl);
   free(freqs);

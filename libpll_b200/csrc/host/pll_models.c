@@ -286,7 +286,7 @@ PLL_EXPORT int pll_update_prob_matrices(pll_partition_t * partition,
     memcpy(ievecs + (size_t)n * K * Kp, p->inv_eigenvecs[pi], (size_t)K * Kp * sizeof(double));
     pinv[n] = p->prop_invar[pi];
   }
-  int rc = plg_update_pmatrix(g->ctx, matrix_indices, branch_lengths, count, p->rates, pinv,
+  int rc = pllg_dev_update_pmatrix(g, matrix_indices, branch_lengths, count, p->rates, pinv,
                               evals, evecs, ievecs);
   free(buf);
   return rc ? pllg_fail(rc, "pll_update_prob_matrices") : PLL_SUCCESS;
@@ -330,7 +330,7 @@ PLL_EXPORT int pll_update_invariant_sites(pll_partition_t * partition)
   pll_partition_t * p = &g->pub;
   if (!p->invariant && !(p->invariant = (int *)malloc((size_t)g->sites_alloc * sizeof(int))))
     return pll_fail(PLL_ERROR_MEM_ALLOC, "Cannot allocate charmap for invariant sites array.");
-  int rc = plg_update_invariant(g->ctx, p->invariant);
+  int rc = pllg_dev_update_invariant(g, p->invariant);
   return rc ? pllg_fail(rc, "pll_update_invariant_sites") : PLL_SUCCESS;
 }
 
@@ -369,7 +369,7 @@ PLL_EXPORT unsigned int pll_count_invariant_sites(pll_partition_t * partition,
   {
     pllg_partition_t * g = pllg_from(partition);
     if (!g || !(tmp = (int *)malloc((size_t)g->sites_alloc * sizeof(int)))) return 0;
-    if (plg_update_invariant(g->ctx, tmp))
+    if (pllg_dev_update_invariant(g, tmp))
     {
       free(tmp);
       return 0;

@@ -122,7 +122,7 @@ static void free_host(pllg_partition_t * g)
   free(p->tipmap);
   pll_aligned_free(p->ttlookup);
   free(g->tip_stage);
-  if (g->ctx) plg_destroy(g->ctx);
+  pllg_dev_destroy(g);
   g->magic = 0;
   free(g);
 }
@@ -215,11 +215,22 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips,
   dims.prob_matrices = prob_matrices;
   dims.scale_buffers = scale_buffers;
   dims.attributes = attributes & (PLL_ATTRIB_PATTERN_TIP | PLL_ATTRIB_RATE_SCALERS);
-  int rc = plg_create(&dims, pick_device(), &g->ctx);
+  /* one device context per pattern slice (pll_devices.c); a single one unless the caller asked
+   * for more with pll_gpu_set_devices / PLL_GPU_DEVICES */
+  int slices = pll_gpu_current_slices();
+  if (slices > 1 && p->asc_bias_alloc)
+  {
+    /* the per-state sites of the correction live behind the last real site; the host epilogues
+     * read them from one context */
+    pll_fail(PLL_ERROR_GPU_UNSUPPORTED,
+             "Ascertainment-bias correction is not available on a partition spread over several devices.");
+    free_host(g);
+    return NULL;
+  }
+  int rc = pllg_dev_create(g, &dims, pick_device(), slices);
   if (rc != PLG_OK)
   {
     pllg_fail(rc, "pll_partition_create");
-    g->ctx = NULL;
     free_host(g);
     return NULL;
   }
@@ -273,7 +284,7 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips,
   {
     /* reductions cover the real sites; the per-state sites only feed the correction terms */
     rc = plg_set_active_sites(g->ctx, sites);
-    if (!rc) rc = plg_set_pattern_weights(g->ctx, p->pattern_weights);
+    if (!rc) rc = pllg_dev_set_pattern_weights(g, p->pattern_weights);
     if (rc)
     {
       pllg_fail(rc, "pll_partition_create");
@@ -422,12 +433,12 @@ PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition,
         g->tip_stage[p->sites + j] = (unsigned char)code;
       }
     }
-    if ((rc = plg_set_tipmap(g->ctx, p->tipmap, p->states == 4 ? 16u : p->maxstates)))
+    if ((rc = pllg_dev_set_tipmap(g, p->tipmap, p->states == 4 ? 16u : p->maxstates)))
       return pllg_fail(rc, "pll_set_tip_states");
-    if ((rc = plg_set_tipchars(g->ctx, tip_index, g->tip_stage)))
+    if ((rc = pllg_dev_set_tipchars(g, tip_index, g->tip_stage)))
       return pllg_fail(rc, "pll_set_tip_states");
     /* the staging buffer is reused by the next call */
-    if ((rc = plg_synchronize(g->ctx))) return pllg_fail(rc, "pll_set_tip_states");
+    if ((rc = pllg_dev_synchronize(g))) return pllg_fail(rc, "pll_set_tip_states");
     return PLL_SUCCESS;
   }
 
@@ -449,8 +460,8 @@ PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition,
     for (j = 1; j < p->rate_cats; ++j)
       memcpy(site + j * p->states_padded, site, p->states * sizeof(double));
   }
-  rc = plg_set_clv(g->ctx, tip_index, clv);
-  if (!rc) rc = plg_synchronize(g->ctx);
+  rc = pllg_dev_set_clv(g, tip_index, clv);
+  if (!rc) rc = pllg_dev_synchronize(g);
   free(clv);
   return rc ? pllg_fail(rc, "pll_set_tip_states") : PLL_SUCCESS;
 }
@@ -480,8 +491,8 @@ PLL_EXPORT int pll_set_tip_clv(pll_partition_t * partition,
       memcpy(full + i * span + j * p->states_padded, clv, p->states * sizeof(double));
     clv += padding ? p->states_padded : p->states;
   }
-  int rc = plg_set_clv(g->ctx, tip_index, full);
-  if (!rc) rc = plg_synchronize(g->ctx);
+  int rc = pllg_dev_set_clv(g, tip_index, full);
+  if (!rc) rc = pllg_dev_synchronize(g);
   free(full);
   return rc ? pllg_fail(rc, "pll_set_tip_clv") : PLL_SUCCESS;
 }
@@ -496,8 +507,8 @@ PLL_EXPORT void pll_set_pattern_weights(pll_partition_t * partition,
   memcpy(p->pattern_weights, pattern_weights, sizeof(unsigned int) * p->sites);
   p->pattern_weight_sum = 0;
   for (i = 0; i < p->sites; ++i) p->pattern_weight_sum += pattern_weights[i];
-  int rc = plg_set_pattern_weights(g->ctx, p->pattern_weights);
-  if (!rc) rc = plg_synchronize(g->ctx);
+  int rc = pllg_dev_set_pattern_weights(g, p->pattern_weights);
+  if (!rc) rc = pllg_dev_synchronize(g);
   if (rc) pllg_fail(rc, "pll_set_pattern_weights");
 }
 
@@ -515,7 +526,7 @@ PLL_EXPORT int pll_gpu_sync_clv(pll_partition_t * partition, unsigned int clv_in
   const size_t bytes = (size_t)g->sites_alloc * p->rate_cats * p->states_padded * sizeof(double);
   if (!p->clv[clv_index] && !(p->clv[clv_index] = (double *)zalloc_aligned(bytes)))
     return pll_fail(PLL_ERROR_MEM_ALLOC, "Cannot allocate the host mirror of a CLV.");
-  int rc = plg_get_clv(g->ctx, clv_index, p->clv[clv_index]);
+  int rc = pllg_dev_get_clv(g, clv_index, p->clv[clv_index]);
   return rc ? pllg_fail(rc, "pll_gpu_sync_clv") : PLL_SUCCESS;
 }
 
@@ -526,8 +537,8 @@ PLL_EXPORT int pll_gpu_push_clv(pll_partition_t * partition, unsigned int clv_in
   pll_partition_t * p = &g->pub;
   if (clv_index >= p->tips + p->clv_buffers || !p->clv[clv_index])
     return pll_fail(PLL_ERROR_PARAM_INVALID, "CLV %u has no host mirror", clv_index);
-  int rc = plg_set_clv(g->ctx, clv_index, p->clv[clv_index]);
-  if (!rc) rc = plg_synchronize(g->ctx);
+  int rc = pllg_dev_set_clv(g, clv_index, p->clv[clv_index]);
+  if (!rc) rc = pllg_dev_synchronize(g);
   return rc ? pllg_fail(rc, "pll_gpu_push_clv") : PLL_SUCCESS;
 }
 
@@ -543,7 +554,7 @@ PLL_EXPORT int pll_gpu_sync_scaler(pll_partition_t * partition, unsigned int sca
   if (!p->scale_buffer[scaler_index] &&
       !(p->scale_buffer[scaler_index] = (unsigned int *)calloc(n, sizeof(unsigned int))))
     return pll_fail(PLL_ERROR_MEM_ALLOC, "Cannot allocate the host mirror of a scale buffer.");
-  int rc = plg_get_scaler(g->ctx, scaler_index, p->scale_buffer[scaler_index]);
+  int rc = pllg_dev_get_scaler(g, scaler_index, p->scale_buffer[scaler_index]);
   return rc ? pllg_fail(rc, "pll_gpu_sync_scaler") : PLL_SUCCESS;
 }
 
@@ -557,7 +568,7 @@ PLL_EXPORT int pll_gpu_sync_tipchars(pll_partition_t * partition, unsigned int t
   if (!p->tipchars[tip_index] &&
       !(p->tipchars[tip_index] = (unsigned char *)malloc(g->sites_alloc)))
     return pll_fail(PLL_ERROR_MEM_ALLOC, "Cannot allocate the host mirror of tip characters.");
-  int rc = plg_get_tipchars(g->ctx, tip_index, p->tipchars[tip_index]);
+  int rc = pllg_dev_get_tipchars(g, tip_index, p->tipchars[tip_index]);
   return rc ? pllg_fail(rc, "pll_gpu_sync_tipchars") : PLL_SUCCESS;
 }
 
@@ -577,8 +588,8 @@ PLL_EXPORT int pll_gpu_push_pmatrix(pll_partition_t * partition, unsigned int ma
   if (!g) return pll_fail(PLL_ERROR_PARAM_INVALID, "Not a GPU partition.");
   if (matrix_index >= g->pub.prob_matrices)
     return pll_fail(PLL_ERROR_PARAM_INVALID, "Invalid matrix index %u", matrix_index);
-  int rc = plg_set_pmatrix(g->ctx, matrix_index, g->pub.pmatrix[matrix_index]);
-  if (!rc) rc = plg_synchronize(g->ctx);
+  int rc = pllg_dev_set_pmatrix(g, matrix_index, g->pub.pmatrix[matrix_index]);
+  if (!rc) rc = pllg_dev_synchronize(g);
   return rc ? pllg_fail(rc, "pll_gpu_push_pmatrix") : PLL_SUCCESS;
 }
 
@@ -586,6 +597,6 @@ PLL_EXPORT int pll_gpu_synchronize(pll_partition_t * partition)
 {
   pllg_partition_t * g = pllg_from(partition);
   if (!g) return pll_fail(PLL_ERROR_PARAM_INVALID, "Not a GPU partition.");
-  int rc = plg_synchronize(g->ctx);
+  int rc = pllg_dev_synchronize(g);
   return rc ? pllg_fail(rc, "pll_gpu_synchronize") : PLL_SUCCESS;
 }
