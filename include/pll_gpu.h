@@ -276,6 +276,11 @@ PLL_EXPORT int pll_gpu_device_count(void);
  * `logl +=`, src/core_derivatives_avx2.c:756-765 are the only statements that couple sites).
  * Nothing in the caller changes.  Not combinable with ascertainment-bias correction. */
 PLL_EXPORT int pll_gpu_set_devices(int count);
+/* The slicing rule itself: writes first_site[0 .. n] for `sites` patterns cut into at most
+ * `slices` 64-pattern-aligned slices (first_site[n] = sites) and returns n <= slices; first_site
+ * needs room for slices + 1 entries. */
+PLL_EXPORT unsigned int pll_gpu_slice_bounds(unsigned int sites, unsigned int slices,
+                                             unsigned int * first_site);
 /* Number of pattern slices of a partition (0 if not a GPU partition). */
 PLL_EXPORT int pll_gpu_partition_devices(const pll_partition_t * partition);
 /* Context of one slice and the pattern range it owns (NULL if out of range). */

@@ -173,6 +173,7 @@ _GPU_API = {
     "pll_gpu_device_count": (C.c_int, []),
     "pll_gpu_set_devices": (C.c_int, [C.c_int]),
     "pll_gpu_partition_devices": (C.c_int, [PART_P]),
+    "pll_gpu_slice_bounds": (C.c_uint, [C.c_uint, C.c_uint, c_uint_p]),
     "pll_gpu_context_of": (C.c_void_p, [PART_P, C.c_uint, c_uint_p, c_uint_p]),
     "pll_gpu_context": (C.c_void_p, [PART_P]),
     "pll_gpu_sync_clv": (C.c_int, [PART_P, C.c_uint]),

@@ -59,14 +59,31 @@ PLL_EXPORT plg_context_t * pll_gpu_context_of(const pll_partition_t * partition,
   return g->ctxs[slice];
 }
 
-/* Slice boundaries are multiples of 64 patterns (256-bit vector accesses, whole warp tiles). */
+/* Slice boundaries are multiples of 64 patterns (256-bit vector accesses, whole warp tiles):
+ * equal slices of ceil(sites / slices) rounded up to 64, the last one takes what is left and
+ * slices that would be empty are dropped.  Writes first_site[0 .. n] (first_site[n] = sites) and
+ * returns n. */
+PLL_EXPORT unsigned int pll_gpu_slice_bounds(unsigned int sites, unsigned int slices,
+                                             unsigned int * first_site)
+{
+  if (slices < 1) slices = 1;
+  if (slices > PLLG_MAX_DEVICES) slices = PLLG_MAX_DEVICES;
+  unsigned long long per = ((unsigned long long)sites + slices - 1) / slices;
+  per = (per + 63u) & ~63ull;
+  if (per == 0) per = 64;
+  unsigned int n = (unsigned int)(((unsigned long long)sites + per - 1) / per);
+  if (n < 1) n = 1;
+  for (unsigned int d = 0; d <= n; ++d)
+  {
+    const unsigned long long at = d * per;
+    first_site[d] = at < sites ? (unsigned int)at : sites;
+  }
+  return n;
+}
+
 int pllg_dev_create(pllg_partition_t * g, const plg_dims_t * dims, int first_device, int slices)
 {
-  const unsigned int total = dims->sites;
-  unsigned int per = (total + (unsigned int)slices - 1) / (unsigned int)slices;
-  per = (per + 63u) & ~63u;
-  unsigned int n = (total + per - 1) / per; /* slices that receive at least one pattern */
-  if (n < 1) n = 1;
+  const unsigned int n = pll_gpu_slice_bounds(dims->sites, (unsigned int)(slices < 1 ? 1 : slices), g->lo);
   int visible = plg_device_count();
   if (visible < 1) visible = 1;
 
@@ -74,8 +91,6 @@ int pllg_dev_create(pllg_partition_t * g, const plg_dims_t * dims, int first_dev
   for (unsigned int d = 0; d < n; ++d)
   {
     plg_dims_t slice = *dims;
-    g->lo[d] = d * per;
-    g->lo[d + 1] = (d + 1) * per < total ? (d + 1) * per : total;
     slice.sites = g->lo[d + 1] - g->lo[d];
     int device = first_device;
     if (n > 1) device = ((first_device < 0 ? 0 : first_device) + (int)d) % visible;

@@ -72,6 +72,46 @@ def test_no_cpu_fallback_without_a_device(gpu_lib, has_gpu):
     assert "no CUDA device" in str(e.value) and gpu_lib.errno() == 131
 
 
+def test_force_switch_replaces_the_architecture_bits(gpu_lib, has_gpu, monkeypatch):
+    """PLL_GPU_FORCE=1 (relink-only drop-in): a request for the reference's AVX2 kernels becomes a
+    GPU request - here, without a device, it now fails for the lack of one (131), not as an
+    unsupported architecture (113).  There is still no CPU path."""
+    if has_gpu:
+        pytest.skip("a GPU is present (covered by tests/test_reference_programs_gpu.py)")
+    kw = dict(tips=4, clv_buffers=2, states=4, sites=8, rate_matrices=1, prob_matrices=5, rate_cats=4,
+              scale_buffers=2, attributes=PLL_ATTRIB_ARCH_AVX2 | PLL_ATTRIB_PATTERN_TIP)
+    with pytest.raises(PllError):
+        gpu_lib.partition(**kw)
+    assert gpu_lib.errno() == 113
+    monkeypatch.setenv("PLL_GPU_FORCE", "1")
+    with pytest.raises(PllError) as e:
+        gpu_lib.partition(**kw)
+    assert "no CUDA device" in str(e.value) and gpu_lib.errno() == 131
+    monkeypatch.setenv("PLL_GPU_FORCE", "0")
+    with pytest.raises(PllError):
+        gpu_lib.partition(**kw)
+    assert gpu_lib.errno() == 113
+
+
+@pytest.mark.parametrize("sites", [1, 63, 64, 65, 400, 777, 1000, 5000, 1_000_000, 10_000_000, 4_294_967_295])
+@pytest.mark.parametrize("slices", [1, 2, 3, 5, 8, 16])
+def test_slice_bounds(gpu_lib, sites, slices):
+    """The pattern-slicing rule of multi-device partitions (pll_gpu_slice_bounds): contiguous,
+    64-aligned, covering, no empty slice, balanced to within one 64-pattern granule."""
+    lo = np.zeros(slices + 1, dtype=np.uint32)
+    n = gpu_lib.pll_gpu_slice_bounds(sites, slices, lo.ctypes.data_as(C.POINTER(C.c_uint)))
+    assert 1 <= n <= slices
+    b = lo[:n + 1].astype(np.int64)
+    assert b[0] == 0 and b[-1] == sites
+    assert np.all(np.diff(b) > 0)
+    assert np.all(b[:-1] % 64 == 0)
+    sizes = np.diff(b)
+    assert sizes.max() - (-(-sites // slices)) < 64
+    assert np.all(sizes[:-1] == sizes[0])          # only the last slice is short
+    if sites >= 64 * slices * slices:
+        assert n == slices
+
+
 def test_maps_match_reference(gpu_lib, ref_lib):
     for name in ("pll_map_nt", "pll_map_aa", "pll_map_bin"):
         a = np.array((C.c_uint * 256).in_dll(gpu_lib.dll, name))
