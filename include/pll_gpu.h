@@ -87,6 +87,14 @@ PLL_EXPORT void plg_destroy(plg_context_t * ctx);
 
 PLL_EXPORT int plg_synchronize(plg_context_t * ctx);
 
+/* Deferred results: while enabled, plg_edge_loglikelihood / plg_root_loglikelihood /
+ * plg_likelihood_derivatives only enqueue their kernels and return; plg_collect waits for the
+ * stream and stores the pending results through the output pointers of the last such call (which
+ * must stay valid until then; persite_lnl likewise).  Used by the multi-device host layer to run
+ * the same reduction on all devices at once (libpll_b200/csrc/host/pll_devices.c). */
+PLL_EXPORT int plg_set_deferred(plg_context_t * ctx, int enable);
+PLL_EXPORT int plg_collect(plg_context_t * ctx);
+
 /* ---- uploads / downloads of resident state ---------------------------------------- */
 
 /* replaces: the stores of set_tipchars_4x4 / set_tipchars (reference src/pll.c:825-903):

@@ -131,6 +131,7 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   ctx->stage_host = NULL; ctx->stage_dev = NULL; ctx->stage_size = 0; ctx->stage_off = 0;
   ctx->tables = NULL; ctx->tables_cap = 0; ctx->partials = NULL; ctx->partials_cap = 0;
   ctx->counter = NULL; ctx->result_dev = NULL; ctx->result_host = NULL;
+  ctx->deferred = 0; ctx->pending[0] = ctx->pending[1] = NULL;
   ctx->persite_dev = NULL;
   ctx->lnl_table = NULL; ctx->lnl_table_cap = 0;
   ctx->sumtables = new std::unordered_map<const void *, double *>();
@@ -275,6 +276,24 @@ extern "C" void plg_destroy(plg_context_t * ctx)
 extern "C" int plg_synchronize(plg_context_t * ctx)
 {
   PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PLG_OK;
+}
+
+extern "C" int plg_set_deferred(plg_context_t * ctx, int enable)
+{
+  PLG_CHECK_CTX(ctx);
+  ctx->deferred = enable ? 1 : 0;
+  ctx->pending[0] = ctx->pending[1] = NULL;
+  return PLG_OK;
+}
+
+extern "C" int plg_collect(plg_context_t * ctx)
+{
+  PLG_CHECK_CTX(ctx);
+  PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->pending[0]) *ctx->pending[0] = ctx->result_host[0];
+  if (ctx->pending[1]) *ctx->pending[1] = ctx->result_host[1];
+  ctx->pending[0] = ctx->pending[1] = NULL;
   return PLG_OK;
 }
 

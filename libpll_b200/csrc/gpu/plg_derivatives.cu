@@ -882,11 +882,8 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
     da.nelem = nelem;
     PLG_DISPATCH_R(R, { int lrc = launch_derivatives_dna<RR>(ctx, da, D); if (lrc) return lrc; });
     PLG_LAUNCH_CHECK(ctx);
-    PLG_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->stats.d2h_bytes += 2 * sizeof(double);
-    *d_f = ctx->result_host[0];
-    *dd_f = ctx->result_host[1];
-    return PLG_OK;
+    return plg_finish_result(ctx, d_f, dd_f);
   }
 
   /* device layout of diagp: 20 states is transposed to [R][3][20] exactly like the
@@ -912,11 +909,8 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
   PLG_DISPATCH_R(R, { int lrc = launch_derivatives_aa<RR>(ctx, a, P); if (lrc) return lrc; });
   PLG_LAUNCH_CHECK(ctx);
 
-  PLG_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->stats.d2h_bytes += 2 * sizeof(double);
-  *d_f = ctx->result_host[0];
-  *dd_f = ctx->result_host[1];
-  return PLG_OK;
+  return plg_finish_result(ctx, d_f, dd_f);
 }
 
 extern "C" int plg_get_sumtable_sites(plg_context_t * ctx, const void * key, unsigned int first_site,

@@ -368,10 +368,8 @@ int plg_gen_loglikelihood(plg_context * ctx, const GenLnl & g, const double * fr
   if (persite_lnl)
     PLG_CUDA(cudaMemcpyAsync(persite_lnl, ctx->persite_dev, (size_t)ctx->active_sites * sizeof(double),
                              cudaMemcpyDeviceToHost, ctx->stream));
-  PLG_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->stats.d2h_bytes += sizeof(double) + (persite_lnl ? (size_t)ctx->active_sites * sizeof(double) : 0);
-  *logl_out = ctx->result_host[0];
-  return PLG_OK;
+  return plg_finish_result(ctx, logl_out, NULL);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -519,9 +517,6 @@ int plg_gen_derivatives(plg_context * ctx, const double * sumtable, const double
       sumtable, d_diag, d_rw, d_pinv, d_freqs, ctx->weights, ctx->has_invariant ? ctx->invariant : NULL,
       ctx->active_sites, R, K, Kp, ctx->partials, ctx->counter, ctx->result_dev);
   PLG_LAUNCH_CHECK(ctx);
-  PLG_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->stats.d2h_bytes += 2 * sizeof(double);
-  *d_f = ctx->result_host[0];
-  *dd_f = ctx->result_host[1];
-  return PLG_OK;
+  return plg_finish_result(ctx, d_f, dd_f);
 }

@@ -117,6 +117,10 @@ struct plg_context
   unsigned int * counter; /* "last block done" ticket */
   double * result_dev;    /* device alias of result_host (mapped) */
   double * result_host;   /* pinned, 4 doubles */
+  /* plg_set_deferred: value-returning calls enqueue only and leave their outputs pending
+   * until plg_collect (lets a caller overlap the same call on several devices) */
+  int deferred;
+  double * pending[2];
   double * persite_dev;   /* sites doubles, allocated on first use */
   double * lnl_table;     /* pi-weighted tip lookup of the edge-lnL tip-inner kernels */
   size_t lnl_table_cap;   /* doubles */
@@ -139,6 +143,23 @@ struct plg_context
   std::vector<cudaEvent_t> * prof_events;
   plg_stats_t stats;
 };
+
+/* Delivers the 1 or 2 doubles a reduction kernel left in result_host: waits for the stream and
+ * copies them out - or, in deferred mode, remembers where they go until plg_collect. */
+static inline int plg_finish_result(plg_context * ctx, double * out0, double * out1)
+{
+  if (ctx->deferred)
+  {
+    ctx->pending[0] = out0;
+    ctx->pending[1] = out1;
+    return PLG_OK;
+  }
+  PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (out0) *out0 = ctx->result_host[0];
+  if (out1) *out1 = ctx->result_host[1];
+  return PLG_OK;
+}
+
 
 #define PLG_MAX_DEVICES 64
 

@@ -608,9 +608,7 @@ static int fetch_result(plg_context * ctx, double * persite_lnl, double * logl_o
                              cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.d2h_bytes += (size_t)ctx->active_sites * sizeof(double);
   }
-  PLG_CUDA(cudaStreamSynchronize(ctx->stream));
-  *logl_out = ctx->result_host[0];
-  return PLG_OK;
+  return plg_finish_result(ctx, logl_out, NULL);
 }
 
 #define PLG_DISPATCH_R(R_, ...)                                                         \

@@ -204,22 +204,45 @@ int pllg_dev_update_partials(pllg_partition_t * g, const pll_operation_t * opera
   FOR_EACH_DEVICE(plg_update_partials(ctx, operations, count));
 }
 
+/* Value-returning calls: with several slices the kernels of all devices are enqueued first
+ * (plg_set_deferred) and the partial results collected afterwards, so the devices reduce
+ * concurrently; partial sums are added in slice order. */
+static int begin_deferred(pllg_partition_t * g, unsigned int d)
+{
+  return g->ndev > 1 ? plg_set_deferred(g->ctxs[d], 1) : PLG_OK;
+}
+
+static int collect_all(pllg_partition_t * g, int rc)
+{
+  if (g->ndev < 2) return rc;
+  for (unsigned int d = 0; d < g->ndev; ++d)
+  {
+    int rc2 = plg_collect(g->ctxs[d]); /* also on failure: nothing may stay pending */
+    plg_set_deferred(g->ctxs[d], 0);
+    if (!rc) rc = rc2;
+  }
+  return rc;
+}
+
 int pllg_dev_edge_loglikelihood(pllg_partition_t * g, unsigned int parent_clv_index,
                                 int parent_scaler_index, unsigned int child_clv_index,
                                 int child_scaler_index, unsigned int matrix_index, const double * freqs,
                                 const double * rate_weights, const double * prop_invar,
                                 double * persite_lnl, double * logl_out)
 {
-  double total = 0.0;
-  for (unsigned int d = 0; d < g->ndev; ++d)
+  double part[PLLG_MAX_DEVICES] = {0};
+  int rc = PLG_OK;
+  for (unsigned int d = 0; d < g->ndev && !rc; ++d)
   {
-    double part = 0.0;
-    int rc = plg_edge_loglikelihood(g->ctxs[d], parent_clv_index, parent_scaler_index, child_clv_index,
-                                    child_scaler_index, matrix_index, freqs, rate_weights, prop_invar,
-                                    persite_lnl ? persite_lnl + g->lo[d] : NULL, &part);
-    if (rc) return rc;
-    total = d ? total + part : part;
+    rc = begin_deferred(g, d);
+    if (!rc)
+      rc = plg_edge_loglikelihood(g->ctxs[d], parent_clv_index, parent_scaler_index, child_clv_index,
+                                  child_scaler_index, matrix_index, freqs, rate_weights, prop_invar,
+                                  persite_lnl ? persite_lnl + g->lo[d] : NULL, &part[d]);
   }
+  if ((rc = collect_all(g, rc))) return rc;
+  double total = part[0];
+  for (unsigned int d = 1; d < g->ndev; ++d) total += part[d];
   *logl_out = total;
   return PLG_OK;
 }
@@ -228,15 +251,18 @@ int pllg_dev_root_loglikelihood(pllg_partition_t * g, unsigned int clv_index, in
                                 const double * freqs, const double * rate_weights,
                                 const double * prop_invar, double * persite_lnl, double * logl_out)
 {
-  double total = 0.0;
-  for (unsigned int d = 0; d < g->ndev; ++d)
+  double part[PLLG_MAX_DEVICES] = {0};
+  int rc = PLG_OK;
+  for (unsigned int d = 0; d < g->ndev && !rc; ++d)
   {
-    double part = 0.0;
-    int rc = plg_root_loglikelihood(g->ctxs[d], clv_index, scaler_index, freqs, rate_weights, prop_invar,
-                                    persite_lnl ? persite_lnl + g->lo[d] : NULL, &part);
-    if (rc) return rc;
-    total = d ? total + part : part;
+    rc = begin_deferred(g, d);
+    if (!rc)
+      rc = plg_root_loglikelihood(g->ctxs[d], clv_index, scaler_index, freqs, rate_weights, prop_invar,
+                                  persite_lnl ? persite_lnl + g->lo[d] : NULL, &part[d]);
   }
+  if ((rc = collect_all(g, rc))) return rc;
+  double total = part[0];
+  for (unsigned int d = 1; d < g->ndev; ++d) total += part[d];
   *logl_out = total;
   return PLG_OK;
 }
@@ -256,14 +282,21 @@ int pllg_dev_likelihood_derivatives(pllg_partition_t * g, const void * key, cons
                                     const double * rate_weights, const double * prop_invar,
                                     const double * freqs, double * d_f, double * dd_f)
 {
-  double s1 = 0.0, s2 = 0.0;
-  for (unsigned int d = 0; d < g->ndev; ++d)
+  double a[PLLG_MAX_DEVICES] = {0}, b[PLLG_MAX_DEVICES] = {0};
+  int rc = PLG_OK;
+  for (unsigned int d = 0; d < g->ndev && !rc; ++d)
   {
-    double a = 0.0, b = 0.0;
-    int rc = plg_likelihood_derivatives(g->ctxs[d], key, diagptable, rate_weights, prop_invar, freqs, &a, &b);
-    if (rc) return rc;
-    s1 = d ? s1 + a : a;
-    s2 = d ? s2 + b : b;
+    rc = begin_deferred(g, d);
+    if (!rc)
+      rc = plg_likelihood_derivatives(g->ctxs[d], key, diagptable, rate_weights, prop_invar, freqs,
+                                      &a[d], &b[d]);
+  }
+  if ((rc = collect_all(g, rc))) return rc;
+  double s1 = a[0], s2 = b[0];
+  for (unsigned int d = 1; d < g->ndev; ++d)
+  {
+    s1 += a[d];
+    s2 += b[d];
   }
   *d_f = s1;
   *dd_f = s2;
