@@ -1,0 +1,228 @@
+/*
+ * host_scenarios.c - drives the whole pll.h host layer (libpll_b200/csrc/host/*.c) against the
+ * byte-touching null device (tests/c/null_device.c) under AddressSanitizer + UBSan: every
+ * combination of alphabet size, category count, tip representation, scaler mode, ascertainment
+ * bias type and number of pattern slices goes through create -> model -> tips -> P-matrices ->
+ * traversal -> log-likelihoods -> sumtable / derivatives -> mirrors -> destroy.  Numbers mean
+ * nothing here (the device is a stub); what is checked is that the wrappers hand the device layer
+ * buffers of the extents its contract states, survive their error paths and release everything.
+ * Built and run by tests/test_sanitizers_cpu.py.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pll.h"
+#include "pll_gpu.h"
+
+int null_device_live_contexts(void);
+
+#define CHECK(cond)                                                                          \
+  do                                                                                         \
+  {                                                                                          \
+    if (!(cond))                                                                             \
+    {                                                                                        \
+      fprintf(stderr, "%s:%d: CHECK(%s) failed; pll_errno=%d (%s)\n", __FILE__, __LINE__, #cond, \
+              pll_errno, pll_errmsg);                                                        \
+      exit(3);                                                                               \
+    }                                                                                        \
+  } while (0)
+
+static unsigned int generic_map[256];
+static const unsigned int * map_for(unsigned int states, char * alphabet)
+{
+  if (states == 4) { strcpy(alphabet, "ACGT"); return pll_map_nt; }
+  if (states == 20) { strcpy(alphabet, "ARNDCQEGHILKMFPSTWYV"); return pll_map_aa; }
+  if (states == 2) { strcpy(alphabet, "01"); return pll_map_bin; }
+  memset(generic_map, 0, sizeof(generic_map));
+  for (unsigned int i = 0; i < states; ++i)
+  {
+    alphabet[i] = (char)('A' + i);
+    generic_map['A' + i] = 1u << i;
+    generic_map['a' + i] = 1u << i;
+  }
+  alphabet[states] = 0;
+  generic_map['-'] = (states == 32) ? 0xFFFFFFFFu : ((1u << states) - 1);
+  return generic_map;
+}
+
+static unsigned long scenario(unsigned int states, unsigned int cats, int pattern_tip, int rate_scalers,
+                              unsigned int ab, int slices)
+{
+  const unsigned int tips = 5, inner = 3, sites = 130, matrices = 7;
+  unsigned int attrs = PLL_ATTRIB_ARCH_GPU | (pattern_tip ? PLL_ATTRIB_PATTERN_TIP : 0) |
+                       (rate_scalers ? PLL_ATTRIB_RATE_SCALERS : 0) | ab;
+  char alphabet[64];
+  const unsigned int * map = map_for(states, alphabet);
+
+  CHECK(pll_gpu_set_devices(slices));
+  pll_partition_t * p = pll_partition_create(tips, inner, states, sites, 2, matrices, cats, inner, attrs);
+  pll_gpu_set_devices(0);
+  if ((ab && rate_scalers) || (ab && slices > 1))
+  {
+    CHECK(p == NULL && pll_errno == PLL_ERROR_GPU_UNSUPPORTED);
+    CHECK(null_device_live_contexts() == 0);
+    return 0;
+  }
+  CHECK(p != NULL);
+  CHECK(pll_gpu_partition_devices(p) == (slices > 1 ? 3 : 1));   /* 130 patterns: 64 + 64 + 2 */
+  CHECK(null_device_live_contexts() == pll_gpu_partition_devices(p));
+
+  /* model */
+  double * rates = (double *)malloc(cats * sizeof(double));
+  CHECK(pll_compute_gamma_cats(0.7, cats, rates, PLL_GAMMA_RATES_MEAN));
+  pll_set_category_rates(p, rates);
+  double * w = (double *)malloc(cats * sizeof(double));
+  for (unsigned int i = 0; i < cats; ++i) w[i] = 1.0 / cats;
+  pll_set_category_weights(p, w);
+  const unsigned int n_subst = states * (states - 1) / 2;
+  double * subst = (double *)malloc(n_subst * sizeof(double));
+  double * freqs = (double *)malloc(states * sizeof(double));
+  for (unsigned int m = 0; m < 2; ++m)
+  {
+    for (unsigned int i = 0; i < n_subst; ++i) subst[i] = 0.5 + ((i * 7 + m) % 5) * 0.4;
+    double sum = 0;
+    for (unsigned int i = 0; i < states; ++i) sum += freqs[i] = 1.0 + ((i + m) % 3);
+    for (unsigned int i = 0; i < states; ++i) freqs[i] /= sum;
+    pll_set_subst_params(p, m, subst);
+    pll_set_frequencies(p, m, freqs);
+  }
+  unsigned int * params = (unsigned int *)malloc(cats * sizeof(unsigned int));
+  for (unsigned int i = 0; i < cats; ++i) params[i] = i & 1;
+
+  /* tips: valid sequences, then an illegal character */
+  char * seq = (char *)malloc(sites + 1);
+  for (unsigned int t = 0; t < tips; ++t)
+  {
+    for (unsigned int i = 0; i < sites; ++i) seq[i] = (i % 11 == 10) ? '-' : alphabet[(i * (t + 1) + t) % states];
+    seq[sites] = 0;
+    CHECK(pll_set_tip_states(p, t, map, seq));
+  }
+  seq[17] = '!';
+  CHECK(!pll_set_tip_states(p, 0, map, seq) && pll_errno == PLL_ERROR_TIPDATA_ILLEGALSTATE);
+  seq[17] = alphabet[0];
+  CHECK(pll_set_tip_states(p, 0, map, seq));
+  CHECK(!pll_set_tip_states(p, tips, map, seq));
+  if (!pattern_tip)
+  {
+    double * clv = (double *)calloc((size_t)sites * states, sizeof(double));
+    for (unsigned int i = 0; i < sites; ++i) clv[(size_t)i * states + i % states] = 1.0;
+    CHECK(pll_set_tip_clv(p, 1, clv, 0));
+    free(clv);
+    double * padded = (double *)calloc((size_t)sites * p->states_padded, sizeof(double));
+    CHECK(pll_set_tip_clv(p, 2, padded, 1));
+    free(padded);
+  }
+  else
+  {
+    double dummy[64] = {0};
+    CHECK(!pll_set_tip_clv(p, 1, dummy, 0) && pll_errno == PLL_ERROR_TIPDATA_ILLEGALFUNCTION);
+  }
+  unsigned int * weights = (unsigned int *)malloc(sites * sizeof(unsigned int));
+  for (unsigned int i = 0; i < sites; ++i) weights[i] = 1 + i % 3;
+  pll_set_pattern_weights(p, weights);
+  if (ab)
+  {
+    unsigned int * sw = (unsigned int *)malloc(states * sizeof(unsigned int));
+    for (unsigned int i = 0; i < states; ++i) sw[i] = 1 + i;
+    pll_set_asc_state_weights(p, sw);
+    free(sw);
+    CHECK(pll_set_asc_bias_type(p, (int)ab));
+    CHECK(!pll_set_asc_bias_type(p, 1 << 9));
+    CHECK(!pll_update_invariant_sites_proportion(p, 0, 0.2));
+  }
+  else
+  {
+    CHECK(!pll_set_asc_bias_type(p, PLL_ATTRIB_AB_LEWIS));
+    CHECK(pll_update_invariant_sites(p));
+    CHECK(pll_update_invariant_sites_proportion(p, 0, 0.2));
+    CHECK(!pll_update_invariant_sites_proportion(p, 0, 1.5));
+    unsigned int * per_state = (unsigned int *)malloc(states * sizeof(unsigned int));
+    pll_count_invariant_sites(p, per_state);
+    free(per_state);
+  }
+
+  /* P-matrices (eigendecomposition runs for real on the host) */
+  unsigned int mi[7] = {0, 1, 2, 3, 4, 5, 6};
+  double bl[7] = {0.1, 0.2, 0.0, 0.4, 1e-9, 2.5, 0.05};
+  CHECK(pll_update_prob_matrices(p, params, mi, bl, matrices));
+  for (unsigned int i = 0; i < cats; ++i) CHECK(p->eigen_decomp_valid[params[i]]);
+  for (unsigned int i = 0; i < states; ++i) CHECK(isfinite(p->eigenvals[0][i]));
+
+  /* traversal ((0,1)5,(2,3)6)7 with tip 4 across the evaluation edge */
+  pll_operation_t ops[3] = {{5, 0, 0, 0, PLL_SCALE_BUFFER_NONE, 1, 1, PLL_SCALE_BUFFER_NONE},
+                            {6, 1, 2, 2, PLL_SCALE_BUFFER_NONE, 3, 3, PLL_SCALE_BUFFER_NONE},
+                            {7, 2, 5, 4, 0, 6, 5, 1}};
+  pll_update_partials(p, ops, 3);
+  double * persite = (double *)malloc(sites * sizeof(double));
+  double l1 = pll_compute_edge_loglikelihood(p, 7, 2, 4, PLL_SCALE_BUFFER_NONE, 6, params, persite);
+  double l2 = pll_compute_edge_loglikelihood(p, 7, 2, 6, 1, 6, params, NULL);
+  double l3 = pll_compute_root_loglikelihood(p, 7, 2, params, persite);
+  /* with ascertainment bias the host epilogue takes logs of the stub's all-zero per-state CLVs */
+  if (!ab) CHECK(isfinite(l1) && isfinite(l2) && isfinite(l3));
+
+  /* sumtable + derivatives on an inner-inner and a tip-inner edge */
+  const size_t table_len = (size_t)(sites + (ab ? states : 0)) * cats * p->states_padded;
+  double * table = (double *)pll_aligned_alloc(table_len * sizeof(double), p->alignment);
+  double d1, d2;
+  CHECK(pll_update_sumtable(p, 7, 6, 2, 1, params, table));
+  CHECK(pll_compute_likelihood_derivatives(p, 2, 1, 0.3, params, table, &d1, &d2));
+  CHECK(pll_update_sumtable(p, 7, 4, 2, PLL_SCALE_BUFFER_NONE, params, table));
+  CHECK(pll_compute_likelihood_derivatives(p, 2, PLL_SCALE_BUFFER_NONE, 0.3, params, table, &d1, &d2));
+  pll_aligned_free(table);
+
+  /* mirrors and printing */
+  CHECK(pll_gpu_sync_clv(p, 7) && p->clv[7] != NULL);
+  CHECK(pll_gpu_sync_scaler(p, 2) && p->scale_buffer[2] != NULL);
+  CHECK(pll_gpu_sync_pmatrix(p, 3));
+  CHECK(pll_gpu_push_pmatrix(p, 3));
+  CHECK(pll_gpu_push_clv(p, 7));
+  CHECK(!pll_gpu_sync_clv(p, tips + inner));
+  CHECK(!pll_gpu_sync_scaler(p, inner));
+  if (pattern_tip)
+  {
+    CHECK(pll_gpu_sync_tipchars(p, 0) && p->tipchars[0] != NULL);
+    CHECK(!pll_gpu_sync_clv(p, 0));
+  }
+  else
+    CHECK(pll_gpu_sync_clv(p, 0));
+  pll_show_pmatrix(p, 0, 4);
+  pll_show_clv(p, 7, 2, 4);
+  pll_show_clv(p, 0, PLL_SCALE_BUFFER_NONE, 4);
+  CHECK(pll_gpu_synchronize(p));
+  CHECK(pll_gpu_context(p) != NULL);
+
+  free(persite); free(weights); free(seq); free(params); free(freqs); free(subst); free(w); free(rates);
+  pll_partition_destroy(p);
+  CHECK(null_device_live_contexts() == 0);
+  return 1;
+}
+
+int main(void)
+{
+  const unsigned int states[] = {2, 4, 5, 7, 20, 32};
+  const unsigned int cats[] = {1, 4, 5};
+  const unsigned int abs_[] = {0, PLL_ATTRIB_AB_LEWIS, PLL_ATTRIB_AB_FELSENSTEIN, PLL_ATTRIB_AB_STAMATAKIS,
+                               PLL_ATTRIB_AB_FLAG};
+  unsigned long done = 0, refused = 0;
+  if (!freopen("/dev/null", "w", stdout)) return 2;
+  for (unsigned int s = 0; s < sizeof(states) / sizeof(*states); ++s)
+    for (unsigned int c = 0; c < sizeof(cats) / sizeof(*cats); ++c)
+      for (int tip = 0; tip < 2; ++tip)
+        for (int rs = 0; rs < 2; ++rs)
+          for (unsigned int a = 0; a < sizeof(abs_) / sizeof(*abs_); ++a)
+            for (int slices = 1; slices <= 3; slices += 2)
+            {
+              if (abs_[a] == PLL_ATTRIB_AB_FLAG) continue; /* storage only: set type later, covered below */
+              if (scenario(states[s], cats[c], tip, rs, abs_[a], slices)) ++done; else ++refused;
+            }
+  /* refusals */
+  CHECK(pll_partition_create(4, 2, 4, 10, 1, 5, 4, 2, PLL_ATTRIB_ARCH_AVX2) == NULL);
+  CHECK(pll_partition_create(4, 2, 4, 0, 1, 5, 4, 2, PLL_ATTRIB_ARCH_GPU) == NULL);
+  CHECK(pll_partition_create(4, 2, 4, 10, 1, 5, 4, 2, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_ARCH_AVX) == NULL);
+  CHECK(!pll_gpu_set_devices(-1) && !pll_gpu_set_devices(1000));
+  pll_partition_destroy(NULL);
+  fprintf(stderr, "scenarios=%lu refused=%lu\n", done, refused);
+  return 0;
+}
