@@ -42,6 +42,9 @@ static inline pllg_partition_t * pllg_from(const pll_partition_t * p)
 /* device that pll_partition_create would use in this thread (-1 = current CUDA device) */
 int pll_gpu_current_device(void);
 
+/* PLL_GPU_MIRROR set and not "0": keep the host mirrors of CLVs / scalers / tips current */
+int pll_gpu_mirror_mode(void);
+
 /* number of pattern slices pll_partition_create would use in this thread (pll_devices.c) */
 int pll_gpu_current_slices(void);
 

@@ -20,7 +20,23 @@ PLL_EXPORT void pll_update_partials(pll_partition_t * partition,
     return;
   }
   int rc = pllg_dev_update_partials(g, operations, count);
-  if (rc) pllg_fail(rc, "pll_update_partials");
+  if (rc)
+  {
+    pllg_fail(rc, "pll_update_partials");
+    return;
+  }
+  /* PLL_GPU_MIRROR=1: callers written for the reference that read partition->clv[i] /
+   * ->scale_buffer[i] directly (e.g. reference test/src/scaling.c:84-113) find every array this
+   * call produced downloaded into its host mirror.  A compatibility mode: it moves each result
+   * over PCIe and waits for it. */
+  if (pll_gpu_mirror_mode())
+    for (unsigned int i = 0; i < count; ++i)
+    {
+      if (!pll_gpu_sync_clv(partition, operations[i].parent_clv_index)) return;
+      if (operations[i].parent_scaler_index != PLL_SCALE_BUFFER_NONE &&
+          !pll_gpu_sync_scaler(partition, (unsigned int)operations[i].parent_scaler_index))
+        return;
+    }
 }
 
 /* per-rate frequency vectors / invariant proportions selected by freqs_indices, laid out

@@ -79,6 +79,12 @@ static int pick_device(void)
 
 int pll_gpu_current_device(void) { return pick_device(); }
 
+int pll_gpu_mirror_mode(void)
+{
+  const char * e = getenv("PLL_GPU_MIRROR");
+  return e && *e && strcmp(e, "0") != 0;
+}
+
 /* ------------------------------------------------------------------------------------ */
 static void * zalloc_aligned(size_t bytes)
 {
@@ -439,6 +445,7 @@ PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition,
       return pllg_fail(rc, "pll_set_tip_states");
     /* the staging buffer is reused by the next call */
     if ((rc = pllg_dev_synchronize(g))) return pllg_fail(rc, "pll_set_tip_states");
+    if (pll_gpu_mirror_mode()) return pll_gpu_sync_tipchars(partition, tip_index);
     return PLL_SUCCESS;
   }
 
@@ -463,7 +470,8 @@ PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition,
   rc = pllg_dev_set_clv(g, tip_index, clv);
   if (!rc) rc = pllg_dev_synchronize(g);
   free(clv);
-  return rc ? pllg_fail(rc, "pll_set_tip_states") : PLL_SUCCESS;
+  if (rc) return pllg_fail(rc, "pll_set_tip_states");
+  return pll_gpu_mirror_mode() ? pll_gpu_sync_clv(partition, tip_index) : PLL_SUCCESS;
 }
 
 PLL_EXPORT int pll_set_tip_clv(pll_partition_t * partition,
@@ -494,7 +502,8 @@ PLL_EXPORT int pll_set_tip_clv(pll_partition_t * partition,
   int rc = pllg_dev_set_clv(g, tip_index, full);
   if (!rc) rc = pllg_dev_synchronize(g);
   free(full);
-  return rc ? pllg_fail(rc, "pll_set_tip_clv") : PLL_SUCCESS;
+  if (rc) return pllg_fail(rc, "pll_set_tip_clv");
+  return pll_gpu_mirror_mode() ? pll_gpu_sync_clv(partition, tip_index) : PLL_SUCCESS;
 }
 
 PLL_EXPORT void pll_set_pattern_weights(pll_partition_t * partition,
