@@ -73,8 +73,10 @@ def test_host_layer_against_the_null_device(tmp_path_factory):
     exe = _build(tmp_path_factory, "host_scenarios",
                  [os.path.join(ROOT, "tests", "c", "host_scenarios.c"), os.path.join(ROOT, "tests", "c", "null_device.c")]
                  + sorted(glob.glob(os.path.join(HOST, "*.c"))))
-    run = subprocess.run([exe], capture_output=True, text=True, timeout=300,
-                         env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0"))
-    assert run.returncode == 0, run.stderr[-4000:]
-    m = re.search(r"scenarios=(\d+) refused=(\d+)", run.stderr)
-    assert m and int(m.group(1)) == 252 and int(m.group(2)) == 324, run.stderr[-500:]
+    for mirror in ("0", "1"):      # PLL_GPU_MIRROR=1: host mirrors refreshed by every update / tip upload
+        run = subprocess.run([exe], capture_output=True, text=True, timeout=300,
+                             env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0",
+                                      PLL_GPU_MIRROR=mirror))
+        assert run.returncode == 0, run.stderr[-4000:]
+        m = re.search(r"scenarios=(\d+) refused=(\d+)", run.stderr)
+        assert m and int(m.group(1)) == 252 and int(m.group(2)) == 324, run.stderr[-500:]
