@@ -110,6 +110,13 @@ extern "C" {
 #define PLL_GAMMA_RATES_MEAN 0
 #define PLL_GAMMA_RATES_MEDIAN 1
 
+/* fields printed by pll_utree_show_ascii (reference src/pll.h:171-175) */
+#define PLL_UTREE_SHOW_LABEL (1 << 0)
+#define PLL_UTREE_SHOW_BRANCH_LENGTH (1 << 1)
+#define PLL_UTREE_SHOW_CLV_INDEX (1 << 2)
+#define PLL_UTREE_SHOW_SCALER_INDEX (1 << 3)
+#define PLL_UTREE_SHOW_PMATRIX_INDEX (1 << 4)
+
 #define PLL_TREE_TRAVERSE_POSTORDER 1
 #define PLL_TREE_TRAVERSE_PREORDER 2
 
@@ -451,6 +458,8 @@ PLL_EXPORT void pll_utree_reset_template_indices(pll_unode_t * node, unsigned in
 PLL_EXPORT pll_utree_t * pll_utree_wraptree(pll_unode_t * root, unsigned int tip_count);
 PLL_EXPORT char * pll_utree_export_newick(const pll_unode_t * root,
                                           char * (*cb_serialize)(const pll_unode_t *));
+/* ASCII drawing on stdout (reference src/utree.c:122-157); options = PLL_UTREE_SHOW_* */
+PLL_EXPORT void pll_utree_show_ascii(const pll_unode_t * root, int options);
 PLL_EXPORT int pll_utree_traverse(pll_unode_t * root,
                                   int traversal,
                                   int (*cbtrav)(pll_unode_t *),

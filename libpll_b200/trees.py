@@ -60,6 +60,7 @@ _TREE_API = {
                                                        C.POINTER(C.c_uint), C.POINTER(C.c_uint),
                                                        C.POINTER(C.c_int), C.POINTER(C.c_uint)]),
     "pll_utree_check_integrity": (C.c_int, [UTREE_P]),
+    "pll_utree_show_ascii": (None, [UNODE_P, C.c_int]),
     "pll_utree_clone": (UTREE_P, [UTREE_P]),
     "pll_utree_graph_clone": (UNODE_P, [UNODE_P]),
     "pll_fasta_open": (C.c_void_p, [C.c_char_p, C.POINTER(C.c_uint)]),

@@ -68,7 +68,16 @@ def main(out):
     write_fasta(os.path.join(out, "2000.fas"), alignment(rng, names, 300))
     names = [f"seq{i:03d}" for i in range(246)]
     open(os.path.join(out, "246x4465.tree"), "w").write(random_unrooted_tree(rng, names, last_is_tip=False))
-    write_fasta(os.path.join(out, "246x4465.fas"), alignment(rng, names, 4465, p_mut=0.2))
+    rows = alignment(rng, names, 4465, p_mut=0.2)
+    write_fasta(os.path.join(out, "246x4465.fas"), rows)
+    # the same alignment as interleaved PHYLIP (reference examples/newick-phylip-unrooted)
+    with open(os.path.join(out, "246x4465.phy"), "w") as f:
+        f.write(f" {len(rows)} {len(rows[0][1])}\n")
+        width = 60
+        for start in range(0, len(rows[0][1]), width):
+            for name, seq in rows:
+                f.write((f"{name:<12s}" if start == 0 else "") + seq[start:start + width] + "\n")
+            f.write("\n")
 
 
 if __name__ == "__main__":

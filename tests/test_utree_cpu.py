@@ -158,6 +158,48 @@ def test_clone_and_integrity_match_reference(lib, ref):
     t.destroy()
 
 
+def _captured_stdout(fn, tmp_path, name):
+    """Runs fn() with the C-level stdout (fd 1) redirected to a file; returns what was printed."""
+    libc = C.CDLL(None)
+    path = str(tmp_path / name)
+    libc.fflush(None)
+    saved = os.dup(1)
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+    os.dup2(fd, 1)
+    try:
+        fn()
+        libc.fflush(None)
+    finally:
+        os.dup2(saved, 1)
+        os.close(fd)
+        os.close(saved)
+    return open(path).read()
+
+
+@pytest.mark.parametrize("tips,seed,caterpillar", [(3, 1, False), (4, 2, False), (9, 3, False), (60, 4, False),
+                                                   (40, 5, True)])
+def test_ascii_drawing_matches_reference(lib, ref, tmp_path, tips, seed, caterpillar):
+    """pll_utree_show_ascii (reference src/utree.c:122-157): same drawing, character for character,
+    from the parse root, from a tip and from another inner node, for every combination of fields."""
+    t = T.Tree(lib, newick=random_newick(tips, seed, caterpillar))
+    starts = [t.root, t.node(0), t.node(tips)]
+    for k, start in enumerate(starts):
+        for options in (0, 1, 2, 31, 5, 24):
+            ours = _captured_stdout(lambda: lib.pll_utree_show_ascii(start, options), tmp_path, "ours.txt")
+            theirs = _captured_stdout(lambda: ref.pll_utree_show_ascii(start, options), tmp_path, "ref.txt")
+            assert ours == theirs, (k, options)
+            assert ours.count("\n") == 2 * (2 * tips - 3)
+    t.destroy()
+
+
+def test_ascii_drawing_of_a_deep_tree(lib, tmp_path):
+    tips = 1_500      # the drawing is quadratic in depth: 6 000 lines of up to 6 000 characters
+    t = T.Tree(lib, newick=random_newick(tips, 3, caterpillar=True))
+    text = _captured_stdout(lambda: lib.pll_utree_show_ascii(t.root, 1), tmp_path, "deep.txt")
+    assert text.count("\n") == 2 * (2 * tips - 3)
+    t.destroy()
+
+
 def test_deep_tree_needs_no_recursion(lib):
     """A 200 000-taxon caterpillar: the reference's recursive walks would need ~200 000 stack
     frames; the reader, template, traversal, operations and export here are all iterative."""
