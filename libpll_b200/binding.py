@@ -193,6 +193,7 @@ _GPU_API = {
     "plg_flush_l2": (C.c_int, [C.c_void_p]),
     "plg_mem_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "plg_synchronize": (C.c_int, [C.c_void_p]),
+    "plg_set_scaler": (C.c_int, [C.c_void_p, C.c_uint, c_uint_p]),
 }
 
 

@@ -23,6 +23,7 @@
  * The file is compiled with -fmad=false so nothing is contracted behind our back.
  */
 #include <algorithm>
+#include <array>
 #include <cmath>
 
 #include <unordered_map>
@@ -1026,6 +1027,11 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
    * relation with, on CLV slots and on scaler slots.  Executing levels in increasing order
    * is therefore equivalent to the reference's strictly sequential loop. */
   std::vector<int> clv_w(n_clv, -1), clv_r(n_clv, -1), sc_w(n_sc, -1), sc_r(n_sc, -1);
+  /* the operation (list index) that last wrote a slot, and per operation the producers of what it
+   * reads: lets the reordering below be checked against ALL read-after-write relations, also
+   * those that exist through a scaler only */
+  std::vector<int> clv_writer(n_clv, -1), sc_writer(n_sc, -1);
+  std::vector<std::array<int, 4>> producers(count);
 
   struct Item
   {
@@ -1151,7 +1157,11 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
     {
       if (read_clv[c] >= 0) after(clv_w[read_clv[c]]);
       if (read_sc[c] >= 0) after(sc_w[read_sc[c]]);
+      producers[i][c] = read_clv[c] >= 0 ? clv_writer[read_clv[c]] : -1;
+      producers[i][2 + c] = read_sc[c] >= 0 ? sc_writer[read_sc[c]] : -1;
     }
+    clv_writer[o.parent_clv_index] = (int)i;
+    if (it.op.pscale) sc_writer[o.parent_scaler_index] = (int)i;
     /* `after(l)` left level = 1 + max over predecessors (0 when there is none) */
     it.level = level;
 
@@ -1239,7 +1249,22 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
           if (first >= 0) stack.push_back({(unsigned int)first, 0}); /* popped next: runs first */
         }
       }
-      if (exec.size() != count) /* a CLV consumed twice or a cycle: fall back to the list order */
+      /* The walk follows CLV edges only.  Keep it only if it is a permutation (no CLV consumed
+       * twice) in which every operation still runs after the producers of all it reads - a list
+       * may also chain operations through a scaler alone; otherwise execute the list as given. */
+      bool valid = exec.size() == count;
+      if (valid)
+      {
+        std::vector<unsigned int> position(count, count);
+        for (unsigned int x = 0; x < count; ++x) position[exec[x]] = x;
+        for (unsigned int i = 0; i < count && valid; ++i)
+        {
+          if (position[i] == count) valid = false;
+          for (int c = 0; c < 4 && valid; ++c)
+            if (producers[i][c] >= 0 && position[producers[i][c]] > position[i]) valid = false;
+        }
+      }
+      if (!valid)
       {
         exec.clear();
         for (unsigned int i = 0; i < count; ++i) exec.push_back(i);

@@ -61,3 +61,41 @@ def test_fused_with_rescaling_and_recycled_slots(gpu_lib, monkeypatch, rate_scal
     ref = _run(gpu_lib, monkeypatch, w, attrs, fused=False)
     got = _run(gpu_lib, monkeypatch, w, attrs, fused=True)
     assert got[0] == ref[0] and got[1] == ref[1] and got[2] == ref[2]
+
+
+def test_operations_chained_through_a_scaler_only(gpu_lib, monkeypatch):
+    """A legal if odd list in which operation B reads the scaler that operation A wrote while none
+    of B's CLVs comes from A: A, D, B, C with C = parent of A and B.  The depth-first reordering of
+    the single-kernel traversal (larger subtree first: D, B, A, C) would let B read the scaler
+    before A has written it; the planner checks the new order against every read-after-write
+    relation of the list and then executes it as given.  Scaler 0 is pre-filled with a marker that
+    A (tip-tip: zeroes its scaler, reference src/core_partials_avx.c:598-599) must clear first."""
+    from libpll_b200.binding import OP_DTYPE
+    import ctypes as C
+
+    w = S.make_workload(8, 640, states=4, seed=21)
+    results = []
+    for fused in (False, True):
+        monkeypatch.setenv("PLL_GPU_FUSED", "1" if fused else "0")
+        part, pidx = S.build_partition(gpu_lib, w, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP)
+        mats = np.arange(w.prob_matrices, dtype=np.uint32)
+        part.update_prob_matrices(pidx, mats, np.linspace(0.05, 0.4, w.prob_matrices))
+        T, NONE = w.tips, -1
+        prev = np.array([(T + 3, NONE, 4, 4, NONE, 5, 5, NONE)], dtype=OP_DTYPE)      # an earlier call
+        part.update_partials(prev)
+        marker = np.full(w.sites, 7, dtype=np.uint32)
+        assert gpu_lib.plg_set_scaler(part.ctx(), 0, marker.ctypes.data_as(C.POINTER(C.c_uint))) == 0
+        ops = np.array([(T + 0, 0, 0, 0, NONE, 1, 1, NONE),          # A: tip-tip, clears scaler 0
+                        (T + 4, NONE, 2, 2, NONE, 3, 3, NONE),        # D: tip-tip
+                        (T + 1, 1, T + 4, 6, NONE, T + 3, 7, 0),      # B: reads scaler 0 with a CLV of `prev`
+                        (T + 2, 2, T + 0, 8, 0, T + 1, 9, 1)],        # C: parent of A and B
+                       dtype=OP_DTYPE)
+        part.update_partials(ops)
+        results.append(([part.get_clv(T + k).tobytes() for k in range(5)],
+                        [part.get_scaler(k).copy() for k in range(3)]))
+        part.destroy()
+    (clv0, sc0), (clv1, sc1) = results
+    assert clv0 == clv1
+    for a, b in zip(sc0, sc1):
+        assert np.array_equal(a, b)
+    assert not sc0[0].any() and not sc0[1].any() and not sc0[2].any(), "the marker leaked into a result"
