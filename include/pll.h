@@ -14,6 +14,14 @@
  * This build implements the GPU architecture ONLY: there is no CPU fallback.  A partition
  * created without PLL_ATTRIB_ARCH_GPU, or on a machine without a usable CUDA device, fails with
  * pll_errno set.
+ *
+ * Environment switches for callers that cannot be recompiled (all off by default):
+ *   PLL_GPU_FORCE=1     programs built against the reference's header ask for
+ *                       PLL_ATTRIB_ARCH_CPU/SSE/AVX/AVX2: replace those bits by PLL_ATTRIB_ARCH_GPU
+ *   PLL_GPU_MIRROR=1    keep partition->clv[i] / ->scale_buffer[i] / ->tipchars[i] current for
+ *                       callers that read them directly (every result is downloaded)
+ *   PLL_GPU_DEVICES=n   spread every partition over n GPUs of this process (pll_gpu.h:
+ *                       pll_gpu_set_devices)
  */
 #ifndef PLL_B200_PLL_H_
 #define PLL_B200_PLL_H_
@@ -124,7 +132,8 @@ extern "C" {
  *
  * Under PLL_ATTRIB_ARCH_GPU the big arrays live in HBM for the partition's lifetime:
  *   clv[i], scale_buffer[i], tipchars[i]   are NULL until pll_gpu_sync_clv / _scaler /
- *                                          _tipchars downloads a host mirror (pll_gpu.h);
+ *                                          _tipchars downloads a host mirror (pll_gpu.h), or
+ *                                          always current with PLL_GPU_MIRROR=1;
  *   pmatrix[i]                             host mirror, refreshed by pll_gpu_sync_pmatrix;
  *   rates, rate_weights, subst_params, frequencies, prop_invar, eigen*, pattern_weights,
  *   invariant, charmap, tipmap             are ordinary, always-valid host arrays.
