@@ -232,6 +232,30 @@ typedef struct pll_fasta
 
 /* ---- multiple sequence alignment and the PHYLIP reader state (reference
  * src/pll.h:271-278,295-308) ---- */
+/* rooted binary tree: plain left / right / parent links (reference src/pll.h:336-361) */
+typedef struct pll_rnode_s
+{
+  char * label;
+  double length;
+  unsigned int node_index;
+  unsigned int clv_index;
+  int scaler_index;
+  unsigned int pmatrix_index;
+  struct pll_rnode_s * left;
+  struct pll_rnode_s * right;
+  struct pll_rnode_s * parent;
+  void * data;
+} pll_rnode_t;
+
+typedef struct pll_rtree_s
+{
+  unsigned int tip_count;
+  unsigned int inner_count;
+  unsigned int edge_count;
+  pll_rnode_t ** nodes; /* tips first, then inner nodes in post-order, the root last */
+  pll_rnode_t * root;
+} pll_rtree_t;
+
 typedef struct pll_msa_s
 {
   int count;
@@ -480,6 +504,32 @@ PLL_EXPORT int pll_utree_check_integrity(const pll_utree_t * tree);
 PLL_EXPORT pll_unode_t * pll_utree_graph_clone(const pll_unode_t * root);
 PLL_EXPORT pll_utree_t * pll_utree_clone(const pll_utree_t * tree);
 PLL_EXPORT void pll_utree_create_operations(pll_unode_t * const * trav_buffer,
+                                            unsigned int trav_buffer_size,
+                                            double * branches,
+                                            unsigned int * pmatrix_indices,
+                                            pll_operation_t * ops,
+                                            unsigned int * matrix_count,
+                                            unsigned int * ops_count);
+
+/* ---- rooted trees: Newick reader (strictly binary, also at the root), index template,
+ * traversal, traversal -> operations for pll_compute_root_loglikelihood, export, drawing
+ * (reference src/parse_rtree.y:46-400, src/rtree.c:24-330, prototypes src/pll.h:685-810).
+ * Iterative like the unrooted code. ---- */
+PLL_EXPORT pll_rtree_t * pll_rtree_parse_newick(const char * filename);
+PLL_EXPORT pll_rtree_t * pll_rtree_parse_newick_string(const char * s);
+PLL_EXPORT void pll_rtree_destroy(pll_rtree_t * tree, void (*cb_destroy)(void *));
+PLL_EXPORT void pll_rtree_graph_destroy(pll_rnode_t * root, void (*cb_destroy)(void *));
+PLL_EXPORT void pll_rtree_reset_template_indices(pll_rnode_t * root, unsigned int tip_count);
+PLL_EXPORT pll_rtree_t * pll_rtree_wraptree(pll_rnode_t * root, unsigned int tip_count);
+PLL_EXPORT void pll_rtree_show_ascii(const pll_rnode_t * root, int options);
+PLL_EXPORT char * pll_rtree_export_newick(const pll_rnode_t * root,
+                                          char * (*cb_serialize)(const pll_rnode_t *));
+PLL_EXPORT int pll_rtree_traverse(pll_rnode_t * root,
+                                  int traversal,
+                                  int (*cbtrav)(pll_rnode_t *),
+                                  pll_rnode_t ** outbuffer,
+                                  unsigned int * trav_size);
+PLL_EXPORT void pll_rtree_create_operations(pll_rnode_t * const * trav_buffer,
                                             unsigned int trav_buffer_size,
                                             double * branches,
                                             unsigned int * pmatrix_indices,

@@ -42,6 +42,28 @@ def random_unrooted_tree(rng, names, last_is_tip=True):
     return f"({a}:{blen()},{b}:{blen()},{third}:{blen()});\n"
 
 
+def random_rooted_tree(rng, names, tip_at_root=False):
+    """Strictly binary rooted Newick (reference src/parse_rtree.y:120-160); with tip_at_root one
+    child of the root is a single tip (the reference's small.rooted.tip.tree)."""
+    def blen():
+        return f"{rng.uniform(0.005, 0.25):.6f}"
+
+    def join(parts):
+        parts = list(parts)
+        while len(parts) > 1:
+            a = parts.pop(rng.randrange(len(parts)))
+            b = parts.pop(rng.randrange(len(parts)))
+            parts.append(f"({a}:{blen()},{b}:{blen()})")
+        return parts[0]
+
+    names = list(names)
+    rng.shuffle(names)
+    if tip_at_root:
+        return f"({join(names[:-1])}:{blen()},{names[-1]}:{blen()});\n"
+    half = len(names) // 2
+    return f"({join(names[:half])}:{blen()},{join(names[half:])}:{blen()});\n"
+
+
 def alignment(rng, names, sites, alphabet="ACGT", gap="-", p_mut=0.3, p_gap=0.01):
     root = [rng.choice(alphabet) for _ in range(sites)]
     rows = []
@@ -68,6 +90,10 @@ def main(out):
     write_fasta(os.path.join(out, "2000.fas"), alignment(rng, names, 300))
     names = [f"seq{i:03d}" for i in range(246)]
     open(os.path.join(out, "246x4465.tree"), "w").write(random_unrooted_tree(rng, names, last_is_tip=False))
+    small = [f"sp{i:02d}" for i in range(12)]
+    open(os.path.join(out, "small.rooted.tree"), "w").write(random_rooted_tree(rng, small))
+    open(os.path.join(out, "small.rooted.tip.tree"), "w").write(random_rooted_tree(rng, small, tip_at_root=True))
+    write_fasta(os.path.join(out, "small.fas"), alignment(rng, small, 500, p_mut=0.25))
     rows = alignment(rng, names, 4465, p_mut=0.2)
     write_fasta(os.path.join(out, "246x4465.fas"), rows)
     # the same alignment as interleaved PHYLIP (reference examples/newick-phylip-unrooted)

@@ -62,6 +62,13 @@ static const char * const NEWICK_SEEDS[] = {
   "((a,b),(c,d));",            /* rooted: must be rejected or unrooted as the reference does */
   "(a,b);", "a;", "();", "((a,b,c),d,e);", "(a:0.1,b:0.2,c:0.3)",
 };
+static const char * const ROOTED_SEEDS[] = {
+  "((a:0.1,b:0.2):0.05,(c:0.3,d:0.4):0.1);",
+  "(a,b);",
+  "(((a,b)x:1e-3,c)'y z':2.5E+1,(d,(e,f)));",
+  "((((a,b),c),d),e)root:0.1;",
+  "(a,b,c);", "((a,b),(c,d))", "a;", "();",
+};
 static const char * const FASTA_SEEDS[] = {
   ">s1\nACGTACGT\n>s2\nACGTTCGA\n>s3 description\nAC-TNCGT\n",
   ">a\nAC\nGT\n\n>b\nTTTT\n",
@@ -126,6 +133,38 @@ static int label_cb(pll_unode_t * node)
   return 1;
 }
 
+static int rvisit_all(pll_rnode_t * node) { return node != NULL; }
+
+static unsigned long exercise_rooted(pll_rtree_t * tree)
+{
+  const unsigned int T = tree->tip_count, I = tree->inner_count;
+  if (I != T - 1 || tree->edge_count != 2 * T - 2 || tree->nodes[T + I - 1] != tree->root)
+  {
+    fprintf(stderr, "rooted tree: inconsistent counts\n");
+    exit(3);
+  }
+  pll_rnode_t ** buf = (pll_rnode_t **)malloc((size_t)(T + I) * sizeof(*buf));
+  double * br = (double *)malloc((size_t)(T + I) * sizeof(double));
+  unsigned int * mi = (unsigned int *)malloc((size_t)(T + I) * sizeof(unsigned int));
+  pll_operation_t * ops = (pll_operation_t *)malloc((size_t)I * sizeof(*ops));
+  unsigned int n = 0, mc = 0, oc = 0;
+  for (int order = PLL_TREE_TRAVERSE_POSTORDER; order <= PLL_TREE_TRAVERSE_PREORDER; ++order)
+  {
+    if (!pll_rtree_traverse(tree->root, order, rvisit_all, buf, &n) || n != T + I)
+    {
+      fprintf(stderr, "rooted traversal visits %u of %u nodes\n", n, T + I);
+      exit(3);
+    }
+  }
+  pll_rtree_traverse(tree->root, PLL_TREE_TRAVERSE_POSTORDER, rvisit_all, buf, &n);
+  pll_rtree_create_operations(buf, n, br, mi, ops, &mc, &oc);
+  if (oc != I || mc != 2 * T - 2) { fprintf(stderr, "rooted operations: %u ops, %u matrices\n", oc, mc); exit(3); }
+  free(buf); free(br); free(mi); free(ops);
+  char * text = pll_rtree_export_newick(tree->root, NULL);
+  free(text);
+  return oc;
+}
+
 static unsigned long exercise_tree(pll_utree_t * tree)
 {
   unsigned long work = 0;
@@ -177,7 +216,7 @@ int main(int argc, char ** argv)
   rng_state = 0x9E3779B97F4A7C15ull ^ (unsigned long long)atoll(argv[2]);
   char path[4096];
   snprintf(path, sizeof(path), "%s/fuzz_input.txt", argv[3]);
-  unsigned long trees = 0, records = 0, alignments = 0, compressed = 0, work = 0;
+  unsigned long trees = 0, rooted_trees = 0, records = 0, alignments = 0, compressed = 0, work = 0;
 
   for (long it = 0; it < iterations; ++it)
   {
@@ -189,6 +228,17 @@ int main(int argc, char ** argv)
     else tree = pll_utree_parse_newick_string(s);
     if (tree) { ++trees; work += exercise_tree(tree); pll_utree_destroy(tree, NULL); }
     free(s);
+
+    /* rooted Newick */
+    if (it % 2 == 1)
+    {
+      s = mutate(ROOTED_SEEDS[rnd() % (sizeof(ROOTED_SEEDS) / sizeof(*ROOTED_SEEDS))], &len);
+      pll_rtree_t * rooted;
+      if (it % 16 == 1) { write_file(path, s, len); rooted = pll_rtree_parse_newick(path); }
+      else rooted = pll_rtree_parse_newick_string(s);
+      if (rooted) { ++rooted_trees; work += exercise_rooted(rooted); pll_rtree_destroy(rooted, NULL); }
+      free(s);
+    }
 
     /* FASTA */
     if (it % 4 == 1)
@@ -269,7 +319,7 @@ int main(int argc, char ** argv)
     }
   }
   remove(path);
-  printf("iterations=%ld trees=%lu fasta_records=%lu alignments=%lu compressed=%lu work=%lu\n", iterations, trees,
-         records, alignments, compressed, work);
+  printf("iterations=%ld trees=%lu fasta_records=%lu alignments=%lu compressed=%lu rooted=%lu work=%lu\n", iterations,
+         trees, records, alignments, compressed, rooted_trees, work);
   return 0;
 }

@@ -46,11 +46,11 @@ def test_front_end_survives_mutated_inputs(fuzzer, tmp_path, seed):
     run = subprocess.run([fuzzer, "20000", str(seed), str(tmp_path)], capture_output=True, text=True,
                          timeout=300, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0"))
     assert run.returncode == 0, (run.stdout[-500:], run.stderr[-3000:])
-    m = re.search(r"trees=(\d+) fasta_records=(\d+) alignments=(\d+) compressed=(\d+)", run.stdout)
+    m = re.search(r"trees=(\d+) fasta_records=(\d+) alignments=(\d+) compressed=(\d+) rooted=(\d+)", run.stdout)
     assert m, run.stdout
-    trees, records, alignments, compressed = map(int, m.groups())
+    trees, records, alignments, compressed, rooted = map(int, m.groups())
     # the mutations must leave enough valid inputs to exercise the accepting paths too
-    assert trees > 1000 and records > 2000 and alignments > 300 and compressed > 1000
+    assert trees > 1000 and records > 2000 and alignments > 300 and compressed > 1000 and rooted > 500
 
 
 def _build(tmp_path_factory, name, sources):

@@ -413,3 +413,145 @@ def test_recycled_operations_give_identical_likelihood_on_reference(lib, ref):
     recycled = evaluate(used, ops, mi, bl, (eclv[0], esc[0], eclv[1], esc[1], r.pmatrix_index))
     assert np.isfinite(plain) and plain == recycled
     t.destroy()
+
+
+# ---- rooted trees (pll_rtree_*, reference src/parse_rtree.y + src/rtree.c) ------------------
+class RNode(C.Structure):
+    pass
+
+
+RNode._fields_ = [("label", C.c_char_p), ("length", C.c_double), ("node_index", C.c_uint), ("clv_index", C.c_uint),
+                  ("scaler_index", C.c_int), ("pmatrix_index", C.c_uint), ("left", C.POINTER(RNode)),
+                  ("right", C.POINTER(RNode)), ("parent", C.POINTER(RNode)), ("data", C.c_void_p)]
+
+
+class RTree(C.Structure):
+    _fields_ = [("tip_count", C.c_uint), ("inner_count", C.c_uint), ("edge_count", C.c_uint),
+                ("nodes", C.POINTER(C.POINTER(RNode))), ("root", C.POINTER(RNode))]
+
+
+RTRAV_CB = C.CFUNCTYPE(C.c_int, C.POINTER(RNode))
+
+
+def _bind_rtree(dll, with_parser):
+    dll.pll_rtree_traverse.restype = C.c_int
+    dll.pll_rtree_traverse.argtypes = [C.POINTER(RNode), C.c_int, RTRAV_CB, C.POINTER(C.POINTER(RNode)),
+                                       C.POINTER(C.c_uint)]
+    dll.pll_rtree_create_operations.restype = None
+    dll.pll_rtree_create_operations.argtypes = [C.POINTER(C.POINTER(RNode)), C.c_uint, C.POINTER(C.c_double),
+                                                C.POINTER(C.c_uint), C.c_void_p, C.POINTER(C.c_uint),
+                                                C.POINTER(C.c_uint)]
+    dll.pll_rtree_export_newick.restype = C.c_void_p
+    dll.pll_rtree_export_newick.argtypes = [C.POINTER(RNode), C.c_void_p]
+    dll.pll_rtree_show_ascii.restype = None
+    dll.pll_rtree_show_ascii.argtypes = [C.POINTER(RNode), C.c_int]
+    if with_parser:
+        dll.pll_rtree_parse_newick_string.restype = C.POINTER(RTree)
+        dll.pll_rtree_parse_newick_string.argtypes = [C.c_char_p]
+        dll.pll_rtree_parse_newick.restype = C.POINTER(RTree)
+        dll.pll_rtree_parse_newick.argtypes = [C.c_char_p]
+        dll.pll_rtree_destroy.restype = None
+        dll.pll_rtree_destroy.argtypes = [C.POINTER(RTree), C.c_void_p]
+        dll.pll_rtree_wraptree.restype = C.POINTER(RTree)
+        dll.pll_rtree_wraptree.argtypes = [C.POINTER(RNode), C.c_uint]
+    return dll
+
+
+def random_rooted_newick(tips, seed, caterpillar=False):
+    rng = np.random.default_rng(seed)
+    nodes = [f"t{i}:{rng.uniform(0.01, 0.3):.6f}" for i in range(tips)]
+    k = 0
+    while len(nodes) > 1:
+        if caterpillar:
+            a, b = nodes.pop(0), nodes.pop(0)
+        else:
+            a = nodes.pop(int(rng.integers(0, len(nodes))))
+            b = nodes.pop(int(rng.integers(0, len(nodes))))
+        last = len(nodes) == 0
+        label = f"n{k}" if k % 3 == 0 else ""
+        k += 1
+        new = f"({a},{b}){label}" + ("" if last else f":{rng.uniform(0.01, 0.3):.6f}")
+        nodes.insert(0, new) if caterpillar else nodes.append(new)
+    return nodes[0] + ";"
+
+
+def _rtree_views(dll, root, tips, traversal, prune=None):
+    """(node_index list of the traversal, ops bytes, matrix indices, branches) computed by `dll`."""
+    n = 2 * tips - 1
+    buf = (C.POINTER(RNode) * n)()
+    size = C.c_uint(0)
+    cb = RTRAV_CB(lambda node: 0 if prune is not None and node.contents.node_index in prune else 1)
+    assert dll.pll_rtree_traverse(root, traversal, cb, buf, C.byref(size)) == 1
+    order = [buf[i].contents.node_index for i in range(size.value)]
+    from libpll_b200.binding import OP_DTYPE
+    ops = np.zeros(n, dtype=OP_DTYPE)
+    branches = np.zeros(n)
+    mats = np.zeros(n, dtype=np.uint32)
+    mc, oc = C.c_uint(0), C.c_uint(0)
+    dll.pll_rtree_create_operations(buf, size.value, branches.ctypes.data_as(C.POINTER(C.c_double)),
+                                    mats.ctypes.data_as(C.POINTER(C.c_uint)), ops.ctypes.data, C.byref(mc), C.byref(oc))
+    return order, ops[:oc.value].tobytes(), mats[:mc.value].tobytes(), branches[:mc.value].tobytes()
+
+
+@pytest.mark.parametrize("tips,seed,caterpillar", [(2, 1, False), (3, 2, False), (17, 3, False), (120, 4, False),
+                                                   (60, 5, True)])
+def test_rooted_tree_functions_match_reference(lib, ref_lib, tmp_path, tips, seed, caterpillar):
+    """Trees parsed by this library's rooted reader (the reference's is bison code that is not
+    built) handed to the reference's pll_rtree_traverse / _create_operations / _export_newick /
+    _show_ascii in process (same struct layout): identical traversals (full and pruned, post- and
+    pre-order), operation lists, matrix lists, Newick text and drawings."""
+    ours = _bind_rtree(lib.dll, True)
+    theirs = _bind_rtree(ref_lib.dll, False)
+    text = random_rooted_newick(tips, seed, caterpillar)
+    tp = ours.pll_rtree_parse_newick_string(text.encode())
+    assert tp, lib.errmsg()
+    t = tp.contents
+    assert (t.tip_count, t.inner_count, t.edge_count) == (tips, tips - 1, 2 * tips - 2)
+    # index template (reference src/parse_rtree.y:167-230): tips 0.. left to right, inner nodes
+    # T.. in post-order with scalers 0.., nodes[] in the same numbering, the root last
+    for i in range(2 * tips - 1):
+        node = t.nodes[i].contents
+        assert node.node_index == i == node.clv_index
+        assert node.scaler_index == (-1 if i < tips else i - tips)
+        assert bool(node.left) == (i >= tips)
+        if i < 2 * tips - 2:
+            assert node.pmatrix_index == i and node.parent
+    assert t.root.contents.node_index == 2 * tips - 2 and t.root.contents.pmatrix_index == 0 and not t.root.contents.parent
+    rng = np.random.default_rng(seed)
+    for traversal in (1, 2):
+        for prune in (None, set(int(x) for x in rng.integers(0, 2 * tips - 2, size=max(1, tips // 5)))):
+            assert _rtree_views(ours, t.root, tips, traversal, prune) == _rtree_views(theirs, t.root, tips, traversal, prune)
+    a, b = ours.pll_rtree_export_newick(t.root, None), theirs.pll_rtree_export_newick(t.root, None)
+    assert C.string_at(a) == C.string_at(b)
+    again = ours.pll_rtree_parse_newick_string(C.string_at(a))
+    assert again and again.contents.tip_count == tips
+    ours.pll_rtree_destroy(again, None)
+    for options in (0, 1, 31):
+        x = _captured_stdout(lambda: ours.pll_rtree_show_ascii(t.root, options), tmp_path, "ours.txt")
+        y = _captured_stdout(lambda: theirs.pll_rtree_show_ascii(t.root, options), tmp_path, "ref.txt")
+        assert x == y, options
+    # from a file; wraptree with a counted tip number
+    path = tmp_path / "rooted.tree"
+    path.write_text(text)
+    tf = ours.pll_rtree_parse_newick(str(path).encode())
+    assert tf and tf.contents.tip_count == tips
+    ours.pll_rtree_destroy(tf, None)
+    ours.pll_rtree_destroy(tp, None)
+
+
+@pytest.mark.parametrize("bad", ["(a,b,c);", "(a);", "((a,b),c)", "(a,b));", "(a,,b);", "a;", "(a:x,b);", "((a,b,c),d);",
+                                 "", "(a,b)", "(a,(b,c);"])
+def test_rooted_syntax_errors(lib, bad):
+    ours = _bind_rtree(lib.dll, True)
+    assert not ours.pll_rtree_parse_newick_string(bad.encode())
+    assert lib.errno() == 111          # PLL_ERROR_NEWICK_SYNTAX
+
+
+def test_rooted_deep_tree(lib):
+    ours = _bind_rtree(lib.dll, True)
+    tips = 20_000
+    tp = ours.pll_rtree_parse_newick_string(random_rooted_newick(tips, 9, caterpillar=True).encode())
+    assert tp and tp.contents.tip_count == tips
+    order, ops, mats, _ = _rtree_views(ours, tp.contents.root, tips, 1)
+    assert len(order) == 2 * tips - 1 and len(ops) == 32 * (tips - 1) and len(mats) == 4 * (2 * tips - 2)
+    ours.pll_rtree_destroy(tp, None)
