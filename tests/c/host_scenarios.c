@@ -17,6 +17,8 @@
 #include "pll_gpu.h"
 
 int null_device_live_contexts(void);
+void null_device_fail_create_in(int n);
+void null_device_fail_calls(int on);
 
 #define CHECK(cond)                                                                          \
   do                                                                                         \
@@ -217,6 +219,43 @@ int main(void)
               if (abs_[a] == PLL_ATTRIB_AB_FLAG) continue; /* storage only: set type later, covered below */
               if (scenario(states[s], cats[c], tip, rs, abs_[a], slices)) ++done; else ++refused;
             }
+  /* device failures: the 2nd of 3 slice contexts cannot be created -> no partition, nothing left
+   * behind; then every device call fails -> the wrappers report it through pll_errno and the
+   * value-returning ones return -inf / PLL_FAILURE, with nothing pending on any slice */
+  {
+    CHECK(pll_gpu_set_devices(3));
+    null_device_fail_create_in(2);
+    pll_partition_t * p = pll_partition_create(5, 3, 4, 400, 1, 7, 4, 3, PLL_ATTRIB_ARCH_GPU);
+    CHECK(p == NULL && pll_errno == PLL_ERROR_MEM_ALLOC && null_device_live_contexts() == 0);
+    null_device_fail_create_in(0);
+    p = pll_partition_create(5, 3, 4, 400, 1, 7, 4, 3, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP);
+    pll_gpu_set_devices(0);
+    CHECK(p != NULL && pll_gpu_partition_devices(p) == 3);
+    unsigned int params[4] = {0, 0, 0, 0};
+    pll_operation_t op = {5, 0, 0, 0, PLL_SCALE_BUFFER_NONE, 1, 1, PLL_SCALE_BUFFER_NONE};
+    unsigned int w[400];
+    for (int i = 0; i < 400; ++i) w[i] = 1;
+    null_device_fail_calls(1);
+    pll_errno = 0;
+    pll_update_partials(p, &op, 1);
+    CHECK(pll_errno == PLL_ERROR_GPU_RUNTIME);
+    pll_errno = 0;
+    pll_set_pattern_weights(p, w);
+    CHECK(pll_errno == PLL_ERROR_GPU_RUNTIME);
+    CHECK(!pll_update_invariant_sites(p));
+    double l = pll_compute_edge_loglikelihood(p, 5, 0, 6, 1, 2, params, NULL);
+    CHECK(isinf(l) && l < 0 && pll_errno == PLL_ERROR_GPU_RUNTIME);
+    l = pll_compute_root_loglikelihood(p, 5, 0, params, NULL);
+    CHECK(isinf(l) && l < 0);
+    double table[4], d1, d2;
+    CHECK(!pll_compute_likelihood_derivatives(p, 0, 1, 0.1, params, table, &d1, &d2));
+    null_device_fail_calls(0);
+    l = pll_compute_edge_loglikelihood(p, 5, 0, 6, 1, 2, params, NULL);
+    CHECK(l == -400.0);   /* the null device returns -(patterns of the slice): 192 + 192 + 16 summed */
+    pll_partition_destroy(p);
+    CHECK(null_device_live_contexts() == 0);
+  }
+
   /* refusals */
   CHECK(pll_partition_create(4, 2, 4, 10, 1, 5, 4, 2, PLL_ATTRIB_ARCH_AVX2) == NULL);
   CHECK(pll_partition_create(4, 2, 4, 0, 1, 5, 4, 2, PLL_ATTRIB_ARCH_GPU) == NULL);

@@ -48,12 +48,20 @@ static size_t pmatrix_len(const plg_context_t * c)
 
 int null_device_live_contexts(void) { return live_contexts; }
 
+/* failure injection: the n-th plg_create from now on fails (0 = never); every other call fails
+ * with PLG_E_CUDA while fail_calls is set */
+static int fail_create_in, fail_calls;
+void null_device_fail_create_in(int n) { fail_create_in = n; }
+void null_device_fail_calls(int on) { fail_calls = on; }
+#define MAYBE_FAIL() do { if (fail_calls) return PLG_E_CUDA; } while (0)
+
 const char * plg_last_error(void) { return "null device"; }
 int plg_device_count(void) { return 2; }
 
 int plg_create(const plg_dims_t * dims, int device, plg_context_t ** out)
 {
   if (!dims || !out || dims->sites == 0 || dims->states_padded < dims->states || device >= 2) return PLG_E_INVALID;
+  if (fail_create_in && --fail_create_in == 0) return PLG_E_NOMEM;
   plg_context_t * c = (plg_context_t *)calloc(1, sizeof(*c));
   if (!c) return PLG_E_NOMEM;
   c->d = *dims;
@@ -140,11 +148,13 @@ int plg_get_scaler(plg_context_t * ctx, unsigned int scaler_index, unsigned int 
 }
 int plg_set_pattern_weights(plg_context_t * ctx, const unsigned int * weights)
 {
+  MAYBE_FAIL();
   touch_in(weights, ctx->d.sites * sizeof(unsigned int));
   return PLG_OK;
 }
 int plg_update_invariant(plg_context_t * ctx, int * invariant_out)
 {
+  MAYBE_FAIL();
   if (invariant_out) touch_out(invariant_out, ctx->d.sites * sizeof(int), 0xff); /* -1 everywhere */
   return PLG_OK;
 }
@@ -207,6 +217,7 @@ int plg_update_pmatrix(plg_context_t * ctx, const unsigned int * matrix_indices,
 }
 int plg_update_partials(plg_context_t * ctx, const pll_operation_t * operations, unsigned int count)
 {
+  MAYBE_FAIL();
   touch_in(operations, count * sizeof(pll_operation_t));
   ctx->calls += count;
   return PLG_OK;
@@ -223,6 +234,7 @@ int plg_edge_loglikelihood(plg_context_t * ctx, unsigned int parent_clv_index, i
                            unsigned int matrix_index, const double * freqs, const double * rate_weights,
                            const double * prop_invar, double * persite_lnl, double * logl_out)
 {
+  MAYBE_FAIL();
   touch_model(ctx, freqs, rate_weights, prop_invar);
   if (persite_lnl) touch_out(persite_lnl, ctx->active_sites * sizeof(double), 0);
   return deliver(ctx, logl_out, NULL);
@@ -231,6 +243,7 @@ int plg_root_loglikelihood(plg_context_t * ctx, unsigned int clv_index, int scal
                            const double * freqs, const double * rate_weights, const double * prop_invar,
                            double * persite_lnl, double * logl_out)
 {
+  MAYBE_FAIL();
   touch_model(ctx, freqs, rate_weights, prop_invar);
   if (persite_lnl) touch_out(persite_lnl, ctx->active_sites * sizeof(double), 0);
   return deliver(ctx, logl_out, NULL);
@@ -256,6 +269,7 @@ int plg_likelihood_derivatives(plg_context_t * ctx, const void * key, const doub
                                const double * rate_weights, const double * prop_invar,
                                const double * freqs, double * d_f, double * dd_f)
 {
+  MAYBE_FAIL();
   touch_in(diagptable, (size_t)ctx->d.rate_cats * ctx->d.states * 4 * sizeof(double));
   touch_model(ctx, freqs, rate_weights, prop_invar);
   return deliver(ctx, d_f, dd_f);
