@@ -99,7 +99,8 @@ def test_reference_program_prints_its_fixture(name, attrs, capsys):
     if not (os.path.exists(exe) and os.path.exists(expected)):
         pytest.skip("oracle/_ref/dropin not built (needs /root/reference at build time)")
     env = dict(os.environ, PLL_GPU_FORCE="1", **EXTRA_ENV.get(name, {}))
-    out = subprocess.run([exe, *attrs], capture_output=True, text=True, timeout=300, env=env, cwd=DROPIN)
+    limit = 60 if name.startswith("rooted") else 300     # first-run programs must not stall the suite
+    out = subprocess.run([exe, *attrs], capture_output=True, text=True, timeout=limit, env=env, cwd=DROPIN)
     if out.stdout == "Skip\n":           # the program itself declines this attribute set
         pytest.skip(f"{name} skips {attrs}")   # (reference test/out/skip.out, runtest.py:339-345)
     assert out.returncode == 0, (out.returncode, out.stderr[-2000:], out.stdout[-2000:])
@@ -130,7 +131,8 @@ def test_reference_example_prints_what_it_prints_on_the_reference(name, capsys):
         pytest.skip("oracle/_ref/dropin not built (needs /root/reference at build time)")
     args = open(os.path.join(DROPIN, "expected", f"example-{name}.args")).read().split()
     env = dict(os.environ, PLL_GPU_FORCE="1")
-    out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=300, env=env, cwd=DROPIN)
+    limit = 60 if "rooted" in name and "unrooted" not in name else 300
+    out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=limit, env=env, cwd=DROPIN)
     assert out.returncode == 0, (out.returncode, out.stderr[-2000:], out.stdout[-2000:])
     inexact, total = compare_text(out.stdout, open(expected).read(), f"example {name}")
     with capsys.disabled():
