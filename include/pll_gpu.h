@@ -72,6 +72,12 @@ typedef struct plg_stats
   unsigned long long kind_ns[3];
   unsigned long long kind_bytes[3];
   unsigned long long kind_launches[3];
+  /* bytes the executed CLV-update plans HAD to move over the HBM interface: equal to
+   * algorithmic_bytes on the level-by-level kernels; for the single-kernel traversals every
+   * observable parent CLV / scaler written once + tip characters + tile-cache misses read back
+   * (computed from the plan, not measured) */
+  unsigned long long compulsory_bytes;
+  unsigned long long graph_evictions;   /* cached operation-list graphs dropped (LRU) */
 } plg_stats_t;
 
 PLL_EXPORT const char * plg_last_error(void);
@@ -311,6 +317,13 @@ PLL_EXPORT int pll_gpu_push_pmatrix(pll_partition_t * partition, unsigned int ma
 PLL_EXPORT int pll_gpu_push_clv(pll_partition_t * partition, unsigned int clv_index);
 
 PLL_EXPORT int pll_gpu_synchronize(pll_partition_t * partition);
+
+/* The `sumtable` argument of pll_update_sumtable / pll_compute_likelihood_derivatives is an
+ * opaque key under the GPU flag: the table lives in HBM (sites * rate_cats * states_padded
+ * doubles per key) until the partition is destroyed.  A caller that frees its host buffer
+ * earlier calls this first; tables that were never released are reclaimed least-recently-used
+ * first when device memory runs out. */
+PLL_EXPORT int pll_gpu_free_sumtable(pll_partition_t * partition, const double * sumtable);
 
 #ifdef __cplusplus
 }

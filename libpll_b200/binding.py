@@ -126,6 +126,8 @@ class PlgStats(C.Structure):
         ("kind_ns", C.c_ulonglong * 3),
         ("kind_bytes", C.c_ulonglong * 3),
         ("kind_launches", C.c_ulonglong * 3),
+        ("compulsory_bytes", C.c_ulonglong),
+        ("graph_evictions", C.c_ulonglong),
     ]
 
 
@@ -183,6 +185,7 @@ _GPU_API = {
     "pll_gpu_push_pmatrix": (C.c_int, [PART_P, C.c_uint]),
     "pll_gpu_push_clv": (C.c_int, [PART_P, C.c_uint]),
     "pll_gpu_synchronize": (C.c_int, [PART_P]),
+    "pll_gpu_free_sumtable": (C.c_int, [PART_P, C.c_void_p]),
     "plg_last_error": (C.c_char_p, []),
     "plg_device_count": (C.c_int, []),
     "plg_timer_start": (C.c_int, [C.c_void_p]),

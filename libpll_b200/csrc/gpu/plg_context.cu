@@ -135,10 +135,20 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   ctx->persite_dev = NULL;
   ctx->lnl_table = NULL; ctx->lnl_table_cap = 0;
   ctx->sumtables = new std::unordered_map<const void *, double *>();
+  ctx->sumtable_used = new std::unordered_map<const void *, unsigned long long>();
+  ctx->sumtable_clock = 0;
   ctx->graphs = new std::unordered_map<uint64_t, plg_graph_entry *>();
   ctx->seen_lists = new std::unordered_map<uint64_t, unsigned int>();
   const char * g = getenv("PLL_GPU_GRAPHS");
   ctx->use_graphs = g ? atoi(g) : 1;
+  {
+    const char * gc = getenv("PLL_GPU_GRAPH_CACHE");
+    int cap = gc ? atoi(gc) : 64;
+    ctx->graph_cap = cap < 1 ? 1u : (unsigned int)cap;
+  }
+  ctx->graph_clock = 0;
+  ctx->list_buf = NULL;
+  ctx->list_buf_cap = 0;
   const char * ex = getenv("PLL_GPU_AA_EXACT");
   ctx->aa_exact = (ex && *ex && *ex != '0') ? 1 : 0;
   {
@@ -243,6 +253,7 @@ extern "C" void plg_destroy(plg_context_t * ctx)
   {
     for (auto & kv : *ctx->sumtables) cudaFree(kv.second);
     delete ctx->sumtables;
+    delete ctx->sumtable_used;
   }
   cudaFree(ctx->clv);
   cudaFree(ctx->scalers);
@@ -260,6 +271,7 @@ extern "C" void plg_destroy(plg_context_t * ctx)
   if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
   cudaFree(ctx->lnl_scratch);
   cudaFree(ctx->fused_records);
+  cudaFree(ctx->list_buf);
   if (ctx->result_host) cudaFreeHost(ctx->result_host);
   if (ctx->prof_events)
   {

@@ -610,8 +610,13 @@ static int launch_derivatives_aa(plg_context * ctx, const DerArgs & a, const Der
     default: plg_set_error("rate_cats=%u unsupported", R_); return PLG_E_UNSUPPORTED;   \
   }
 
+/* Device slot of the sumtable the caller identifies by `key` (its host pointer).  Slots live
+ * until plg_free_sumtable / plg_destroy; a caller that allocates and frees a host sumtable per
+ * branch without telling us leaves slots behind, so when HBM runs out the least recently used
+ * slots are reclaimed before giving up. */
 static int sumtable_slot(plg_context * ctx, const void * key, double ** out)
 {
+  (*ctx->sumtable_used)[key] = ++ctx->sumtable_clock;
   auto it = ctx->sumtables->find(key);
   if (it != ctx->sumtables->end())
   {
@@ -619,7 +624,30 @@ static int sumtable_slot(plg_context * ctx, const void * key, double ** out)
     return PLG_OK;
   }
   double * dev = NULL;
-  PLG_CUDA(cudaMalloc(&dev, (size_t)ctx->d.sites * ctx->span * sizeof(double)));
+  const size_t bytes = (size_t)ctx->d.sites * ctx->span * sizeof(double);
+  cudaError_t err = cudaMalloc(&dev, bytes);
+  while (err == cudaErrorMemoryAllocation && !ctx->sumtables->empty())
+  {
+    cudaGetLastError();
+    const void * victim = NULL;
+    unsigned long long oldest = ~0ull;
+    for (const auto & kv : *ctx->sumtables)
+    {
+      const unsigned long long used = (*ctx->sumtable_used)[kv.first];
+      if (used < oldest) { oldest = used; victim = kv.first; }
+    }
+    PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree((*ctx->sumtables)[victim]);
+    ctx->sumtables->erase(victim);
+    ctx->sumtable_used->erase(victim);
+    err = cudaMalloc(&dev, bytes);
+  }
+  if (err != cudaSuccess)
+  {
+    cudaGetLastError();
+    plg_set_error("plg_update_sumtable: cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(err));
+    return err == cudaErrorMemoryAllocation ? PLG_E_NOMEM : PLG_E_CUDA;
+  }
   (*ctx->sumtables)[key] = dev;
   *out = dev;
   return PLG_OK;
@@ -808,6 +836,7 @@ extern "C" int plg_free_sumtable(plg_context_t * ctx, const void * key)
   PLG_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaFree(it->second);
   ctx->sumtables->erase(it);
+  ctx->sumtable_used->erase(key);
   return PLG_OK;
 }
 
@@ -824,6 +853,7 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
                   "(call pll_update_sumtable first)");
     return PLG_E_INVALID;
   }
+  (*ctx->sumtable_used)[key] = ++ctx->sumtable_clock;
   if (!plg_fast_path(ctx))
     return plg_gen_derivatives(ctx, it->second, diagptable, rate_weights, prop_invar, freqs, d_f, dd_f);
   const unsigned int R = ctx->d.rate_cats, K = ctx->d.states;

@@ -59,6 +59,8 @@ struct plg_graph_entry
   unsigned long long kernels;
   unsigned long long levels;
   unsigned long long algorithmic_bytes;
+  unsigned long long compulsory_bytes;
+  unsigned long long last_used; /* LRU clock of the graph cache */
 };
 
 #define PLG_CHECK_CTX(ctx)                                                             \
@@ -127,11 +129,17 @@ struct plg_context
 
   /* device-resident sumtables keyed by the caller's host pointer */
   std::unordered_map<const void *, double *> * sumtables;
+  std::unordered_map<const void *, unsigned long long> * sumtable_used; /* key -> LRU clock */
+  unsigned long long sumtable_clock;
 
   /* cached CUDA graphs of whole operation lists, keyed by a hash of the list */
   std::unordered_map<uint64_t, plg_graph_entry *> * graphs;
   std::unordered_map<uint64_t, unsigned int> * seen_lists; /* hash -> times seen, lists not (yet) captured */
   int use_graphs;
+  unsigned int graph_cap;        /* cached graphs kept per context (PLL_GPU_GRAPH_CACHE, default 64); LRU eviction */
+  unsigned long long graph_clock;
+  char * list_buf;               /* device home of operation lists too long for the staging ring */
+  size_t list_buf_cap;
   int aa_exact; /* 20 states: 1 = bit-exact vector-pipe kernels, 0 = DMMA tensor-core kernels */
 
   /* L2 flush buffer (allocated on first plg_flush_l2) */
@@ -298,6 +306,36 @@ __device__ __forceinline__ d4 ld_stream(const double * p)
   asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
                : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
                : "l"(p));
+  return r;
+}
+/* The same access without .nc: for data that THIS launch may have written (a fused traversal
+ * reading back a tile it stored earlier; PTX guarantees .nc only for memory that is read-only
+ * for the kernel's lifetime). */
+__device__ __forceinline__ d4 ld_stream_coherent(const double * p)
+{
+  d4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ double2 ld_stream_coherent2(const double * p)
+{
+  double2 r;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ double ld_stream_coherent1(const double * p)
+{
+  double r;
+  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ unsigned int ld_coherent_u32(const unsigned int * p)
+{
+  unsigned int r;
+  asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
   return r;
 }
 __device__ __forceinline__ void st_stream(double * p, d4 v)

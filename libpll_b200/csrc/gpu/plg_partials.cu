@@ -1011,6 +1011,10 @@ struct Plan
   unsigned int fused_hits, fused_misses;
   unsigned long long levels;
   unsigned long long algorithmic_bytes;
+  /* bytes that MUST cross the HBM interface for this list on the path that runs it: level by
+   * level that is the algorithmic figure; the fused traversal writes every observable parent
+   * CLV / scaler once and reads tip characters and tile-cache misses only */
+  unsigned long long compulsory_bytes;
   size_t table_doubles;
 };
 
@@ -1176,6 +1180,7 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
   }
   plan.levels = (unsigned long long)(max_level + 1);
   plan.table_doubles = n_tables * table_len;
+  plan.compulsory_bytes = plan.algorithmic_bytes;
 
   /* stable sort by (level, kind, scale_mode) -> contiguous groups */
   std::vector<unsigned int> order(count);
@@ -1308,9 +1313,16 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
      * must reach HBM only if some operation of the list reads it from there (tile-cache miss).
      * `pad` = 1 marks the operations whose result is written through. */
     std::unordered_map<const void *, unsigned int> last_clv, last_sc;
-    auto need_hbm = [&](const void * buffer) {
-      auto w = last_clv.find(buffer);
+    /* a child read back from HBM needs BOTH its CLV and its scaler there, and with slot
+     * recycling the two may have been written by different operations */
+    auto need_hbm = [&](const void * clv_buffer, const void * sc_buffer) {
+      auto w = last_clv.find(clv_buffer);
       if (w != last_clv.end()) plan.fused[w->second].pad = 1;
+      if (sc_buffer)
+      {
+        auto v = last_sc.find(sc_buffer);
+        if (v != last_sc.end()) plan.fused[v->second].pad = 1;
+      }
     };
     plan.fused.resize(count);
     for (unsigned int x = 0; x < count; ++x)
@@ -1332,8 +1344,8 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
       f.rslot = (forward[x] == 2) ? -2 : ((it.kind != PLG_KIND_TT) ? lookup(it.op.right, it.op.rscale) : -1);
       if (it.kind == PLG_KIND_II) (f.lslot != -1 ? plan.fused_hits : plan.fused_misses)++;
       if (it.kind != PLG_KIND_TT) (f.rslot != -1 ? plan.fused_hits : plan.fused_misses)++;
-      if (it.kind == PLG_KIND_II && f.lslot == -1) need_hbm(it.op.left);
-      if (it.kind != PLG_KIND_TT && f.rslot == -1) need_hbm(it.op.right);
+      if (it.kind == PLG_KIND_II && f.lslot == -1) need_hbm(it.op.left, it.op.lscale);
+      if (it.kind != PLG_KIND_TT && f.rslot == -1) need_hbm(it.op.right, it.op.rscale);
       last_clv[it.op.parent] = x;
       if (it.op.pscale) last_sc[it.op.pscale] = x;
       /* stale copies of what this operation overwrites */
@@ -1364,6 +1376,16 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
     }
     for (const auto & kv : last_clv) plan.fused[kv.second].pad = 1;
     for (const auto & kv : last_sc) plan.fused[kv.second].pad = 1;
+
+    unsigned long long per_site = 0;
+    for (const FusedOp & f : plan.fused)
+    {
+      if (f.pad) per_site += span_bytes + (f.op.pscale ? scaler_unit : 0);
+      if (f.kind == PLG_KIND_II && f.lslot == -1) per_site += span_bytes + (f.op.lscale ? scaler_unit : 0);
+      if (f.kind != PLG_KIND_TT && f.rslot == -1) per_site += span_bytes + (f.op.rscale ? scaler_unit : 0);
+      per_site += (f.kind == PLG_KIND_TT) ? 2 : (f.kind == PLG_KIND_TI ? 1 : 0);
+    }
+    plan.compulsory_bytes = per_site * ctx->d.sites;
   }
   return PLG_OK;
 }
@@ -1662,12 +1684,14 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
         memcmp(hit->second->key_bytes.data(), operations, key_bytes) == 0)
     {
       plg_graph_entry * ge = hit->second;
+      ge->last_used = ++ctx->graph_clock;
       PLG_CUDA(cudaGraphLaunch(ge->exec, ctx->stream));
       ctx->stats.graph_launches++;
       ctx->stats.kernel_launches += ge->kernels;
       ctx->stats.partial_ops += count;
       ctx->stats.partial_levels += ge->levels;
       ctx->stats.algorithmic_bytes += ge->algorithmic_bytes;
+      ctx->stats.compulsory_bytes += ge->compulsory_bytes;
       return PLG_OK;
     }
   }
@@ -1719,11 +1743,26 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
   const bool graph_fits = plan.fused.size() * plg_fused_record_bytes(ctx->d.rate_cats) <= ((size_t)64 << 20);
   /* capture on the SECOND sighting of a list: one-off lists (partial traversals during a tree
    * search) do not pay for cudaGraphInstantiate */
-  bool capture = try_graph && graph_fits && ctx->graphs->size() < 64;
+  bool capture = try_graph && graph_fits;
   if (capture)
   {
     if (ctx->seen_lists->size() > 4096) ctx->seen_lists->clear();
     capture = ++(*ctx->seen_lists)[key] >= 2;
+  }
+  if (capture && ctx->graphs->size() >= ctx->graph_cap && ctx->graphs->find(key) == ctx->graphs->end())
+  {
+    /* cache full: the least recently replayed list makes room (a tree search keeps issuing new
+     * partial traversals; the lists of the current neighbourhood stay, old ones go) */
+    auto victim = ctx->graphs->begin();
+    for (auto it = ctx->graphs->begin(); it != ctx->graphs->end(); ++it)
+      if (it->second->last_used < victim->second->last_used) victim = it;
+    PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (victim->second->exec) cudaGraphExecDestroy(victim->second->exec);
+    cudaFree(victim->second->dev_tables);
+    ctx->seen_lists->erase(victim->first);
+    delete victim->second;
+    ctx->graphs->erase(victim);
+    ctx->stats.graph_evictions++;
   }
   if (capture)
   {
@@ -1770,7 +1809,9 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
     ge->dev_tables = dev;
     ge->kernels = kernels;
     ge->levels = plan.levels;
+    ge->last_used = ++ctx->graph_clock;
     ge->algorithmic_bytes = plan.algorithmic_bytes;
+    ge->compulsory_bytes = fused ? plan.compulsory_bytes : plan.algorithmic_bytes;
     auto old = ctx->graphs->find(key);
     if (old != ctx->graphs->end())
     {
@@ -1786,14 +1827,43 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
   }
   else
   {
-    if (plg_stage_reserve(ctx, ops_bytes + jobs_bytes + 1024)) return PLG_E_CUDA;
-    const void * dev_ops = plg_stage(ctx, ops_src, ops_bytes);
-    if (!dev_ops) return PLG_E_CUDA;
+    const void * dev_ops = NULL;
     const TableJob * dev_jobs = NULL;
-    if (jobs_bytes)
+    if (ops_bytes + jobs_bytes + 1024 > ctx->stage_size / 2)
     {
-      dev_jobs = (const TableJob *)plg_stage(ctx, plan.jobs.data(), jobs_bytes);
-      if (!dev_jobs) return PLG_E_CUDA;
+      /* a list too long for the staging ring (the reference accepts any count) gets a
+       * grow-only device buffer of its own; copies and kernels are ordered by the stream */
+      const size_t need = ops_bytes_al + jobs_bytes + 256;
+      if (need > ctx->list_buf_cap)
+      {
+        PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->list_buf);
+        ctx->list_buf = NULL;
+        ctx->list_buf_cap = 0;
+        PLG_CUDA(cudaMalloc(&ctx->list_buf, need + need / 2));
+        ctx->list_buf_cap = need + need / 2;
+      }
+      PLG_CUDA(cudaMemcpyAsync(ctx->list_buf, ops_src, ops_bytes, cudaMemcpyHostToDevice, ctx->stream));
+      dev_ops = ctx->list_buf;
+      if (jobs_bytes)
+      {
+        PLG_CUDA(cudaMemcpyAsync(ctx->list_buf + ops_bytes_al, plan.jobs.data(), jobs_bytes,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+        dev_jobs = (const TableJob *)(ctx->list_buf + ops_bytes_al);
+      }
+      ctx->stats.h2d_bytes += ops_bytes + jobs_bytes;
+    }
+    else
+    {
+      int src = plg_stage_reserve(ctx, ops_bytes + jobs_bytes + 1024);
+      if (src) return src;
+      dev_ops = plg_stage(ctx, ops_src, ops_bytes);
+      if (!dev_ops) return PLG_E_CUDA;
+      if (jobs_bytes)
+      {
+        dev_jobs = (const TableJob *)plg_stage(ctx, plan.jobs.data(), jobs_bytes);
+        if (!dev_jobs) return PLG_E_CUDA;
+      }
     }
     unsigned char * records = NULL;
     if (fused)
@@ -1817,5 +1887,6 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
   ctx->stats.partial_ops += count;
   ctx->stats.partial_levels += plan.levels;
   ctx->stats.algorithmic_bytes += plan.algorithmic_bytes;
+  ctx->stats.compulsory_bytes += fused ? plan.compulsory_bytes : plan.algorithmic_bytes;
   return PLG_OK;
 }

@@ -34,15 +34,6 @@
 #define PLG_FUSED_WARPS 11 /* + 1 producer warp = 12: registers are allocated per 4 warps */
 #endif
 
-__device__ __forceinline__ d4 ld_cached(const double * p)
-{
-  d4 r;
-  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
-               : "l"(p));
-  return r;
-}
-
 __device__ __forceinline__ d4 fmatvec(const d4 (&M)[4], const d4 & c)
 {
   d4 y;
@@ -233,8 +224,11 @@ __device__ __forceinline__ d4 child_term(const WarpCache<EPT> & cache, int slot,
     return cache.load(slot, j, lane);
   }
   const bool valid = FULL || e < nelem;
-  if (MODE != 0 && scaler && valid) sc += __ldg(scaler + (MODE == 2 ? e : e / R));
-  return valid ? ld_stream(clv + (size_t)e * 4) : d4{0.0, 0.0, 0.0, 0.0};
+  /* coherent loads: the tile may have been stored earlier in THIS launch (by this lane; a
+   * per-site scaler by the rate-0 lane of the site, ordered by the __syncwarp that ends every
+   * operation) - .nc / __ldg are only defined for data the kernel never writes */
+  if (MODE != 0 && scaler && valid) sc += ld_coherent_u32(scaler + (MODE == 2 ? e : e / R));
+  return valid ? ld_stream_coherent(clv + (size_t)e * 4) : d4{0.0, 0.0, 0.0, 0.0};
 }
 
 /* One operation on the EPT elements of this lane.  KIND, MODE (scaling), FULL (no element of the

@@ -278,6 +278,20 @@ int pllg_dev_update_sumtable(pllg_partition_t * g, unsigned int parent_clv_index
                                       host_copy ? host_copy + lo * span : NULL));
 }
 
+/* Releases the device copy of the sumtable a caller is about to free (the host pointer is only a
+ * key, reference src/derivatives.c:164-234 writes through it; see pll.h). */
+PLL_EXPORT int pll_gpu_free_sumtable(pll_partition_t * partition, const double * sumtable)
+{
+  pllg_partition_t * g = pllg_from(partition);
+  if (!g) return pll_fail(PLL_ERROR_PARAM_INVALID, "pll_gpu_free_sumtable: not a GPU partition");
+  for (unsigned int d = 0; d < g->ndev; ++d)
+  {
+    int rc = plg_free_sumtable(g->ctxs[d], sumtable);
+    if (rc) return pllg_fail(rc, "pll_gpu_free_sumtable");
+  }
+  return PLL_SUCCESS;
+}
+
 int pllg_dev_likelihood_derivatives(pllg_partition_t * g, const void * key, const double * diagptable,
                                     const double * rate_weights, const double * prop_invar,
                                     const double * freqs, double * d_f, double * dd_f)

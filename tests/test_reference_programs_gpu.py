@@ -36,13 +36,9 @@ PROGRAMS = ["00010_NMDU_lkcalc", "00011_NMAU_lkcalc", "00012_NMOU_lkcalc", "0002
             # data-driven programs on synthetic stand-ins for the reference's downloadable test data
             # (oracle/make_testdata.py); expected text = what the reference library prints for them
             "scaling", "asc-bias", "partial-traversal"]
-# Rooted-tree callers (pll_rtree_*, libpll_b200/csrc/host/pll_utree.c).  The tree code is pinned on
-# the CPU against the reference's own functions (tests/test_utree_cpu.py) and the programs link
-# and record their expected text at build time, but they were written after this round's GPU
-# budget was spent: their FIRST run on a device is the round-end one, so a mismatch is reported
-# as an expected failure instead of stopping the suite (remove the mark once seen green).
-FIRST_DEVICE_RUN = pytest.mark.xfail(strict=False, reason="rooted-tree programs: not yet run on a device")
-PROGRAMS += [pytest.param("rooted", marks=FIRST_DEVICE_RUN), pytest.param("rooted-tipinner", marks=FIRST_DEVICE_RUN)]
+# Rooted-tree callers (pll_rtree_*, libpll_b200/csrc/host/pll_utree.c): green on the device since
+# the round-1 driver run, ordinary members of the list now.
+PROGRAMS += ["rooted", "rooted-tipinner"]
 # scaling.c reads partition->scale_buffer[i] directly (test/src/scaling.c:84-101): it needs the
 # host mirrors kept current
 EXTRA_ENV = {"scaling": {"PLL_GPU_MIRROR": "1"}}
@@ -113,8 +109,7 @@ def test_reference_program_prints_its_fixture(name, attrs, capsys):
 
 
 EXAMPLES = ["unrooted", "newton", "heterotachy", "lg4", "newick-fasta-unrooted", "newick-phylip-unrooted",
-            "protein-list", pytest.param("rooted", marks=FIRST_DEVICE_RUN),
-            pytest.param("newick-fasta-rooted", marks=FIRST_DEVICE_RUN)]
+            "protein-list", "rooted", "newick-fasta-rooted"]
 
 
 @pytest.mark.parametrize("name", EXAMPLES)
