@@ -109,6 +109,12 @@ PLL_EXPORT int plg_set_tipchars(plg_context_t * ctx, unsigned int tip_index,
                                 const unsigned char * chars);
 PLL_EXPORT int plg_get_tipchars(plg_context_t * ctx, unsigned int tip_index,
                                 unsigned char * chars);
+/* Synthetic DNA tip row generated on the device (benchmarks; SURVEY.md 8d "tips generated
+ * directly on device"): the state mask of pattern first_site + i of tip `tip_index` is a pure
+ * function of (seed, tip_index, first_site + i); libpll_b200/synthetic.py: hash_tip_sequence is
+ * the host restatement.  4-state pattern-tip partitions only. */
+PLL_EXPORT int plg_generate_tipchars(plg_context_t * ctx, unsigned int tip_index, unsigned long long seed,
+                                     unsigned long long first_site);
 /* replaces: partition->tipmap / maxstates maintenance (reference src/pll.c:136-397) */
 PLL_EXPORT int plg_set_tipmap(plg_context_t * ctx, const unsigned int * tipmap,
                               unsigned int maxstates);
@@ -317,6 +323,11 @@ PLL_EXPORT int pll_gpu_push_pmatrix(pll_partition_t * partition, unsigned int ma
 PLL_EXPORT int pll_gpu_push_clv(pll_partition_t * partition, unsigned int clv_index);
 
 PLL_EXPORT int pll_gpu_synchronize(pll_partition_t * partition);
+
+/* pll_set_tip_states for a synthetic DNA tip whose characters are generated on the device
+ * (plg_generate_tipchars); `first_site` is the alignment column of the partition's pattern 0. */
+PLL_EXPORT int pll_gpu_generate_tip_states(pll_partition_t * partition, unsigned int tip_index,
+                                           unsigned long long seed, unsigned long long first_site);
 
 /* The `sumtable` argument of pll_update_sumtable / pll_compute_likelihood_derivatives is an
  * opaque key under the GPU flag: the table lives in HBM (sites * rate_cats * states_padded

@@ -186,6 +186,7 @@ _GPU_API = {
     "pll_gpu_push_clv": (C.c_int, [PART_P, C.c_uint]),
     "pll_gpu_synchronize": (C.c_int, [PART_P]),
     "pll_gpu_free_sumtable": (C.c_int, [PART_P, C.c_void_p]),
+    "pll_gpu_generate_tip_states": (C.c_int, [PART_P, C.c_uint, C.c_ulonglong, C.c_ulonglong]),
     "plg_last_error": (C.c_char_p, []),
     "plg_device_count": (C.c_int, []),
     "plg_timer_start": (C.c_int, [C.c_void_p]),

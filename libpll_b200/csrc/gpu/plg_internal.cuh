@@ -208,7 +208,8 @@ struct FusedOp /* 128 bytes: it travels by TMA bulk copy */
   int scale_mode;
   int lslot, rslot, pslot;
   unsigned int lbytes, rbytes; /* bytes of the packed left / right block this operation reads */
-  int pad;                     /* 1: write the result through to HBM; 0: dead store (see build_plan) */
+  int pad;                     /* bit 0: write the result through to HBM (0: dead store, see build_plan);
+                                  bit 1: its scaler is read back from HBM later in the list */
   const double * lsrc;         /* P-matrix set of the left / right child (tip or inner) */
   const double * rsrc;
 };
@@ -218,6 +219,14 @@ static inline size_t plg_fused_block_bytes(unsigned int R) { return (size_t)16 *
 static inline size_t plg_fused_record_bytes(unsigned int R) { return 128 + 2 * plg_fused_block_bytes(R); }
 int plg_launch_fused(plg_context * ctx, const FusedOp * dev_ops, unsigned char * dev_records, unsigned int n_ops,
                      unsigned int nslot);
+/* the same for 20 states on the FP64 tensor cores (plg_traverse_aa.cu) */
+#define PLG_AAF_WARPS 12
+int plg_launch_fused_aa(plg_context * ctx, const FusedOp * dev_ops, unsigned char * dev_records, unsigned int n_ops,
+                        unsigned int nslot);
+/* tile-cache slots per warp that fit next to the operation ring (0: configuration not supported) */
+unsigned int plg_fused_aa_slots(unsigned int rate_cats, unsigned int wanted);
+size_t plg_fused_aa_record_bytes(unsigned int rate_cats);
+unsigned int plg_fused_aa_max_codes(unsigned int rate_cats); /* tip codes a packed table has room for */
 
 /* one operation-shaped launch on the specialised kernels (plg_partials.cu) */
 int plg_launch_single_op(plg_context * ctx, int kind, const DevOp & op);

@@ -30,6 +30,7 @@
 
 #include "plg_internal.cuh"
 #include "plg_async.cuh"
+#include "plg_dmma.cuh"
 
 /* ------------------------------------------------------------------------------------ */
 /* descriptors                                                                           */
@@ -654,10 +655,10 @@ k_partial_tt_aa(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mo
  *
  *   Y[s][i] = sum_j c[s][k][j] * P_k[i][j]      M = 8 sites per warp-tile,
  *                                               N = parent states (20, padded to 3 x 8), K = 20
- *   The 20 child states are fed in 5 k-steps with the permutation j(ks, q) = 4q + ks for
- *   ks < 4 and 16 + q for ks = 4 (any order works as long as A and B agree), so that
- *   A fragment (ks)    : lane (g, q) holds c[site g][j(ks, q)] - its four ks < 4 values are
- *                        32 contiguous bytes: ONE 256-bit load + one 64-bit load per (site, rate)
+ *   The 20 child states are fed in 5 k-steps in the order of plg_dmma.cuh (shared with the
+ *   single-kernel traversal, so both produce the same bits):
+ *   A fragment (ks)    : lane (g, q) holds c[site g][j(ks, q)] - two 16-byte pieces (states
+ *                        2q, 2q+1 and 8+2q, 9+2q) and one 8-byte piece of the CLV row
  *   B fragment (nt, ks): lane holds P[8nt + g][j(ks, q)]             (shared memory, per op)
  *   D fragment (nt)    : lane holds Y[site g][8nt + 2q + {0,1}]      -> 128-bit stores
  *
@@ -669,13 +670,6 @@ k_partial_tt_aa(const DevOp * __restrict__ ops, unsigned int nelem, int scale_mo
  */
 #define PLG_DMMA_THREADS 256
 
-__device__ __forceinline__ void dmma884(double & d0, double & d1, double a, double b)
-{
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
-}
-
 __device__ __forceinline__ double ldg_stream64(const double * p)
 {
   double v;
@@ -683,23 +677,12 @@ __device__ __forceinline__ double ldg_stream64(const double * p)
   return v;
 }
 
-/* the five A-fragment values of one (site, rate): states 4q..4q+3 and 16+q */
+/* the five A-fragment values of one (site, rate), in k-step order (plg_dmma.cuh) */
 struct afrag5
 {
   double2 lo0, lo1;
   double hi;
 };
-
-/* D(8 sites x 8 states) += A(8 x 20) . B(20 x 8) for one N tile */
-__device__ __forceinline__ void dmma_row(double & d0, double & d1, const afrag5 & a,
-                                         const double * __restrict__ bfrag /* [5][32] */, unsigned int lane)
-{
-  dmma884(d0, d1, a.lo0.x, bfrag[0 * 32 + lane]);
-  dmma884(d0, d1, a.lo0.y, bfrag[1 * 32 + lane]);
-  dmma884(d0, d1, a.lo1.x, bfrag[2 * 32 + lane]);
-  dmma884(d0, d1, a.lo1.y, bfrag[3 * 32 + lane]);
-  dmma884(d0, d1, a.hi, bfrag[4 * 32 + lane]);
-}
 
 __device__ __forceinline__ void cp_async16(void * dst_smem, const void * src_gmem)
 {
@@ -733,7 +716,9 @@ template <int R>
 struct dmma_geom
 {
   static constexpr int ROW = R * 20;        /* doubles per site                       */
-  static constexpr int PITCH = ROW + 2;     /* padded: (PITCH*2) % 32 == 4 words      */
+  /* padded so that consecutive sites start 16 banks apart (PITCH = 8 mod 16 doubles): the four
+   * lanes of a site read 64 contiguous bytes, a quarter warp (two sites) all 32 banks */
+  static constexpr int PITCH = ROW + ((24 - ROW % 16) % 16);
   static constexpr int UNIT = 8 * PITCH;    /* doubles per child per unit (8 sites)   */
 };
 
@@ -750,6 +735,7 @@ k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned i
   double * bfrag = smem_d;                                   /* [child][rate][nt][ks][lane] */
   const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned int g = lane >> 2, q = lane & 3u;
+  const unsigned int hi_state = dmma_child_state(4, q);
   double * ring = smem_d + NCHILD * R * 15 * 32 + (size_t)warp * NSLOT * NCHILD * G::UNIT; /* [slot][child][8][PITCH] */
   uint64_t * full = reinterpret_cast<uint64_t *>(smem_d + NCHILD * R * 15 * 32 +
                                                  (size_t)PLG_DMMA_WARPS * NSLOT * NCHILD * G::UNIT) + 2 * warp;
@@ -785,12 +771,9 @@ k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned i
   for (unsigned int t = threadIdx.x; t < NCHILD * R * 15 * 32; t += blockDim.x)
   {
     const unsigned int l = t & 31u, f = (t >> 5) % 15, kc = (t >> 5) / 15; /* kc = child*R + k */
-    const unsigned int nt = f / 5, ks = f % 5;
-    const unsigned int row = 8 * nt + (l >> 2);
-    const unsigned int col = (ks < 4) ? 4 * (l & 3u) + ks : 16 + (l & 3u);
     const double * M = (NCHILD == 2 && kc < (unsigned)R) ? op.lmat : op.rmat;
     const unsigned int k = kc % R;
-    bfrag[t] = (row < 20) ? __ldg(M + (size_t)k * 400 + row * 20 + col) : 0.0;
+    bfrag[t] = dmma_bfrag_value(M + (size_t)k * 400, f, l);
   }
   __syncthreads();
   const double * BL = bfrag;                               /* left child (ii only) */
@@ -850,14 +833,14 @@ k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned i
 #pragma unroll
       for (int k = 0; k < R; ++k)
       {
-        pre_r[k].lo0 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 4 * q);
-        pre_r[k].lo1 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 4 * q + 2);
-        pre_r[k].hi = rowR[k * 20 + 16 + q];
+        pre_r[k].lo0 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 2 * q);
+        pre_r[k].lo1 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 8 + 2 * q);
+        pre_r[k].hi = rowR[k * 20 + hi_state];
         if (KIND == PLG_KIND_II)
         {
-          pre_l[k].lo0 = *reinterpret_cast<const double2 *>(rowL + k * 20 + 4 * q);
-          pre_l[k].lo1 = *reinterpret_cast<const double2 *>(rowL + k * 20 + 4 * q + 2);
-          pre_l[k].hi = rowL[k * 20 + 16 + q];
+          pre_l[k].lo0 = *reinterpret_cast<const double2 *>(rowL + k * 20 + 2 * q);
+          pre_l[k].lo1 = *reinterpret_cast<const double2 *>(rowL + k * 20 + 8 + 2 * q);
+          pre_l[k].hi = rowL[k * 20 + hi_state];
         }
       }
       __syncwarp();
@@ -876,9 +859,9 @@ k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned i
       }
       else
       {
-        ar.lo0 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 4 * q);
-        ar.lo1 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 4 * q + 2);
-        ar.hi = rowR[k * 20 + 16 + q];
+        ar.lo0 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 2 * q);
+        ar.lo1 = *reinterpret_cast<const double2 *>(rowR + k * 20 + 8 + 2 * q);
+        ar.hi = rowR[k * 20 + hi_state];
       }
 
       /* six independent accumulator chains (3 N tiles x {left, right}) advance one k-step
@@ -1009,6 +992,7 @@ struct Plan
   std::vector<Group> groups;
   std::vector<FusedOp> fused;  /* DNA: the same list for the single-kernel traversal */
   unsigned int fused_hits, fused_misses;
+  unsigned int fused_nslot;    /* tile-cache slots per warp the plan was made for */
   unsigned long long levels;
   unsigned long long algorithmic_bytes;
   /* bytes that MUST cross the HBM interface for this list on the path that runs it: level by
@@ -1208,7 +1192,12 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
   /* ---- the single-kernel traversal (plg_traverse.cu): execution order + tile cache ---- */
   plan.fused.clear();
   plan.fused_hits = plan.fused_misses = 0;
-  if (ctx->use_fused && K == 4 && plg_fast_path(ctx) && count >= 2)
+  /* 20 states: the tensor-core traversal (plg_traverse_aa.cu) - 1, 2 or 4 rate categories, tip
+   * tables of at most 23 (four categories) or 24 codes, not in bit-exact mode */
+  const unsigned int aa_slots = (K == 20 && !ctx->aa_exact &&
+                                 (!ctx->pattern_tip || ctx->maxstates <= plg_fused_aa_max_codes(R)))
+                                    ? plg_fused_aa_slots(R, ctx->fused_slots) : 0;
+  if (ctx->use_fused && (K == 4 || aa_slots > 0) && plg_fast_path(ctx) && count >= 2)
   {
     /* Execution order.  A list without slot recycling is a forest: walk it depth-first, the
      * larger subtree first, so that few results are waiting for their parent at any time.
@@ -1277,7 +1266,8 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
     }
 
     /* Tile cache of a warp, simulated here: slot tags are (CLV address, scaler address). */
-    const unsigned int nslot = ctx->fused_slots;
+    const unsigned int nslot = (K == 4) ? ctx->fused_slots : aa_slots;
+    plan.fused_nslot = nslot;
     std::vector<const double *> tag_clv(nslot, nullptr);
     std::vector<const unsigned int *> tag_sc(nslot, nullptr);
     std::vector<unsigned long long> born(nslot, 0);
@@ -1300,10 +1290,23 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
     std::vector<signed char> forward(count, 0); /* 1: left child is the previous result, 2: right */
     for (unsigned int x = 1; x < count; ++x)
     {
-      const Item & it = items[exec[x]];
+      Item & it = items[exec[x]];
       const Item & pv = items[exec[x - 1]];
       if (it.kind == PLG_KIND_II && it.op.left == pv.op.parent && (!it.op.lscale || it.op.lscale == pv.op.pscale))
+      {
         forward[x] = 1;
+        if (K == 20)
+        {
+          /* the tensor-core traversal has ONE straight-line inner-inner path (the right child
+           * arrives in registers): the two sides of the product commute bit for bit, so the
+           * children simply change places */
+          std::swap(it.op.left, it.op.right);
+          std::swap(it.op.lmat, it.op.rmat);
+          std::swap(it.op.lscale, it.op.rscale);
+          std::swap(it.src_l, it.src_r);
+          forward[x] = 2;
+        }
+      }
       else if (it.kind != PLG_KIND_TT && it.op.right == pv.op.parent &&
                (!it.op.rscale || it.op.rscale == pv.op.pscale))
         forward[x] = 2;
@@ -1317,11 +1320,13 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
      * recycling the two may have been written by different operations */
     auto need_hbm = [&](const void * clv_buffer, const void * sc_buffer) {
       auto w = last_clv.find(clv_buffer);
-      if (w != last_clv.end()) plan.fused[w->second].pad = 1;
+      if (w != last_clv.end()) plan.fused[w->second].pad |= 1;
       if (sc_buffer)
       {
+        /* bit 1: this scaler is read back from HBM later in the list (the 20-state kernel then
+         * lets every rate warp store it, so that each warp re-reads its own store) */
         auto v = last_sc.find(sc_buffer);
-        if (v != last_sc.end()) plan.fused[v->second].pad = 1;
+        if (v != last_sc.end()) plan.fused[v->second].pad |= 3;
       }
     };
     plan.fused.resize(count);
@@ -1374,8 +1379,8 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
       tag_sc[dst] = it.op.pscale;
       born[dst] = ++clock;
     }
-    for (const auto & kv : last_clv) plan.fused[kv.second].pad = 1;
-    for (const auto & kv : last_sc) plan.fused[kv.second].pad = 1;
+    for (const auto & kv : last_clv) plan.fused[kv.second].pad |= 1;
+    for (const auto & kv : last_sc) plan.fused[kv.second].pad |= 1;
 
     unsigned long long per_site = 0;
     for (const FusedOp & f : plan.fused)
@@ -1529,8 +1534,11 @@ static int enqueue_plan(plg_context * ctx, const Plan & plan, const void * dev_p
   if (fused)
   {
     /* the whole list in one kernel (plg_traverse.cu) */
-    int frc = plg_launch_fused(ctx, (const FusedOp *)dev_payload, dev_records, (unsigned int)plan.fused.size(),
-                               ctx->fused_slots);
+    int frc = (ctx->d.states == 4)
+                  ? plg_launch_fused(ctx, (const FusedOp *)dev_payload, dev_records, (unsigned int)plan.fused.size(),
+                                     plan.fused_nslot)
+                  : plg_launch_fused_aa(ctx, (const FusedOp *)dev_payload, dev_records,
+                                        (unsigned int)plan.fused.size(), plan.fused_nslot);
     if (frc) return frc;
     cudaError_t ferr = cudaGetLastError();
     if (ferr != cudaSuccess)
@@ -1597,6 +1605,11 @@ static int enqueue_plan(plg_context * ctx, const Plan & plan, const void * dev_p
   }
   *kernels = launched;
   return PLG_OK;
+}
+
+static size_t fused_record_bytes(const plg_context * ctx)
+{
+  return ctx->d.states == 4 ? plg_fused_record_bytes(ctx->d.rate_cats) : plg_fused_aa_record_bytes(ctx->d.rate_cats);
 }
 
 static uint64_t fnv1a(const void * data, size_t bytes)
@@ -1740,7 +1753,7 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
 
   /* a cached graph owns its descriptors (and, fused path, its packed records: 4.7 KB per
    * operation); very long lists are not worth pinning that much memory per distinct list */
-  const bool graph_fits = plan.fused.size() * plg_fused_record_bytes(ctx->d.rate_cats) <= ((size_t)64 << 20);
+  const bool graph_fits = plan.fused.size() * fused_record_bytes(ctx) <= ((size_t)64 << 20);
   /* capture on the SECOND sighting of a list: one-off lists (partial traversals during a tree
    * search) do not pay for cudaGraphInstantiate */
   bool capture = try_graph && graph_fits;
@@ -1768,7 +1781,7 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
   {
     /* descriptors get a stable home, then the whole list is captured once */
     void * dev = NULL;
-    const size_t rec_bytes = fused ? plan.fused.size() * plg_fused_record_bytes(ctx->d.rate_cats) : 0;
+    const size_t rec_bytes = fused ? plan.fused.size() * fused_record_bytes(ctx) : 0;
     const size_t jobs_bytes_al = (jobs_bytes + 255) / 256 * 256;
     PLG_CUDA(cudaMalloc(&dev, ops_bytes_al + jobs_bytes_al + rec_bytes + 256));
     PLG_CUDA(cudaMemcpyAsync(dev, ops_src, ops_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -1868,7 +1881,7 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
     unsigned char * records = NULL;
     if (fused)
     {
-      const size_t need = plan.fused.size() * plg_fused_record_bytes(ctx->d.rate_cats);
+      const size_t need = plan.fused.size() * fused_record_bytes(ctx);
       if (need > ctx->fused_records_cap)
       {
         PLG_CUDA(cudaStreamSynchronize(ctx->stream));

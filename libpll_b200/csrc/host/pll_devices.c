@@ -152,6 +152,12 @@ int pllg_dev_set_tipchars(pllg_partition_t * g, unsigned int tip_index, const un
   FOR_EACH_DEVICE(plg_set_tipchars(ctx, tip_index, chars + lo));
 }
 
+int pllg_dev_generate_tipchars(pllg_partition_t * g, unsigned int tip_index, unsigned long long seed,
+                               unsigned long long first_site)
+{
+  FOR_EACH_DEVICE(plg_generate_tipchars(ctx, tip_index, seed, first_site + lo));
+}
+
 int pllg_dev_get_tipchars(pllg_partition_t * g, unsigned int tip_index, unsigned char * chars)
 {
   FOR_EACH_DEVICE(plg_get_tipchars(ctx, tip_index, chars + lo));

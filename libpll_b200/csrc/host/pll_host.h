@@ -56,6 +56,8 @@ void pllg_dev_destroy(pllg_partition_t * g);
 int pllg_dev_synchronize(pllg_partition_t * g);
 int pllg_dev_set_tipmap(pllg_partition_t * g, const unsigned int * tipmap, unsigned int maxstates);
 int pllg_dev_set_tipchars(pllg_partition_t * g, unsigned int tip_index, const unsigned char * chars);
+int pllg_dev_generate_tipchars(pllg_partition_t * g, unsigned int tip_index, unsigned long long seed,
+                               unsigned long long first_site);
 int pllg_dev_get_tipchars(pllg_partition_t * g, unsigned int tip_index, unsigned char * chars);
 int pllg_dev_set_clv(pllg_partition_t * g, unsigned int clv_index, const double * clv);
 int pllg_dev_get_clv(pllg_partition_t * g, unsigned int clv_index, double * clv);

@@ -474,6 +474,31 @@ PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition,
   return pll_gpu_mirror_mode() ? pll_gpu_sync_clv(partition, tip_index) : PLL_SUCCESS;
 }
 
+PLL_EXPORT int pll_gpu_generate_tip_states(pll_partition_t * partition, unsigned int tip_index,
+                                           unsigned long long seed, unsigned long long first_site)
+{
+  pllg_partition_t * g = pllg_from(partition);
+  if (!g) return pll_fail(PLL_ERROR_PARAM_INVALID, "Not a GPU partition.");
+  pll_partition_t * p = &g->pub;
+  int rc;
+  if (tip_index >= p->tips) return pll_fail(PLL_ERROR_PARAM_INVALID, "Invalid tip index %u", tip_index);
+  if (!(p->attributes & PLL_ATTRIB_PATTERN_TIP) || p->states != 4 || g->sites_alloc != p->sites)
+    return pll_fail(PLL_ERROR_PARAM_INVALID,
+                    "pll_gpu_generate_tip_states: 4-state pattern-tip partitions without ascertainment bias only");
+  if (!merge_charmap(p, pll_map_nt)) return PLL_FAILURE;
+  if (!p->tipchars)
+  {
+    p->tipchars = (unsigned char **)calloc(p->tips, sizeof(unsigned char *));
+    if (!p->tipchars)
+      return pll_fail(PLL_ERROR_MEM_ALLOC, "Cannot allocate space for storing tip characters.");
+  }
+  if ((rc = pllg_dev_set_tipmap(g, p->tipmap, 16u))) return pllg_fail(rc, "pll_gpu_generate_tip_states");
+  if ((rc = pllg_dev_generate_tipchars(g, tip_index, seed, first_site)))
+    return pllg_fail(rc, "pll_gpu_generate_tip_states");
+  if (pll_gpu_mirror_mode()) return pll_gpu_sync_tipchars(partition, tip_index);
+  return PLL_SUCCESS;
+}
+
 PLL_EXPORT int pll_set_tip_clv(pll_partition_t * partition,
                                unsigned int tip_index,
                                const double * clv,

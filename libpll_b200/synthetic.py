@@ -287,3 +287,39 @@ def full_evaluation(part: Partition, w: Workload, pidx: np.ndarray) -> float:
     part.update_partials(w.ops)
     return part.edge_loglikelihood(w.root_a, w.scaler_of(w.root_a), w.root_b, w.scaler_of(w.root_b),
                                    w.root_matrix, pidx)
+
+
+# ---- counter-based tips (generated on the device for the 10 M-pattern config) ----
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    """Vectorised splitmix64 finaliser over uint64 (wrap-around arithmetic), the function
+    libpll_b200/csrc/gpu/plg_synth.cu evaluates per character."""
+    with np.errstate(over="ignore"):
+        x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+        z = x
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        return z ^ (z >> np.uint64(31))
+
+
+def hash_tip_sequence(seed: int, tip: int, lo: int, hi: int) -> bytes:
+    """Host restatement of plg_generate_tipchars (DNA): ASCII characters of tip `tip` for alignment
+    columns [lo, hi) - root state w.p. 0.7 else uniform, 1 % N, 0.5 % R / Y."""
+    site = np.arange(lo, hi, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        root = _splitmix64(np.uint64(seed) ^ ((site * np.uint64(0xD1342543DE82EF95)) & _M64)) & np.uint64(3)
+        tip_key = _splitmix64(np.array([(seed + 0x632BE59BD9B4E019 * (tip + 1)) & 0xFFFFFFFFFFFFFFFF],
+                                       dtype=np.uint64))[0]
+        h = _splitmix64(tip_key ^ site)
+    u = h & np.uint64(0xFFFF)
+    alt = (h >> np.uint64(16)) & np.uint64(3)
+    u2 = (h >> np.uint64(32)) & np.uint64(0xFFFF)
+    state = np.where(u < 45875, root, alt).astype(np.intp)
+    chars = DNA_ALPHABET[state].copy()
+    two = (u2 >= 655) & (u2 < 983)
+    chars[two & ((alt & np.uint64(1)) == 0)] = ord("R")
+    chars[two & ((alt & np.uint64(1)) == 1)] = ord("Y")
+    chars[u2 < 655] = ord("N")
+    return chars.tobytes()

@@ -109,6 +109,11 @@ int plg_set_tipchars(plg_context_t * ctx, unsigned int tip_index, const unsigned
   touch_in(chars, ctx->d.sites);
   return PLG_OK;
 }
+int plg_generate_tipchars(plg_context_t * ctx, unsigned int tip_index, unsigned long long seed,
+                          unsigned long long first_site)
+{
+  return tip_index < ctx->d.tips ? PLG_OK : PLG_E_INVALID;
+}
 int plg_get_tipchars(plg_context_t * ctx, unsigned int tip_index, unsigned char * chars)
 {
   if (tip_index >= ctx->d.tips) return PLG_E_INVALID;
