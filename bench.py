@@ -1,15 +1,16 @@
 #!/usr/bin/env python3
 """Headline benchmark: full post-order CLV traversal + edge log-likelihood of a synthetic
-1,000-taxon x 1M-pattern GTR+G4 DNA partition per B200 (BASELINE.json configs[1]).
+1,000-taxon x 1M-pattern GTR+G4 DNA partition per B200 (BASELINE.json configs[1]), with the other
+BASELINE configurations as sub-records of the same JSON line.
 
     python bench.py --gpus N --steps K --warmup W          # this repository's CUDA path
     python bench.py --impl reference ...                   # the reference's own AVX2 CPU path
 
-One "step" = one full-tree evaluation: all P-matrices, the whole traversal
-(`pll_update_partials` over T-2 operations) and `pll_compute_edge_loglikelihood`.  With N > 1
-(torchrun, one rank per GPU) the site patterns are sharded: every rank owns a contiguous slice
-of 1M patterns of EVERY CLV (weak scaling: the alignment has N x 1M patterns) and only the
-per-rank partial lnL crosses NVLink (one scalar NCCL all-reduce per step).
+One "step" = one full-tree evaluation: the whole traversal (`pll_update_partials`
+over T-2 operations) and `pll_compute_edge_loglikelihood`.  With N > 1 (torchrun, one rank per GPU)
+the site patterns are sharded: every rank owns a contiguous slice of 1M patterns of EVERY CLV (weak
+scaling: the alignment has N x 1M patterns) and only the per-rank partial lnL crosses NVLink (one
+scalar NCCL all-reduce per step).
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   value        CLV site-updates/s, device-timed (CUDA events on the library's own stream) with
@@ -17,10 +18,19 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   e2e          the same metric through the public pll.h API from HOST buffers, wall-clocked:
                each step uploads fresh branch lengths / matrix indices / the operations array
                (pinned staging -> HBM), recomputes all P-matrices, traverses, reads lnL back
-  roofline     dominant kernel (inner-inner CLV update): algorithmic bytes / CUDA-event time
-               per launch, measured live in profiling mode, against MEASURED_PEAKS.json
-  cpu_baseline the reference (oracle/_ref) timed on this box's host cores on a bounded sample
-  lnl_evals_per_s  full-tree lnL evaluations/s (1 / e2e step time) - BASELINE.json's 2nd metric
+  roofline     dominant kernel (k_traverse_dna, the whole list in one launch): COMPULSORY DRAM
+               bytes of its plan (every observable parent CLV / scaler written once, tip characters
+               and tile-cache misses read; plg_stats.compulsory_bytes) / CUDA-event time per launch
+               against MEASURED_PEAKS.json; SURVEY 8d's algorithmic figure under `algorithmic`
+  cpu_baseline the reference (oracle/_ref) timed on this box's host cores on the same workload
+  lnl_check    the GPU lnL against the sum of the CPU arm's slice lnLs (rel <= 1e-10 or the run fails)
+  also         the other BASELINE configurations, each bounded to a few seconds:
+                 lists  e2e with a DIFFERENT partial traversal every step (moving virtual root)
+                 c4     Newton branch-length optimisation: sumtable + 32 derivative passes on the
+                        evaluation edge and 9 re-rooted edges (configs[3])
+                 c3     500-taxon x 200k-pattern protein LG+G4 traversal + edge lnL (configs[2])
+                 c5     5,000-taxon x 10M-pattern DNA sharded over the N GPUs, strong scaling, 64
+                        recycled CLV slots, tips generated on the device (configs[4])
 """
 from __future__ import annotations
 
@@ -42,6 +52,7 @@ print_json = print
 
 METRIC = "CLV site-updates/sec (full post-order traversal + edge logL, GTR+G4 DNA)"
 UNIT = "site-updates/s"
+DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200 (tools/ubench/dmma_peak.cu, profiles/)
 
 
 def log(*a):
@@ -73,6 +84,7 @@ class ClockSampler:
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+        return self
 
     def stop(self) -> dict:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -107,6 +119,50 @@ class ClockSampler:
         return out
 
 
+def hbm_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        if "hbm_gbs" in peaks:
+            return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        pass
+    return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def measured_traffic(key: str, **must_match):
+    """DRAM bytes per launch from an ncu capture of the SAME command (profiles/r02_traffic.json);
+    None unless the capture matches this run's configuration."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(key)
+    except Exception:
+        return None, None
+    if not t or any(t.get(k) != v for k, v in must_match.items()):
+        return None, None
+    return t["dram_bytes_per_launch"], t.get("source")
+
+
+# ----------------------------------------------------------------------------------------
+# tips are generated once per process and shared by every partition built from them
+# ----------------------------------------------------------------------------------------
+def memoize_tips():
+    from libpll_b200 import synthetic as S
+
+    cache = {}
+    orig = S.tip_sequence
+
+    def memo(w, tip, lo=0, hi=None):
+        hi = w.sites if hi is None else hi
+        if w.sites > 2_000_000:          # a rank of a multi-GPU run only ever asks for its own slice
+            return orig(w, tip, lo, hi)
+        key = (w.tips, w.sites, w.states, w.seed, tip)
+        if key not in cache:
+            cache[key] = orig(w, tip, 0, w.sites)
+        return cache[key][lo:hi]
+
+    S.tip_sequence = memo
+    return cache
+
+
 # ----------------------------------------------------------------------------------------
 # CPU baseline = the reference's own AVX2 path on host cores
 # ----------------------------------------------------------------------------------------
@@ -119,30 +175,48 @@ def _ref_library():
     return None, "port"
 
 
-def cpu_traversal_rate(w_full, threads: int, sites_per_thread: int, reps: int, warm: int = 1,
-                       use_mean: bool = False):
-    """Downstream convention for the single-threaded reference: `threads`
-    host threads, each owning an independent partition over a contiguous slice of
-    `sites_per_thread` patterns of the SAME workload; time = slowest thread.  Returns
-    (site-updates/s, seconds per step, lnL of the sample)."""
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_traversal(w_full, slices, reps: int, warm: int, use_mean: bool = False):
+    """Downstream convention for the single-threaded reference: one host thread
+    per entry of `slices` = [(lo, hi)], each owning an independent partition over that contiguous
+    pattern slice of the SAME workload; time = slowest thread.  Returns (site-updates/s, seconds
+    per step, [lnL per slice], kind)."""
     from libpll_b200 import synthetic as S
     from libpll_b200.binding import PLL_ATTRIB_ARCH_AVX2, PLL_ATTRIB_PATTERN_TIP
 
     ref, kind = _ref_library()
+    threads = len(slices)
+    total_sites = sum(hi - lo for lo, hi in slices)
     if ref is None:
         from oracle import port as oracle_port
 
-        return oracle_port.cpu_traversal_rate(w_full, threads, sites_per_thread, reps) + (kind,)
+        spt = slices[0][1] - slices[0][0]
+        rate, t, lnl = oracle_port.cpu_traversal_rate(w_full, threads, spt, reps)
+        return rate, t, [lnl], kind
 
     parts = [None] * threads
-    pidx = None
+    pidx = [None]
 
     def setup(t):
-        nonlocal pidx
-        lo = t * sites_per_thread
-        parts[t], pidx_t = S.build_partition(ref, w_full, PLL_ATTRIB_ARCH_AVX2 | PLL_ATTRIB_PATTERN_TIP,
-                                             lo=lo, hi=lo + sites_per_thread)
-        pidx = pidx_t
+        lo, hi = slices[t]
+        parts[t], pidx[0] = S.build_partition(ref, w_full, PLL_ATTRIB_ARCH_AVX2 | PLL_ATTRIB_PATTERN_TIP,
+                                              lo=lo, hi=hi)
 
     ths = [threading.Thread(target=setup, args=(t,)) for t in range(threads)]
     [t.start() for t in ths]
@@ -156,7 +230,7 @@ def cpu_traversal_rate(w_full, threads: int, sites_per_thread: int, reps: int, w
         for r in range(warm + reps):
             barrier.wait()
             t0 = time.perf_counter()
-            lnl[t] = S.full_evaluation(parts[t], w_full, pidx)  # ctypes releases the GIL
+            lnl[t] = S.full_evaluation(parts[t], w_full, pidx[0])  # ctypes releases the GIL
             times[t, r] = time.perf_counter() - t0
 
     ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
@@ -166,53 +240,375 @@ def cpu_traversal_rate(w_full, threads: int, sites_per_thread: int, reps: int, w
         p.destroy()
     step = times[:, warm:].max(axis=0)  # slowest thread per repetition
     t = float(step.mean()) if use_mean else float(step.min())
-    rate = len(w_full.ops) * threads * sites_per_thread / t
-    return rate, t, float(lnl.sum()), kind
+    return len(w_full.ops) * total_sites / t, t, [float(x) for x in lnl], kind
 
 
-def host_cores() -> int:
-    try:
-        return len(os.sched_getaffinity(0))
-    except Exception:
-        return os.cpu_count() or 1
+def even_slices(sites: int, parts: int):
+    """`parts` contiguous pattern slices, 64-pattern aligned (the device slicing rule)."""
+    per = ((sites + parts - 1) // parts + 63) // 64 * 64
+    out = []
+    lo = 0
+    while lo < sites:
+        out.append((lo, min(lo + per, sites)))
+        lo += per
+    return out
+
+
+CPU_SLOTS = 64  # the CPU arm keeps its CLVs in a pool of recycled slots so that host RAM holds 1M patterns
+
+
+def full_config_cpu(w, cores: int, reps: int, warm: int, use_mean: bool):
+    """The reference on the WHOLE workload: `cores` threads x (sites / cores) patterns.  Same tree,
+    tips, model and operations; the inner CLVs live in 64 recycled slots per thread (legal pll.h
+    use; the plain list would need 128 B x 998 x 1M = 128 GB of host memory)."""
+    from libpll_b200 import synthetic as S
+
+    wr = S.recycle_slots(w, CPU_SLOTS)
+    slices = even_slices(w.sites, cores)
+    rate, t, lnls, kind = cpu_traversal(wr, slices, reps=reps, warm=warm, use_mean=use_mean)
+    return rate, t, lnls, kind, slices
 
 
 # ----------------------------------------------------------------------------------------
+def workload_string(tips: int, sites: int, per_gpu: int) -> str:
+    return (f"synthetic {tips}-taxon x {sites}-pattern GTR+G4 DNA ({per_gpu} patterns per GPU), "
+            f"full post-order traversal + edge logL")
+
+
 def run_reference(args, rank: int, world: int):
-    """--impl reference: the reference's own CPU implementation of the path on host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on host cores, on the
+    full configuration of the GPU arm (all patterns, all operations)."""
     if rank != 0:
         return
     from libpll_b200 import synthetic as S
 
+    memoize_tips()
     cores = host_cores()
-    w = S.make_workload(args.tips, args.sites_per_gpu * max(world, 1), states=4)
-    spt = args.cpu_sites_per_thread
-    # warmup + steps: each "step" is one traversal of the bounded sample on all cores
-    rate, best, lnl, kind = cpu_traversal_rate(w, cores, spt, reps=args.steps, warm=args.warmup,
-                                               use_mean=True)
-    sample = (f"{cores} threads x {spt} patterns each ({cores * spt} of {w.sites} patterns), "
-              f"{len(w.ops)} operations per traversal, mean of {args.steps} steps")
+    total = args.sites_per_gpu * max(world, 1)
+    w = S.make_workload(args.tips, total, states=4)
+    t0 = time.time()
+    rate, step_s, lnls, kind, slices = full_config_cpu(w, cores, reps=args.steps, warm=args.warmup, use_mean=True)
+    log(f"[bench] reference arm: {cores} threads, {step_s:.2f} s per step, total {time.time() - t0:.0f} s")
+    # one-thread row (SURVEY 8d): a 10,000-pattern slice on a single core
+    one_rate, one_t, _, _ = cpu_traversal(S.recycle_slots(w, CPU_SLOTS), [(0, min(10_000, total))], reps=1, warm=0)
+    sample = (f"ALL {total} patterns: {cores} threads x {slices[0][1] - slices[0][0]} patterns each, "
+              f"{len(w.ops)} operations per traversal, inner CLVs in {CPU_SLOTS} recycled slots per thread, "
+              f"mean of {args.steps} steps")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": best * 1e3,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        # the same workload definition as the GPU arm (what is timed is the bounded sample of it
-        # described in cpu_baseline.sample; throughput is linear in the number of patterns)
-        "config": {"workload": f"synthetic {args.tips}-taxon x {w.sites}-pattern GTR+G4 DNA "
-                               f"({args.sites_per_gpu} patterns per GPU), full post-order traversal + edge logL",
+        "config": {"workload": workload_string(args.tips, total, args.sites_per_gpu),
                    "attributes": "PLL_ATTRIB_ARCH_AVX2|PLL_ATTRIB_PATTERN_TIP, per-site scalers",
-                   "operations": len(w.ops), "rate_cats": 4, "timed": "bounded CPU sample, see cpu_baseline.sample"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                   "operations": len(w.ops), "rate_cats": 4,
+                   "timed": "the whole configuration (no extrapolation), see cpu_baseline.sample"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "cpu_model": cpu_model(),
+                         "one_thread": {"value": one_rate, "unit": UNIT, "cores": 1,
+                                        "sample": f"one thread x {min(10_000, total)} patterns, {one_t:.2f} s"}},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "lnl": float(np.sum(lnls)),
     }
     print_json(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------
-def run_gpu(args, rank: int, world: int, local_rank: int):
-    import torch  # plumbing only: torch.distributed (NCCL) for the scalar all-reduce / barriers
+# GPU legs
+# ----------------------------------------------------------------------------------------
+class Dist:
+    """torch.distributed plumbing (NCCL): barriers and the scalar all-reduce of a step."""
 
+    def __init__(self, world: int, local_rank: int):
+        import torch
+
+        self.torch = torch
+        self.world = world
+        torch.cuda.set_device(local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _reduce(self, x: float, op) -> float:
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x: float) -> float:
+        return self._reduce(x, self.dist.ReduceOp.MAX if self.dist else None)
+
+    def sum(self, x: float) -> float:
+        return self._reduce(x, self.dist.ReduceOp.SUM if self.dist else None)
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def leg_lists(lib, part, pidx, tips: int, sites: int, steps: int):
+    """e2e with a DIFFERENT operations list every step: the virtual root moves to a random inner
+    node, the partial traversal that re-orients the CLVs (pll_utree_traverse with a pruning
+    callback, reference test/src/partial-traversal.c) is issued through the public API together
+    with its P-matrices, and the edge lnL is read back.  No list repeats, so nothing replays a
+    cached CUDA graph: build_plan + staging + the uncaptured launch are inside the timed calls.
+    Wall clock of the three pll.h calls vs. the device time between CUDA events on the stream."""
+    from libpll_b200 import trees as T
+
+    T.bind(lib)
+    tree = T.Tree(lib, newick=T.random_newick(tips, 4242))
+    walker = T.RootWalker(lib, tree)
+    rng = np.random.default_rng(7)
+
+    def evaluate(root, timed):
+        ops, mats, bls = walker.move(root)
+        e = walker.edge(root)
+        t0 = time.perf_counter()
+        if timed:
+            part.timer_start()
+        part.update_prob_matrices(pidx, mats, bls)
+        part.update_partials(ops)
+        lnl = part.edge_loglikelihood(e[0], e[1], e[2], e[3], e[4], pidx)
+        dev_ms = part.timer_stop() if timed else 0.0
+        return lnl, len(ops), (time.perf_counter() - t0) * 1e3, dev_ms
+
+    ops, mats, bls = walker.full(tree.root)
+    part.update_prob_matrices(pidx, mats, bls)
+    part.update_partials(ops)
+    e = walker.edge(tree.root)
+    lnl0 = part.edge_loglikelihood(e[0], e[1], e[2], e[3], e[4], pidx)
+
+    def random_root():
+        node = tree.node(tips + int(rng.integers(0, tree.inner)))
+        for _ in range(int(rng.integers(0, 3))):
+            node = node.contents.next
+        return node
+
+    for _ in range(3):
+        evaluate(random_root(), False)
+    part.reset_stats()
+    wall, dev, nops, worst = [], [], [], 0.0
+    for _ in range(steps):
+        lnl, n, w_ms, d_ms = evaluate(random_root(), True)
+        if n == 0:
+            continue
+        wall.append(w_ms)
+        dev.append(d_ms)
+        nops.append(n)
+        worst = max(worst, abs(lnl - lnl0) / abs(lnl0))
+    st = part.stats()
+    out = {
+        "what": "moving virtual root: a different partial traversal + its P-matrices + edge lnL per step, "
+                "through pll_update_prob_matrices / pll_update_partials / pll_compute_edge_loglikelihood",
+        "steps": len(wall), "operations_per_step_mean": float(np.mean(nops)), "operations_per_step_max": int(max(nops)),
+        "wall_ms_per_step": float(np.mean(wall)), "device_ms_per_step": float(np.mean(dev)),
+        "host_overhead_ms_per_step": float(np.mean(wall) - np.mean(dev)),
+        "host_overhead_frac_of_device": float((np.mean(wall) - np.mean(dev)) / np.mean(dev)),
+        "value": float(np.sum(nops)) * sites / (np.sum(wall) * 1e-3), "unit": UNIT,
+        "graph_launches": st["graph_launches"], "gpu_launches": st["kernel_launches"],
+        "h2d_bytes_per_step": st["h2d_bytes"] // max(len(wall), 1),
+        "lnl_drift_rel": worst,
+    }
+    assert worst < 1e-9, f"moving the virtual root changed the likelihood (rel {worst})"
+    return out, tree, walker
+
+
+def leg_c4(lib, part, pidx, tree, walker, sites: int, branches: int = 10, iters: int = 32):
+    """BASELINE configs[3]: Newton branch-length optimisation (reference examples/newton/newton.c
+    :31-100) on the evaluation edge and on `branches - 1` further edges reached by re-rooting
+    (each move = a short partial traversal): pll_update_sumtable once per edge, then `iters`
+    pll_compute_likelihood_derivatives calls with the Newton update between them."""
+    import ctypes as C
+
+    def ring(rec):
+        out, n = [rec], rec.contents.next
+        while n and C.addressof(n.contents) != C.addressof(rec.contents):
+            out.append(n)
+            n = n.contents.next
+        return out
+
+    root = tree.root
+    seen_edges = set()
+    key = np.zeros(8)  # under the GPU flag the sumtable argument is only a key (include/pll.h)
+    t_move = t_sum = t_der = 0.0
+    n_der = 0
+    lengths = []
+    part.synchronize()
+    t_all = time.perf_counter()
+    for b in range(branches):
+        if b:
+            # next edge: another record of this inner node, or one of the node across the edge
+            here = ring(root)
+            across = ring(root.contents.back) if root.contents.back.contents.next else []
+            root = next(r for r in here[1:] + across[1:] + here if r.contents.pmatrix_index not in seen_edges)
+        seen_edges.add(root.contents.pmatrix_index)
+        t0 = time.perf_counter()
+        ops, mats, bls = walker.move(root)
+        part.update_prob_matrices(pidx, mats, bls)
+        part.update_partials(ops)
+        part.synchronize()
+        t_move += time.perf_counter() - t0
+        e = walker.edge(root)
+        t0 = time.perf_counter()
+        part.update_sumtable(e[0], e[2], e[1], e[3], pidx, key)
+        part.synchronize()
+        t_sum += time.perf_counter() - t0
+        length = root.contents.length
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            d1, d2 = part.likelihood_derivatives(e[1], e[3], length, pidx, key)
+            n_der += 1
+            step = d1 / d2 if d2 > 0 else -d1            # Newton; gradient step if not convex here
+            length = min(max(length - step, 1e-6), 10.0)
+        t_der += time.perf_counter() - t0
+        lengths.append(length)
+    total = time.perf_counter() - t_all
+    return {
+        "what": f"Newton on {branches} branches (the evaluation edge + {branches - 1} re-rooted ones): "
+                f"partial traversal, pll_update_sumtable, {iters} x pll_compute_likelihood_derivatives each",
+        "branches": branches, "iterations_per_branch": iters,
+        "value": n_der / total, "unit": "Newton iterations/s",
+        "derivative_call_us": t_der / n_der * 1e6, "sumtable_call_us": t_sum / branches * 1e6,
+        "reroot_call_us": t_move / branches * 1e6, "newton_32_iterations_ms": t_der / branches * 1e3,
+        "ms_per_branch": total / branches * 1e3,
+        "derivative_pass_GBps": (4 * 4 * 8 + 4) * sites / (t_der / n_der) / 1e9,
+        "optimised_lengths": [round(x, 6) for x in lengths[:3]],
+    }
+
+
+def leg_c3(lib, steps: int, warmup: int, local_rank: int):
+    """BASELINE configs[2]: 500 taxa x 200k patterns, LG+G4 protein, traversal + edge lnL."""
+    from libpll_b200 import synthetic as S
+    from libpll_b200.binding import PLL_ATTRIB_ARCH_GPU, PLL_ATTRIB_PATTERN_TIP
+
+    tips, sites = 500, 200_000
+    w = S.make_workload(tips, sites, states=20)
+    part, pidx = S.build_partition(lib, w, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP)
+    root = (w.root_a, w.scaler_of(w.root_a), w.root_b, w.scaler_of(w.root_b), w.root_matrix, pidx)
+    part.update_prob_matrices(pidx, w.matrix_indices, w.branch_lengths)
+    sampler = ClockSampler(local_rank).start()
+    for _ in range(max(warmup, 3)):
+        part.update_partials(w.ops)
+        lnl = part.edge_loglikelihood(*root)
+    part.reset_stats()
+    part.timer_start()
+    for _ in range(steps):
+        part.update_partials(w.ops)
+        lnl = part.edge_loglikelihood(*root)
+    ms = part.timer_stop() / steps
+    stats = part.stats()
+    part.reset_stats()
+    part.timer_start()
+    for _ in range(steps):
+        part.update_partials(w.ops)
+    trav_ms = part.timer_stop() / steps
+    trav = part.stats()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        bl = w.branch_lengths * (1.0 + 1e-3 * ((i % 7) - 3))
+        part.update_prob_matrices(pidx, w.matrix_indices, bl)
+        part.update_partials(w.ops.copy())
+        part.edge_loglikelihood(*root)
+    e2e_s = (time.perf_counter() - t0) / steps
+    clocks = sampler.stop()
+    part.destroy()
+    tt, ti, ii = w.op_kinds()
+    peak, peak_src = hbm_peak()
+    comp = trav["compulsory_bytes"] / steps
+    alg = trav["algorithmic_bytes"] / steps
+    issued = sites / 8 * 4 * 15 * 512.0 * (2 * ii + ti)       # DMMA flops issued (N padded 20 -> 24)
+    useful = sites * 4 * 20 * 20 * 2.0 * (2 * ii + ti)
+    fused = trav["kernel_launches"] <= 3 * steps
+    return {
+        "workload": f"synthetic {tips}-taxon x {sites}-pattern LG+G4 protein, full traversal + edge logL",
+        "operations": len(w.ops), "ops_tt_ti_ii": [tt, ti, ii],
+        "value": len(w.ops) * sites / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+        "e2e": {"value": len(w.ops) * sites / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": stats["kernel_launches"], "clocks": clocks, "lnl": lnl,
+        "roofline": {
+            "kernel": "k_traverse_aa (whole list, FP64 tensor cores)" if fused else "k_partial_dmma_aa (level by level)",
+            "avg_traversal_ms": trav_ms,
+            "hbm": {"compulsory_bytes_per_launch": comp, "achieved": comp / (trav_ms * 1e-3) / 1e9, "peak": peak,
+                    "unit": "GB/s", "frac": comp / (trav_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src},
+            "tensor": {"dmma_flops_issued": issued, "useful_flops": useful,
+                       "achieved": issued / (trav_ms * 1e-3) / 1e12, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                       "frac": issued / (trav_ms * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS,
+                       "peak_source": "measured DMMA m8n8k4 peak (tools/ubench/dmma_chains.cu)"},
+            "algorithmic": {"bytes_per_launch": alg, "GBps": alg / (trav_ms * 1e-3) / 1e9},
+        },
+    }
+
+
+def leg_c5(lib, D: Dist, rank: int, world: int, local_rank: int, steps: int, slots: int):
+    """BASELINE configs[4]: 5,000 taxa x 10M patterns sharded over the GPUs (strong scaling: the
+    alignment is fixed), CLVs / scalers in a pool of recycled slots, tips generated on the device
+     from a counter-based generator the host can restate for any slice."""
+    from libpll_b200 import synthetic as S
+    from libpll_b200.binding import PLL_ATTRIB_ARCH_GPU, PLL_ATTRIB_PATTERN_TIP
+
+    tips, total = 5000, 10_000_000
+    per = (total // world + 63) // 64 * 64
+    lo, hi = rank * per, min((rank + 1) * per, total)
+    w = S.recycle_slots(S.make_workload(tips, 64, states=4), slots)   # tree / operations only
+    t0 = time.time()
+    part = lib.partition(tips=tips, clv_buffers=w.inner, states=4, sites=hi - lo, rate_matrices=1,
+                         prob_matrices=w.prob_matrices, rate_cats=4, scale_buffers=w.inner,
+                         attributes=PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP)
+    part.set_frequencies(0, S.GTR_FREQS)
+    part.set_subst_params(0, S.GTR_RATES)
+    part.set_category_rates(lib.gamma_rates(w.alpha, 4))
+    part.set_category_weights(np.full(4, 0.25))
+    for t in range(tips):
+        assert lib.pll_gpu_generate_tip_states(part.ptr, t, 43, lo) == 1, lib.errmsg()
+    pidx = np.zeros(4, np.uint32)
+    part.update_prob_matrices(pidx, w.matrix_indices, w.branch_lengths)
+    root = (w.root_a, w.scaler_of(w.root_a), w.root_b, w.scaler_of(w.root_b), w.root_matrix, pidx)
+    setup_s = time.time() - t0
+
+    def step():
+        part.update_partials(w.ops)
+        return D.sum(part.edge_loglikelihood(*root))
+
+    sampler = ClockSampler(local_rank).start()
+    for _ in range(3):
+        lnl = step()
+    D.barrier()
+    part.reset_stats()
+    part.timer_start()
+    for _ in range(steps):
+        lnl = step()
+    ms = D.max(part.timer_stop()) / steps
+    D.barrier()
+    clocks = sampler.stop()
+    st = part.stats()
+    part.destroy()
+    peak, peak_src = hbm_peak()
+    comp = st["compulsory_bytes"] / steps
+    return {
+        "workload": f"synthetic {tips}-taxon x {total}-pattern GTR+G4 DNA sharded over {world} GPU(s) "
+                    f"({hi - lo} patterns on rank 0), {slots} recycled CLV slots, device-generated tips",
+        "scaling": "strong", "n_gpus": world, "operations": len(w.ops),
+        "value": len(w.ops) * total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+        "setup_s": setup_s, "gpu_launches": st["kernel_launches"], "clocks": clocks, "lnl": lnl,
+        "roofline": {"kernel": "k_traverse_dna", "compulsory_bytes_per_launch_per_gpu": comp,
+                     "achieved": comp / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": comp / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                     "note": "per GPU; only the last value of each recycled buffer and tile-cache misses are "
+                             "stored (dead-store elimination), tip characters are read",
+                     "algorithmic_GBps_per_gpu": st["algorithmic_bytes"] / steps / (ms * 1e-3) / 1e9},
+    }
+
+
+def run_gpu(args, rank: int, world: int, local_rank: int):
     import libpll_b200
     from libpll_b200 import synthetic as S
     from libpll_b200.binding import PLL_ATTRIB_ARCH_GPU, PLL_ATTRIB_PATTERN_TIP
@@ -220,44 +616,16 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     lib = libpll_b200.load()
     if lib.plg_device_count() == 0:
         raise SystemExit("bench.py: no B200 visible - the CUDA path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
+    D = Dist(world, local_rank)  # torch: plumbing only (NCCL scalar all-reduce, barriers)
     lib.pll_gpu_set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def allreduce_max(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allreduce_sum(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    memoize_tips()
+    also = args.also
+    if also == "auto":
+        also = "lists,c4,c3,c5" if world == 1 else "c5"
+    also = [x for x in also.split(",") if x and x != "none"]
 
     S_gpu = args.sites_per_gpu
-    if args.workload == "c5":
-        # BASELINE.json configs[4]: 5,000 taxa x 10M patterns sharded over the GPUs (strong
-        # scaling: the alignment is fixed), CLVs / scalers in a pool of recycled slots
-        args.tips, total_sites = 5000, 10_000_000
-        S_gpu = (total_sites // world + 63) // 64 * 64
-        w = S.recycle_slots(S.make_workload(args.tips, S_gpu * world, states=4), args.slots)
-        distinct = [S.tip_sequence(w, t, rank * S_gpu, (rank + 1) * S_gpu) for t in range(args.distinct_tips)]
-        S.tip_sequence = lambda w_, t, lo=0, hi=None: distinct[t % len(distinct)]
-    else:
-        w = S.make_workload(args.tips, S_gpu * world, states=4)
+    w = S.make_workload(args.tips, S_gpu * world, states=4)
     lo, hi = rank * S_gpu, (rank + 1) * S_gpu
     t0 = time.time()
     part, pidx = S.build_partition(lib, w, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP, lo=lo, hi=hi)
@@ -272,64 +640,64 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
 
     def resident_step():
         part.update_partials(w.ops)
-        return allreduce_sum(part.edge_loglikelihood(*root))
+        return D.sum(part.edge_loglikelihood(*root))
 
     # clocks are sampled from the warm-up on: nvidia-smi needs ~0.2 s to deliver its first
     # sample and the timed region of a short run is not much longer (same load throughout)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(local_rank).start()
     for _ in range(max(args.warmup, 3)):
         lnl = resident_step()
-    barrier()
+    D.barrier()
     part.reset_stats()
     part.timer_start()
     for _ in range(args.steps):
         lnl = resident_step()
     ms = part.timer_stop()
-    barrier()
+    D.barrier()
     clocks = sampler.stop()
     stats = part.stats()
-    ms = allreduce_max(ms)
-    ms_per_step = ms / args.steps
+    ms_per_step = D.max(ms) / args.steps
     value = n_ops * S_gpu * world / (ms_per_step * 1e-3)
 
     # ---- leg B: end to end through the public API, host buffers, wall clock -------------
-    rng = np.random.default_rng(1234 + rank)
-
     def e2e_step(i):
         # fresh host inputs every step: branch lengths change, so every P-matrix is recomputed
         bl = w.branch_lengths * (1.0 + 1e-3 * ((i % 7) - 3))
         ops = w.ops.copy()
         part.update_prob_matrices(pidx, w.matrix_indices, bl)
         part.update_partials(ops)
-        return allreduce_sum(part.edge_loglikelihood(*root))
+        return D.sum(part.edge_loglikelihood(*root))
 
     for i in range(max(args.warmup, 3)):
         e2e_step(i)
-    barrier()
+    D.barrier()
     part.reset_stats()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        e2e_lnl = e2e_step(i)
-    barrier()
-    e2e_s = allreduce_max(time.perf_counter() - t0) / args.steps
+        e2e_step(i)
+    D.barrier()
+    e2e_s = D.max(time.perf_counter() - t0) / args.steps
     e2e_stats = part.stats()
     e2e_value = n_ops * S_gpu * world / e2e_s
 
     # ---- leg C: roofline of the dominant kernel, CUDA events per launch ------------------
-    # (1) the traversal as the library runs it: by default ONE kernel walks the whole list
+    # (1) the traversal as the library runs it: ONE kernel walks the whole list
     #     (k_traverse_dna, libpll_b200/csrc/gpu/plg_traverse.cu); timed alone, on its stream
     n_trav = max(args.steps, 3)
+    part.update_prob_matrices(pidx, w.matrix_indices, w.branch_lengths)
     for _ in range(2):
         part.update_partials(w.ops)
     part.reset_stats()
     part.timer_start()
     for _ in range(n_trav):
         part.update_partials(w.ops)
-    trav_ms = allreduce_max(part.timer_stop()) / n_trav
+    trav_ms = D.max(part.timer_stop()) / n_trav
     trav_stats = part.stats()
     fused = trav_stats["kernel_launches"] <= 3 * n_trav  # pack + traverse (+ nothing else) per call
     alg_bytes = trav_stats["algorithmic_bytes"] / n_trav
+    comp_bytes = trav_stats["compulsory_bytes"] / n_trav
+    persite = np.zeros(S_gpu)
+    lnl = D.sum(part.edge_loglikelihood(*root, persite=persite))   # same state as the resident leg
     # (2) the level-by-level kernels (one launch per dependency level and kind), per-kind times
     part.set_profiling(True)
     part.reset_stats()
@@ -349,17 +717,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                 "launches_per_traversal": prof["kind_launches"][i] // 3,
             }
     dom = int(np.argmax(prof["kind_ns"]))
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-    except Exception:
-        traffic = {}
+    peak, peak_src = hbm_peak()
     level_achieved = prof["kind_bytes"][dom] / max(prof["kind_ns"][dom], 1)
     level_path = {
         "kernel": f"{KERNEL_NAMES[dom]} ({kinds[dom]})", "achieved": level_achieved, "frac": level_achieved / peak,
@@ -368,22 +726,20 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         "traversal_ms": tot_ns / 3 * 1e-6, "by_kind": shares,
     }
     if fused:
-        achieved = alg_bytes / (trav_ms * 1e-3) / 1e9
+        achieved = comp_bytes / (trav_ms * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic("c2_k_traverse_dna", tips=args.tips, sites=S_gpu)
         roofline = {
             "bound": "hbm", "kernel": "k_traverse_dna (the whole operations list in one launch)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-            "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": trav_ms,
-            "note": "algorithmic bytes count every child CLV read (SURVEY 8d); the kernel keeps freshly produced "
-                    "tiles in shared memory until their parent consumes them, so its DRAM traffic is about half "
-                    "of that and frac can exceed 1; dram_GBps = traffic / launch time is the HBM-level figure",
+            "traffic": traffic, "traffic_source": traffic_src,
+            "compulsory_bytes_per_launch": comp_bytes, "avg_launch_ms": trav_ms,
+            "bytes_model": "compulsory DRAM bytes of the executed plan: every observable parent CLV + scaler written "
+                           "once, tip characters and tile-cache misses read (plg_stats.compulsory_bytes)",
+            "algorithmic": {"bytes_per_launch": alg_bytes, "GBps": alg_bytes / (trav_ms * 1e-3) / 1e9,
+                            "note": "SURVEY 8d counts every child CLV read; the kernel keeps fresh tiles on chip, "
+                                    "so this figure exceeds the DRAM-level one"},
+            "level_by_level_path": level_path,
         }
-        t = traffic.get("fused")
-        if t:
-            roofline["traffic"] = t["dram_bytes_per_algorithmic_byte"] * alg_bytes
-            roofline["traffic_source"] = t["source"]
-            roofline["dram_GBps"] = roofline["traffic"] / (trav_ms * 1e-3) / 1e9
-            roofline["dram_frac_of_peak"] = roofline["dram_GBps"] / peak
-        roofline["level_by_level_path"] = level_path
     else:
         roofline = {
             "bound": "hbm", "kernel": level_path["kernel"], "achieved": level_achieved,
@@ -391,43 +747,72 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             "traffic": None, "algorithmic_bytes_per_launch": level_path["algorithmic_bytes_per_launch"],
             "avg_launch_ms": level_path["avg_launch_ms"], "by_kind": shares,
         }
-        t = traffic.get(kinds[dom])
-        if t:
-            roofline["traffic"] = t["dram_bytes_per_algorithmic_byte"] * roofline["algorithmic_bytes_per_launch"]
-            roofline["traffic_source"] = t["source"]
-    roofline["whole_traversal_GBps"] = stats["algorithmic_bytes"] / args.steps / (ms_per_step * 1e-3) / 1e9
-    roofline["whole_traversal_frac_of_8TBps_nominal"] = roofline["whole_traversal_GBps"] * 1e9 / 8e12
+    roofline["frac_of_8TBps_nominal"] = roofline["achieved"] * 1e9 / 8e12
 
+    # ---- the other configurations ---------------------------------------------------------
+    extra = {}
+    tree = walker = None
+    if "lists" in also or "c4" in also:
+        try:
+            extra["lists"], tree, walker = leg_lists(lib, part, pidx, args.tips, S_gpu, steps=24)
+            if "lists" not in also:
+                extra.pop("lists")
+        except Exception as e:  # pragma: no cover
+            extra["lists"] = {"error": repr(e)}
+    if "c4" in also and tree is not None:
+        try:
+            extra["c4"] = leg_c4(lib, part, pidx, tree, walker, S_gpu)
+        except Exception as e:  # pragma: no cover
+            extra["c4"] = {"error": repr(e)}
+    if tree is not None:
+        tree.destroy()
     part.destroy()
+    if "c3" in also and rank == 0:
+        try:
+            extra["c3"] = leg_c3(lib, steps=5, warmup=3, local_rank=local_rank)
+        except Exception as e:  # pragma: no cover
+            extra["c3"] = {"error": repr(e)}
+    if "c5" in also:
+        try:
+            extra["c5"] = leg_c5(lib, D, rank, world, local_rank, steps=3, slots=args.slots)
+        except Exception as e:  # pragma: no cover
+            extra["c5"] = {"error": repr(e)}
 
-    # ---- leg D: CPU baseline (rank 0, N = 1 only) ---------------------------------------
+    # ---- CPU baseline (rank 0, N = 1 only): the whole workload on all host cores ----------
     cpu = None
+    lnl_check = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        spt = args.cpu_sites_per_thread
         try:
-            rate, best, cpu_lnl, kind = cpu_traversal_rate(w, cores, spt, reps=2, warm=1)
-            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
-                   "sample": f"{cores} threads x {spt} patterns each of the same workload "
-                             f"({len(w.ops)} ops per traversal), best of 2, {best:.2f} s per step"}
+            if args.cpu_sites_per_thread:
+                spt = args.cpu_sites_per_thread
+                slices = [(t * spt, (t + 1) * spt) for t in range(cores)]
+                rate, best, lnls, kind = cpu_traversal(S.recycle_slots(w, CPU_SLOTS), slices, reps=2, warm=1)
+                sample = f"{cores} threads x {spt} patterns each ({cores * spt} of {w.sites})"
+            else:
+                rate, best, lnls, kind, slices = full_config_cpu(w, cores, reps=2, warm=1, use_mean=False)
+                sample = f"ALL {w.sites} patterns: {cores} threads x {slices[0][1] - slices[0][0]} patterns each"
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "cpu_model": cpu_model(),
+                   "sample": sample + f", {n_ops} operations per traversal, inner CLVs in {CPU_SLOTS} recycled slots "
+                                      f"per thread, best of 2, {best:.2f} s per step"}
+            cpu_lnl = float(np.sum(lnls))
+            gpu_lnl = float(sum(persite[a:b].sum() for a, b in slices))
+            rel = abs(gpu_lnl - cpu_lnl) / abs(cpu_lnl)
+            lnl_check = {"gpu": gpu_lnl, "cpu": cpu_lnl, "rel": rel, "ok": bool(rel <= 1e-10),
+                         "over": f"{sum(b - a for a, b in slices)} patterns ({len(slices)} CPU slices)"}
         except Exception as e:  # pragma: no cover
-            cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "unavailable", "sample": str(e)}
+            cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "unavailable", "sample": repr(e)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if args.workload == "c5" else "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"synthetic {args.tips}-taxon x {S_gpu * world}-pattern GTR+G4 DNA "
-                            f"({S_gpu} patterns per GPU), full post-order traversal + edge logL"
-                            + (f", {args.slots} recycled CLV slots, {args.distinct_tips} distinct tip rows"
-                               if args.workload == "c5" else ""),
+                "workload": workload_string(args.tips, S_gpu * world, S_gpu),
                 "attributes": "PLL_ATTRIB_ARCH_GPU|PLL_ATTRIB_PATTERN_TIP, per-site scalers",
                 "operations": n_ops, "rate_cats": 4,
-                "l2": "no flush needed: each step streams %.0f GB per GPU through a 126 MB L2" %
-                      (stats["algorithmic_bytes"] / args.steps / 1e9),
+                "l2": "no flush needed: each step writes %.0f GB per GPU through a 126 MB L2" % (comp_bytes / 1e9),
                 "sharding": "site patterns, scalar NCCL all-reduce of lnL" if world > 1 else "single GPU",
             },
             "e2e": {"value": e2e_value, "unit": UNIT,
@@ -441,10 +826,14 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "lnl": lnl,
+            "lnl_check": lnl_check,
+            "also": extra,
         }
         print_json(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+        if lnl_check is not None and not lnl_check["ok"]:
+            D.close()
+            raise SystemExit(f"bench.py: GPU lnL differs from the reference's: {lnl_check}")
+    D.close()
 
 
 def main():
@@ -467,14 +856,12 @@ def main():
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
     ap.add_argument("--tips", type=int, default=1000)
     ap.add_argument("--sites-per-gpu", type=int, default=1_000_000)
-    ap.add_argument("--cpu-sites-per-thread", type=int, default=10_000)
+    ap.add_argument("--cpu-sites-per-thread", type=int, default=0,
+                    help="GPU arm's cpu_baseline: 0 = the whole workload (default), else a bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
-                    help="c2: 1000 taxa x 1M patterns per GPU (weak scaling, the judged default); "
-                         "c5: 5000 taxa x 10M patterns sharded over the GPUs with CLV-slot recycling")
+    ap.add_argument("--also", default="auto",
+                    help="comma list of sub-records: lists,c4,c3,c5 | none | auto (1 GPU: all; N > 1: c5)")
     ap.add_argument("--slots", type=int, default=64, help="c5: recycled CLV / scaler slots")
-    ap.add_argument("--distinct-tips", type=int, default=64,
-                    help="c5: number of distinct synthetic tip rows (tips reuse them cyclically)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -37,6 +37,15 @@ __device__ __forceinline__ void dmma884(double & d0, double & d1, double a, doub
                : "d"(a), "d"(b));
 }
 
+/* The same instruction without `volatile`: the compiler may interleave other work (stores, loads,
+ * the epilogue of the previous group) between the DMMAs of straight-line, convergent code. */
+__device__ __forceinline__ void dmma884_free(double & d0, double & d1, double a, double b)
+{
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+
 /* doubles of one P-matrix set as B fragments: [rate][nt * 5 + ks][lane] */
 #define PLG_DMMA_FRAGS 15
 __host__ __device__ constexpr unsigned int dmma_bfrag_doubles(unsigned int R) { return R * PLG_DMMA_FRAGS * 32u; }

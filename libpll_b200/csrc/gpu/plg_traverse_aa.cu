@@ -60,7 +60,7 @@ template <int R>
 struct AaStage
 {
   FusedOp desc;
-  double L[R * AAF_BLOCK_DOUBLES];  /* B fragments [rate][nt*5+ks][lane] or tip table [code][pitch] */
+  double L[R * AAF_BLOCK_DOUBLES];  /* B fragments (k_fused_pack_aa) or tip table [code][pitch] */
   double Rr[R * AAF_BLOCK_DOUBLES];
 };
 
@@ -104,8 +104,15 @@ __global__ void k_fused_pack_aa(const FusedOp * __restrict__ ops, unsigned char 
       }
     }
     else
+      /* B fragments: [rate][pair j < 7][lane][2] holds fragments 2j and 2j + 1 (one 16-byte load
+       * per pair), then [lane] fragment 14 */
       for (unsigned int t = threadIdx.x; t < (unsigned int)R * AAF_BLOCK_DOUBLES; t += blockDim.x)
-        dst[t] = dmma_bfrag_value(src + (size_t)(t / AAF_BLOCK_DOUBLES) * 400, (t >> 5) % 15u, t & 31u);
+      {
+        const unsigned int k = t / AAF_BLOCK_DOUBLES, within = t % AAF_BLOCK_DOUBLES;
+        const unsigned int f = within < 448u ? (within >> 6) * 2u + (within & 1u) : 14u;
+        const unsigned int l = within < 448u ? (within >> 1) & 31u : within - 448u;
+        dst[t] = dmma_bfrag_value(src + (size_t)k * 400, f, l);
+      }
   }
 }
 
@@ -114,6 +121,9 @@ __global__ void k_fused_pack_aa(const FusedOp * __restrict__ ops, unsigned char 
 /* ------------------------------------------------------------------------------------ */
 __device__ __forceinline__ void st_stream2_aa(double * p, double x, double y)
 {
+#ifdef AAF_EXP_NOSTG
+  if (x == 1.2345e-300) /* timing experiment (tools/exp_variants.sh): stores never happen */
+#endif
   asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(x), "d"(y) : "memory");
 }
 
@@ -150,6 +160,9 @@ struct AaCache
   }
   __device__ __forceinline__ void store(int slot, int sg, const double (&a)[5], unsigned int s) const
   {
+#ifdef AAF_EXP_NOCACHE
+    if (a[0] != 1.2345e-300) return;
+#endif
     v2[((slot * AAF_NSG + sg) * 2 + 0) * 32] = make_double2(a[0], a[1]);
     v2[((slot * AAF_NSG + sg) * 2 + 1) * 32] = make_double2(a[2], a[3]);
     v1[(slot * AAF_NSG + sg) * 32] = a[4];
@@ -174,8 +187,16 @@ __device__ __forceinline__ void afrag_from_tile(const double (&t)[3][2], unsigne
 __device__ __forceinline__ void load_bfrag(const double * __restrict__ blk, unsigned int k, unsigned int lane,
                                            double (&B)[PLG_DMMA_FRAGS])
 {
+  const double * mine = blk + (size_t)k * AAF_BLOCK_DOUBLES;
+  const double2 * b2 = reinterpret_cast<const double2 *>(mine) + lane;
 #pragma unroll
-  for (int f = 0; f < PLG_DMMA_FRAGS; ++f) B[f] = blk[(k * PLG_DMMA_FRAGS + f) * 32 + lane];
+  for (int j = 0; j < 7; ++j)
+  {
+    const double2 v = b2[j * 32];
+    B[2 * j] = v.x;
+    B[2 * j + 1] = v.y;
+  }
+  B[14] = mine[448 + lane];
 }
 
 /* two 8-pattern groups at once: six independent accumulator chains, k-step outer - the chain of
@@ -190,8 +211,13 @@ __device__ __forceinline__ void mma_pair(const double (&B)[PLG_DMMA_FRAGS], cons
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt)
     {
+#ifdef AAF_EXP_NOMMA
+      d0[nt][0] += a0[ks] * B[nt * 5 + ks];
+      d1[nt][0] += a1[ks] * B[nt * 5 + ks];
+#else
       dmma884(d0[nt][0], d0[nt][1], a0[ks], B[nt * 5 + ks]);
       dmma884(d1[nt][0], d1[nt][1], a1[ks], B[nt * 5 + ks]);
+#endif
     }
 }
 
@@ -202,7 +228,48 @@ __device__ __forceinline__ void mma_one(const double (&B)[PLG_DMMA_FRAGS], const
 #pragma unroll
   for (int ks = 0; ks < 5; ++ks)
 #pragma unroll
-    for (int nt = 0; nt < 3; ++nt) dmma884(d[nt][0], d[nt][1], a[ks], B[nt * 5 + ks]);
+    for (int nt = 0; nt < 3; ++nt)
+#ifdef AAF_EXP_NOMMA
+      d[nt][0] += a[ks] * B[nt * 5 + ks];
+#else
+      dmma884(d[nt][0], d[nt][1], a[ks], B[nt * 5 + ks]);
+#endif
+}
+
+/* the same chains with schedulable DMMAs (fast path: straight-line, all lanes active) */
+__device__ __forceinline__ void mma_pair_free(const double (&B)[PLG_DMMA_FRAGS], const double (&a0)[5],
+                                              const double (&a1)[5], double (&d0)[3][2], double (&d1)[3][2])
+{
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt) d0[nt][0] = d0[nt][1] = d1[nt][0] = d1[nt][1] = 0.0;
+#pragma unroll
+  for (int ks = 0; ks < 5; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+    {
+      dmma884_free(d0[nt][0], d0[nt][1], a0[ks], B[nt * 5 + ks]);
+      dmma884_free(d1[nt][0], d1[nt][1], a1[ks], B[nt * 5 + ks]);
+    }
+}
+
+__device__ __forceinline__ void mma_one_free(const double (&B)[PLG_DMMA_FRAGS], const double (&a)[5],
+                                             double (&d)[3][2])
+{
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt) d[nt][0] = d[nt][1] = 0.0;
+#pragma unroll
+  for (int ks = 0; ks < 5; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) dmma884_free(d[nt][0], d[nt][1], a[ks], B[nt * 5 + ks]);
+}
+
+/* streaming 16-byte store the compiler may schedule (st.global.cs) */
+__device__ __forceinline__ void st_cs2(double * p, double x, double y)
+{
+#ifdef AAF_EXP_NOSTG
+  if (x == 1.2345e-300)
+#endif
+  __stcs(reinterpret_cast<double2 *>(p), make_double2(x, y));
 }
 
 /* A fragments (and scaler count) of a child that is not handed over in registers: from the
@@ -241,6 +308,9 @@ __device__ __forceinline__ double2 table_pair(const double * __restrict__ tab, u
                                               int nt, unsigned int q)
 {
   if (nt == 2 && q >= 2u) return make_double2(0.0, 0.0);
+#ifdef AAF_EXP_NOTABLE
+  return make_double2(0.25 + code, 0.5);
+#endif
   return *reinterpret_cast<const double2 *>(tab + (size_t)code * aa_table_pitch(R) + k * 20 + 8 * nt + 2 * q);
 }
 
@@ -267,8 +337,40 @@ template <int R>
 __device__ __forceinline__ void team_vote(AaWarp & w, unsigned int (&vote)[AAF_NSG])
 {
   if (R == 1) return;
+#ifdef AAF_EXP_NOVOTE
+  return;
+#endif
   uint4 * mine = w.votes + (size_t)w.vbuf * AAF_W + w.team * R;
   if (w.lane == 0) mine[w.k] = make_uint4(vote[0], vote[1], vote[2], vote[3]);
+  named_barrier(1 + w.team, R * 32);
+#pragma unroll
+  for (int kk = 0; kk < R; ++kk)
+  {
+    const uint4 o = mine[kk];
+    vote[0] &= o.x; vote[1] &= o.y; vote[2] &= o.z; vote[3] &= o.w;
+  }
+  w.vbuf ^= 1u;
+}
+
+/* the two halves of team_vote: publish this warp's bits; later, meet the team and combine */
+template <int R>
+__device__ __forceinline__ void team_vote_post(AaWarp & w, const unsigned int (&vote)[AAF_NSG])
+{
+  if (R == 1) return;
+#ifdef AAF_EXP_NOVOTE
+  return;
+#endif
+  uint4 * mine = w.votes + (size_t)w.vbuf * AAF_W + w.team * R;
+  if (w.lane == 0) mine[w.k] = make_uint4(vote[0], vote[1], vote[2], vote[3]);
+}
+template <int R>
+__device__ __forceinline__ void team_vote_collect(AaWarp & w, unsigned int (&vote)[AAF_NSG])
+{
+  if (R == 1) return;
+#ifdef AAF_EXP_NOVOTE
+  return;
+#endif
+  const uint4 * mine = w.votes + (size_t)w.vbuf * AAF_W + w.team * R;
   named_barrier(1 + w.team, R * 32);
 #pragma unroll
   for (int kk = 0; kk < R; ++kk)
@@ -547,7 +649,7 @@ __device__ __forceinline__ void fast_op_aa(const AaStage<R> & st, const AaCache 
       double a0[5], a1[5], d0[3][2], d1[3][2];
       afrag_from_tile(p[sg], lane, q, a0);
       afrag_from_tile(p[sg + 1], lane, q, a1);
-      mma_pair(B, a0, a1, d0, d1);
+      mma_pair_free(B, a0, a1, d0, d1);
 #pragma unroll
       for (int nt = 0; nt < 3; ++nt)
       {
@@ -569,7 +671,7 @@ __device__ __forceinline__ void fast_op_aa(const AaStage<R> & st, const AaCache 
         double a[5], d[3][2];
         cache.load(lslot, sg, a);
         if (has_l) sc[sg] += cache.scaler(lslot, sg);
-        mma_one(B, a, d);
+        mma_one_free(B, a, d);
 #pragma unroll
         for (int nt = 0; nt < 3; ++nt)
         {
@@ -596,13 +698,53 @@ __device__ __forceinline__ void fast_op_aa(const AaStage<R> & st, const AaCache 
     }
   }
 
-  /* ---- per-site rescaling vote over the R warps of the team ---- */
+  /* ---- epilogue: the stores do not wait for the rescaling vote.  Rescaling is rare, so the
+   * tile is written through (and kept) as computed while the team's votes are collected, and
+   * the few tiles in which some pattern does rescale are multiplied and stored once more. ---- */
+  unsigned int vote[AAF_NSG];
+#pragma unroll
+  for (int sg = 0; sg < AAF_NSG; ++sg) vote[sg] = 0;
   if (KIND != PLG_KIND_TT)
   {
-    unsigned int vote[AAF_NSG];
 #pragma unroll
     for (int sg = 0; sg < AAF_NSG; ++sg) vote[sg] = below_votes(p[sg], q);
-    team_vote<R>(w, vote);
+    team_vote_post<R>(w, vote);
+  }
+  double * const out = parent + w.clv_off;
+  unsigned int * const so = pscale + w.first_site + g;
+  const bool store_sc = pscale != nullptr && (k == 0u || (pad & 2)) && q == 0u;
+  auto write_out = [&]()
+  {
+    if (pad & 1)
+    {
+#pragma unroll
+      for (int sg = 0; sg < AAF_NSG; ++sg)
+      {
+        st_cs2(out + sg * (8 * R * 20), p[sg][0][0], p[sg][0][1]);
+        st_cs2(out + sg * (8 * R * 20) + 8, p[sg][1][0], p[sg][1][1]);
+        if (q < 2u) st_cs2(out + sg * (8 * R * 20) + 16, p[sg][2][0], p[sg][2][1]);
+      }
+      if (store_sc)
+      {
+#pragma unroll
+        for (int sg = 0; sg < AAF_NSG; ++sg) so[sg * 8] = sc[sg];
+      }
+    }
+    if (pslot >= 0)
+    {
+#pragma unroll
+      for (int sg = 0; sg < AAF_NSG; ++sg)
+      {
+        double a[5];
+        afrag_from_tile(p[sg], lane, q, a);
+        cache.store(pslot, sg, a, sc[sg]);
+      }
+    }
+  };
+  write_out();
+  if (KIND != PLG_KIND_TT)
+  {
+    team_vote_collect<R>(w, vote);
     if ((vote[0] | vote[1] | vote[2] | vote[3]) != 0u)
     {
       /* rare (warp-uniform): some pattern of the tile is rescaled */
@@ -619,40 +761,11 @@ __device__ __forceinline__ void fast_op_aa(const AaStage<R> & st, const AaCache 
         }
         sc[sg] += scale ? 1u : 0u;
       }
+      write_out();
     }
   }
 #pragma unroll
   for (int sg = 0; sg < AAF_NSG; ++sg) psc[sg] = sc[sg];
-
-  /* ---- write through ---- */
-  if (pad & 1)
-  {
-    double * out = parent + w.clv_off;
-#pragma unroll
-    for (int sg = 0; sg < AAF_NSG; ++sg)
-    {
-      st_stream2_aa(out + sg * (8 * R * 20), p[sg][0][0], p[sg][0][1]);
-      st_stream2_aa(out + sg * (8 * R * 20) + 8, p[sg][1][0], p[sg][1][1]);
-      if (q < 2u) st_stream2_aa(out + sg * (8 * R * 20) + 16, p[sg][2][0], p[sg][2][1]);
-    }
-    if (pscale != nullptr && (k == 0u || (pad & 2)) && q == 0u)
-    {
-      unsigned int * so = pscale + w.first_site + g;
-#pragma unroll
-      for (int sg = 0; sg < AAF_NSG; ++sg) so[sg * 8] = sc[sg];
-    }
-  }
-  /* ---- keep for a later parent ---- */
-  if (pslot >= 0)
-  {
-#pragma unroll
-    for (int sg = 0; sg < AAF_NSG; ++sg)
-    {
-      double a[5];
-      afrag_from_tile(p[sg], lane, q, a);
-      cache.store(pslot, sg, a, sc[sg]);
-    }
-  }
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -813,7 +926,7 @@ k_traverse_aa(const unsigned char * __restrict__ records, unsigned int n_ops, un
         const Stage & st = stages[s];
         const int kind = st.desc.kind;
         const int fwd = (kind == PLG_KIND_TT) ? 0 : (st.desc.rslot == -2 ? 2 : (st.desc.lslot == -2 ? 1 : 0));
-        const bool fast = w.full && (kind == PLG_KIND_TT ||
+        const bool fast = w.full && ((kind == PLG_KIND_TT && st.desc.scale_mode != 2) ||
                                      (st.desc.scale_mode == 1 && fwd == 2 &&
                                       (kind == PLG_KIND_TI || st.desc.lslot >= 0)));
         if (fast)

@@ -262,3 +262,81 @@ def read_phylip(lib: PllLibrary, path: str, interleaved: bool = False, twice: bo
     err = lib.errno()
     lib.pll_phylip_close(fd)
     return out, err
+
+
+# ---- synthetic trees and a moving virtual root (benchmarks, tests) -----------------------------
+def random_newick(tips: int, seed: int, caterpillar: bool = False, labels: bool = True) -> str:
+    """Random-join (Yule-like) unrooted binary tree as a Newick string with tips t0..t{tips-1} and
+    branch lengths U(0.01, 0.3); `caterpillar` gives the ladder instead."""
+    rng = np.random.default_rng(seed)
+    if caterpillar and tips > 3:
+        lens = rng.uniform(0.01, 0.3, 2 * tips)
+        inner = ("(" * (tips - 3) + f"t0:{lens[0]:.6f},t1:{lens[1]:.6f}"
+                 + "".join(f"):{lens[tips + i]:.6f},t{i}:{lens[i]:.6f}" for i in range(2, tips - 2))
+                 + f"):{lens[tips]:.6f}")
+        return f"({inner},t{tips - 2}:{lens[tips - 2]:.6f},t{tips - 1}:{lens[tips - 1]:.6f});"
+    nodes = [f"t{i}:{rng.uniform(0.01, 0.3):.6f}" for i in range(tips)]
+    if not labels:
+        nodes = [f"{i}:{rng.uniform(0.01, 0.3):.6f}" for i in range(tips)]
+    while len(nodes) > 3:
+        if caterpillar:
+            a, b = nodes.pop(0), nodes.pop(0)
+            nodes.insert(0, f"({a},{b}):{rng.uniform(0.01, 0.3):.6f}")
+        else:
+            i = int(rng.integers(0, len(nodes)))
+            a = nodes.pop(i)
+            j = int(rng.integers(0, len(nodes)))
+            b = nodes.pop(j)
+            nodes.append(f"({a},{b}):{rng.uniform(0.01, 0.3):.6f}")
+    return f"({nodes[0]},{nodes[1]},{nodes[2]});"
+
+
+class RootWalker:
+    """Moves the virtual root of an unrooted tree the way a tree search does (reference
+    test/src/partial-traversal.c, examples/partial-traversal/partial.c:373-431): every move
+    traverses only the subtrees whose CLVs are not yet oriented towards the new root
+    (pll_utree_traverse with a pruning callback) and returns that PARTIAL operations list with the
+    P-matrices it needs.  `edge(root)` names the evaluation edge of a root record."""
+
+    def __init__(self, lib: PllLibrary, tree: Tree):
+        self.lib, self.tree = bind(lib), tree
+        self.oriented: dict[int, bool] = {}
+        n = 2 * tree.tips - 3
+        self._branches = np.zeros(n)
+        self._matrices = np.zeros(n, dtype=np.uint32)
+        self._ops = np.zeros(tree.inner, dtype=OP_DTYPE)
+
+        @TRAV_CB
+        def partial(node):
+            rec = node.contents
+            if not rec.next:
+                return 1
+            me = C.addressof(rec)
+            if self.oriented.get(me):
+                return 0
+            self.oriented[me] = True
+            self.oriented[C.addressof(rec.next.contents)] = False
+            self.oriented[C.addressof(rec.next.contents.next.contents)] = False
+            return 1
+
+        self._cb = partial
+
+    def move(self, root):
+        """(ops, matrix_indices, branch_lengths) that re-orient the tree towards `root`."""
+        buf, n = self.tree.traverse(self.lib, root, cb=self._cb)
+        nm, no = C.c_uint(0), C.c_uint(0)
+        self.lib.pll_utree_create_operations(buf, n, self._branches.ctypes.data_as(C.POINTER(C.c_double)),
+                                             self._matrices.ctypes.data_as(C.POINTER(C.c_uint)),
+                                             self._ops.ctypes.data, C.byref(nm), C.byref(no))
+        return self._ops[:no.value].copy(), self._matrices[:nm.value].copy(), self._branches[:nm.value].copy()
+
+    def full(self, root):
+        self.oriented.clear()
+        return self.move(root)
+
+    @staticmethod
+    def edge(root):
+        """(parent_clv, parent_scaler, child_clv, child_scaler, matrix) of the edge at `root`."""
+        r = root.contents
+        b = r.back.contents
+        return r.clv_index, r.scaler_index, b.clv_index, b.scaler_index, r.pmatrix_index

@@ -34,29 +34,7 @@ def ref(ref_lib):
     return T.bind(ref_lib)
 
 
-def random_newick(tips, seed, caterpillar=False, labels=True):
-    rng = np.random.default_rng(seed)
-    if caterpillar and tips > 3:
-        # ((((t0,t1),t2),t3)...,t[T-2],t[T-1]); built by one join (string surgery is quadratic)
-        lens = rng.uniform(0.01, 0.3, 2 * tips)
-        inner = ("(" * (tips - 3) + f"t0:{lens[0]:.6f},t1:{lens[1]:.6f}"
-                 + "".join(f"):{lens[tips + i]:.6f},t{i}:{lens[i]:.6f}" for i in range(2, tips - 2))
-                 + f"):{lens[tips]:.6f}")
-        return f"({inner},t{tips - 2}:{lens[tips - 2]:.6f},t{tips - 1}:{lens[tips - 1]:.6f});"
-    nodes = [f"t{i}:{rng.uniform(0.01, 0.3):.6f}" for i in range(tips)]
-    if not labels:
-        nodes = [f"{i}:{rng.uniform(0.01, 0.3):.6f}" for i in range(tips)]
-    while len(nodes) > 3:
-        if caterpillar:
-            a, b = nodes.pop(0), nodes.pop(0)
-            nodes.insert(0, f"({a},{b}):{rng.uniform(0.01, 0.3):.6f}")
-        else:
-            i = int(rng.integers(0, len(nodes)))
-            a = nodes.pop(i)
-            j = int(rng.integers(0, len(nodes)))
-            b = nodes.pop(j)
-            nodes.append(f"({a},{b}):{rng.uniform(0.01, 0.3):.6f}")
-    return f"({nodes[0]},{nodes[1]},{nodes[2]});"
+from libpll_b200.trees import random_newick  # noqa: E402,F401  (other test modules import it from here)
 
 
 # ---- golden: the reference's lg4 example ----------------------------------------------------

@@ -21,6 +21,9 @@ ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--fast-tips", action="store_true", help="reuse 8 distinct tip sequences")
 a = ap.parse_args()
 
+import os
+if os.environ.get("PLL_B200_LIB"):  # developer experiments: another build of the library
+    libpll_b200.LIB_PATH = os.path.abspath(os.environ["PLL_B200_LIB"])
 lib = libpll_b200.load()
 w = S.make_workload(a.tips, a.sites, states=a.states)
 t0 = time.time()
