@@ -467,8 +467,9 @@ def leg_c4(lib, part, pidx, tree, walker, sites: int, branches: int = 10, iters:
         for _ in range(iters):
             d1, d2 = part.likelihood_derivatives(e[1], e[3], length, pidx, key)
             n_der += 1
-            step = d1 / d2 if d2 > 0 else -d1            # Newton; gradient step if not convex here
-            length = min(max(length - step, 1e-6), 10.0)
+            # Newton where -lnL is convex, otherwise a bounded move downhill
+            length = length - d1 / d2 if d2 > 0 else (length * 0.5 if d1 > 0 else length * 2.0)
+            length = min(max(length, 1e-6), 10.0)
         t_der += time.perf_counter() - t0
         lengths.append(length)
     total = time.perf_counter() - t_all

@@ -1194,7 +1194,7 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
   plan.fused_hits = plan.fused_misses = 0;
   /* 20 states: the tensor-core traversal (plg_traverse_aa.cu) - 1, 2 or 4 rate categories, tip
    * tables of at most 23 (four categories) or 24 codes, not in bit-exact mode */
-  const unsigned int aa_slots = (K == 20 && !ctx->aa_exact &&
+  const unsigned int aa_slots = (K == 20 && ctx->use_fused_aa && !ctx->aa_exact &&
                                  (!ctx->pattern_tip || ctx->maxstates <= plg_fused_aa_max_codes(R)))
                                     ? plg_fused_aa_slots(R, ctx->fused_slots) : 0;
   if (ctx->use_fused && (K == 4 || aa_slots > 0) && plg_fast_path(ctx) && count >= 2)

@@ -1,5 +1,5 @@
-"""GPU: the 20-state single-kernel traversal (libpll_b200/csrc/gpu/plg_traverse_aa.cu, the default
-for protein partitions with 1, 2 or 4 rate categories) against
+"""GPU: the 20-state single-kernel traversal (libpll_b200/csrc/gpu/plg_traverse_aa.cu; opt-in with
+PLL_GPU_FUSED_AA=1 for protein partitions with 1, 2 or 4 rate categories) against
 
   * the level-by-level tensor-core kernels (PLL_GPU_FUSED=0): both run the same DMMA chains in the
     same order, so every CLV and every scaler array must be BIT-identical - plain and
@@ -22,6 +22,7 @@ pytestmark = pytest.mark.gpu
 
 def _run(gpu_lib, monkeypatch, w, attrs, fused, slots=3, variant="default"):
     monkeypatch.setenv("PLL_GPU_FUSED", "1" if fused else "0")
+    monkeypatch.setenv("PLL_GPU_FUSED_AA", "1" if fused else "0")
     monkeypatch.setenv("PLL_GPU_FUSED_SLOTS", str(slots))
     monkeypatch.setenv("PLL_GPU_AA_EXACT", "0")
     part, pidx = S.build_partition(gpu_lib, w, PLL_ATTRIB_ARCH_GPU | attrs, variant=variant)
@@ -99,6 +100,7 @@ def test_fused_with_rescaling_and_recycled_slots(gpu_lib, monkeypatch, rate_scal
 @pytest.mark.parametrize("tips,sites", [(200, 5000), (30, 333)])
 def test_fused_against_the_reference(gpu_lib, ref_lib, monkeypatch, tips, sites):
     monkeypatch.setenv("PLL_GPU_FUSED", "1")
+    monkeypatch.setenv("PLL_GPU_FUSED_AA", "1")
     monkeypatch.setenv("PLL_GPU_AA_EXACT", "0")
     w = S.make_workload(tips, sites, states=20, seed=tips)
     rates = ref_lib.gamma_rates(w.alpha, w.rate_cats)
@@ -129,6 +131,7 @@ def test_fused_against_the_reference(gpu_lib, ref_lib, monkeypatch, tips, sites)
 def test_repeated_calls_replay_a_graph(gpu_lib, monkeypatch):
     """The second sighting of a list captures a CUDA graph (pack + traverse); replays give the same bits."""
     monkeypatch.setenv("PLL_GPU_FUSED", "1")
+    monkeypatch.setenv("PLL_GPU_FUSED_AA", "1")
     monkeypatch.setenv("PLL_GPU_AA_EXACT", "0")
     w = S.make_workload(50, 2000, states=20, seed=4)
     part, pidx = S.build_partition(gpu_lib, w, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP)
