@@ -101,6 +101,23 @@ PLL_EXPORT int plg_synchronize(plg_context_t * ctx);
 PLL_EXPORT int plg_set_deferred(plg_context_t * ctx, int enable);
 PLL_EXPORT int plg_collect(plg_context_t * ctx);
 
+/* Device groups: the contexts of ONE partition cut into pattern slices over several GPUs
+ * (members[0] is the leader).  Between plg_group_begin and plg_group_collect every member's
+ * plg_edge_loglikelihood / plg_root_loglikelihood / plg_likelihood_derivatives call only
+ * enqueues; the last block of each device publishes its partial sums into a slot of the
+ * leader's memory (NVLink peer access), the device that arrives last adds the slots in member
+ * order and writes the total to the leader's mapped host words, and plg_group_collect waits for
+ * that ONE flag: the scalar all-reduce of reference src/core_likelihood_avx.c:1259 (`logl +=`)
+ * and src/core_derivatives_avx2.c:756-765 across devices, with a single host wake-up.
+ * plg_group_create fails with PLG_E_UNSUPPORTED when a member cannot reach the leader's memory
+ * (the host layer then adds the per-device results itself); plg_group_abort clears a call that
+ * failed half way.  The group dissolves when any member is destroyed. */
+#define PLL_GPU_MAX_GROUP 16
+PLL_EXPORT int plg_group_create(plg_context_t * const * members, unsigned int n);
+PLL_EXPORT int plg_group_begin(plg_context_t * leader);
+PLL_EXPORT int plg_group_collect(plg_context_t * leader, double * out0, double * out1);
+PLL_EXPORT int plg_group_abort(plg_context_t * leader);
+
 /* ---- uploads / downloads of resident state ---------------------------------------- */
 
 /* replaces: the stores of set_tipchars_4x4 / set_tipchars (reference src/pll.c:825-903):

@@ -132,6 +132,7 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   ctx->tables = NULL; ctx->tables_cap = 0; ctx->partials = NULL; ctx->partials_cap = 0;
   ctx->counter = NULL; ctx->result_dev = NULL; ctx->result_host = NULL;
   ctx->deferred = 0; ctx->pending[0] = ctx->pending[1] = NULL;
+  ctx->result_seq = 0; ctx->copy_pending = 0; ctx->group = NULL; ctx->group_rank = 0;
   ctx->persite_dev = NULL;
   ctx->lnl_table = NULL; ctx->lnl_table_cap = 0;
   ctx->sumtables = new std::unordered_map<const void *, double *>();
@@ -218,8 +219,10 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   PLG_CREATE_CUDA(cudaMemsetAsync(ctx->counter, 0, 64 * sizeof(unsigned int), ctx->stream));
   /* scalar results (lnL, d_f, dd_f) are written by the last block straight into mapped pinned
    * host memory: a value-returning call is launch + stream synchronise, no D2H copy */
-  PLG_CREATE_CUDA(cudaHostAlloc(&ctx->result_host, 8 * sizeof(double), cudaHostAllocMapped));
+  PLG_CREATE_CUDA(cudaHostAlloc(&ctx->result_host, 8 * sizeof(double),
+                                cudaHostAllocMapped | cudaHostAllocPortable));
   PLG_CREATE_CUDA(cudaHostGetDevicePointer((void **)&ctx->result_dev, ctx->result_host, 0));
+  memset(ctx->result_host, 0, 8 * sizeof(double));
 
   /* pattern weights default to 1 (reference src/pll.c:784) */
   {
@@ -235,11 +238,15 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   return PLG_OK;
 }
 
+static void plg_group_release(plg_context * ctx);
+
 extern "C" void plg_destroy(plg_context_t * ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  plg_group_release(ctx); /* the whole group dissolves with its first member to go */
+  cudaSetDevice(ctx->device);
   if (ctx->graphs)
   {
     for (auto & kv : *ctx->graphs)
@@ -301,13 +308,218 @@ extern "C" int plg_set_deferred(plg_context_t * ctx, int enable)
   return PLG_OK;
 }
 
+PlgSink plg_make_sink(plg_context * ctx)
+{
+  PlgSink s;
+  memset(&s, 0, sizeof(s));
+  s.result = ctx->result_dev;
+  plg_group * g = ctx->group;
+  if (g && g->active)
+  {
+    s.seq = g->seq;
+    s.group_slots = g->slots;
+    s.group_counter = g->counter;
+    s.group_result = g->members[0]->result_dev;
+    s.group_size = g->n;
+    s.group_rank = ctx->group_rank;
+  }
+  else
+    s.seq = ++ctx->result_seq;
+  return s;
+}
+
+int plg_wait_flag(plg_context * ctx, unsigned long long seq, plg_context * const * watch, unsigned int n_watch)
+{
+  const unsigned long long * flag = reinterpret_cast<const unsigned long long *>(ctx->result_host + 4);
+  /* ~100 us of polling covers a reduction on an idle stream; behind a long traversal the
+   * thread sleeps in the driver instead of burning a core */
+  for (unsigned int spin = 0; spin < 2500u; ++spin) /* `pause` is ~40 ns on current x86 cores */
+  {
+    if (__atomic_load_n(flag, __ATOMIC_ACQUIRE) == seq) return PLG_OK;
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  for (unsigned int i = 0; i < n_watch; ++i)
+  {
+    PLG_CUDA(cudaSetDevice(watch[i]->device));
+    PLG_CUDA(cudaStreamSynchronize(watch[i]->stream));
+  }
+  /* every feeding stream has drained: the last publisher's host writes are on their way (a
+   * peer write followed by a system-scope fence), give them a moment */
+  for (unsigned int spin = 0; spin < 50000000u; ++spin)
+  {
+    if (__atomic_load_n(flag, __ATOMIC_ACQUIRE) == seq) return PLG_OK;
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  plg_set_error("the result of a reduction never arrived (sequence %llu, flag %llu)", seq,
+                __atomic_load_n(flag, __ATOMIC_ACQUIRE));
+  return PLG_E_CUDA;
+}
+
+int plg_finish_result(plg_context * ctx, double * out0, double * out1)
+{
+  if (ctx->group && ctx->group->active)
+    return PLG_OK; /* delivered by plg_group_collect */
+  if (ctx->deferred)
+  {
+    ctx->pending[0] = out0;
+    ctx->pending[1] = out1;
+    return PLG_OK;
+  }
+  if (ctx->copy_pending)
+  {
+    ctx->copy_pending = 0;
+    PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  int rc = plg_wait_flag(ctx, ctx->result_seq, &ctx, 1);
+  if (rc) return rc;
+  if (out0) *out0 = ctx->result_host[0];
+  if (out1) *out1 = ctx->result_host[1];
+  return PLG_OK;
+}
+
 extern "C" int plg_collect(plg_context_t * ctx)
 {
   PLG_CHECK_CTX(ctx);
   PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->copy_pending = 0;
+  int rc = plg_wait_flag(ctx, ctx->result_seq, &ctx, 1);
+  if (rc) return rc;
   if (ctx->pending[0]) *ctx->pending[0] = ctx->result_host[0];
   if (ctx->pending[1]) *ctx->pending[1] = ctx->result_host[1];
   ctx->pending[0] = ctx->pending[1] = NULL;
+  return PLG_OK;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* device groups: one partition over several GPUs, scalar results combined on the devices  */
+/* ------------------------------------------------------------------------------------ */
+extern "C" int plg_group_create(plg_context_t * const * members, unsigned int n)
+{
+  if (!members || n < 2 || n > PLL_GPU_MAX_GROUP)
+  {
+    plg_set_error("plg_group_create: 2..%d contexts", PLL_GPU_MAX_GROUP);
+    return PLG_E_INVALID;
+  }
+  plg_context * leader = members[0];
+  for (unsigned int d = 0; d < n; ++d)
+    if (!members[d] || members[d]->group)
+    {
+      plg_set_error("plg_group_create: context %u is NULL or already grouped", d);
+      return PLG_E_INVALID;
+    }
+  /* every member must be able to write the leader's memory */
+  for (unsigned int d = 1; d < n; ++d)
+  {
+    if (members[d]->device == leader->device) continue;
+    int can = 0;
+    PLG_CUDA(cudaDeviceCanAccessPeer(&can, members[d]->device, leader->device));
+    if (!can)
+    {
+      plg_set_error("plg_group_create: device %d cannot access device %d", members[d]->device, leader->device);
+      return PLG_E_UNSUPPORTED;
+    }
+    PLG_CUDA(cudaSetDevice(members[d]->device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(leader->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+    {
+      plg_set_error("plg_group_create: cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return PLG_E_CUDA;
+    }
+    cudaGetLastError();
+  }
+  plg_group * g = new plg_group();
+  memset(g, 0, sizeof(*g));
+  g->n = n;
+  PLG_CUDA(cudaSetDevice(leader->device));
+  if (cudaMalloc(&g->slots, 2 * PLL_GPU_MAX_GROUP * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&g->counter, 64) != cudaSuccess || cudaMemset(g->counter, 0, 64) != cudaSuccess ||
+      cudaDeviceSynchronize() != cudaSuccess)
+  {
+    cudaFree(g->slots);
+    cudaFree(g->counter);
+    delete g;
+    cudaGetLastError();
+    plg_set_error("plg_group_create: device allocation failed");
+    return PLG_E_NOMEM;
+  }
+  for (unsigned int d = 0; d < n; ++d)
+  {
+    g->members[d] = members[d];
+    members[d]->group = g;
+    members[d]->group_rank = d;
+  }
+  return PLG_OK;
+}
+
+/* called by the leader's plg_destroy (members detach) */
+static void plg_group_release(plg_context * ctx)
+{
+  plg_group * g = ctx->group;
+  if (!g) return;
+  for (unsigned int d = 0; d < g->n; ++d)
+    if (g->members[d]) g->members[d]->group = NULL;
+  cudaSetDevice(g->members[0] ? g->members[0]->device : ctx->device);
+  cudaFree(g->slots);
+  cudaFree(g->counter);
+  delete g;
+}
+
+extern "C" int plg_group_begin(plg_context_t * leader)
+{
+  if (!leader || !leader->group || leader->group_rank != 0)
+  {
+    plg_set_error("plg_group_begin: not the leader of a device group");
+    return PLG_E_INVALID;
+  }
+  plg_group * g = leader->group;
+  g->seq = ++leader->result_seq;
+  g->active = 1;
+  return PLG_OK;
+}
+
+extern "C" int plg_group_collect(plg_context_t * leader, double * out0, double * out1)
+{
+  if (!leader || !leader->group || !leader->group->active)
+  {
+    plg_set_error("plg_group_collect: no group call in flight");
+    return PLG_E_INVALID;
+  }
+  plg_group * g = leader->group;
+  int rc = plg_wait_flag(leader, g->seq, g->members, g->n);
+  g->active = 0;
+  for (unsigned int d = 0; d < g->n && !rc; ++d)
+    if (g->members[d]->copy_pending)
+    {
+      /* per-pattern values were requested too: their device-to-host copies follow the kernels */
+      g->members[d]->copy_pending = 0;
+      PLG_CUDA(cudaSetDevice(g->members[d]->device));
+      PLG_CUDA(cudaStreamSynchronize(g->members[d]->stream));
+    }
+  if (rc) return rc;
+  if (out0) *out0 = leader->result_host[0];
+  if (out1) *out1 = leader->result_host[1];
+  return PLG_OK;
+}
+
+extern "C" int plg_group_abort(plg_context_t * leader)
+{
+  if (!leader || !leader->group) return PLG_OK;
+  plg_group * g = leader->group;
+  g->active = 0;
+  for (unsigned int d = 0; d < g->n; ++d)
+  {
+    cudaSetDevice(g->members[d]->device);
+    cudaStreamSynchronize(g->members[d]->stream);
+  }
+  cudaSetDevice(leader->device);
+  cudaMemset(g->counter, 0, 64);
+  cudaDeviceSynchronize();
+  cudaGetLastError();
   return PLG_OK;
 }
 

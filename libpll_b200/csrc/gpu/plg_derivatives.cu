@@ -314,7 +314,7 @@ struct DerArgs
   const int * invariant;
   double * partials; /* 2 * gridDim.x */
   unsigned int * counter;
-  double * result; /* [0] = d_f, [1] = dd_f */
+  PlgSink sink; /* d_f, dd_f */
   unsigned int nelem;
 };
 
@@ -445,8 +445,7 @@ k_derivatives_dna(const DerArgs a, const __grid_constant__ DerDnaParams P)
     const double r2 = block_sum<PLG_DER_THREADS>(t2, red);
     if (threadIdx.x == 0)
     {
-      a.result[0] = r1;
-      a.result[1] = r2;
+      plg_publish(a.sink, r1, r2);
       *a.counter = 0u;
     }
   }
@@ -571,8 +570,7 @@ k_derivatives_aa(const DerArgs a, const __grid_constant__ DerParams P)
     const double r2 = block_sum<PLG_DER_THREADS>(t2, red);
     if (threadIdx.x == 0)
     {
-      a.result[0] = r1;
-      a.result[1] = r2;
+      plg_publish(a.sink, r1, r2);
       *a.counter = 0u;
     }
   }
@@ -908,7 +906,7 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
     da.invariant = ctx->has_invariant ? ctx->invariant : NULL;
     da.partials = ctx->partials;
     da.counter = ctx->counter;
-    da.result = ctx->result_dev;
+    da.sink = plg_make_sink(ctx);
     da.nelem = nelem;
     PLG_DISPATCH_R(R, { int lrc = launch_derivatives_dna<RR>(ctx, da, D); if (lrc) return lrc; });
     PLG_LAUNCH_CHECK(ctx);
@@ -933,7 +931,7 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
   a.invariant = ctx->has_invariant ? ctx->invariant : NULL;
   a.partials = ctx->partials;
   a.counter = ctx->counter;
-  a.result = ctx->result_dev;
+  a.sink = plg_make_sink(ctx);
   a.nelem = nelem;
 
   PLG_DISPATCH_R(R, { int lrc = launch_derivatives_aa<RR>(ctx, a, P); if (lrc) return lrc; });

@@ -186,7 +186,7 @@ int plg_gen_partials(plg_context * ctx, int kind, int scale_mode, const DevOp * 
  * last block to finish adds the block partials in order */
 template <int NV>
 __device__ __forceinline__ void gen_finish(double v0, double v1, double * partials, unsigned int * counter,
-                                           double * result)
+                                           const PlgSink & sink)
 {
   __shared__ double red[PLG_GEN_THREADS / 32];
   __shared__ bool is_last;
@@ -216,8 +216,7 @@ __device__ __forceinline__ void gen_finish(double v0, double v1, double * partia
     const double r1 = (NV == 2) ? block_sum<PLG_GEN_THREADS>(t1, red) : 0.0;
     if (threadIdx.x == 0)
     {
-      result[0] = r0;
-      if (NV == 2) result[1] = r1;
+      plg_publish(sink, r0, (NV == 2) ? r1 : 0.0);
       *counter = 0u;
     }
   }
@@ -235,7 +234,7 @@ struct GenLnlDev
   double * persite;
   double * partials;
   unsigned int * counter;
-  double * result;
+  PlgSink sink;
   double log_threshold;
   unsigned int sites, R, K, Kp;
   int per_rate, use_map;
@@ -320,7 +319,7 @@ __global__ void __launch_bounds__(PLG_GEN_THREADS) k_gen_lnl(const GenLnlDev a)
     site_lk = __dmul_rn(site_lk, (double)a.weights[n]);
     if (a.persite) a.persite[n] = site_lk;
   }
-  gen_finish<1>(site_lk, 0.0, a.partials, a.counter, a.result);
+  gen_finish<1>(site_lk, 0.0, a.partials, a.counter, a.sink);
 }
 
 int plg_gen_loglikelihood(plg_context * ctx, const GenLnl & g, const double * freqs, const double * rate_weights,
@@ -355,7 +354,7 @@ int plg_gen_loglikelihood(plg_context * ctx, const GenLnl & g, const double * fr
   a.persite = persite_lnl ? ctx->persite_dev : NULL;
   a.partials = ctx->partials;
   a.counter = ctx->counter;
-  a.result = ctx->result_dev;
+  a.sink = plg_make_sink(ctx);
   a.log_threshold = log(PLL_SCALE_THRESHOLD);
   a.sites = ctx->active_sites;
   a.R = R;
@@ -366,8 +365,11 @@ int plg_gen_loglikelihood(plg_context * ctx, const GenLnl & g, const double * fr
   k_gen_lnl<<<nblocks, PLG_GEN_THREADS, 0, ctx->stream>>>(a);
   PLG_LAUNCH_CHECK(ctx);
   if (persite_lnl)
-    PLG_CUDA(cudaMemcpyAsync(persite_lnl, ctx->persite_dev, (size_t)ctx->active_sites * sizeof(double),
+  {
+      PLG_CUDA(cudaMemcpyAsync(persite_lnl, ctx->persite_dev, (size_t)ctx->active_sites * sizeof(double),
                              cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->copy_pending = 1;
+  }
   ctx->stats.d2h_bytes += sizeof(double) + (persite_lnl ? (size_t)ctx->active_sites * sizeof(double) : 0);
   return plg_finish_result(ctx, logl_out, NULL);
 }
@@ -452,7 +454,7 @@ k_gen_derivatives(const double * __restrict__ sumtable, const double * __restric
                   const double * __restrict__ rate_weights, const double * __restrict__ prop_invar,
                   const double * __restrict__ freqs, const unsigned int * __restrict__ weights,
                   const int * __restrict__ invariant, unsigned int sites, unsigned int R, unsigned int K,
-                  unsigned int Kp, double * partials, unsigned int * counter, double * result)
+                  unsigned int Kp, double * partials, unsigned int * counter, const PlgSink sink)
 {
   const unsigned int n = blockIdx.x * PLG_GEN_THREADS + threadIdx.x;
   double df = 0.0, ddf = 0.0;
@@ -489,7 +491,7 @@ k_gen_derivatives(const double * __restrict__ sumtable, const double * __restric
     df = __dmul_rn((double)weights[n], d1);
     ddf = __dmul_rn((double)weights[n], d2);
   }
-  gen_finish<2>(df, ddf, partials, counter, result);
+  gen_finish<2>(df, ddf, partials, counter, sink);
 }
 
 int plg_gen_derivatives(plg_context * ctx, const double * sumtable, const double * diagptable,
@@ -515,7 +517,7 @@ int plg_gen_derivatives(plg_context * ctx, const double * sumtable, const double
   if (!d_diag || !d_rw || !d_pinv || !d_freqs) return PLG_E_CUDA;
   k_gen_derivatives<<<nblocks, PLG_GEN_THREADS, 0, ctx->stream>>>(
       sumtable, d_diag, d_rw, d_pinv, d_freqs, ctx->weights, ctx->has_invariant ? ctx->invariant : NULL,
-      ctx->active_sites, R, K, Kp, ctx->partials, ctx->counter, ctx->result_dev);
+      ctx->active_sites, R, K, Kp, ctx->partials, ctx->counter, plg_make_sink(ctx));
   PLG_LAUNCH_CHECK(ctx);
   ctx->stats.d2h_bytes += 2 * sizeof(double);
   return plg_finish_result(ctx, d_f, dd_f);

@@ -69,6 +69,33 @@ struct plg_graph_entry
     PLG_CUDA(cudaSetDevice((ctx)->device));                                            \
   } while (0)
 
+/* Where a reduction kernel delivers its 1 or 2 doubles.  A lone context: its own mapped pinned
+ * host words ([0], [1] = values, [4] = sequence flag the host polls).  A context of a device
+ * group (pll_gpu_set_devices: one partition over several GPUs): a slot in the LEADER device's
+ * memory, written over NVLink peer access; the member whose last block arrives last adds the
+ * slots in member order and hands the total to the leader's host words - the one cross-device
+ * exchange of the path (reference src/core_likelihood_avx.c:1259 `logl +=`,
+ * src/core_derivatives_avx2.c:756-765), done on the devices with a single host wake-up. */
+struct PlgSink
+{
+  double * result;
+  unsigned long long seq;
+  double * group_slots;          /* [group_size][2] on the leader; NULL outside a group call */
+  unsigned int * group_counter;  /* arrivals of the current call, on the leader */
+  double * group_result;         /* the leader's mapped host words */
+  unsigned int group_size, group_rank;
+};
+
+struct plg_group
+{
+  unsigned int n;
+  plg_context * members[PLL_GPU_MAX_GROUP];
+  double * slots;          /* leader device memory */
+  unsigned int * counter;
+  unsigned long long seq;  /* of the call in flight */
+  int active;              /* between plg_group_begin and plg_group_collect / _abort */
+};
+
 struct plg_context
 {
   plg_dims_t d;
@@ -125,6 +152,10 @@ struct plg_context
    * until plg_collect (lets a caller overlap the same call on several devices) */
   int deferred;
   double * pending[2];
+  unsigned long long result_seq; /* sequence number of the last value-returning call (flag in result_host[4]) */
+  int copy_pending;              /* a D2H copy was enqueued behind the reduction: wait for the stream, not the flag */
+  plg_group * group;             /* device group this context belongs to (NULL: none) */
+  unsigned int group_rank;
   double * persite_dev;   /* sites doubles, allocated on first use */
   double * lnl_table;     /* pi-weighted tip lookup of the edge-lnL tip-inner kernels */
   size_t lnl_table_cap;   /* doubles */
@@ -154,21 +185,16 @@ struct plg_context
   plg_stats_t stats;
 };
 
-/* Delivers the 1 or 2 doubles a reduction kernel left in result_host: waits for the stream and
- * copies them out - or, in deferred mode, remembers where they go until plg_collect. */
-static inline int plg_finish_result(plg_context * ctx, double * out0, double * out1)
-{
-  if (ctx->deferred)
-  {
-    ctx->pending[0] = out0;
-    ctx->pending[1] = out1;
-    return PLG_OK;
-  }
-  PLG_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (out0) *out0 = ctx->result_host[0];
-  if (out1) *out1 = ctx->result_host[1];
-  return PLG_OK;
-}
+/* The sink of the next reduction kernel of this context (advances the sequence number). */
+PlgSink plg_make_sink(plg_context * ctx);
+/* Waits until the mapped host words of `ctx` carry sequence number `seq`: a short spin on the
+ * flag (a value-returning call on an idle stream costs no wake-up through the driver), then a
+ * blocking stream synchronise.  `watch` are the contexts whose streams feed the result. */
+int plg_wait_flag(plg_context * ctx, unsigned long long seq, plg_context * const * watch, unsigned int n_watch);
+
+/* Delivers the 1 or 2 doubles a reduction kernel left in result_host: waits for them and copies
+ * them out - or, in deferred mode, remembers where they go until plg_collect. */
+int plg_finish_result(plg_context * ctx, double * out0, double * out1);
 
 
 #define PLG_MAX_DEVICES 64
@@ -369,6 +395,40 @@ __device__ __forceinline__ double dot4_unfused(double m0, double m1, double m2, 
                                                const d4 & c)
 {
   return hsum4(__dmul_rn(m0, c.x), __dmul_rn(m1, c.y), __dmul_rn(m2, c.z), __dmul_rn(m3, c.w));
+}
+
+/* called by ONE thread of the block that holds the final sums of a reduction */
+__device__ __forceinline__ void plg_publish(const PlgSink & s, double r0, double r1)
+{
+  if (!s.group_slots)
+  {
+    s.result[0] = r0;
+    s.result[1] = r1;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(s.result + 4) = s.seq;
+    return;
+  }
+  volatile double * slot = s.group_slots + 2 * s.group_rank;
+  slot[0] = r0;
+  slot[1] = r1;
+  __threadfence_system();
+  if (atomicAdd_system(s.group_counter, 1u) == s.group_size - 1)
+  {
+    /* every member has published: fixed-order sum (member 0 first, as a host loop would) */
+    __threadfence_system();
+    const volatile double * all = s.group_slots;
+    double t0 = all[0], t1 = all[1];
+    for (unsigned int d = 1; d < s.group_size; ++d)
+    {
+      t0 = __dadd_rn(t0, all[2 * d]);
+      t1 = __dadd_rn(t1, all[2 * d + 1]);
+    }
+    *s.group_counter = 0u;
+    s.group_result[0] = t0;
+    s.group_result[1] = t1;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(s.group_result + 4) = s.seq;
+  }
 }
 
 #define PLG_SCALE_THRESHOLD 0x1p-256

@@ -47,7 +47,7 @@ struct LnlArgs
   double * persite;             /* may be NULL */
   double * partials;
   unsigned int * counter;
-  double * result;
+  PlgSink sink;
   unsigned int nelem;           /* sites * R */
   int per_rate_scaling;
 };
@@ -170,7 +170,7 @@ __device__ __forceinline__ void finish_sum(double v, const LnlArgs & a)
     const double total = block_sum<THREADS>(s, red);
     if (threadIdx.x == 0)
     {
-      a.result[0] = total;
+      plg_publish(a.sink, total, 0.0);
       *a.counter = 0u;
     }
   }
@@ -593,7 +593,7 @@ static int common_args(plg_context * ctx, LnlArgs & a, double * persite_lnl, uns
   a.persite = persite_lnl ? ctx->persite_dev : NULL;
   a.partials = ctx->partials;
   a.counter = ctx->counter;
-  a.result = ctx->result_dev;
+  a.sink = plg_make_sink(ctx);
   a.nelem = nelem;
   a.per_rate_scaling = ctx->rate_scalers ? 1 : 0;
   return PLG_OK;
@@ -606,6 +606,7 @@ static int fetch_result(plg_context * ctx, double * persite_lnl, double * logl_o
   {
     PLG_CUDA(cudaMemcpyAsync(persite_lnl, ctx->persite_dev, (size_t)ctx->active_sites * sizeof(double),
                              cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->copy_pending = 1;
     ctx->stats.d2h_bytes += (size_t)ctx->active_sites * sizeof(double);
   }
   return plg_finish_result(ctx, logl_out, NULL);

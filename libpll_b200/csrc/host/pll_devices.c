@@ -104,6 +104,20 @@ int pllg_dev_create(pllg_partition_t * g, const plg_dims_t * dims, int first_dev
     g->ndev = d + 1;
   }
   g->ctx = g->ctxs[0];
+  /* scalar results are combined on the devices when every slice can reach the first one's
+   * memory; otherwise (PLG_E_UNSUPPORTED) the per-slice results are added here on the host */
+  g->grouped = 0;
+  if (g->ndev > 1)
+  {
+    const char * e = getenv("PLL_GPU_HOST_REDUCE");
+    int rc = (e && *e && *e != '0') ? PLG_E_UNSUPPORTED : plg_group_create(g->ctxs, g->ndev);
+    if (rc == PLG_OK) g->grouped = 1;
+    else if (rc != PLG_E_UNSUPPORTED)
+    {
+      pllg_dev_destroy(g);
+      return rc;
+    }
+  }
   return PLG_OK;
 }
 
@@ -210,6 +224,19 @@ int pllg_dev_update_partials(pllg_partition_t * g, const pll_operation_t * opera
   FOR_EACH_DEVICE(plg_update_partials(ctx, operations, count));
 }
 
+/* Device group (plg_group_*): all slices enqueue, the devices add their partial results among
+ * themselves and the host waits for one flag. */
+static int group_begin(pllg_partition_t * g) { return g->grouped ? plg_group_begin(g->ctxs[0]) : PLG_OK; }
+static int group_finish(pllg_partition_t * g, int rc, double * out0, double * out1)
+{
+  if (rc)
+  {
+    plg_group_abort(g->ctxs[0]);
+    return rc;
+  }
+  return plg_group_collect(g->ctxs[0], out0, out1);
+}
+
 /* Value-returning calls: with several slices the kernels of all devices are enqueued first
  * (plg_set_deferred) and the partial results collected afterwards, so the devices reduce
  * concurrently; partial sums are added in slice order. */
@@ -237,15 +264,17 @@ int pllg_dev_edge_loglikelihood(pllg_partition_t * g, unsigned int parent_clv_in
                                 double * persite_lnl, double * logl_out)
 {
   double part[PLLG_MAX_DEVICES] = {0};
-  int rc = PLG_OK;
+  int rc = group_begin(g);
+  if (rc) return rc;
   for (unsigned int d = 0; d < g->ndev && !rc; ++d)
   {
-    rc = begin_deferred(g, d);
+    if (!g->grouped) rc = begin_deferred(g, d);
     if (!rc)
       rc = plg_edge_loglikelihood(g->ctxs[d], parent_clv_index, parent_scaler_index, child_clv_index,
                                   child_scaler_index, matrix_index, freqs, rate_weights, prop_invar,
                                   persite_lnl ? persite_lnl + g->lo[d] : NULL, &part[d]);
   }
+  if (g->grouped) return group_finish(g, rc, logl_out, NULL);
   if ((rc = collect_all(g, rc))) return rc;
   double total = part[0];
   for (unsigned int d = 1; d < g->ndev; ++d) total += part[d];
@@ -258,14 +287,16 @@ int pllg_dev_root_loglikelihood(pllg_partition_t * g, unsigned int clv_index, in
                                 const double * prop_invar, double * persite_lnl, double * logl_out)
 {
   double part[PLLG_MAX_DEVICES] = {0};
-  int rc = PLG_OK;
+  int rc = group_begin(g);
+  if (rc) return rc;
   for (unsigned int d = 0; d < g->ndev && !rc; ++d)
   {
-    rc = begin_deferred(g, d);
+    if (!g->grouped) rc = begin_deferred(g, d);
     if (!rc)
       rc = plg_root_loglikelihood(g->ctxs[d], clv_index, scaler_index, freqs, rate_weights, prop_invar,
                                   persite_lnl ? persite_lnl + g->lo[d] : NULL, &part[d]);
   }
+  if (g->grouped) return group_finish(g, rc, logl_out, NULL);
   if ((rc = collect_all(g, rc))) return rc;
   double total = part[0];
   for (unsigned int d = 1; d < g->ndev; ++d) total += part[d];
@@ -303,14 +334,16 @@ int pllg_dev_likelihood_derivatives(pllg_partition_t * g, const void * key, cons
                                     const double * freqs, double * d_f, double * dd_f)
 {
   double a[PLLG_MAX_DEVICES] = {0}, b[PLLG_MAX_DEVICES] = {0};
-  int rc = PLG_OK;
+  int rc = group_begin(g);
+  if (rc) return rc;
   for (unsigned int d = 0; d < g->ndev && !rc; ++d)
   {
-    rc = begin_deferred(g, d);
+    if (!g->grouped) rc = begin_deferred(g, d);
     if (!rc)
       rc = plg_likelihood_derivatives(g->ctxs[d], key, diagptable, rate_weights, prop_invar, freqs,
                                       &a[d], &b[d]);
   }
+  if (g->grouped) return group_finish(g, rc, d_f, dd_f);
   if ((rc = collect_all(g, rc))) return rc;
   double s1 = a[0], s2 = b[0];
   for (unsigned int d = 1; d < g->ndev; ++d)

@@ -29,6 +29,7 @@ typedef struct pllg_partition
   unsigned char * tip_stage; /* sites_alloc bytes: encoding buffer for one tip   */
   /* pattern slices over several devices (pll_devices.c): context d owns [lo[d], lo[d+1]) */
   unsigned int ndev;
+  int grouped;               /* 1: scalar results are combined on the devices (plg_group_*) */
   plg_context_t * ctxs[PLLG_MAX_DEVICES];
   unsigned int lo[PLLG_MAX_DEVICES + 1];
 } pllg_partition_t;

@@ -103,6 +103,11 @@ static int deliver(plg_context_t * ctx, double * a, double * b)
   return PLG_OK;
 }
 
+/* no peer memory in the null device: the host layer adds the per-slice results itself */
+int plg_group_create(plg_context_t * const * members, unsigned int n) { return PLG_E_UNSUPPORTED; }
+int plg_group_begin(plg_context_t * leader) { return PLG_E_INVALID; }
+int plg_group_collect(plg_context_t * leader, double * out0, double * out1) { return PLG_E_INVALID; }
+int plg_group_abort(plg_context_t * leader) { return PLG_OK; }
 int plg_set_tipchars(plg_context_t * ctx, unsigned int tip_index, const unsigned char * chars)
 {
   if (tip_index >= ctx->d.tips) return PLG_E_INVALID;
