@@ -422,14 +422,20 @@ class Partition:
 
     def likelihood_derivatives(self, parent_scaler, child_scaler, branch_length, params_indices,
                                sumtable: np.ndarray):
-        pi = _as_uint(params_indices)
-        d1, d2 = C.c_double(0), C.c_double(0)
-        self._check(
-            self.lib.pll_compute_likelihood_derivatives(self.ptr, parent_scaler, child_scaler,
-                                                        branch_length, pi.ctypes.data_as(c_uint_p),
-                                                        sumtable.ctypes.data_as(c_double_p),
-                                                        C.byref(d1), C.byref(d2)),
-            "pll_compute_likelihood_derivatives")
+        # called up to 32 times per branch: the ctypes arguments are built once per (indices, table)
+        cache = self.__dict__.setdefault("_der_args", {})
+        key = (id(params_indices), sumtable.ctypes.data)
+        args = cache.get(key)
+        if args is None:
+            pi = _as_uint(params_indices)
+            args = (pi, pi.ctypes.data_as(c_uint_p), sumtable.ctypes.data_as(c_double_p), C.c_double(0), C.c_double(0))
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = args
+        _, pi_p, tab_p, d1, d2 = args
+        if not self.lib.pll_compute_likelihood_derivatives(self.ptr, parent_scaler, child_scaler, branch_length,
+                                                           pi_p, tab_p, C.byref(d1), C.byref(d2)):
+            self._check(0, "pll_compute_likelihood_derivatives")
         return d1.value, d2.value
 
     # -- reading state back (host arrays in the reference, mirrors under the GPU backend) --

@@ -451,6 +451,37 @@ k_derivatives_dna(const DerArgs a, const __grid_constant__ DerDnaParams P)
   }
 }
 
+/* Launch configuration of a derivative pass: the sumtable is re-read by every pass of a Newton
+ * loop (reference examples/newton/newton.c:64-93: up to 32 calls per branch), so the launch asks
+ * L2 to keep as much of it as the device lets persist; the rest streams. */
+struct DerLaunch
+{
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  DerLaunch(plg_context * ctx, unsigned int nblocks, const double * sumtable, size_t table_bytes)
+  {
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(nblocks);
+    cfg.blockDim = dim3(PLG_DER_THREADS);
+    cfg.stream = ctx->stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 0;
+    if (ctx->l2_persist_bytes && table_bytes)
+    {
+      const size_t window = table_bytes < ctx->l2_window_max ? table_bytes : ctx->l2_window_max;
+      const double ratio = (double)ctx->l2_persist_bytes / (double)window;
+      attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+      attr[0].val.accessPolicyWindow.base_ptr = const_cast<double *>(sumtable);
+      attr[0].val.accessPolicyWindow.num_bytes = window;
+      attr[0].val.accessPolicyWindow.hitRatio = (float)(ratio < 1.0 ? ratio : 1.0);
+      attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cfg.numAttrs = 1;
+      ctx->l2_pinned = 1;
+    }
+  }
+};
+
 template <int R>
 static int launch_derivatives_dna(plg_context * ctx, const DerArgs & a, const DerDnaParams & P)
 {
@@ -466,7 +497,8 @@ static int launch_derivatives_dna(plg_context * ctx, const DerArgs & a, const De
   if (rc) return rc;
   DerArgs b = a;
   b.partials = ctx->partials;
-  k_derivatives_dna<R><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(b, P);
+  DerLaunch launch(ctx, nblocks, b.sumtable, (size_t)b.nelem * 4 * sizeof(double));
+  PLG_CUDA(cudaLaunchKernelEx(&launch.cfg, k_derivatives_dna<R>, b, P));
   return PLG_OK;
 }
 
@@ -590,7 +622,8 @@ static int launch_derivatives_aa(plg_context * ctx, const DerArgs & a, const Der
   if (rc) return rc;
   DerArgs b = a;
   b.partials = ctx->partials;
-  k_derivatives_aa<R><<<nblocks, PLG_DER_THREADS, 0, ctx->stream>>>(b, P);
+  DerLaunch launch(ctx, nblocks, b.sumtable, (size_t)b.nelem * 20 * sizeof(double));
+  PLG_CUDA(cudaLaunchKernelEx(&launch.cfg, k_derivatives_aa<R>, b, P));
   return PLG_OK;
 }
 
@@ -658,6 +691,7 @@ extern "C" int plg_update_sumtable(plg_context_t * ctx, unsigned int parent_clv_
                                    double * host_copy)
 {
   PLG_CHECK_CTX(ctx);
+  plg_release_l2(ctx);
   const unsigned int n_clv = ctx->d.tips + ctx->d.clv_buffers;
   if (parent_clv_index >= n_clv || child_clv_index >= n_clv ||
       parent_scaler_index >= (int)ctx->d.scale_buffers ||

@@ -175,6 +175,12 @@ struct plg_context
   size_t list_buf_cap;
   int aa_exact; /* 20 states: 1 = bit-exact vector-pipe kernels, 0 = DMMA tensor-core kernels */
 
+  /* L2 residency of a sumtable between the derivative passes of a Newton loop: bytes of L2 set
+   * aside for persisting lines (0: off, PLL_GPU_L2_PERSIST=0) and the largest access-policy window */
+  size_t l2_persist_bytes;
+  size_t l2_window_max;
+  int l2_pinned;       /* a derivative pass may have left persisting lines: demote them before other work */
+
   /* L2 flush buffer (allocated on first plg_flush_l2) */
   char * flush_buf;
   size_t flush_bytes;
@@ -292,6 +298,16 @@ void * plg_stage(plg_context * ctx, const void * src, size_t bytes);
 /* Guarantees that the next `bytes` (callers add 256 per item for alignment) of plg_stage calls
  * come from one contiguous, not-yet-recycled region of the ring.  Returns 0 on success. */
 int plg_stage_reserve(plg_context * ctx, size_t bytes);
+
+/* Hands the L2 lines a Newton loop pinned (the sumtable) back to ordinary replacement. */
+static inline void plg_release_l2(plg_context * ctx)
+{
+  if (ctx->l2_pinned)
+  {
+    cudaCtxResetPersistingL2Cache();
+    ctx->l2_pinned = 0;
+  }
+}
 
 int plg_ensure_tables(plg_context * ctx, size_t doubles);
 int plg_ensure_partials(plg_context * ctx, size_t doubles);

@@ -1666,6 +1666,7 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
 {
   PLG_CHECK_CTX(ctx);
   if (count == 0) return PLG_OK;
+  plg_release_l2(ctx);
   if (!operations)
   {
     plg_set_error("plg_update_partials: NULL operations");
