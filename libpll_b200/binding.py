@@ -424,7 +424,7 @@ class Partition:
                                sumtable: np.ndarray):
         # called up to 32 times per branch: the ctypes arguments are built once per (indices, table)
         cache = self.__dict__.setdefault("_der_args", {})
-        key = (id(params_indices), sumtable.ctypes.data)
+        key = (tuple(int(x) for x in params_indices), sumtable.ctypes.data)
         args = cache.get(key)
         if args is None:
             pi = _as_uint(params_indices)
