@@ -350,6 +350,24 @@ class Dist:
     def sum(self, x: float) -> float:
         return self._reduce(x, self.dist.ReduceOp.SUM if self.dist else None)
 
+    def library_comm(self, lib, rank: int):
+        """Hands the library its own communicator: the 128-byte NCCL id of rank 0 travels over
+        torch.distributed, pll_gpu_comm_init does the rest.  From here on the pll.h calls return
+        the sums over all ranks (the scalar all-reduce happens inside the library, on the
+        partition's stream) - no Python all-reduce on the path."""
+        import ctypes as C
+
+        if self.dist is None:
+            return False
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            assert lib.pll_gpu_comm_unique_id(buf) == 1, lib.errmsg()
+        t = self.torch.tensor(list(buf.raw), dtype=self.torch.uint8, device="cuda")
+        self.dist.broadcast(t, 0)
+        buf = C.create_string_buffer(bytes(t.cpu().tolist()), 128)
+        assert lib.pll_gpu_comm_init(buf, self.world, rank) == 1, lib.errmsg()
+        return True
+
     def close(self):
         if self.dist is not None:
             self.dist.destroy_process_group()
@@ -577,7 +595,7 @@ def leg_c5(lib, D: Dist, rank: int, world: int, local_rank: int, steps: int, slo
 
     def step():
         part.update_partials(w.ops)
-        return D.sum(part.edge_loglikelihood(*root))
+        return part.edge_loglikelihood(*root)          # summed over the ranks inside the library
 
     sampler = ClockSampler(local_rank).start()
     for _ in range(3):
@@ -619,6 +637,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         raise SystemExit("bench.py: no B200 visible - the CUDA path has no CPU fallback")
     D = Dist(world, local_rank)  # torch: plumbing only (NCCL scalar all-reduce, barriers)
     lib.pll_gpu_set_device(local_rank)
+    in_library = D.library_comm(lib, rank)   # N > 1: lnL / derivatives are all-reduced inside the library
     memoize_tips()
     also = args.also
     if also == "auto":
@@ -641,7 +660,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
 
     def resident_step():
         part.update_partials(w.ops)
-        return D.sum(part.edge_loglikelihood(*root))
+        return part.edge_loglikelihood(*root)          # N > 1: already the sum over the ranks
 
     # clocks are sampled from the warm-up on: nvidia-smi needs ~0.2 s to deliver its first
     # sample and the timed region of a short run is not much longer (same load throughout)
@@ -667,7 +686,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         ops = w.ops.copy()
         part.update_prob_matrices(pidx, w.matrix_indices, bl)
         part.update_partials(ops)
-        return D.sum(part.edge_loglikelihood(*root))
+        return part.edge_loglikelihood(*root)
 
     for i in range(max(args.warmup, 3)):
         e2e_step(i)
@@ -698,7 +717,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     alg_bytes = trav_stats["algorithmic_bytes"] / n_trav
     comp_bytes = trav_stats["compulsory_bytes"] / n_trav
     persite = np.zeros(S_gpu)
-    lnl = D.sum(part.edge_loglikelihood(*root, persite=persite))   # same state as the resident leg
+    lnl = part.edge_loglikelihood(*root, persite=persite)   # same state as the resident leg
     # (2) the level-by-level kernels (one launch per dependency level and kind), per-kind times
     part.set_profiling(True)
     part.reset_stats()
@@ -814,7 +833,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                 "attributes": "PLL_ATTRIB_ARCH_GPU|PLL_ATTRIB_PATTERN_TIP, per-site scalers",
                 "operations": n_ops, "rate_cats": 4,
                 "l2": "no flush needed: each step writes %.0f GB per GPU through a 126 MB L2" % (comp_bytes / 1e9),
-                "sharding": "site patterns, scalar NCCL all-reduce of lnL" if world > 1 else "single GPU",
+                "sharding": ("site patterns; scalar ncclAllReduce of lnL inside the library (pll_gpu_comm_init), "
+                             f"{stats['collectives']} all-reduces in the timed region") if world > 1 else "single GPU",
             },
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": e2e_stats["h2d_bytes"] // args.steps,
@@ -834,6 +854,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         if lnl_check is not None and not lnl_check["ok"]:
             D.close()
             raise SystemExit(f"bench.py: GPU lnL differs from the reference's: {lnl_check}")
+    if in_library:
+        lib.pll_gpu_comm_finalize()
     D.close()
 
 

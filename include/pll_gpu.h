@@ -78,6 +78,7 @@ typedef struct plg_stats
    * (computed from the plan, not measured) */
   unsigned long long compulsory_bytes;
   unsigned long long graph_evictions;   /* cached operation-list graphs dropped (LRU) */
+  unsigned long long collectives;       /* cross-rank all-reduces of scalar results (plg_comm_*) */
 } plg_stats_t;
 
 PLL_EXPORT const char * plg_last_error(void);
@@ -117,6 +118,19 @@ PLL_EXPORT int plg_group_create(plg_context_t * const * members, unsigned int n)
 PLL_EXPORT int plg_group_begin(plg_context_t * leader);
 PLL_EXPORT int plg_group_collect(plg_context_t * leader, double * out0, double * out1);
 PLL_EXPORT int plg_group_abort(plg_context_t * leader);
+
+/* Cross-process site sharding (one rank per GPU, each owning a pattern slice of every CLV):
+ * after plg_comm_init the scalar results of every context created on `device` - edge / root
+ * log-likelihood, d_f / dd_f - are summed over the ranks by an ncclAllReduce of 1-2 doubles on
+ * the context's stream before they reach the host (the `logl +=` / `d_f +=` coupling of reference
+ * src/core_likelihood_avx.c:1259, src/core_derivatives_avx2.c:756-765).  NCCL is dlopen'ed
+ * (libnccl.so.2, or $PLL_GPU_NCCL_LIB).  id = 128 bytes from plg_comm_unique_id on rank 0, carried
+ * to the other ranks by the caller.  Per-pattern outputs (persite_lnl) stay local. */
+#define PLL_GPU_COMM_ID_BYTES 128
+PLL_EXPORT int plg_comm_unique_id(unsigned char * id);
+PLL_EXPORT int plg_comm_init(const unsigned char * id, int nranks, int rank, int device);
+PLL_EXPORT int plg_comm_finalize(void);
+PLL_EXPORT int plg_comm_size(void);
 
 /* ---- uploads / downloads of resident state ---------------------------------------- */
 
@@ -340,6 +354,15 @@ PLL_EXPORT int pll_gpu_push_pmatrix(pll_partition_t * partition, unsigned int ma
 PLL_EXPORT int pll_gpu_push_clv(pll_partition_t * partition, unsigned int clv_index);
 
 PLL_EXPORT int pll_gpu_synchronize(pll_partition_t * partition);
+
+/* One rank per GPU under mpirun / torchrun, every rank holding a pattern slice in its own
+ * partition: after pll_gpu_comm_init (same device rule as pll_partition_create) the
+ * log-likelihoods and derivatives returned by the pll.h calls of partitions created afterwards
+ * are the sums over all ranks (scalar NCCL all-reduce inside the call).  Rank 0 obtains the id
+ * with pll_gpu_comm_unique_id and the caller distributes it. */
+PLL_EXPORT int pll_gpu_comm_unique_id(unsigned char id[PLL_GPU_COMM_ID_BYTES]);
+PLL_EXPORT int pll_gpu_comm_init(const unsigned char id[PLL_GPU_COMM_ID_BYTES], int nranks, int rank);
+PLL_EXPORT int pll_gpu_comm_finalize(void);
 
 /* pll_set_tip_states for a synthetic DNA tip whose characters are generated on the device
  * (plg_generate_tipchars); `first_site` is the alignment column of the partition's pattern 0. */

@@ -128,6 +128,7 @@ class PlgStats(C.Structure):
         ("kind_launches", C.c_ulonglong * 3),
         ("compulsory_bytes", C.c_ulonglong),
         ("graph_evictions", C.c_ulonglong),
+        ("collectives", C.c_ulonglong),
     ]
 
 
@@ -186,6 +187,9 @@ _GPU_API = {
     "pll_gpu_push_clv": (C.c_int, [PART_P, C.c_uint]),
     "pll_gpu_synchronize": (C.c_int, [PART_P]),
     "pll_gpu_free_sumtable": (C.c_int, [PART_P, C.c_void_p]),
+    "pll_gpu_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "pll_gpu_comm_init": (C.c_int, [C.c_char_p, C.c_int, C.c_int]),
+    "pll_gpu_comm_finalize": (C.c_int, []),
     "pll_gpu_generate_tip_states": (C.c_int, [PART_P, C.c_uint, C.c_ulonglong, C.c_ulonglong]),
     "plg_last_error": (C.c_char_p, []),
     "plg_device_count": (C.c_int, []),

@@ -133,6 +133,7 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   ctx->counter = NULL; ctx->result_dev = NULL; ctx->result_host = NULL;
   ctx->deferred = 0; ctx->pending[0] = ctx->pending[1] = NULL;
   ctx->result_seq = 0; ctx->copy_pending = 0; ctx->group = NULL; ctx->group_rank = 0;
+  ctx->comm_buf = NULL; ctx->comm_seq = 0;
   ctx->persite_dev = NULL;
   ctx->lnl_table = NULL; ctx->lnl_table_cap = 0;
   ctx->sumtables = new std::unordered_map<const void *, double *>();
@@ -243,6 +244,13 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   PLG_CREATE_CUDA(cudaHostGetDevicePointer((void **)&ctx->result_dev, ctx->result_host, 0));
   memset(ctx->result_host, 0, 8 * sizeof(double));
 
+  /* one rank of a sharded run (pll_gpu_comm_init): scalar results go through an all-reduce */
+  if (plg_comm_covers(device))
+  {
+    PLG_CREATE_CUDA(cudaMalloc(&ctx->comm_buf, 8 * sizeof(double)));
+    PLG_CREATE_CUDA(cudaMemsetAsync(ctx->comm_buf, 0, 8 * sizeof(double), ctx->stream));
+  }
+
   /* pattern weights default to 1 (reference src/pll.c:784) */
   {
     std::vector<unsigned int> ones(dims->sites, 1u);
@@ -300,6 +308,7 @@ extern "C" void plg_destroy(plg_context_t * ctx)
   cudaFree(ctx->lnl_scratch);
   cudaFree(ctx->fused_records);
   cudaFree(ctx->list_buf);
+  cudaFree(ctx->comm_buf);
   if (ctx->result_host) cudaFreeHost(ctx->result_host);
   if (ctx->prof_events)
   {
@@ -343,7 +352,17 @@ PlgSink plg_make_sink(plg_context * ctx)
     s.group_rank = ctx->group_rank;
   }
   else
+  {
     s.seq = ++ctx->result_seq;
+    if (ctx->comm_buf)
+    {
+      /* sharded over processes: the kernel leaves its sums in device scratch, the all-reduce and
+       * the hand-over to the host follow on the stream (plg_finish_result) */
+      s.result = ctx->comm_buf;
+      s.seq = 0;
+      ctx->comm_seq = ctx->result_seq;
+    }
+  }
   return s;
 }
 
@@ -382,6 +401,13 @@ int plg_finish_result(plg_context * ctx, double * out0, double * out1)
 {
   if (ctx->group && ctx->group->active)
     return PLG_OK; /* delivered by plg_group_collect */
+  if (ctx->comm_seq)
+  {
+    const unsigned long long seq = ctx->comm_seq;
+    ctx->comm_seq = 0;
+    int crc = plg_comm_allreduce_publish(ctx, seq);
+    if (crc) return crc;
+  }
   if (ctx->deferred)
   {
     ctx->pending[0] = out0;
@@ -403,8 +429,11 @@ int plg_finish_result(plg_context * ctx, double * out0, double * out1)
 extern "C" int plg_collect(plg_context_t * ctx)
 {
   PLG_CHECK_CTX(ctx);
-  PLG_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->copy_pending = 0;
+  if (ctx->copy_pending)
+  {
+    ctx->copy_pending = 0;
+    PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   int rc = plg_wait_flag(ctx, ctx->result_seq, &ctx, 1);
   if (rc) return rc;
   if (ctx->pending[0]) *ctx->pending[0] = ctx->result_host[0];
@@ -429,6 +458,13 @@ extern "C" int plg_group_create(plg_context_t * const * members, unsigned int n)
     {
       plg_set_error("plg_group_create: context %u is NULL or already grouped", d);
       return PLG_E_INVALID;
+    }
+  for (unsigned int d = 0; d < n; ++d)
+    if (members[d]->comm_buf)
+    {
+      /* ranks of a sharded run all-reduce every slice's sums; the host adds the slices */
+      plg_set_error("plg_group_create: contexts of a cross-process communicator are not grouped");
+      return PLG_E_UNSUPPORTED;
     }
   /* every member must be able to write the leader's memory */
   for (unsigned int d = 1; d < n; ++d)

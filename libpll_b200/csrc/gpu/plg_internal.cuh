@@ -156,6 +156,8 @@ struct plg_context
   int copy_pending;              /* a D2H copy was enqueued behind the reduction: wait for the stream, not the flag */
   plg_group * group;             /* device group this context belongs to (NULL: none) */
   unsigned int group_rank;
+  double * comm_buf;             /* device scratch of the cross-rank all-reduce (plg_comm.cu); NULL: not sharded */
+  unsigned long long comm_seq;   /* sequence number of a reduction waiting for its all-reduce (0: none) */
   double * persite_dev;   /* sites doubles, allocated on first use */
   double * lnl_table;     /* pi-weighted tip lookup of the edge-lnL tip-inner kernels */
   size_t lnl_table_cap;   /* doubles */
@@ -190,6 +192,10 @@ struct plg_context
   std::vector<cudaEvent_t> * prof_events;
   plg_stats_t stats;
 };
+
+/* cross-process sharding (plg_comm.cu) */
+bool plg_comm_covers(int device);
+int plg_comm_allreduce_publish(plg_context * ctx, unsigned long long seq);
 
 /* The sink of the next reduction kernel of this context (advances the sequence number). */
 PlgSink plg_make_sink(plg_context * ctx);

@@ -79,6 +79,24 @@ static int pick_device(void)
 
 int pll_gpu_current_device(void) { return pick_device(); }
 
+PLL_EXPORT int pll_gpu_comm_unique_id(unsigned char id[PLL_GPU_COMM_ID_BYTES])
+{
+  int rc = plg_comm_unique_id(id);
+  return rc ? pllg_fail(rc, "pll_gpu_comm_unique_id") : PLL_SUCCESS;
+}
+
+PLL_EXPORT int pll_gpu_comm_init(const unsigned char id[PLL_GPU_COMM_ID_BYTES], int nranks, int rank)
+{
+  int rc = plg_comm_init(id, nranks, rank, pick_device());
+  return rc ? pllg_fail(rc, "pll_gpu_comm_init") : PLL_SUCCESS;
+}
+
+PLL_EXPORT int pll_gpu_comm_finalize(void)
+{
+  plg_comm_finalize();
+  return PLL_SUCCESS;
+}
+
 int pll_gpu_mirror_mode(void)
 {
   const char * e = getenv("PLL_GPU_MIRROR");

@@ -103,6 +103,10 @@ static int deliver(plg_context_t * ctx, double * a, double * b)
   return PLG_OK;
 }
 
+int plg_comm_unique_id(unsigned char * id) { return PLG_E_UNSUPPORTED; }
+int plg_comm_init(const unsigned char * id, int nranks, int rank, int device) { return PLG_E_UNSUPPORTED; }
+int plg_comm_finalize(void) { return PLG_OK; }
+int plg_comm_size(void) { return 0; }
 /* no peer memory in the null device: the host layer adds the per-slice results itself */
 int plg_group_create(plg_context_t * const * members, unsigned int n) { return PLG_E_UNSUPPORTED; }
 int plg_group_begin(plg_context_t * leader) { return PLG_E_INVALID; }

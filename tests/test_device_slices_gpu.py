@@ -19,6 +19,15 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-10   # north_star tolerance against the reference
 
 
+@pytest.fixture(autouse=True, params=["host-sum", "device-reduce"])
+def reduction_mode(request, monkeypatch):
+    """Both ways of combining the per-slice scalars: every device writes its own mapped host words
+    and the host layer adds them (default), or the devices add them among themselves through
+    peer-mapped slots on the first device (plg_group_*, PLL_GPU_DEVICE_REDUCE=1)."""
+    monkeypatch.setenv("PLL_GPU_DEVICE_REDUCE", "1" if request.param == "device-reduce" else "0")
+    return request.param
+
+
 def evaluate(lib, w, attributes, slices, pinv=0.0):
     assert lib.pll_gpu_set_devices(slices) == 1
     try:
