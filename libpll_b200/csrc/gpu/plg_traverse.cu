@@ -205,30 +205,49 @@ __device__ __forceinline__ void load_matrix(const double * M, d4 (&out)[4])
   for (int r = 0; r < 4; ++r) out[r] = lds_d4(M + r * 4);
 }
 
-/* child term of one element: handed over in registers by the previous operation (slot -2), from
- * the warp's tile cache (slot >= 0), or - rare - from HBM (slot -1) */
-template <int R, int EPT, int MODE, bool FULL>
-__device__ __forceinline__ d4 child_term(const WarpCache<EPT> & cache, int slot, int j, unsigned int lane,
-                                         const double * clv, const unsigned int * scaler, unsigned int e,
-                                         unsigned int nelem, const d4 & prev, unsigned int prev_sc,
-                                         unsigned int & sc)
+/* Child terms of the EPT elements of this lane: handed over in registers by the previous
+ * operation (slot -2), from the warp's tile cache (slot >= 0), or - rare - from HBM (slot -1).
+ * The source is warp-uniform, so it is decided once per operation, outside the element loop;
+ * `use(j, x)` consumes element j's child vector. */
+template <int R, int EPT, int MODE, bool FULL, typename Use>
+__device__ __forceinline__ void for_each_child(const WarpCache<EPT> & cache, int slot, unsigned int lane,
+                                               const double * clv, const unsigned int * scaler, unsigned int e0,
+                                               unsigned int nelem, const d4 (&prev)[EPT],
+                                               const unsigned int (&prev_sc)[EPT], unsigned int (&sc)[EPT], Use use)
 {
+  const bool count = MODE != 0 && scaler != nullptr;
   if (slot == -2)
   {
-    if (MODE != 0 && scaler) sc += prev_sc;
-    return prev;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j)
+    {
+      if (count) sc[j] += prev_sc[j];
+      use(j, prev[j]);
+    }
   }
-  if (slot >= 0)
+  else if (slot >= 0)
   {
-    if (MODE != 0 && scaler) sc += cache.scaler(slot, j, lane);
-    return cache.load(slot, j, lane);
+#pragma unroll
+    for (int j = 0; j < EPT; ++j)
+    {
+      if (count) sc[j] += cache.scaler(slot, j, lane);
+      use(j, cache.load(slot, j, lane));
+    }
   }
-  const bool valid = FULL || e < nelem;
-  /* coherent loads: the tile may have been stored earlier in THIS launch (by this lane; a
-   * per-site scaler by the rate-0 lane of the site, ordered by the __syncwarp that ends every
-   * operation) - .nc / __ldg are only defined for data the kernel never writes */
-  if (MODE != 0 && scaler && valid) sc += ld_coherent_u32(scaler + (MODE == 2 ? e : e / R));
-  return valid ? ld_stream_coherent(clv + (size_t)e * 4) : d4{0.0, 0.0, 0.0, 0.0};
+  else
+  {
+    /* coherent loads: the tile may have been stored earlier in THIS launch (by this lane; a
+     * per-site scaler by the rate-0 lane of the site, ordered by the __syncwarp that ends every
+     * operation) - .nc / __ldg are only defined for data the kernel never writes */
+#pragma unroll
+    for (int j = 0; j < EPT; ++j)
+    {
+      const unsigned int e = e0 + j * 32;
+      const bool valid = FULL || e < nelem;
+      if (count && valid) sc[j] += ld_coherent_u32(scaler + (MODE == 2 ? e : e / R));
+      use(j, valid ? ld_stream_coherent(clv + (size_t)e * 4) : d4{0.0, 0.0, 0.0, 0.0});
+    }
+  }
 }
 
 /* One operation on the EPT elements of this lane.  KIND, MODE (scaling), FULL (no element of the
@@ -280,13 +299,9 @@ __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> 
     {
       d4 Lm[4];
       load_matrix(st.L + k * FusedStage<R>::MPITCH, Lm);
-#pragma unroll
-      for (int j = 0; j < EPT; ++j)
-      {
-        const d4 x = child_term<R, EPT, MODE, FULL>(cache, lslot, j, lane, st.desc.op.left, lscale, e0 + j * 32,
-                                                    nelem, p[j], 0u, sc[j]);
-        p[j] = fmul4(fmatvec(Lm, x), p[j]);
-      }
+      /* lslot is never -2 here (the right child was the one handed over) */
+      for_each_child<R, EPT, MODE, FULL>(cache, lslot, lane, st.desc.op.left, lscale, e0, nelem, p, psc, sc,
+                                         [&](int j, const d4 & x) { p[j] = fmul4(fmatvec(Lm, x), p[j]); });
     }
     else
     {
@@ -302,13 +317,9 @@ __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> 
       d4 Lm[4];
       load_matrix(st.L + k * FusedStage<R>::MPITCH, Lm);
 #pragma unroll
-      for (int j = 0; j < EPT; ++j)
-      {
-        sc[j] = 0;
-        const d4 x = child_term<R, EPT, MODE, FULL>(cache, lslot, j, lane, st.desc.op.left, lscale, e0 + j * 32,
-                                                    nelem, p[j], psc[j], sc[j]);
-        p[j] = fmatvec(Lm, x);
-      }
+      for (int j = 0; j < EPT; ++j) sc[j] = 0;
+      for_each_child<R, EPT, MODE, FULL>(cache, lslot, lane, st.desc.op.left, lscale, e0, nelem, p, psc, sc,
+                                         [&](int j, const d4 & x) { p[j] = fmatvec(Lm, x); });
     }
     else
     {
@@ -321,14 +332,9 @@ __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> 
     }
     d4 Rm[4];
     load_matrix(st.Rr + k * FusedStage<R>::MPITCH, Rm);
-#pragma unroll
-    for (int j = 0; j < EPT; ++j)
-    {
-      /* rslot is never -2 here */
-      const d4 y = child_term<R, EPT, MODE, FULL>(cache, rslot, j, lane, st.desc.op.right, rscale, e0 + j * 32,
-                                                  nelem, p[j], 0u, sc[j]);
-      p[j] = fmul4(p[j], fmatvec(Rm, y));
-    }
+    /* rslot is never -2 here */
+    for_each_child<R, EPT, MODE, FULL>(cache, rslot, lane, st.desc.op.right, rscale, e0, nelem, p, psc, sc,
+                                       [&](int j, const d4 & y) { p[j] = fmul4(p[j], fmatvec(Rm, y)); });
   }
   /* rescaling votes (tip-tip never rescales and zeroes the scaler, reference
    * src/core_partials_avx.c:113-116), then the write-back */
@@ -417,8 +423,14 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
 
   constexpr unsigned int TILE = 32u * EPT;
   const unsigned int ntiles = (nelem + TILE - 1) / TILE;
-  const unsigned int tiles_per_pass = gridDim.x * NW;
-  const unsigned int passes = (ntiles + tiles_per_pass - 1) / tiles_per_pass;
+  /* Every CTA owns a contiguous run of tiles, the runs differing by at most one tile, and walks
+   * it NW tiles per pass.  All CTAs then make the same number of passes and the remainder is a
+   * LIGHT last pass everywhere (a few active warps per CTA, which finish sooner) instead of a full
+   * extra pass on a few SMs while the others idle. */
+  const unsigned int base_tiles = ntiles / gridDim.x, extra_tiles = ntiles % gridDim.x;
+  const unsigned int my_tiles = base_tiles + (blockIdx.x < extra_tiles ? 1u : 0u);
+  const unsigned int first_tile = blockIdx.x * base_tiles + (blockIdx.x < extra_tiles ? blockIdx.x : extra_tiles);
+  const unsigned int passes = (my_tiles + NW - 1) / NW;
 
   if (warp == NW)
   {
@@ -511,18 +523,19 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
   }
   unsigned int it = 0;
   const unsigned int total_its = passes * n_ops;
+  if (total_its)
   {
     mbar_wait(&full[0], 0);
-    const unsigned int tile0 = blockIdx.x * NW + warp;
-    prefetch_codes(stages[0], tile0, tile0 < ntiles, 0);
+    prefetch_codes(stages[0], first_tile + warp, warp < my_tiles, 0);
   }
   for (unsigned int pass = 0; pass < passes; ++pass)
   {
-    const unsigned int tile = (pass * gridDim.x + blockIdx.x) * NW + warp;
-    const bool have = tile < ntiles;
+    const unsigned int tile = first_tile + pass * NW + warp;
+    const bool have = pass * NW + warp < my_tiles;
     const unsigned int e0 = tile * TILE + lane;
     const bool tile_full = (tile + 1) * TILE <= nelem;
-    const unsigned int tile_next = ((pass + 1) * gridDim.x + blockIdx.x) * NW + warp;
+    const unsigned int tile_next = tile + NW;
+    const bool have_next = (pass + 1) * NW + warp < my_tiles;
     for (unsigned int i = 0; i < n_ops; ++i, ++it)
     {
       /* stage `it` is known to be full: it was waited for when its tip codes were requested */
@@ -537,7 +550,7 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
         const unsigned int itn = it + 1;
         mbar_wait(&full[itn % S], (itn / S) & 1u);
         if (i + 1 == n_ops)
-          prefetch_codes(stages[itn % S], tile_next, tile_next < ntiles, buf ^ 1u);
+          prefetch_codes(stages[itn % S], tile_next, have_next, buf ^ 1u);
         else
           prefetch_codes(stages[itn % S], tile, have, buf ^ 1u);
       }
