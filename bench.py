@@ -440,6 +440,26 @@ def leg_lists(lib, part, pidx, tips: int, sites: int, steps: int):
     return out, tree, walker
 
 
+def c_caller_latencies():
+    """The same pll.h calls issued by a C program (tools/newton_c.c, built by build()): per-call
+    latency without the ctypes argument marshalling that the Python loop of this leg pays."""
+    exe = os.path.join(ROOT, "tools", "newton_c")
+    if not os.path.exists(exe):
+        return None
+    try:
+        run = subprocess.run([exe, "64", "1000000"], capture_output=True, text=True, timeout=120)
+        out = {"program": "tools/newton_c.c: 64-taxon ladder x 1M patterns, GTR+G4, one inner-inner edge"}
+        for line in run.stdout.splitlines():
+            f = line.split()
+            if line.startswith("pll_") and "us" in f:
+                out[f[0] + "_us"] = float(f[f.index("us") - 1])
+            elif line.startswith("Newton"):
+                out["newton_32_iterations_ms"] = float(f[f.index("ms") - 1])
+        return out
+    except Exception as e:  # pragma: no cover
+        return {"error": repr(e)}
+
+
 def leg_c4(lib, part, pidx, tree, walker, sites: int, branches: int = 10, iters: int = 32):
     """BASELINE configs[3]: Newton branch-length optimisation (reference examples/newton/newton.c
     :31-100) on the evaluation edge and on `branches - 1` further edges reached by re-rooting
@@ -492,6 +512,7 @@ def leg_c4(lib, part, pidx, tree, walker, sites: int, branches: int = 10, iters:
         lengths.append(length)
     total = time.perf_counter() - t_all
     return {
+        "c_caller": c_caller_latencies(),
         "what": f"Newton on {branches} branches (the evaluation edge + {branches - 1} re-rooted ones): "
                 f"partial traversal, pll_update_sumtable, {iters} x pll_compute_likelihood_derivatives each",
         "branches": branches, "iterations_per_branch": iters,
@@ -708,10 +729,12 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     for _ in range(2):
         part.update_partials(w.ops)
     part.reset_stats()
-    part.timer_start()
+    trav_ms = 0.0
     for _ in range(n_trav):
-        part.update_partials(w.ops)
-    trav_ms = D.max(part.timer_stop()) / n_trav
+        part.timer_start()              # CUDA events on the library's stream around ONE call:
+        part.update_partials(w.ops)     # k_fused_pack (6 us) + k_traverse_dna
+        trav_ms += part.timer_stop()
+    trav_ms = D.max(trav_ms) / n_trav
     trav_stats = part.stats()
     fused = trav_stats["kernel_launches"] <= 3 * n_trav  # pack + traverse (+ nothing else) per call
     alg_bytes = trav_stats["algorithmic_bytes"] / n_trav
