@@ -1385,7 +1385,7 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
     unsigned long long per_site = 0;
     for (const FusedOp & f : plan.fused)
     {
-      if (f.pad) per_site += span_bytes + (f.op.pscale ? scaler_unit : 0);
+      if (f.pad & 1) per_site += span_bytes + (f.op.pscale ? scaler_unit : 0);
       if (f.kind == PLG_KIND_II && f.lslot == -1) per_site += span_bytes + (f.op.lscale ? scaler_unit : 0);
       if (f.kind != PLG_KIND_TT && f.rslot == -1) per_site += span_bytes + (f.op.rscale ? scaler_unit : 0);
       per_site += (f.kind == PLG_KIND_TT) ? 2 : (f.kind == PLG_KIND_TI ? 1 : 0);

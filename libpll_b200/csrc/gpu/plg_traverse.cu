@@ -269,7 +269,7 @@ __device__ __forceinline__ void run_op(const FusedStage<R> & st, WarpCache<EPT> 
   unsigned int * pscale = st.desc.op.pscale;
   /* 0: a dead store - the buffer is overwritten later in this list and nobody reads this value
    * from HBM (slot-recycling lists; see build_plan) */
-  const bool write_back = st.desc.pad != 0;
+  const bool write_back = (st.desc.pad & 1) != 0;
   unsigned int sc[EPT];
 
   if (KIND == PLG_KIND_TT)
