@@ -111,6 +111,7 @@ struct plg_context
   int use_fused_aa;          /* 20 states: the same on the tensor cores (PLL_GPU_FUSED_AA, default 0: measured
                                 slower than the level-by-level kernels at BASELINE configs[2]) */
   unsigned int fused_slots;  /* tiles a warp keeps in shared memory (PLL_GPU_FUSED_SLOTS, default 3) */
+  int walk_split;            /* 20-state walk (plg_walk_aa.cu): warps per tile team (PLL_GPU_WALK_SPLIT) */
   unsigned char * fused_records; /* packed operation records of the non-graph path */
   size_t fused_records_cap;
 
@@ -267,6 +268,16 @@ int plg_launch_fused_aa(plg_context * ctx, const FusedOp * dev_ops, unsigned cha
 unsigned int plg_fused_aa_slots(unsigned int rate_cats, unsigned int wanted);
 size_t plg_fused_aa_record_bytes(unsigned int rate_cats);
 unsigned int plg_fused_aa_max_codes(unsigned int rate_cats); /* tip codes a packed table has room for */
+
+/* 20 states, second design (plg_walk_aa.cu, PLL_GPU_FUSED_AA=2): FusedOp::lbytes = bytes of the
+ * operation's record the ring needs, FusedOp::rbytes = first row of its tip table (rows of
+ * plg_walk_aa_row_bytes) in the table area behind the records */
+#define PLG_WALK_AA_SLOTS 2
+int plg_launch_walk_aa(plg_context * ctx, const FusedOp * dev_ops, unsigned char * dev_records, unsigned char * dev_tables,
+                       unsigned int n_ops);
+size_t plg_walk_aa_record_bytes(unsigned int rate_cats);
+size_t plg_walk_aa_row_bytes(unsigned int rate_cats);
+bool plg_walk_aa_supported(unsigned int rate_cats, unsigned int ncodes);
 
 /* one operation-shaped launch on the specialised kernels (plg_partials.cu) */
 int plg_launch_single_op(plg_context * ctx, int kind, const DevOp & op);

@@ -993,6 +993,8 @@ struct Plan
   std::vector<FusedOp> fused;  /* DNA: the same list for the single-kernel traversal */
   unsigned int fused_hits, fused_misses;
   unsigned int fused_nslot;    /* tile-cache slots per warp the plan was made for */
+  size_t fused_scratch_bytes;  /* device scratch of the fused path: packed records (+ tip tables) */
+  size_t fused_table_offset;   /* 20-state walk: where the tip tables start inside that scratch */
   unsigned long long levels;
   unsigned long long algorithmic_bytes;
   /* bytes that MUST cross the HBM interface for this list on the path that runs it: level by
@@ -1194,9 +1196,15 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
   plan.fused_hits = plan.fused_misses = 0;
   /* 20 states: the tensor-core traversal (plg_traverse_aa.cu) - 1, 2 or 4 rate categories, tip
    * tables of at most 23 (four categories) or 24 codes, not in bit-exact mode */
-  const unsigned int aa_slots = (K == 20 && ctx->use_fused_aa && !ctx->aa_exact &&
-                                 (!ctx->pattern_tip || ctx->maxstates <= plg_fused_aa_max_codes(R)))
-                                    ? plg_fused_aa_slots(R, ctx->fused_slots) : 0;
+  const bool aa_walk = K == 20 && ctx->use_fused_aa == 2 && !ctx->aa_exact && !ctx->rate_scalers &&
+                       plg_walk_aa_supported(R, ctx->pattern_tip ? ctx->maxstates : 1u);
+  const unsigned int aa_slots =
+      aa_walk ? (ctx->fused_slots < PLG_WALK_AA_SLOTS ? ctx->fused_slots : PLG_WALK_AA_SLOTS)
+              : ((K == 20 && ctx->use_fused_aa == 1 && !ctx->aa_exact &&
+                  (!ctx->pattern_tip || ctx->maxstates <= plg_fused_aa_max_codes(R)))
+                     ? plg_fused_aa_slots(R, ctx->fused_slots) : 0);
+  plan.fused_scratch_bytes = 0;
+  plan.fused_table_offset = 0;
   if (ctx->use_fused && (K == 4 || aa_slots > 0) && plg_fast_path(ctx) && count >= 2)
   {
     /* Execution order.  A list without slot recycling is a forest: walk it depth-first, the
@@ -1391,6 +1399,28 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
       per_site += (f.kind == PLG_KIND_TT) ? 2 : (f.kind == PLG_KIND_TI ? 1 : 0);
     }
     plan.compulsory_bytes = per_site * ctx->d.sites;
+
+    if (aa_walk)
+    {
+      const unsigned int mat = 3200u * R;
+      unsigned long long rows = 0;
+      const unsigned long long nc = ctx->maxstates;
+      for (FusedOp & f : plan.fused)
+      {
+        f.lbytes = 128u + (f.kind == PLG_KIND_II ? 2u * mat : (f.kind == PLG_KIND_TI ? mat : 0u));
+        if (rows > 0xffffffffull)
+        {
+          plg_set_error("plg_update_partials: tip tables of this list exceed the 20-state walk's index range");
+          return PLG_E_UNSUPPORTED;
+        }
+        f.rbytes = (unsigned int)rows;
+        rows += f.kind == PLG_KIND_TT ? nc * nc : (f.kind == PLG_KIND_TI ? nc : 0ull);
+      }
+      plan.fused_table_offset = plan.fused.size() * plg_walk_aa_record_bytes(R);
+      plan.fused_scratch_bytes = plan.fused_table_offset + (size_t)rows * plg_walk_aa_row_bytes(R);
+    }
+    else
+      plan.fused_scratch_bytes = plan.fused.size() * (K == 4 ? plg_fused_record_bytes(R) : plg_fused_aa_record_bytes(R));
   }
   return PLG_OK;
 }
@@ -1537,8 +1567,11 @@ static int enqueue_plan(plg_context * ctx, const Plan & plan, const void * dev_p
     int frc = (ctx->d.states == 4)
                   ? plg_launch_fused(ctx, (const FusedOp *)dev_payload, dev_records, (unsigned int)plan.fused.size(),
                                      plan.fused_nslot)
-                  : plg_launch_fused_aa(ctx, (const FusedOp *)dev_payload, dev_records,
-                                        (unsigned int)plan.fused.size(), plan.fused_nslot);
+                  : (plan.fused_table_offset
+                         ? plg_launch_walk_aa(ctx, (const FusedOp *)dev_payload, dev_records,
+                                              dev_records + plan.fused_table_offset, (unsigned int)plan.fused.size())
+                         : plg_launch_fused_aa(ctx, (const FusedOp *)dev_payload, dev_records,
+                                               (unsigned int)plan.fused.size(), plan.fused_nslot));
     if (frc) return frc;
     cudaError_t ferr = cudaGetLastError();
     if (ferr != cudaSuccess)
@@ -1605,11 +1638,6 @@ static int enqueue_plan(plg_context * ctx, const Plan & plan, const void * dev_p
   }
   *kernels = launched;
   return PLG_OK;
-}
-
-static size_t fused_record_bytes(const plg_context * ctx)
-{
-  return ctx->d.states == 4 ? plg_fused_record_bytes(ctx->d.rate_cats) : plg_fused_aa_record_bytes(ctx->d.rate_cats);
 }
 
 static uint64_t fnv1a(const void * data, size_t bytes)
@@ -1754,7 +1782,7 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
 
   /* a cached graph owns its descriptors (and, fused path, its packed records: 4.7 KB per
    * operation); very long lists are not worth pinning that much memory per distinct list */
-  const bool graph_fits = plan.fused.size() * fused_record_bytes(ctx) <= ((size_t)64 << 20);
+  const bool graph_fits = plan.fused_scratch_bytes <= ((size_t)(ctx->d.states == 4 ? 64 : 512) << 20);
   /* capture on the SECOND sighting of a list: one-off lists (partial traversals during a tree
    * search) do not pay for cudaGraphInstantiate */
   bool capture = try_graph && graph_fits;
@@ -1782,7 +1810,7 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
   {
     /* descriptors get a stable home, then the whole list is captured once */
     void * dev = NULL;
-    const size_t rec_bytes = fused ? plan.fused.size() * fused_record_bytes(ctx) : 0;
+    const size_t rec_bytes = fused ? plan.fused_scratch_bytes : 0;
     const size_t jobs_bytes_al = (jobs_bytes + 255) / 256 * 256;
     PLG_CUDA(cudaMalloc(&dev, ops_bytes_al + jobs_bytes_al + rec_bytes + 256));
     PLG_CUDA(cudaMemcpyAsync(dev, ops_src, ops_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -1882,7 +1910,7 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
     unsigned char * records = NULL;
     if (fused)
     {
-      const size_t need = plan.fused.size() * fused_record_bytes(ctx);
+      const size_t need = plan.fused_scratch_bytes;
       if (need > ctx->fused_records_cap)
       {
         PLG_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -19,10 +19,24 @@ from test_parity_gpu import _caterpillar
 
 pytestmark = pytest.mark.gpu
 
+#: which whole-list kernel the module exercises: "1" = plg_traverse_aa.cu, "2" / "2s" = plg_walk_aa.cu
+#: with one / two warps per tile team
+IMPL = __import__("os").environ.get("PLL_TEST_FUSED_AA", "2")
+
+
+def _select(monkeypatch, fused=True):
+    monkeypatch.setenv("PLL_GPU_FUSED_AA", IMPL[0] if fused else "0")
+    monkeypatch.setenv("PLL_GPU_WALK_SPLIT", "2" if IMPL.endswith("s") else "1")
+
+
+def _fused_here(rate_scalers):
+    """The second design keeps per-rate scalers on the level-by-level kernels."""
+    return not (IMPL[0] == "2" and rate_scalers)
+
 
 def _run(gpu_lib, monkeypatch, w, attrs, fused, slots=3, variant="default"):
     monkeypatch.setenv("PLL_GPU_FUSED", "1" if fused else "0")
-    monkeypatch.setenv("PLL_GPU_FUSED_AA", "1" if fused else "0")
+    _select(monkeypatch, fused)
     monkeypatch.setenv("PLL_GPU_FUSED_SLOTS", str(slots))
     monkeypatch.setenv("PLL_GPU_AA_EXACT", "0")
     part, pidx = S.build_partition(gpu_lib, w, PLL_ATTRIB_ARCH_GPU | attrs, variant=variant)
@@ -58,7 +72,7 @@ def test_fused_equals_level_by_level(gpu_lib, monkeypatch, tips, sites, cats, ra
     assert ref[3] > 3, "the level-by-level path launches one kernel per level and kind"
     for slots in (1, 2, 3):
         got = _run(gpu_lib, monkeypatch, w, attrs, fused=True, slots=slots)
-        assert got[3] == 2, "pack + traverse"
+        assert (got[3] == 2) == _fused_here(rate_scalers), "pack + traverse"
         _same(got, ref, f"{slots} cache slots")
 
 
@@ -100,7 +114,7 @@ def test_fused_with_rescaling_and_recycled_slots(gpu_lib, monkeypatch, rate_scal
 @pytest.mark.parametrize("tips,sites", [(200, 5000), (30, 333)])
 def test_fused_against_the_reference(gpu_lib, ref_lib, monkeypatch, tips, sites):
     monkeypatch.setenv("PLL_GPU_FUSED", "1")
-    monkeypatch.setenv("PLL_GPU_FUSED_AA", "1")
+    _select(monkeypatch)
     monkeypatch.setenv("PLL_GPU_AA_EXACT", "0")
     w = S.make_workload(tips, sites, states=20, seed=tips)
     rates = ref_lib.gamma_rates(w.alpha, w.rate_cats)
@@ -131,7 +145,7 @@ def test_fused_against_the_reference(gpu_lib, ref_lib, monkeypatch, tips, sites)
 def test_repeated_calls_replay_a_graph(gpu_lib, monkeypatch):
     """The second sighting of a list captures a CUDA graph (pack + traverse); replays give the same bits."""
     monkeypatch.setenv("PLL_GPU_FUSED", "1")
-    monkeypatch.setenv("PLL_GPU_FUSED_AA", "1")
+    _select(monkeypatch)
     monkeypatch.setenv("PLL_GPU_AA_EXACT", "0")
     w = S.make_workload(50, 2000, states=20, seed=4)
     part, pidx = S.build_partition(gpu_lib, w, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP)
