@@ -1416,6 +1416,10 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
         f.rbytes = (unsigned int)rows;
         rows += f.kind == PLG_KIND_TT ? nc * nc : (f.kind == PLG_KIND_TI ? nc : 0ull);
       }
+      /* the ring of the walk is refilled by whichever warp frees a stage last: the size of the
+       * record two operations ahead travels in this operation's descriptor (upper half) */
+      const size_t nf = plan.fused.size();
+      for (size_t x = 0; x < nf; ++x) plan.fused[x].lbytes |= (plan.fused[(x + 2) % nf].lbytes & 0xffffu) << 16;
       plan.fused_table_offset = plan.fused.size() * plg_walk_aa_record_bytes(R);
       plan.fused_scratch_bytes = plan.fused_table_offset + (size_t)rows * plg_walk_aa_row_bytes(R);
     }

@@ -130,9 +130,15 @@ __global__ void k_walk_pack_aa(const FusedOp * __restrict__ ops, unsigned char *
 /* ------------------------------------------------------------------------------------ */
 /* device helpers                                                                        */
 /* ------------------------------------------------------------------------------------ */
-__device__ __forceinline__ void aw_named_barrier(unsigned int id, unsigned int threads)
+/* One elected lane of a converged warp (the same lane every time: its bulk async-groups are the
+ * ones the warp waits on).  The TMA instructions take warp-uniform operands: issued under this
+ * predicate with uniform addresses they are single instructions, issued per lane with lane-
+ * dependent addresses the compiler serialises them into a 30-instruction loop per copy. */
+__device__ __forceinline__ bool aw_elect()
 {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+  unsigned int p;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+  return p != 0;
 }
 
 /* B fragments of one matrix from its packed block (smem) */
@@ -188,27 +194,25 @@ struct AwLane
 {
   unsigned int lane, g, q, hi_state, hi_off;
   unsigned int roff[2]; /* byte offset of this lane's quarter in its pattern row of group 0 / 1 */
-  unsigned int k0;      /* first rate category of this warp */
 };
 
-/* The arithmetic of one tip-inner / inner-inner operation on this warp's rate categories of a
- * tile: products into the result slot, `below` = every entry this lane produced is under the
- * rescaling threshold.  FAST: both inner children sit in slots and the tip rows were gathered
- * into the result slot (the common case, no run-time source decisions). */
-template <int R, int NRW, int KIND, bool FAST>
+/* The arithmetic of one tip-inner / inner-inner operation on a tile: products into the result
+ * slot, `below` = every entry this lane produced is under the rescaling threshold.  FAST: both
+ * inner children sit in slots and the tip rows were gathered into the result slot (the common
+ * case, no run-time source decisions).  The result slot may only be touched once `ready` has
+ * completed (the DMA warp has drained the store that last read it / landed the tip rows). */
+template <int R, int KIND, bool FAST>
 __device__ __forceinline__ void aw_compute(const unsigned char * stage, const unsigned char * slots, unsigned char * oslot,
                                            int lphys, int rphys, const double * left, const double * right,
                                            const unsigned char * tip_rows, const unsigned int (&tcode)[2], bool gather,
-                                           uint64_t * mybar, unsigned int & bar_phase, const AwLane & L,
+                                           uint64_t * ready, unsigned int ready_parity, bool & ready_seen, const AwLane & L,
                                            unsigned int first_site, const bool (&ok)[2], bool (&below)[2])
 {
   using G = AwGeom<R>;
   const unsigned int q = L.q;
-  bool tip_waited = false;
 #pragma unroll
-  for (int kk = 0; kk < NRW; ++kk)
+  for (int k = 0; k < R; ++k)
   {
-    const unsigned int k = L.k0 + kk;
     double BR[PLG_DMMA_FRAGS], BL[PLG_DMMA_FRAGS];
     aw_load_bfrag(stage + 128 + k * G::MAT_BYTES, L.lane, BR);
     if (KIND == PLG_KIND_II) aw_load_bfrag(stage + 128 + (R + k) * G::MAT_BYTES, L.lane, BL);
@@ -226,14 +230,14 @@ __device__ __forceinline__ void aw_compute(const unsigned char * stage, const un
         else aw_afrag_hbm(left + (size_t)(first_site + sg * 8 + L.g) * (R * 20) + k * 20, q, L.hi_state, ok[sg], all_[sg]);
       }
     }
+    double y[2][3][2], x[2][3][2];
 #pragma unroll
     for (int sg = 0; sg < 2; ++sg)
     {
       const double (&ar)[5] = arr[sg];
       const double (&al)[5] = all_[sg];
-      double y[3][2], x[3][2];
 #pragma unroll
-      for (int nt = 0; nt < 3; ++nt) y[nt][0] = y[nt][1] = x[nt][0] = x[nt][1] = 0.0;
+      for (int nt = 0; nt < 3; ++nt) y[sg][nt][0] = y[sg][nt][1] = x[sg][nt][0] = x[sg][nt][1] = 0.0;
       if (KIND == PLG_KIND_II)
       {
 #pragma unroll
@@ -241,8 +245,8 @@ __device__ __forceinline__ void aw_compute(const unsigned char * stage, const un
 #pragma unroll
           for (int nt = 0; nt < 3; ++nt)
           {
-            dmma884_free(y[nt][0], y[nt][1], ar[ks], BR[nt * 5 + ks]);
-            dmma884_free(x[nt][0], x[nt][1], al[ks], BL[nt * 5 + ks]);
+            dmma884_free(y[sg][nt][0], y[sg][nt][1], ar[ks], BR[nt * 5 + ks]);
+            dmma884_free(x[sg][nt][0], x[sg][nt][1], al[ks], BL[nt * 5 + ks]);
           }
       }
       else
@@ -250,22 +254,28 @@ __device__ __forceinline__ void aw_compute(const unsigned char * stage, const un
 #pragma unroll
         for (int ks = 0; ks < 5; ++ks)
 #pragma unroll
-          for (int nt = 0; nt < 3; ++nt) dmma884_free(y[nt][0], y[nt][1], ar[ks], BR[nt * 5 + ks]);
+          for (int nt = 0; nt < 3; ++nt) dmma884_free(y[sg][nt][0], y[sg][nt][1], ar[ks], BR[nt * 5 + ks]);
+      }
+    }
+    if (!ready_seen)
+    {
+      plg_async::mbar_wait(ready, ready_parity);
+      ready_seen = true;
+    }
+#pragma unroll
+    for (int sg = 0; sg < 2; ++sg)
+    {
+      if (KIND == PLG_KIND_TI)
+      {
         if (FAST || gather)
         {
-          if (!tip_waited)
-          {
-            plg_async::mbar_wait(mybar, bar_phase);
-            bar_phase ^= 1u;
-            tip_waited = true;
-          }
 #pragma unroll
           for (int nt = 0; nt < 3; ++nt)
             if (nt < 2 || q < 2u)
             {
               const double2 t = *reinterpret_cast<const double2 *>(oslot + L.roff[sg] + k * 160u + nt * 64);
-              x[nt][0] = t.x;
-              x[nt][1] = t.y;
+              x[sg][nt][0] = t.x;
+              x[sg][nt][1] = t.y;
             }
         }
         else
@@ -276,8 +286,8 @@ __device__ __forceinline__ void aw_compute(const unsigned char * stage, const un
             {
               const double2 t = __ldg(reinterpret_cast<const double2 *>(tip_rows + (size_t)tcode[sg] * G::ROWB + k * 160u +
                                                                          nt * 64 + 16u * q));
-              x[nt][0] = t.x;
-              x[nt][1] = t.y;
+              x[sg][nt][0] = t.x;
+              x[sg][nt][1] = t.y;
             }
         }
       }
@@ -285,8 +295,8 @@ __device__ __forceinline__ void aw_compute(const unsigned char * stage, const un
       for (int nt = 0; nt < 3; ++nt)
         if (nt < 2 || q < 2u)
         {
-          const double p0 = __dmul_rn(x[nt][0], y[nt][0]);
-          const double p1 = __dmul_rn(x[nt][1], y[nt][1]);
+          const double p0 = __dmul_rn(x[sg][nt][0], y[sg][nt][0]);
+          const double p1 = __dmul_rn(x[sg][nt][1], y[sg][nt][1]);
           below[sg] = below[sg] && (p0 < PLG_SCALE_THRESHOLD) && (p1 < PLG_SCALE_THRESHOLD);
           *reinterpret_cast<double2 *>(oslot + L.roff[sg] + k * 160u + nt * 64) = make_double2(p0, p1);
         }
@@ -294,20 +304,81 @@ __device__ __forceinline__ void aw_compute(const unsigned char * stage, const un
   }
 }
 
+/* where the tiles of an operation live.  Both warps of a team run this on the same descriptors
+ * and therefore agree: a result the planner keeps (pslot >= 0) goes to that cache slot, any other
+ * to one of the two staging slots, which alternate each time one is used - so the staging slot
+ * of a tip-tip operation is normally idle while the operation before it runs (gather look-ahead) */
+struct AwSlots
+{
+  int prev_out;
+  unsigned int toggle;
+  int out, lphys, rphys;
+  __device__ __forceinline__ void place(int lslot, int rslot, int pslot)
+  {
+    out = pslot >= 0 ? pslot : 2 + (int)toggle;
+    lphys = lslot == -2 ? prev_out : lslot;
+    rphys = rslot == -2 ? prev_out : rslot;
+  }
+  __device__ __forceinline__ void advance(int pslot)
+  {
+    if (pslot < 0) toggle ^= 1u;
+    prev_out = out;
+  }
+};
+
+__device__ __forceinline__ unsigned int aw_atom_inc(unsigned int * p, unsigned int wrap)
+{
+  unsigned int old;
+  asm volatile("atom.relaxed.cta.shared::cta.inc.u32 %0, [%1], %2;"
+               : "=r"(old)
+               : "r"(plg_async::smem_addr(p)), "r"(wrap)
+               : "memory");
+  return old;
+}
+
+/* TMA bulk copies with an L2 eviction-priority hint: tables and records are re-read by every
+ * tile and should survive the 64 GB write stream (evict_last), result rows are never read again
+ * by this launch (evict_first) */
+__device__ __forceinline__ unsigned long long aw_policy_keep()
+{
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long aw_policy_stream()
+{
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void aw_g2s(void * dst_smem, const void * src_gmem, uint32_t bytes, uint64_t * bar,
+                                       unsigned long long policy)
+{
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(plg_async::smem_addr(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(plg_async::smem_addr(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void aw_s2g(void * dst_gmem, const void * src_smem, uint32_t bytes, unsigned long long policy)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+               "r"(plg_async::smem_addr(src_smem)), "r"(bytes), "l"(policy)
+               : "memory");
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* the walk                                                                              */
 /* ------------------------------------------------------------------------------------ */
-template <int R, int SPLIT>
-__global__ void __launch_bounds__((AW_TEAMS * SPLIT + 1) * 32, 1)
+#define AW_CONSUMERS (2 * AW_TEAMS)
+
+template <int R>
+__global__ void __launch_bounds__(2 * AW_TEAMS * 32, 1)
 k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ records,
           const unsigned char * __restrict__ tables, unsigned int n_ops, unsigned int sites, unsigned int ncodes)
 {
   using namespace plg_async;
   using G = AwGeom<R>;
-  constexpr int NMATH = AW_TEAMS * SPLIT;
-  constexpr int NRW = R / SPLIT;          /* rate categories per warp */
-  constexpr int PARTB = NRW * 160;        /* bytes of a row this warp owns */
-  static_assert(R % SPLIT == 0, "rates split evenly");
 
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char * stage_base = smem;                                             /* AW_STAGES records */
@@ -315,8 +386,9 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
   unsigned char * code_base = slot_base + AW_TEAMS * AW_SLOTS * G::SLOT_BYTES;   /* [team][buf][side][16] */
   uint64_t * full = reinterpret_cast<uint64_t *>(code_base + AW_TEAMS * AW_CODEBUFS * 32);
   uint64_t * empty = full + AW_STAGES;
-  uint64_t * tilebar = empty + AW_STAGES;                                         /* [NMATH] */
-  unsigned int * votes = reinterpret_cast<unsigned int *>(tilebar + NMATH);       /* [team][2 bufs][half][2] */
+  uint64_t * ready_all = empty + AW_STAGES;                                       /* [team][2] */
+  uint64_t * done_all = ready_all + AW_TEAMS * 2;                                 /* [team][2] */
+  unsigned int * ticket = reinterpret_cast<unsigned int *>(done_all + AW_TEAMS * 2); /* [AW_STAGES] */
 
   const unsigned int lane = threadIdx.x & 31u;
   const unsigned int warp = threadIdx.x >> 5;
@@ -324,191 +396,164 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
   const unsigned int tiles_per_pass = gridDim.x * AW_TEAMS;
   const unsigned int passes = (ntiles + tiles_per_pass - 1) / tiles_per_pass;
   const unsigned int total_its = passes * n_ops;
+  const unsigned long long keep = aw_policy_keep();
 
   if (threadIdx.x == 0)
   {
     for (int s = 0; s < AW_STAGES; ++s)
     {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], NMATH);
+      mbar_init(&empty[s], AW_CONSUMERS);
+      ticket[s] = 0;
     }
-    for (int w = 0; w < NMATH; ++w) mbar_init(&tilebar[w], 1);
+    for (int w = 0; w < AW_TEAMS * 2; ++w)
+    {
+      mbar_init(&ready_all[w], 1);
+      mbar_init(&done_all[w], 1);
+    }
     fence_barrier_init();
+    for (unsigned int it0 = 0; it0 < (unsigned int)AW_STAGES && it0 < total_its; ++it0)
+    {
+      const unsigned int i0 = it0 % n_ops;
+      const unsigned int bytes = ops[i0].lbytes & 0xffffu;
+      mbar_arrive_expect_tx(&full[it0], bytes);
+      aw_g2s(stage_base + it0 * G::REC_BYTES, records + (size_t)i0 * G::REC_BYTES, bytes, &full[it0], keep);
+    }
   }
   __syncthreads();
 
-  if (warp == NMATH)
-  {
-    /* producer: operation records through the ring */
-    if (lane == 0)
-    {
-      unsigned int i = 0;
-      for (unsigned int it = 0; it < total_its; ++it)
-      {
-        const unsigned int s = it % AW_STAGES;
-        if (it >= AW_STAGES) mbar_wait(&empty[s], ((it / AW_STAGES) - 1u) & 1u);
-        const unsigned int bytes = __ldg(&ops[i].lbytes);
-        mbar_arrive_expect_tx(&full[s], bytes);
-        bulk_g2s(stage_base + s * G::REC_BYTES, records + (size_t)i * G::REC_BYTES, bytes, &full[s]);
-        if (++i == n_ops) i = 0;
-      }
-    }
-    return;
-  }
-
-  const unsigned int team = warp % AW_TEAMS, half = warp / AW_TEAMS;
-  AwLane L;
-  L.lane = lane;
-  L.g = lane >> 2;
-  L.q = lane & 3u;
-  L.hi_state = dmma_child_state(4, L.q);
-  L.hi_off = 8u * L.hi_state - 16u * L.q; /* from a row's rate block + 16 q to its ks = 4 state */
-  L.roff[0] = (unsigned int)G::row_off((int)L.g) + 16u * L.q;
-  L.roff[1] = (unsigned int)G::row_off((int)L.g + 8) + 16u * L.q;
-  L.k0 = half * NRW;
-  const unsigned int g = L.g, q = L.q, k0 = L.k0;
+  const unsigned int team = warp % AW_TEAMS;
+  const bool is_math = warp < AW_TEAMS;
   unsigned char * const slots = slot_base + team * AW_SLOTS * G::SLOT_BYTES;
   unsigned char * const codes = code_base + team * AW_CODEBUFS * 32;
-  uint64_t * const mybar = &tilebar[warp];
-  unsigned int bar_phase = 0;
-  /* the row this lane copies (lanes 0..15) */
-  const unsigned int copy_off = (unsigned int)G::row_off((int)(lane & 15u)) + k0 * 160u;
+  uint64_t * const ready = ready_all + team * 2;
+  uint64_t * const done = done_all + team * 2;
 
-  /* tip characters two operations ahead: cp.async of 16 bytes per tip row */
-  auto fetch_codes = [&](unsigned int it_t)
+  /* hands ring stage s back; the last of the consumers to do so refills it with the record two
+   * operations ahead, whose size travels in this operation's descriptor */
+  auto release = [&](unsigned int s, unsigned int it, unsigned int i, unsigned int ahead_bytes)
   {
-    if (it_t < total_its)
+    __syncwarp();
+    if (lane == 0)
     {
-      const unsigned int i_t = it_t % n_ops;
-      const unsigned int tile_t = ((it_t / n_ops) * gridDim.x + blockIdx.x) * AW_TEAMS + team;
-      const int kind_t = __ldg(&ops[i_t].kind);
-      if (kind_t != PLG_KIND_II && tile_t < ntiles && half == 0 && lane < (kind_t == PLG_KIND_TT ? 2u : 1u))
+      mbar_arrive(&empty[s]);
+      if (aw_atom_inc(&ticket[s], AW_CONSUMERS - 1) == AW_CONSUMERS - 1 && it + AW_STAGES < total_its)
       {
-        const unsigned long long tip = __ldg(reinterpret_cast<const unsigned long long *>(lane ? &ops[i_t].op.rtip : &ops[i_t].op.ltip));
-        const unsigned char * src = reinterpret_cast<const unsigned char *>(tip) + (size_t)tile_t * AW_TILE;
-        unsigned char * dst = codes + (it_t % AW_CODEBUFS) * 32 + lane * 16;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+        mbar_wait(&empty[s], (it / AW_STAGES) & 1u);
+        unsigned int i2 = i + AW_STAGES;
+        while (i2 >= n_ops) i2 -= n_ops;
+        mbar_arrive_expect_tx(&full[s], ahead_bytes);
+        aw_g2s(stage_base + s * G::REC_BYTES, records + (size_t)i2 * G::REC_BYTES, ahead_bytes, &full[s], keep);
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  if (SPLIT == 1 || half == 0)
-  {
-    fetch_codes(0);
-    fetch_codes(1);
-  }
 
-  int prev_out = -1;
+  AwSlots sl;
+  sl.prev_out = -1;
+  sl.toggle = 0;
   unsigned int it = 0;
-  for (unsigned int pass = 0; pass < passes; ++pass)
+
+  if (is_math)
   {
-    const unsigned int tile = (pass * gridDim.x + blockIdx.x) * AW_TEAMS + team;
-    const bool have = tile < ntiles;
-    const unsigned int first_site = tile * AW_TILE;
-    const unsigned int nrows = have ? min((unsigned int)AW_TILE, sites - first_site) : 0u;
-    const bool ok[2] = {first_site + g < sites && have, first_site + 8 + g < sites && have};
-    const size_t my_row_doubles = (size_t)(first_site + (lane & 15u)) * (R * 20) + k0 * 20; /* the row this lane copies */
+    /* ================= math warp: fragments, DMMA, products, vote ================= */
+    AwLane L;
+    L.lane = lane;
+    L.g = lane >> 2;
+    L.q = lane & 3u;
+    L.hi_state = dmma_child_state(4, L.q);
+    L.hi_off = 8u * L.hi_state - 16u * L.q; /* from a row's rate block + 16 q to its ks = 4 state */
+    L.roff[0] = (unsigned int)G::row_off((int)L.g) + 16u * L.q;
+    L.roff[1] = (unsigned int)G::row_off((int)L.g + 8) + 16u * L.q;
+    const unsigned int g = L.g, q = L.q;
 
-    for (unsigned int i = 0; i < n_ops; ++i, ++it)
+    for (unsigned int pass = 0; pass < passes; ++pass)
     {
-      const unsigned int s = it % AW_STAGES;
-      mbar_wait(&full[s], (it / AW_STAGES) & 1u);
-      const unsigned char * stage = stage_base + s * G::REC_BYTES;
-      const FusedOp & d = *reinterpret_cast<const FusedOp *>(stage);
-      const int kind = d.kind;
+      const unsigned int tile = (pass * gridDim.x + blockIdx.x) * AW_TEAMS + team;
+      const bool have = tile < ntiles;
+      const unsigned int first_site = tile * AW_TILE;
+      const unsigned int nrows = have ? min((unsigned int)AW_TILE, sites - first_site) : 0u;
+      const bool ok[2] = {first_site + g < sites && have, first_site + 8 + g < sites && have};
 
-      /* tip characters: those of this operation have landed, request those of it + 2 */
-      if (SPLIT == 1 || half == 0)
+      for (unsigned int i = 0; i < n_ops; ++i, ++it)
       {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        fetch_codes(it + 2);
-      }
-      if (SPLIT == 2) aw_named_barrier(1 + team, 64); /* the partner reads the strip too */
-      else __syncwarp();
-
-      if (!have)
-      {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-        continue;
-      }
-
-      const int mode = d.scale_mode;
-      const int pad = d.pad;
-      const int pslot = d.pslot;
-      const int out = pslot >= 0 ? pslot : 2 + (int)(it & 1u);
-      const int lphys = d.lslot == -2 ? prev_out : d.lslot;
-      const int rphys = d.rslot == -2 ? prev_out : d.rslot;
-      double * const parent = d.op.parent;
-      unsigned int * const pscale = d.op.pscale;
-      const double * const left = d.op.left;
-      const double * const right = d.op.right;
-      const unsigned int * const lscale = d.op.lscale;
-      const unsigned int * const rscale = d.op.rscale;
-      unsigned char * const oslot = slots + out * G::SLOT_BYTES;
-      const unsigned char * const cbuf = codes + (it % AW_CODEBUFS) * 32;
-
-      /* the slot about to be written is no longer the source of a store in flight: stores are
-       * issued once per operation, so all but the latest have been read out - unless the latest
-       * came from this very slot */
-      if (out == prev_out) bulk_wait_read<0>();
-      else bulk_wait_read<1>();
-      const bool miss = (kind == PLG_KIND_II && lphys < 0) || (kind != PLG_KIND_TT && rphys < 0);
-      if (miss)
-      {
-        /* a child is read back from HBM: this warp's own stores must have landed */
-        bulk_wait<0>();
-        asm volatile("fence.proxy.async;" ::: "memory");
-      }
-      __syncwarp();
-
-      /* ---- tip rows: TMA gather into the result slot ---- */
-      /* a tip-inner operation whose result replaces its child in place reads the rows from L2 */
-      const bool gather = kind == PLG_KIND_TT || (kind == PLG_KIND_TI && out != rphys);
-      const unsigned char * tip_rows = tables + (size_t)d.rbytes * G::ROWB;
-      if (kind != PLG_KIND_II)
-      {
-        if (gather)
+        const unsigned int s = it % AW_STAGES;
+        mbar_wait(&full[s], (it / AW_STAGES) & 1u);
+        const unsigned char * stage = stage_base + s * G::REC_BYTES;
+        const FusedOp & d = *reinterpret_cast<const FusedOp *>(stage);
+        const unsigned int ahead = d.lbytes >> 16;
+        if (!have)
         {
-          if (lane == 0) mbar_arrive_expect_tx(mybar, nrows * PARTB);
-          __syncwarp();
-          if (lane < nrows)
-          {
-            unsigned int row = min((unsigned int)cbuf[lane], ncodes - 1u);
-            if (kind == PLG_KIND_TT) row = row * ncodes + min((unsigned int)cbuf[16 + lane], ncodes - 1u);
-            bulk_g2s(oslot + copy_off, tip_rows + (size_t)row * G::ROWB + k0 * 160u, PARTB, mybar);
-          }
+          release(s, it, i, ahead);
+          continue;
         }
-      }
+        const int kind = d.kind;
+        const int mode = d.scale_mode;
+        const int pad = d.pad;
+        sl.place(d.lslot, d.rslot, d.pslot);
+        const int out = sl.out, lphys = sl.lphys, rphys = sl.rphys;
+        sl.advance(d.pslot);
+        uint64_t * const rb = &ready[it & 1u];
+        const unsigned int rpar = (it >> 1) & 1u;
+        bool ready_seen = false;
 
-      unsigned int vote[2] = {0u, 0u};
-      if (kind != PLG_KIND_TT)
-      {
+        if (kind == PLG_KIND_TT)
+        {
+          /* nothing to compute: the DMA warp gathers the rows of the pair table, zeroes the
+           * scaler counts and stores the tile; the next reader of the slot must see it landed */
+          release(s, it, i, ahead);
+          mbar_wait(rb, rpar);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&done[it & 1u]);
+          continue;
+        }
+
+        unsigned int * const pscale = d.op.pscale;
+        const double * const left = d.op.left;
+        const double * const right = d.op.right;
+        const unsigned int * const lscale = d.op.lscale;
+        const unsigned int * const rscale = d.op.rscale;
+        unsigned char * const oslot = slots + out * G::SLOT_BYTES;
+        const unsigned char * tip_rows = tables + (size_t)d.rbytes * G::ROWB;
+        const bool gather = kind == PLG_KIND_TI && out != rphys;
+        const bool miss = (kind == PLG_KIND_II && lphys < 0) || rphys < 0;
+
         bool below[2] = {true, true};
         unsigned int tcode[2] = {0u, 0u};
-        if (kind == PLG_KIND_TI && !gather)
+        if (miss || (kind == PLG_KIND_TI && !gather))
         {
-          tcode[0] = min((unsigned int)cbuf[L.g], ncodes - 1u);
-          tcode[1] = min((unsigned int)cbuf[8 + L.g], ncodes - 1u);
+          /* children read back from HBM need this team's stores landed, in-place tip rows need
+           * the tip characters: both are behind the DMA warp's `ready` */
+          mbar_wait(rb, rpar);
+          ready_seen = true;
+          if (kind == PLG_KIND_TI && !gather)
+          {
+            const unsigned char * cbuf = codes + (it % AW_CODEBUFS) * 32;
+            tcode[0] = min((unsigned int)cbuf[g], ncodes - 1u);
+            tcode[1] = min((unsigned int)cbuf[8 + g], ncodes - 1u);
+          }
         }
         if (kind == PLG_KIND_II)
         {
           if (lphys >= 0 && rphys >= 0)
-            aw_compute<R, NRW, PLG_KIND_II, true>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, gather,
-                                                  mybar, bar_phase, L, first_site, ok, below);
+            aw_compute<R, PLG_KIND_II, true>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, gather, rb, rpar,
+                                             ready_seen, L, first_site, ok, below);
           else
-            aw_compute<R, NRW, PLG_KIND_II, false>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, gather,
-                                                   mybar, bar_phase, L, first_site, ok, below);
+            aw_compute<R, PLG_KIND_II, false>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, gather, rb,
+                                              rpar, ready_seen, L, first_site, ok, below);
         }
         else
         {
           if (rphys >= 0 && gather)
-            aw_compute<R, NRW, PLG_KIND_TI, true>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, gather,
-                                                  mybar, bar_phase, L, first_site, ok, below);
+            aw_compute<R, PLG_KIND_TI, true>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, gather, rb, rpar,
+                                             ready_seen, L, first_site, ok, below);
           else
-            aw_compute<R, NRW, PLG_KIND_TI, false>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, gather,
-                                                   mybar, bar_phase, L, first_site, ok, below);
+            aw_compute<R, PLG_KIND_TI, false>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, gather, rb,
+                                              rpar, ready_seen, L, first_site, ok, below);
         }
+        /* the ring stage has been read (matrices are in registers, the descriptor in locals) */
+        release(s, it, i, ahead);
+
+        unsigned int vote[2] = {0u, 0u};
         if (mode == 1)
         {
 #pragma unroll
@@ -517,86 +562,262 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
             unsigned int b = __ballot_sync(0xffffffffu, below[sg]);
             b &= b >> 1;
             b &= b >> 2;
-            vote[sg] = b & 0x11111111u; /* bit 4g: every entry of pattern g (this warp's rates) is below */
+            vote[sg] = b & 0x11111111u; /* bit 4g: every entry of pattern g is below the threshold */
           }
-        }
-      }
-
-      /* the ring stage has been read (matrices are in registers, the descriptor in locals) */
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
-
-      if (kind == PLG_KIND_TT)
-      {
-        mbar_wait(mybar, bar_phase);
-        bar_phase ^= 1u;
-      }
-      else if (mode == 1)
-      {
-        if (SPLIT == 2)
-        {
-          /* per-site scaling: the two halves of the rate categories must agree */
-          unsigned int * v = votes + (team * 2 + (it & 1u)) * 4;
-          if (lane < 2) v[half * 2 + lane] = lane ? vote[1] : vote[0];
-          aw_named_barrier(1 + team, 64);
-          vote[0] &= v[(half ^ 1u) * 2 + 0];
-          vote[1] &= v[(half ^ 1u) * 2 + 1];
-        }
-        if ((vote[0] | vote[1]) != 0u)
-        {
-          /* rare: some pattern of the tile is rescaled - in its slot, before the store leaves */
-#pragma unroll
-          for (int sg = 0; sg < 2; ++sg)
-            if ((vote[sg] >> (4u * g)) & 1u)
-#pragma unroll 1
-              for (int kk = 0; kk < NRW; ++kk)
-#pragma unroll
-                for (int nt = 0; nt < 3; ++nt)
-                  if (nt < 2 || q < 2u)
-                  {
-                    double2 * ptr = reinterpret_cast<double2 *>(oslot + L.roff[sg] + (k0 + kk) * 160u + nt * 64);
-                    double2 t = *ptr;
-                    t.x = __dmul_rn(t.x, PLG_SCALE_FACTOR);
-                    t.y = __dmul_rn(t.y, PLG_SCALE_FACTOR);
-                    *ptr = t;
-                  }
-        }
-      }
-
-      /* ---- scaler counts of the tile (kept next to it in the slot) ---- */
-      if (mode == 1 && half == 0 && q == 0u)
-      {
-        unsigned int * ostrip = reinterpret_cast<unsigned int *>(oslot + G::ROWS_BYTES);
-#pragma unroll
-        for (int sg = 0; sg < 2; ++sg)
-        {
-          unsigned int sv = 0;
-          if (kind != PLG_KIND_TT)
+          if ((vote[0] | vote[1]) != 0u)
           {
-            if (kind == PLG_KIND_II && lscale)
-              sv += lphys >= 0 ? reinterpret_cast<const unsigned int *>(slots + lphys * G::SLOT_BYTES + G::ROWS_BYTES)[sg * 8 + g]
-                               : (ok[sg] ? ld_coherent_u32(lscale + first_site + sg * 8 + g) : 0u);
-            if (rscale)
-              sv += rphys >= 0 ? reinterpret_cast<const unsigned int *>(slots + rphys * G::SLOT_BYTES + G::ROWS_BYTES)[sg * 8 + g]
-                               : (ok[sg] ? ld_coherent_u32(rscale + first_site + sg * 8 + g) : 0u);
-            sv += (vote[sg] >> (4u * g)) & 1u;
+            /* rare: some pattern of the tile is rescaled - in its slot, before the store leaves */
+#pragma unroll
+            for (int sg = 0; sg < 2; ++sg)
+              if ((vote[sg] >> (4u * g)) & 1u)
+#pragma unroll 1
+                for (int k = 0; k < R; ++k)
+#pragma unroll
+                  for (int nt = 0; nt < 3; ++nt)
+                    if (nt < 2 || q < 2u)
+                    {
+                      double2 * ptr = reinterpret_cast<double2 *>(oslot + L.roff[sg] + k * 160u + nt * 64);
+                      double2 t = *ptr;
+                      t.x = __dmul_rn(t.x, PLG_SCALE_FACTOR);
+                      t.y = __dmul_rn(t.y, PLG_SCALE_FACTOR);
+                      *ptr = t;
+                    }
           }
-          ostrip[sg * 8 + g] = sv;
-          if ((pad & 1) && nrows < AW_TILE && ok[sg]) pscale[first_site + sg * 8 + g] = sv; /* ragged last tile */
+          /* scaler counts of the tile, kept next to it in the slot */
+          if (q == 0u)
+          {
+            unsigned int * ostrip = reinterpret_cast<unsigned int *>(oslot + G::ROWS_BYTES);
+#pragma unroll
+            for (int sg = 0; sg < 2; ++sg)
+            {
+              unsigned int sv = (vote[sg] >> (4u * g)) & 1u;
+              if (kind == PLG_KIND_II && lscale)
+                sv += lphys >= 0 ? reinterpret_cast<const unsigned int *>(slots + lphys * G::SLOT_BYTES + G::ROWS_BYTES)[sg * 8 + g]
+                                 : (ok[sg] ? ld_coherent_u32(lscale + first_site + sg * 8 + g) : 0u);
+              if (rscale)
+                sv += rphys >= 0 ? reinterpret_cast<const unsigned int *>(slots + rphys * G::SLOT_BYTES + G::ROWS_BYTES)[sg * 8 + g]
+                                 : (ok[sg] ? ld_coherent_u32(rscale + first_site + sg * 8 + g) : 0u);
+              ostrip[sg * 8 + g] = sv;
+              if ((pad & 1) && nrows < AW_TILE && ok[sg]) pscale[first_site + sg * 8 + g] = sv; /* ragged last tile */
+            }
+          }
         }
-      }
-
-      /* ---- write through: one TMA bulk store per pattern row ---- */
-      if (pad & 1)
-      {
+        /* the tile is complete: over to the DMA warp (its TMA reads come after this fence) */
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane < nrows) bulk_s2g(parent + my_row_doubles, oslot + copy_off, PARTB);
-        else if (lane == 16u && half == 0 && mode == 1 && nrows == AW_TILE)
-          bulk_s2g(pscale + first_site, oslot + G::ROWS_BYTES, 64);
+        if (lane == 0) mbar_arrive(&done[it & 1u]);
       }
+    }
+    return;
+  }
+
+  /* ================= DMA warp: tip characters, gathers, stores ================= */
+  const unsigned long long stream = aw_policy_stream();
+  int last_store_slot = -1; /* source slot of the most recently committed store group */
+
+  /* tip characters three operations ahead (cp.async of 16 bytes per tip row); what that needs of
+   * the descriptor - kind and tip pointers - is loaded one operation earlier still: `pend`
+   * describes operation it + 3 when iteration it starts */
+  struct Pend { int kind; unsigned long long ltip, rtip; unsigned int tile; bool valid; } pend;
+  auto load_pend = [&](unsigned int i_t, unsigned int pass_t)
+  {
+    while (i_t >= n_ops) { i_t -= n_ops; ++pass_t; }
+    pend.valid = pass_t < passes;
+    pend.tile = (pass_t * gridDim.x + blockIdx.x) * AW_TEAMS + team;
+    if (pend.valid)
+    {
+      pend.kind = __ldg(&ops[i_t].kind);
+      pend.ltip = __ldg(reinterpret_cast<const unsigned long long *>(&ops[i_t].op.ltip));
+      pend.rtip = __ldg(reinterpret_cast<const unsigned long long *>(&ops[i_t].op.rtip));
+    }
+  };
+  auto issue_codes = [&](unsigned int buf)
+  {
+    if (pend.valid && pend.kind != PLG_KIND_II && pend.tile < ntiles && lane < (pend.kind == PLG_KIND_TT ? 2u : 1u))
+    {
+      const unsigned char * src = reinterpret_cast<const unsigned char *>(lane ? pend.rtip : pend.ltip) + (size_t)pend.tile * AW_TILE;
+      unsigned char * dst = codes + buf * 32 + lane * 16;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_pend(0, 0);
+  issue_codes(0);
+  load_pend(1, 0);
+  issue_codes(1);
+  load_pend(2, 0);
+  issue_codes(2);
+  load_pend(3, 0);
+
+  /* what must happen before the math warp may touch the result slot of operation `it_x`: the
+   * store that last read the slot has drained, tip rows are on their way (completion = bytes on
+   * `ready`), a tile-cache miss finds this team's stores landed */
+  auto prepare = [&](const FusedOp & dx, unsigned int it_x, int out_x, int rphys_x, bool miss_x, unsigned int nrows_x)
+  {
+    if (out_x == last_store_slot) bulk_wait_read<0>();
+    else bulk_wait_read<1>();
+    uint64_t * rb = &ready[it_x & 1u];
+    unsigned char * oslot = slots + out_x * G::SLOT_BYTES;
+    const int kind_x = dx.kind;
+    const bool gather = kind_x == PLG_KIND_TT || (kind_x == PLG_KIND_TI && out_x != rphys_x);
+    if (miss_x)
+    {
+      bulk_wait<0>();
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    if (gather)
+    {
+      const unsigned char * cbuf = codes + (it_x % AW_CODEBUFS) * 32;
+      /* lane r works out the table row of pattern r; the elected lane needs the 16 byte offsets
+       * as warp-uniform values: one shuffle each */
+      unsigned int my_off = 0;
+      if (lane < AW_TILE)
+      {
+        unsigned int row = min((unsigned int)cbuf[lane], ncodes - 1u);
+        if (kind_x == PLG_KIND_TT)
+        {
+          row = row * ncodes + min((unsigned int)cbuf[16 + lane], ncodes - 1u);
+          if (dx.scale_mode == 1) reinterpret_cast<unsigned int *>(oslot + G::ROWS_BYTES)[lane] = 0u;
+        }
+        my_off = row * (unsigned int)G::ROWB;
+      }
+      unsigned int offs[AW_TILE];
+#pragma unroll
+      for (int r = 0; r < AW_TILE; ++r) offs[r] = __shfl_sync(0xffffffffu, my_off, r);
+      const unsigned char * src0 = tables + (size_t)dx.rbytes * G::ROWB;
+      fence_proxy_async_smem(); /* the zeroed counts: read by the TMA store of this tile */
+      __syncwarp();
+      if (aw_elect())
+      {
+        mbar_arrive_expect_tx(rb, nrows_x * G::ROWB);
+        if (nrows_x == AW_TILE)
+        {
+#pragma unroll
+          for (int r = 0; r < AW_TILE; ++r) aw_g2s(oslot + G::row_off(r), src0 + offs[r], G::ROWB, rb, keep);
+        }
+        else
+        {
+#pragma unroll
+          for (int r = 0; r < AW_TILE; ++r)
+            if ((unsigned int)r < nrows_x) aw_g2s(oslot + G::row_off(r), src0 + offs[r], G::ROWB, rb, keep);
+        }
+      }
+    }
+    else
+    {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rb);
+    }
+    __syncwarp();
+  };
+
+  bool prepared = false; /* the current operation was prepared during the previous one */
+  for (unsigned int pass = 0; pass < passes; ++pass)
+  {
+    const unsigned int tile = (pass * gridDim.x + blockIdx.x) * AW_TEAMS + team;
+    const bool have = tile < ntiles;
+    const unsigned int first_site = tile * AW_TILE;
+    const unsigned int nrows = have ? min((unsigned int)AW_TILE, sites - first_site) : 0u;
+
+    for (unsigned int i = 0; i < n_ops; ++i, ++it)
+    {
+      const unsigned int s = it % AW_STAGES;
+      /* tip characters: request those of it + 3; those of it and it + 1 have landed */
+      issue_codes((it + 3u) % AW_CODEBUFS);
+      load_pend(i + 4, pass);
+      asm volatile("cp.async.wait_group 2;" ::: "memory");
+      __syncwarp();
+
+      mbar_wait(&full[s], (it / AW_STAGES) & 1u);
+      const FusedOp & d = *reinterpret_cast<const FusedOp *>(stage_base + s * G::REC_BYTES);
+      const unsigned int ahead = d.lbytes >> 16;
+      if (!have)
+      {
+        release(s, it, i, ahead);
+        continue;
+      }
+      const int kind = d.kind;
+      const int pad = d.pad;
+      const int mode = d.scale_mode;
+      double * const parent = d.op.parent;
+      unsigned int * const pscale = d.op.pscale;
+      const int pslot = d.pslot;
+      sl.place(d.lslot, d.rslot, pslot);
+      const int out = sl.out, lphys = sl.lphys, rphys = sl.rphys;
+      if (!prepared)
+      {
+        const bool miss = (kind == PLG_KIND_II && lphys < 0) || (kind != PLG_KIND_TT && rphys < 0);
+        prepare(d, it, out, rphys, miss, nrows);
+      }
+      prepared = false;
+      sl.advance(pslot);
+      /* everything this warp needs of the record is in registers: hand the stage back early, the
+       * refill then has a whole operation to arrive */
+      release(s, it, i, ahead);
+
+      /* The next operation of this tile.  While the math warp is still busy with this one, tip
+       * rows can already be gathered if nobody uses their slot; once it has finished, any slot
+       * but this operation's own result is free.  Either way the math warp finds its next
+       * operation ready before this one's stores are even issued. */
+      const bool next_here = i + 1 < n_ops;
+      const FusedOp & dn = *reinterpret_cast<const FusedOp *>(stage_base + (s ^ 1u) * G::REC_BYTES);
+      const unsigned int next_parity = ((it + 1u) / AW_STAGES) & 1u;
+      if (next_here && mbar_try_wait(&full[s ^ 1u], next_parity))
+      {
+        AwSlots sn = sl;
+        sn.place(dn.lslot, dn.rslot, dn.pslot);
+        const bool gather_n = dn.kind == PLG_KIND_TT || (dn.kind == PLG_KIND_TI && sn.out != sn.rphys && sn.rphys >= 0);
+        if (gather_n && sn.out != out && sn.out != lphys && sn.out != rphys)
+        {
+          prepare(dn, it + 1u, sn.out, sn.rphys, false, nrows);
+          prepared = true;
+        }
+      }
+
+      /* the tile is complete when its rows have landed (tip-tip) or the math warp says so */
+      if (kind == PLG_KIND_TT) mbar_wait(&ready[it & 1u], (it >> 1) & 1u);
+      else mbar_wait(&done[it & 1u], (it >> 1) & 1u);
+
+      if (next_here && !prepared)
+      {
+        mbar_wait(&full[s ^ 1u], next_parity);
+        AwSlots sn = sl;
+        sn.place(dn.lslot, dn.rslot, dn.pslot);
+        const bool miss_n = (dn.kind == PLG_KIND_II && sn.lphys < 0) || (dn.kind != PLG_KIND_TT && sn.rphys < 0);
+        /* a child read back from HBM may be this very result: its store comes first */
+        if (!miss_n && sn.out != out)
+        {
+          prepare(dn, it + 1u, sn.out, sn.rphys, false, nrows);
+          prepared = true;
+        }
+      }
+
+      unsigned char * const oslot = slots + out * G::SLOT_BYTES;
+      if (pad & 1)
+      {
+        if (kind == PLG_KIND_TT && mode == 1 && nrows < AW_TILE && lane < nrows) pscale[first_site + lane] = 0u;
+        __syncwarp();
+        if (aw_elect())
+        {
+          double * dst0 = parent + (size_t)first_site * (R * 20);
+          if (nrows == AW_TILE)
+          {
+#pragma unroll
+            for (int r = 0; r < AW_TILE; ++r) aw_s2g(dst0 + (size_t)r * (R * 20), oslot + G::row_off(r), G::ROWB, stream);
+            if (mode == 1) aw_s2g(pscale + first_site, oslot + G::ROWS_BYTES, 64, stream);
+          }
+          else
+          {
+#pragma unroll
+            for (int r = 0; r < AW_TILE; ++r)
+              if ((unsigned int)r < nrows) aw_s2g(dst0 + (size_t)r * (R * 20), oslot + G::row_off(r), G::ROWB, stream);
+          }
+        }
+        last_store_slot = out;
+      }
+      else
+        last_store_slot = -1;
       bulk_commit();
-      prev_out = out;
     }
   }
   /* the last stores must have left shared memory before the CTA goes away */
@@ -605,11 +826,11 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
 
 /* ------------------------------------------------------------------------------------ */
 template <int R>
-static size_t walk_smem(int split)
+static size_t walk_smem()
 {
   using G = AwGeom<R>;
   return (size_t)AW_STAGES * G::REC_BYTES + (size_t)AW_TEAMS * AW_SLOTS * G::SLOT_BYTES + AW_TEAMS * AW_CODEBUFS * 32 +
-         (2 * AW_STAGES + AW_TEAMS * split) * sizeof(uint64_t) + AW_TEAMS * 2 * 4 * sizeof(unsigned int);
+         (2 * AW_STAGES + 4 * AW_TEAMS) * sizeof(uint64_t) + AW_STAGES * sizeof(unsigned int) + 8;
 }
 
 size_t plg_walk_aa_record_bytes(unsigned int rate_cats) { return 128 + 2 * (size_t)rate_cats * 3200; }
@@ -621,16 +842,16 @@ bool plg_walk_aa_supported(unsigned int rate_cats, unsigned int ncodes)
          2 * (size_t)ncodes * rate_cats * 20 * sizeof(double) <= 96 * 1024;
 }
 
-template <int R, int SPLIT>
+template <int R>
 static int launch_walk(plg_context * ctx, const FusedOp * dev_ops, unsigned char * dev_records, unsigned char * dev_tables,
                        unsigned int n_ops)
 {
-  const size_t smem = walk_smem<R>(SPLIT);
+  const size_t smem = walk_smem<R>();
   const size_t pack_smem = 2 * (size_t)ctx->maxstates * R * 20 * sizeof(double);
   static bool configured[PLG_MAX_DEVICES] = {};
   if (!configured[ctx->device % PLG_MAX_DEVICES])
   {
-    PLG_CUDA(cudaFuncSetAttribute(k_walk_aa<R, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PLG_CUDA(cudaFuncSetAttribute(k_walk_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PLG_CUDA(cudaFuncSetAttribute(k_walk_pack_aa<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     configured[ctx->device % PLG_MAX_DEVICES] = true;
   }
@@ -641,22 +862,19 @@ static int launch_walk(plg_context * ctx, const FusedOp * dev_ops, unsigned char
   TipmapArg tm;
   memcpy(tm.map, ctx->tipmap, sizeof(tm.map));
   k_walk_pack_aa<R><<<n_ops, 256, pack_smem, ctx->stream>>>(dev_ops, dev_records, dev_tables, ctx->maxstates, tm);
-  k_walk_aa<R, SPLIT><<<blocks, (AW_TEAMS * SPLIT + 1) * 32, smem, ctx->stream>>>(dev_ops, dev_records, dev_tables, n_ops,
-                                                                                  ctx->d.sites, ctx->maxstates);
+  k_walk_aa<R><<<blocks, 2 * AW_TEAMS * 32, smem, ctx->stream>>>(dev_ops, dev_records, dev_tables, n_ops, ctx->d.sites,
+                                                                 ctx->maxstates);
   return PLG_OK;
 }
 
 int plg_launch_walk_aa(plg_context * ctx, const FusedOp * dev_ops, unsigned char * dev_records, unsigned char * dev_tables,
                        unsigned int n_ops)
 {
-  const bool split = ctx->walk_split == 2;
   switch (ctx->d.rate_cats)
   {
-    case 1: return launch_walk<1, 1>(ctx, dev_ops, dev_records, dev_tables, n_ops);
-    case 2: return split ? launch_walk<2, 2>(ctx, dev_ops, dev_records, dev_tables, n_ops)
-                         : launch_walk<2, 1>(ctx, dev_ops, dev_records, dev_tables, n_ops);
-    case 4: return split ? launch_walk<4, 2>(ctx, dev_ops, dev_records, dev_tables, n_ops)
-                         : launch_walk<4, 1>(ctx, dev_ops, dev_records, dev_tables, n_ops);
+    case 1: return launch_walk<1>(ctx, dev_ops, dev_records, dev_tables, n_ops);
+    case 2: return launch_walk<2>(ctx, dev_ops, dev_records, dev_tables, n_ops);
+    case 4: return launch_walk<4>(ctx, dev_ops, dev_records, dev_tables, n_ops);
     default: plg_set_error("20-state walk: rate_cats=%u unsupported", ctx->d.rate_cats); return PLG_E_UNSUPPORTED;
   }
 }
