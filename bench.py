@@ -575,7 +575,7 @@ def leg_c3(lib, steps: int, warmup: int, local_rank: int):
         "e2e": {"value": len(w.ops) * sites / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3},
         "gpu_launches": stats["kernel_launches"], "clocks": clocks, "lnl": lnl,
         "roofline": {
-            "kernel": "k_traverse_aa (whole list, FP64 tensor cores)" if fused else "k_partial_dmma_aa (level by level)",
+            "kernel": "k_walk_aa (whole list, FP64 tensor cores)" if fused else "k_partial_dmma_aa (level by level)",
             "avg_traversal_ms": trav_ms,
             "hbm": {"compulsory_bytes_per_launch": comp, "achieved": comp / (trav_ms * 1e-3) / 1e9, "peak": peak,
                     "unit": "GB/s", "frac": comp / (trav_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src},

@@ -60,6 +60,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t * bar, uint32_t parity)
   return done != 0;
 }
 
+/* non-blocking probe (try_wait may suspend the warp for a system-dependent time before it
+ * reports failure: wrong tool for a loop that polls several barriers) */
+__device__ __forceinline__ bool mbar_test_wait(uint64_t * bar, uint32_t parity)
+{
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity)
 {
   while (!mbar_try_wait(bar, parity)) { }

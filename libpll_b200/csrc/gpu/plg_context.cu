@@ -159,8 +159,6 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
     ctx->use_fused = fu ? atoi(fu) : 1;
     const char * fa = getenv("PLL_GPU_FUSED_AA");
     ctx->use_fused_aa = fa ? atoi(fa) : 0;
-    const char * ws = getenv("PLL_GPU_WALK_SPLIT");
-    ctx->walk_split = (ws && atoi(ws) == 2) ? 2 : 1;
     ctx->fused_slots = fs ? (unsigned int)atoi(fs) : 3u;
     if (ctx->fused_slots < 1) ctx->fused_slots = 1;
     if (ctx->fused_slots > 3) ctx->fused_slots = 3; /* shared-memory budget of plg_traverse.cu */

@@ -1,7 +1,7 @@
 /*
  * plg_dmma.cuh - the FP64 tensor-core building block of the 20-state kernels
  * (mma.sync.aligned.m8n8k4.f64, SASS DMMA.8x8x4), shared by the level-by-level kernel
- * (plg_partials.cu: k_partial_dmma_aa) and the single-kernel traversal (plg_traverse_aa.cu).
+ * (plg_partials.cu: k_partial_dmma_aa) and the single-kernel walk (plg_walk_aa.cu).
  *
  *   Y[s][i] = sum_j c[s][j] * P[i][j]      M = 8 sites (rows of A), N = parent states in three
  *                                          tiles of 8 (20 -> 24, rows 20..23 of P are zero), K = 20

@@ -108,10 +108,9 @@ struct plg_context
   unsigned int active_sites; /* leading sites the lnL / derivative reductions cover */
   double * lnl_scratch;      /* one CLV-sized scratch (20-state edge lnL), lazily allocated */
   int use_fused;             /* DNA: whole operations list in one kernel (PLL_GPU_FUSED, default 1) */
-  int use_fused_aa;          /* 20 states: the same on the tensor cores (PLL_GPU_FUSED_AA, default 0: measured
-                                slower than the level-by-level kernels at BASELINE configs[2]) */
+  int use_fused_aa;          /* 20 states: the same on the tensor cores (plg_walk_aa.cu; PLL_GPU_FUSED_AA, default 0:
+                                measured 6 % slower than the level-by-level kernels at BASELINE configs[2]) */
   unsigned int fused_slots;  /* tiles a warp keeps in shared memory (PLL_GPU_FUSED_SLOTS, default 3) */
-  int walk_split;            /* 20-state walk (plg_walk_aa.cu): warps per tile team (PLL_GPU_WALK_SPLIT) */
   unsigned char * fused_records; /* packed operation records of the non-graph path */
   size_t fused_records_cap;
 
@@ -260,16 +259,7 @@ static inline size_t plg_fused_block_bytes(unsigned int R) { return (size_t)16 *
 static inline size_t plg_fused_record_bytes(unsigned int R) { return 128 + 2 * plg_fused_block_bytes(R); }
 int plg_launch_fused(plg_context * ctx, const FusedOp * dev_ops, unsigned char * dev_records, unsigned int n_ops,
                      unsigned int nslot);
-/* the same for 20 states on the FP64 tensor cores (plg_traverse_aa.cu) */
-#define PLG_AAF_WARPS 12
-int plg_launch_fused_aa(plg_context * ctx, const FusedOp * dev_ops, unsigned char * dev_records, unsigned int n_ops,
-                        unsigned int nslot);
-/* tile-cache slots per warp that fit next to the operation ring (0: configuration not supported) */
-unsigned int plg_fused_aa_slots(unsigned int rate_cats, unsigned int wanted);
-size_t plg_fused_aa_record_bytes(unsigned int rate_cats);
-unsigned int plg_fused_aa_max_codes(unsigned int rate_cats); /* tip codes a packed table has room for */
-
-/* 20 states, second design (plg_walk_aa.cu, PLL_GPU_FUSED_AA=2): FusedOp::lbytes = bytes of the
+/* the same for 20 states on the FP64 tensor cores (plg_walk_aa.cu, PLL_GPU_FUSED_AA=1): FusedOp::lbytes = bytes of the
  * operation's record the ring needs, FusedOp::rbytes = first row of its tip table (rows of
  * plg_walk_aa_row_bytes) in the table area behind the records */
 #define PLG_WALK_AA_SLOTS 2

@@ -716,10 +716,14 @@ template <int R>
 struct dmma_geom
 {
   static constexpr int ROW = R * 20;        /* doubles per site                       */
-  /* padded so that consecutive sites start 16 banks apart (PITCH = 8 mod 16 doubles): the four
-   * lanes of a site read 64 contiguous bytes, a quarter warp (two sites) all 32 banks */
-  static constexpr int PITCH = ROW + ((24 - ROW % 16) % 16);
-  static constexpr int UNIT = 8 * PITCH;    /* doubles per child per unit (8 sites)   */
+  /* The 8 sites of a unit sit in the ring as two contiguous halves (sites 0..3, sites 4..7), the
+   * second half 64 bytes further modulo 128.  Each half is ONE bulk copy - the TMA unit serves a
+   * request every ~46 cycles per SM whatever its size, so eight row-sized copies per child made
+   * the kernel request-bound (16 x 46 cycles per unit against 480 cycles of DMMA) - and DMMA row
+   * g works on site (g & 1) * 4 + (g >> 1): the two sites of a quarter warp then start 64 bytes
+   * apart modulo 128 and the four lanes of a site read 64 contiguous bytes - conflict free. */
+  static constexpr int HALF = 4 * ROW + 8;  /* doubles from the first half to the second */
+  static constexpr int UNIT = 8 * ROW + 8;  /* doubles per child per unit (8 sites)      */
 };
 
 /* KIND: PLG_KIND_II (two matrix products) or PLG_KIND_TI (tip table x one matrix product) */
@@ -782,8 +786,8 @@ k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned i
   const unsigned int stride = PLG_DMMA_WARPS;
   const unsigned int u_first = u_seg + warp;
 
-  /* TMA row copies of unit u (8 sites x NCHILD children, 640-byte rows into padded rows) into
-   * ring slot `slot`; completion is signalled on the warp's own mbarrier */
+  /* TMA copies of unit u (two 4-site halves x NCHILD children) into ring slot `slot`; completion
+   * is signalled on the warp's own mbarrier */
   auto fetch = [&](unsigned int u, unsigned int slot) {
     if (u < u_stop)
     {
@@ -791,14 +795,15 @@ k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned i
       const unsigned int nrows = (sites - first_site < 8) ? sites - first_site : 8;
       if (lane == 0) plg_async::mbar_arrive_expect_tx(&full[slot], nrows * NCHILD * G::ROW * 8u);
       __syncwarp();
-      if (lane < 8 * NCHILD)
+      if (lane < 2 * NCHILD)
       {
-        const unsigned int c = lane >> 3, row = lane & 7u;
-        if (row < nrows)
+        const unsigned int c = lane >> 1, h = lane & 1u;
+        if (nrows > 4 * h)
         {
-          const double * src = ((NCHILD == 2 && c == 0) ? op.left : op.right) + (size_t)(first_site + row) * G::ROW;
-          double * dst = ring + ((size_t)slot * NCHILD + c) * G::UNIT + row * G::PITCH;
-          plg_async::bulk_g2s(dst, src, G::ROW * 8u, &full[slot]);
+          const unsigned int rows = (nrows - 4 * h < 4) ? nrows - 4 * h : 4;
+          const double * src = ((NCHILD == 2 && c == 0) ? op.left : op.right) + (size_t)(first_site + 4 * h) * G::ROW;
+          double * dst = ring + ((size_t)slot * NCHILD + c) * G::UNIT + h * G::HALF;
+          plg_async::bulk_g2s(dst, src, rows * G::ROW * 8u, &full[slot]);
         }
       }
     }
@@ -809,7 +814,8 @@ k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned i
   for (unsigned int u = u_first; u < u_stop; u += stride, ++it)
   {
     const unsigned int slot = it % NSLOT;
-    const unsigned int site = 8 * u + g; /* this lane's site: A rows and D rows alike */
+    const unsigned int srow = (g & 1u) * 4u + (g >> 1);
+    const unsigned int site = 8 * u + srow; /* this lane's site: A rows and D rows alike */
     const bool ok = site < sites;
     const size_t site_off = (size_t)site * G::ROW;
 
@@ -822,8 +828,9 @@ k_partial_dmma_aa(const DevOp * __restrict__ ops, unsigned int n_ops, unsigned i
     if (KIND == PLG_KIND_TI && ok) code = __ldg(op.ltip + site);
 
     plg_async::mbar_wait(&full[slot], (it / NSLOT) & 1u); /* this unit's rows have landed */
-    const double * rowL = ring + ((size_t)slot * NCHILD + 0) * G::UNIT + g * G::PITCH;
-    const double * rowR = ring + ((size_t)slot * NCHILD + (NCHILD - 1)) * G::UNIT + g * G::PITCH;
+    const unsigned int srow_off = (g & 1u) * G::HALF + (g >> 1) * G::ROW;
+    const double * rowL = ring + ((size_t)slot * NCHILD + 0) * G::UNIT + srow_off;
+    const double * rowR = ring + ((size_t)slot * NCHILD + (NCHILD - 1)) * G::UNIT + srow_off;
 
     /* single-slot ring: pull the whole unit's A fragments into registers, then hand the slot
      * straight back to the TMA for the next unit */
@@ -1194,15 +1201,12 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
   /* ---- the single-kernel traversal (plg_traverse.cu): execution order + tile cache ---- */
   plan.fused.clear();
   plan.fused_hits = plan.fused_misses = 0;
-  /* 20 states: the tensor-core traversal (plg_traverse_aa.cu) - 1, 2 or 4 rate categories, tip
-   * tables of at most 23 (four categories) or 24 codes, not in bit-exact mode */
-  const bool aa_walk = K == 20 && ctx->use_fused_aa == 2 && !ctx->aa_exact && !ctx->rate_scalers &&
+  /* 20 states: the tensor-core walk (plg_walk_aa.cu) - 1, 2 or 4 rate categories, per-site scalers
+   * or none, not in bit-exact mode */
+  const bool aa_walk = K == 20 && ctx->use_fused_aa && !ctx->aa_exact && !ctx->rate_scalers &&
                        plg_walk_aa_supported(R, ctx->pattern_tip ? ctx->maxstates : 1u);
   const unsigned int aa_slots =
-      aa_walk ? (ctx->fused_slots < PLG_WALK_AA_SLOTS ? ctx->fused_slots : PLG_WALK_AA_SLOTS)
-              : ((K == 20 && ctx->use_fused_aa == 1 && !ctx->aa_exact &&
-                  (!ctx->pattern_tip || ctx->maxstates <= plg_fused_aa_max_codes(R)))
-                     ? plg_fused_aa_slots(R, ctx->fused_slots) : 0);
+      aa_walk ? (ctx->fused_slots < PLG_WALK_AA_SLOTS ? ctx->fused_slots : PLG_WALK_AA_SLOTS) : 0;
   plan.fused_scratch_bytes = 0;
   plan.fused_table_offset = 0;
   if (ctx->use_fused && (K == 4 || aa_slots > 0) && plg_fast_path(ctx) && count >= 2)
@@ -1424,7 +1428,7 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
       plan.fused_scratch_bytes = plan.fused_table_offset + (size_t)rows * plg_walk_aa_row_bytes(R);
     }
     else
-      plan.fused_scratch_bytes = plan.fused.size() * (K == 4 ? plg_fused_record_bytes(R) : plg_fused_aa_record_bytes(R));
+      plan.fused_scratch_bytes = plan.fused.size() * plg_fused_record_bytes(R);
   }
   return PLG_OK;
 }
@@ -1571,11 +1575,8 @@ static int enqueue_plan(plg_context * ctx, const Plan & plan, const void * dev_p
     int frc = (ctx->d.states == 4)
                   ? plg_launch_fused(ctx, (const FusedOp *)dev_payload, dev_records, (unsigned int)plan.fused.size(),
                                      plan.fused_nslot)
-                  : (plan.fused_table_offset
-                         ? plg_launch_walk_aa(ctx, (const FusedOp *)dev_payload, dev_records,
-                                              dev_records + plan.fused_table_offset, (unsigned int)plan.fused.size())
-                         : plg_launch_fused_aa(ctx, (const FusedOp *)dev_payload, dev_records,
-                                               (unsigned int)plan.fused.size(), plan.fused_nslot));
+                  : plg_launch_walk_aa(ctx, (const FusedOp *)dev_payload, dev_records,
+                                       dev_records + plan.fused_table_offset, (unsigned int)plan.fused.size());
     if (frc) return frc;
     cudaError_t ferr = cudaGetLastError();
     if (ferr != cudaSuccess)

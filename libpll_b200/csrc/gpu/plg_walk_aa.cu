@@ -1,35 +1,36 @@
 /*
  * plg_walk_aa.cu - the whole operations list of pll_update_partials in ONE kernel, 20 states,
- * second design (PLL_GPU_FUSED_AA=2; plg_traverse_aa.cu is the first).
+ * opt-in with PLL_GPU_FUSED_AA=1 (the level-by-level kernels of plg_partials.cu are the default:
+ * at BASELINE configs[2] this kernel takes 24.4 ms against their 22.3-23.5 ms).
  *
- * What the first kernel taught: the tensor pipe is saturated by ONE warp
- * per scheduler, what costs time is everything around the DMMAs - twelve scattered 128-bit
- * global stores per group, tip-table gathers with bank conflicts, a cross-warp vote, and a
- * load/store unit that is as busy as the tensor pipe.  This kernel moves all global traffic to
- * the TMA unit and keeps the instruction stream of a math warp close to "fragment loads, DMMA,
- * multiply, shared-memory store":
+ * Patterns are independent, so a tile of patterns can walk the entire list with the children it
+ * has just produced kept on chip; only results leave for HBM (64 GB instead of 128 GB at
+ * configs[2]).  The kernel is a warp-specialised pipeline, 12 warps per SM:
  *
- *   - a TILE is 16 patterns x all rates (two 8-pattern DMMA groups).  One tile team per
- *     scheduler (4 per SM) walks the whole list for its tile; a team is one warp, or (SPLIT = 2)
- *     two warps on the same scheduler that own half of the rate categories each.  The B
- *     fragments of a (child, rate) matrix are pulled into registers once per operation and
- *     reused for both groups;
- *   - every result tile is written to a shared-memory SLOT of the team in the natural CLV layout
- *     (rows of R x 20 doubles, padded so that fragment reads and writes are bank-conflict free)
- *     and leaves for HBM as one TMA bulk store per pattern row (cp.async.bulk.global.shared::cta):
- *     no compute lane issues a global store.  The same slot is the tile cache: a parent reads
- *     its children's A fragments from their slots.  Four slots per team: two that the host
- *     planner (build_plan, plg_partials.cu) manages as the tile cache, two that alternate as
- *     the home of results which the very next operation consumes;
+ *   - a TILE is 16 patterns x all rate categories (two 8-pattern DMMA groups).  Four tile teams
+ *     per SM walk the list; a team is two MATH warps, each owning half of the rate categories,
+ *     and one DMA warp.  The B fragments of a (child, rate) matrix are pulled into registers once
+ *     per operation and reused for both groups.  The two math warps that share a scheduler belong
+ *     to different teams; registers move from the DMA to the math warps (setmaxnreg: 64 / 216);
+ *   - every result tile is written to a shared-memory SLOT of the team in the CLV layout (two
+ *     contiguous 8-row halves, see AwGeom) and leaves for HBM as two TMA bulk stores issued by the
+ *     DMA warp: no compute lane issues a global store.  The same slot is the tile cache: a parent
+ *     reads its children's A fragments from their slots.  Four slots per team: two that the host
+ *     planner (build_plan, plg_partials.cu) manages as the tile cache, two that alternate as the
+ *     home of results which the very next operation consumes;
  *   - tip-tip operations do no arithmetic at all: the pack kernel multiplies the two tip tables
- *     into a pair table [left code][right code][rate][state] (L2 resident), the walk gathers
- *     one row per pattern into the slot by TMA and stores it from there.  Tip-inner operations
- *     gather the tip's table rows into the result slot the same way and multiply in place;
- *   - the rescaling vote (all R x 20 entries of a pattern below 2^-256, reference
- *     src/core_partials_avx2.c:788-801) is local to the team; a tile in which some pattern
- *     rescales (rare) is fixed up in its slot before the store is issued;
+ *     into a pair table [left code][right code][rate][state] (L2 resident, evict_last), the DMA
+ *     warp gathers one row per pattern into the slot with 16-byte asynchronous copies - ahead of
+ *     time whenever the slot is idle - and stores the tile from there.  Tip-inner operations read
+ *     the tip's table rows with read-only loads issued before the DMMAs of a category;
+ *   - math and DMA warps meet on mbarriers only: `ready` (the result slot may be written: the
+ *     store that last read it has drained / the rows have landed), `done` (the tile is complete),
+ *     `voted` (the two halves of a team exchange their rescaling votes: all R x 20 entries of a
+ *     pattern below 2^-256, reference src/core_partials_avx2.c:788-801; a tile in which some
+ *     pattern rescales - rare - is fixed up in its slot before the store is issued);
  *   - operation data (descriptor + the matrix sets as B fragments, exactly 3 200 bytes per
- *     matrix) streams through a 2-stage ring filled by a producer warp with TMA bulk copies.
+ *     matrix) streams through a 2-stage ring of TMA bulk copies, fed by the DMA warp of team 0
+ *     whenever it would otherwise spin.
  *
  * Arithmetic: the same DMMA chains in the same order as k_partial_dmma_aa (plg_dmma.cuh): CLVs
  * and scaler counts are bit-identical to the level-by-level path.
@@ -44,19 +45,21 @@
 #define AW_TEAMS 4
 #define AW_STAGES 2
 #define AW_SLOTS 4
-#define AW_CODEBUFS 4
+#define AW_CODEBUFS 8
 
 template <int R>
 struct AwGeom
 {
   static constexpr int ROWB = R * 160; /* bytes of one pattern row */
-  /* byte offset of row s inside a slot: the two rows of a quarter warp must start 64 bytes apart
-   * modulo 128 (four lanes of a pattern touch 64 contiguous bytes) */
-  __host__ __device__ static constexpr int row_off(int s)
-  {
-    return R == 4 ? s * 640 + ((s + 1) >> 1) * 64 : (R == 2 ? s * 320 : s * 192);
-  }
-  static constexpr int ROWS_BYTES = row_off(AW_TILE);
+  /* A slot holds the 16 pattern rows of a tile as two contiguous halves (rows 0..7, rows 8..15:
+   * each half is ONE bulk copy to or from HBM - the TMA unit serves a request every ~46 cycles
+   * per SM whatever its size, row-sized copies starve it), the second half 64 bytes further
+   * modulo 128.  A DMMA group takes four rows of each half (AwLane::row): the two patterns of
+   * a quarter warp then sit 64 bytes apart modulo 128 and the four lanes of a pattern touch 64
+   * contiguous bytes - fragment loads and stores are bank-conflict free. */
+  __host__ __device__ static constexpr int row_off(int s) { return s < 8 ? s * ROWB : 8 * ROWB + 64 + (s - 8) * ROWB; }
+  static constexpr int HALF_BYTES = 8 * ROWB;
+  static constexpr int ROWS_BYTES = 16 * ROWB + 64;
   static constexpr int SLOT_BYTES = ROWS_BYTES + 64; /* + per-pattern scaler counts */
   static constexpr int MAT_BYTES = 3200;             /* one 20 x 20 matrix as B fragments */
   static constexpr int REC_BYTES = 128 + 2 * R * MAT_BYTES;
@@ -193,7 +196,9 @@ __device__ __forceinline__ void aw_afrag_hbm(const double * r, unsigned int q, u
 struct AwLane
 {
   unsigned int lane, g, q, hi_state, hi_off;
-  unsigned int roff[2]; /* byte offset of this lane's quarter in its pattern row of group 0 / 1 */
+  unsigned int row[2];  /* the tile row (pattern) this lane works on in group 0 / 1 */
+  unsigned int roff[2]; /* byte offset of this lane's quarter in that row */
+  unsigned int k0;      /* first rate category of this warp */
 };
 
 /* The arithmetic of one tip-inner / inner-inner operation on a tile: products into the result
@@ -201,43 +206,70 @@ struct AwLane
  * inner children sit in slots and the tip rows were gathered into the result slot (the common
  * case, no run-time source decisions).  The result slot may only be touched once `ready` has
  * completed (the DMA warp has drained the store that last read it / landed the tip rows). */
-template <int R, int KIND, bool FAST>
+template <int R, int NRW, int KIND, bool FAST>
 __device__ __forceinline__ void aw_compute(const unsigned char * stage, const unsigned char * slots, unsigned char * oslot,
                                            int lphys, int rphys, const double * left, const double * right,
-                                           const unsigned char * tip_rows, const unsigned int (&tcode)[2], bool gather,
+                                           const unsigned char * tip_rows, const unsigned int (&tcode)[2],
                                            uint64_t * ready, unsigned int ready_parity, bool & ready_seen, const AwLane & L,
                                            unsigned int first_site, const bool (&ok)[2], bool (&below)[2])
 {
   using G = AwGeom<R>;
   const unsigned int q = L.q;
-#pragma unroll
-  for (int k = 0; k < R; ++k)
+  /* fragments of rate category k + 1 are requested between the DMMAs of category k and its
+   * epilogue: the compiler cannot move shared-memory loads above the epilogue's stores (the
+   * result slot may alias a child's), in this order their latency hides behind the epilogue */
+  double BR[PLG_DMMA_FRAGS], BL[PLG_DMMA_FRAGS];
+  double arr[2][5], all_[2][5];
+  auto load_frags = [&](int kk)
   {
-    double BR[PLG_DMMA_FRAGS], BL[PLG_DMMA_FRAGS];
+    const unsigned int k = L.k0 + kk;
     aw_load_bfrag(stage + 128 + k * G::MAT_BYTES, L.lane, BR);
     if (KIND == PLG_KIND_II) aw_load_bfrag(stage + 128 + (R + k) * G::MAT_BYTES, L.lane, BL);
-    /* all fragment loads of this rate category before its first store: the result slot may be
-     * one of the children's (in place), and the loads then overlap instead of trailing the stores */
-    double arr[2][5], all_[2][5];
 #pragma unroll
     for (int sg = 0; sg < 2; ++sg)
     {
       if (FAST || rphys >= 0) aw_afrag_smem(slots + rphys * G::SLOT_BYTES + L.roff[sg] + k * 160u, L.hi_off, arr[sg]);
-      else aw_afrag_hbm(right + (size_t)(first_site + sg * 8 + L.g) * (R * 20) + k * 20, q, L.hi_state, ok[sg], arr[sg]);
+      else aw_afrag_hbm(right + (size_t)(first_site + L.row[sg]) * (R * 20) + k * 20, q, L.hi_state, ok[sg], arr[sg]);
       if (KIND == PLG_KIND_II)
       {
         if (FAST || lphys >= 0) aw_afrag_smem(slots + lphys * G::SLOT_BYTES + L.roff[sg] + k * 160u, L.hi_off, all_[sg]);
-        else aw_afrag_hbm(left + (size_t)(first_site + sg * 8 + L.g) * (R * 20) + k * 20, q, L.hi_state, ok[sg], all_[sg]);
+        else aw_afrag_hbm(left + (size_t)(first_site + L.row[sg]) * (R * 20) + k * 20, q, L.hi_state, ok[sg], all_[sg]);
       }
     }
+  };
+  load_frags(0);
+#pragma unroll
+  for (int kk = 0; kk < NRW; ++kk)
+  {
+    const unsigned int k = L.k0 + kk;
     double y[2][3][2], x[2][3][2];
+    if (KIND == PLG_KIND_TI)
+    {
+      /* the tip's table rows (L2 / L1 resident, read-only for this launch) are requested before
+       * the DMMAs of the category and arrive behind them */
+#pragma unroll
+      for (int sg = 0; sg < 2; ++sg)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt)
+          if (nt < 2 || q < 2u)
+          {
+            const double2 t = __ldg(reinterpret_cast<const double2 *>(tip_rows + (size_t)tcode[sg] * G::ROWB + k * 160u +
+                                                                       nt * 64 + 16u * q));
+            x[sg][nt][0] = t.x;
+            x[sg][nt][1] = t.y;
+          }
+    }
 #pragma unroll
     for (int sg = 0; sg < 2; ++sg)
     {
       const double (&ar)[5] = arr[sg];
       const double (&al)[5] = all_[sg];
 #pragma unroll
-      for (int nt = 0; nt < 3; ++nt) y[sg][nt][0] = y[sg][nt][1] = x[sg][nt][0] = x[sg][nt][1] = 0.0;
+      for (int nt = 0; nt < 3; ++nt)
+      {
+        y[sg][nt][0] = y[sg][nt][1] = 0.0;
+        if (KIND == PLG_KIND_II) x[sg][nt][0] = x[sg][nt][1] = 0.0;
+      }
       if (KIND == PLG_KIND_II)
       {
 #pragma unroll
@@ -245,8 +277,13 @@ __device__ __forceinline__ void aw_compute(const unsigned char * stage, const un
 #pragma unroll
           for (int nt = 0; nt < 3; ++nt)
           {
+#ifdef AW_EXP_NOMMA
+            y[sg][nt][0] += ar[ks] * BR[nt * 5 + ks];
+            x[sg][nt][0] += al[ks] * BL[nt * 5 + ks];
+#else
             dmma884_free(y[sg][nt][0], y[sg][nt][1], ar[ks], BR[nt * 5 + ks]);
             dmma884_free(x[sg][nt][0], x[sg][nt][1], al[ks], BL[nt * 5 + ks]);
+#endif
           }
       }
       else
@@ -254,9 +291,15 @@ __device__ __forceinline__ void aw_compute(const unsigned char * stage, const un
 #pragma unroll
         for (int ks = 0; ks < 5; ++ks)
 #pragma unroll
-          for (int nt = 0; nt < 3; ++nt) dmma884_free(y[sg][nt][0], y[sg][nt][1], ar[ks], BR[nt * 5 + ks]);
+          for (int nt = 0; nt < 3; ++nt)
+#ifdef AW_EXP_NOMMA
+            y[sg][nt][0] += ar[ks] * BR[nt * 5 + ks];
+#else
+            dmma884_free(y[sg][nt][0], y[sg][nt][1], ar[ks], BR[nt * 5 + ks]);
+#endif
       }
     }
+    if (kk + 1 < NRW) load_frags(kk + 1);
     if (!ready_seen)
     {
       plg_async::mbar_wait(ready, ready_parity);
@@ -265,32 +308,6 @@ __device__ __forceinline__ void aw_compute(const unsigned char * stage, const un
 #pragma unroll
     for (int sg = 0; sg < 2; ++sg)
     {
-      if (KIND == PLG_KIND_TI)
-      {
-        if (FAST || gather)
-        {
-#pragma unroll
-          for (int nt = 0; nt < 3; ++nt)
-            if (nt < 2 || q < 2u)
-            {
-              const double2 t = *reinterpret_cast<const double2 *>(oslot + L.roff[sg] + k * 160u + nt * 64);
-              x[sg][nt][0] = t.x;
-              x[sg][nt][1] = t.y;
-            }
-        }
-        else
-        {
-#pragma unroll
-          for (int nt = 0; nt < 3; ++nt)
-            if (nt < 2 || q < 2u)
-            {
-              const double2 t = __ldg(reinterpret_cast<const double2 *>(tip_rows + (size_t)tcode[sg] * G::ROWB + k * 160u +
-                                                                         nt * 64 + 16u * q));
-              x[sg][nt][0] = t.x;
-              x[sg][nt][1] = t.y;
-            }
-        }
-      }
 #pragma unroll
       for (int nt = 0; nt < 3; ++nt)
         if (nt < 2 || q < 2u)
@@ -326,16 +343,6 @@ struct AwSlots
   }
 };
 
-__device__ __forceinline__ unsigned int aw_atom_inc(unsigned int * p, unsigned int wrap)
-{
-  unsigned int old;
-  asm volatile("atom.relaxed.cta.shared::cta.inc.u32 %0, [%1], %2;"
-               : "=r"(old)
-               : "r"(plg_async::smem_addr(p)), "r"(wrap)
-               : "memory");
-  return old;
-}
-
 /* TMA bulk copies with an L2 eviction-priority hint: tables and records are re-read by every
  * tile and should survive the 64 GB write stream (evict_last), result rows are never read again
  * by this launch (evict_first) */
@@ -370,10 +377,14 @@ __device__ __forceinline__ void aw_s2g(void * dst_gmem, const void * src_smem, u
 /* ------------------------------------------------------------------------------------ */
 /* the walk                                                                              */
 /* ------------------------------------------------------------------------------------ */
-#define AW_CONSUMERS (2 * AW_TEAMS)
+#define AW_MATH_WARPS (2 * AW_TEAMS)           /* two per team: half of the rate categories each */
+#define AW_WARPS (3 * AW_TEAMS)                /* + one DMA warp per team */
+#define AW_CONSUMERS AW_WARPS
+#define AW_REGS_DMA 64
+#define AW_REGS_MATH 216                       /* 8 x 32 x 216 + 4 x 32 x 64 <= 12 x 32 x 168 */
 
 template <int R>
-__global__ void __launch_bounds__(2 * AW_TEAMS * 32, 1)
+__global__ void __launch_bounds__(AW_WARPS * 32, 1)
 k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ records,
           const unsigned char * __restrict__ tables, unsigned int n_ops, unsigned int sites, unsigned int ncodes)
 {
@@ -388,7 +399,8 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
   uint64_t * empty = full + AW_STAGES;
   uint64_t * ready_all = empty + AW_STAGES;                                       /* [team][2] */
   uint64_t * done_all = ready_all + AW_TEAMS * 2;                                 /* [team][2] */
-  unsigned int * ticket = reinterpret_cast<unsigned int *>(done_all + AW_TEAMS * 2); /* [AW_STAGES] */
+  uint64_t * voted_all = done_all + AW_TEAMS * 2;                                 /* [team][2] */
+  unsigned int * votes_all = reinterpret_cast<unsigned int *>(voted_all + AW_TEAMS * 2); /* [team][2][half][2] */
 
   const unsigned int lane = threadIdx.x & 31u;
   const unsigned int warp = threadIdx.x >> 5;
@@ -404,12 +416,12 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
     {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], AW_CONSUMERS);
-      ticket[s] = 0;
     }
     for (int w = 0; w < AW_TEAMS * 2; ++w)
     {
-      mbar_init(&ready_all[w], 1);
-      mbar_init(&done_all[w], 1);
+      mbar_init(&ready_all[w], 32);
+      mbar_init(&done_all[w], 2);
+      mbar_init(&voted_all[w], 2);
     }
     fence_barrier_init();
     for (unsigned int it0 = 0; it0 < (unsigned int)AW_STAGES && it0 < total_its; ++it0)
@@ -422,30 +434,27 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
   }
   __syncthreads();
 
-  const unsigned int team = warp % AW_TEAMS;
-  const bool is_math = warp < AW_TEAMS;
+  /* the two math warps of a scheduler (warps w and w + 4) belong to DIFFERENT teams: the halves
+   * of one team move in lockstep - same phase, nothing to overlap - while two teams drift apart
+   * and one's DMMAs fill the other's epilogue */
+  const bool is_math = warp < AW_MATH_WARPS;
+  const unsigned int team = (warp + (is_math ? warp / AW_TEAMS : 0u)) % AW_TEAMS;
+  /* the two math warps of a team sit on the same scheduler (warps w and w + 4): while one waits
+   * or runs its epilogue the other keeps the tensor pipe busy.  Registers move from the DMA
+   * warps to the math warps (both warpgroup-wide) */
+
   unsigned char * const slots = slot_base + team * AW_SLOTS * G::SLOT_BYTES;
   unsigned char * const codes = code_base + team * AW_CODEBUFS * 32;
   uint64_t * const ready = ready_all + team * 2;
   uint64_t * const done = done_all + team * 2;
+  uint64_t * const voted = voted_all + team * 2;
+  unsigned int * const votes = votes_all + team * 8;
 
-  /* hands ring stage s back; the last of the consumers to do so refills it with the record two
-   * operations ahead, whose size travels in this operation's descriptor */
-  auto release = [&](unsigned int s, unsigned int it, unsigned int i, unsigned int ahead_bytes)
+  /* hands ring stage s back */
+  auto release = [&](unsigned int s)
   {
     __syncwarp();
-    if (lane == 0)
-    {
-      mbar_arrive(&empty[s]);
-      if (aw_atom_inc(&ticket[s], AW_CONSUMERS - 1) == AW_CONSUMERS - 1 && it + AW_STAGES < total_its)
-      {
-        mbar_wait(&empty[s], (it / AW_STAGES) & 1u);
-        unsigned int i2 = i + AW_STAGES;
-        while (i2 >= n_ops) i2 -= n_ops;
-        mbar_arrive_expect_tx(&full[s], ahead_bytes);
-        aw_g2s(stage_base + s * G::REC_BYTES, records + (size_t)i2 * G::REC_BYTES, ahead_bytes, &full[s], keep);
-      }
-    }
+    if (lane == 0) mbar_arrive(&empty[s]);
   };
 
   AwSlots sl;
@@ -456,15 +465,31 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
   if (is_math)
   {
     /* ================= math warp: fragments, DMMA, products, vote ================= */
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AW_REGS_MATH));
     AwLane L;
     L.lane = lane;
     L.g = lane >> 2;
     L.q = lane & 3u;
     L.hi_state = dmma_child_state(4, L.q);
     L.hi_off = 8u * L.hi_state - 16u * L.q; /* from a row's rate block + 16 q to its ks = 4 state */
-    L.roff[0] = (unsigned int)G::row_off((int)L.g) + 16u * L.q;
-    L.roff[1] = (unsigned int)G::row_off((int)L.g + 8) + 16u * L.q;
+    L.row[0] = (L.g & 1u) * 8u + (L.g >> 1);
+    L.row[1] = L.row[0] + 4u;
+    L.roff[0] = (unsigned int)G::row_off((int)L.row[0]) + 16u * L.q;
+    L.roff[1] = (unsigned int)G::row_off((int)L.row[1]) + 16u * L.q;
+    constexpr int NRW = R >= 2 ? R / 2 : 1;
+    const unsigned int half = warp / AW_TEAMS;
+    const bool ghost = R < 2 && half == 1; /* one category: the second warp only keeps the protocol */
+    L.k0 = ghost ? 0u : half * NRW;
     const unsigned int g = L.g, q = L.q;
+    unsigned int vote_phase = 0;
+#ifdef AW_EXP_TIMING
+    long long tb[8] = {0, 0, 0, 0, 0, 0, 0, 0}; /* full, tt, compute, vote wait, epilogue, total */
+    long long t_prev = clock64();
+    const long long t_begin = t_prev;
+#define AW_TICK(b) { const long long t_now = clock64(); tb[b] += t_now - t_prev; t_prev = t_now; }
+#else
+#define AW_TICK(b)
+#endif
 
     for (unsigned int pass = 0; pass < passes; ++pass)
     {
@@ -472,18 +497,19 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
       const bool have = tile < ntiles;
       const unsigned int first_site = tile * AW_TILE;
       const unsigned int nrows = have ? min((unsigned int)AW_TILE, sites - first_site) : 0u;
-      const bool ok[2] = {first_site + g < sites && have, first_site + 8 + g < sites && have};
+      const bool ok[2] = {first_site + L.row[0] < sites && have, first_site + L.row[1] < sites && have};
 
       for (unsigned int i = 0; i < n_ops; ++i, ++it)
       {
         const unsigned int s = it % AW_STAGES;
+        AW_TICK(6)
         mbar_wait(&full[s], (it / AW_STAGES) & 1u);
+        AW_TICK(0)
         const unsigned char * stage = stage_base + s * G::REC_BYTES;
         const FusedOp & d = *reinterpret_cast<const FusedOp *>(stage);
-        const unsigned int ahead = d.lbytes >> 16;
         if (!have)
         {
-          release(s, it, i, ahead);
+          release(s);
           continue;
         }
         const int kind = d.kind;
@@ -500,10 +526,11 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
         {
           /* nothing to compute: the DMA warp gathers the rows of the pair table, zeroes the
            * scaler counts and stores the tile; the next reader of the slot must see it landed */
-          release(s, it, i, ahead);
+          release(s);
           mbar_wait(rb, rpar);
           __syncwarp();
           if (lane == 0) mbar_arrive(&done[it & 1u]);
+          AW_TICK(1)
           continue;
         }
 
@@ -514,44 +541,46 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
         const unsigned int * const rscale = d.op.rscale;
         unsigned char * const oslot = slots + out * G::SLOT_BYTES;
         const unsigned char * tip_rows = tables + (size_t)d.rbytes * G::ROWB;
-        const bool gather = kind == PLG_KIND_TI && out != rphys;
         const bool miss = (kind == PLG_KIND_II && lphys < 0) || rphys < 0;
 
         bool below[2] = {true, true};
         unsigned int tcode[2] = {0u, 0u};
-        if (miss || (kind == PLG_KIND_TI && !gather))
+        if (kind == PLG_KIND_TI)
         {
-          /* children read back from HBM need this team's stores landed, in-place tip rows need
-           * the tip characters: both are behind the DMA warp's `ready` */
+          /* tip characters of this operation: landed before the DMA warp signalled `ready` for the
+           * previous one (it waits for those of three operations at the top of an iteration) */
+          const unsigned char * cbuf = codes + (it % AW_CODEBUFS) * 32;
+          tcode[0] = min((unsigned int)cbuf[L.row[0]], ncodes - 1u);
+          tcode[1] = min((unsigned int)cbuf[L.row[1]], ncodes - 1u);
+        }
+        if (miss)
+        {
+          /* children read back from HBM need this team's stores landed: behind `ready` */
           mbar_wait(rb, rpar);
           ready_seen = true;
-          if (kind == PLG_KIND_TI && !gather)
-          {
-            const unsigned char * cbuf = codes + (it % AW_CODEBUFS) * 32;
-            tcode[0] = min((unsigned int)cbuf[g], ncodes - 1u);
-            tcode[1] = min((unsigned int)cbuf[8 + g], ncodes - 1u);
-          }
         }
-        if (kind == PLG_KIND_II)
+        if (ghost) { }
+        else if (kind == PLG_KIND_II)
         {
           if (lphys >= 0 && rphys >= 0)
-            aw_compute<R, PLG_KIND_II, true>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, gather, rb, rpar,
+            aw_compute<R, NRW, PLG_KIND_II, true>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, rb, rpar,
                                              ready_seen, L, first_site, ok, below);
           else
-            aw_compute<R, PLG_KIND_II, false>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, gather, rb,
+            aw_compute<R, NRW, PLG_KIND_II, false>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, rb,
                                               rpar, ready_seen, L, first_site, ok, below);
         }
         else
         {
-          if (rphys >= 0 && gather)
-            aw_compute<R, PLG_KIND_TI, true>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, gather, rb, rpar,
+          if (rphys >= 0)
+            aw_compute<R, NRW, PLG_KIND_TI, true>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, rb, rpar,
                                              ready_seen, L, first_site, ok, below);
           else
-            aw_compute<R, PLG_KIND_TI, false>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, gather, rb,
+            aw_compute<R, NRW, PLG_KIND_TI, false>(stage, slots, oslot, lphys, rphys, left, right, tip_rows, tcode, rb,
                                               rpar, ready_seen, L, first_site, ok, below);
         }
         /* the ring stage has been read (matrices are in registers, the descriptor in locals) */
-        release(s, it, i, ahead);
+        release(s);
+        AW_TICK(2)
 
         unsigned int vote[2] = {0u, 0u};
         if (mode == 1)
@@ -562,21 +591,32 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
             unsigned int b = __ballot_sync(0xffffffffu, below[sg]);
             b &= b >> 1;
             b &= b >> 2;
-            vote[sg] = b & 0x11111111u; /* bit 4g: every entry of pattern g is below the threshold */
+            vote[sg] = b & 0x11111111u; /* bit 4g: every entry of pattern g (this warp's categories) is below */
           }
-          if ((vote[0] | vote[1]) != 0u)
+          /* per-site scaling: both halves of the categories must agree */
+          unsigned int * v = votes + (it & 1u) * 4;
+          if (lane < 2) v[half * 2 + lane] = lane ? vote[1] : vote[0];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&voted[it & 1u]);
+          AW_TICK(4)
+          mbar_wait(&voted[it & 1u], (vote_phase >> (it & 1u)) & 1u);
+          AW_TICK(3)
+          vote_phase ^= 1u << (it & 1u); /* not every operation votes: the barriers keep their own phase */
+          vote[0] &= v[(half ^ 1u) * 2 + 0];
+          vote[1] &= v[(half ^ 1u) * 2 + 1];
+          if ((vote[0] | vote[1]) != 0u && !ghost)
           {
             /* rare: some pattern of the tile is rescaled - in its slot, before the store leaves */
 #pragma unroll
             for (int sg = 0; sg < 2; ++sg)
               if ((vote[sg] >> (4u * g)) & 1u)
 #pragma unroll 1
-                for (int k = 0; k < R; ++k)
+                for (int kk = 0; kk < NRW; ++kk)
 #pragma unroll
                   for (int nt = 0; nt < 3; ++nt)
                     if (nt < 2 || q < 2u)
                     {
-                      double2 * ptr = reinterpret_cast<double2 *>(oslot + L.roff[sg] + k * 160u + nt * 64);
+                      double2 * ptr = reinterpret_cast<double2 *>(oslot + L.roff[sg] + (L.k0 + kk) * 160u + nt * 64);
                       double2 t = *ptr;
                       t.x = __dmul_rn(t.x, PLG_SCALE_FACTOR);
                       t.y = __dmul_rn(t.y, PLG_SCALE_FACTOR);
@@ -584,7 +624,7 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
                     }
           }
           /* scaler counts of the tile, kept next to it in the slot */
-          if (q == 0u)
+          if (q == 0u && half == 0)
           {
             unsigned int * ostrip = reinterpret_cast<unsigned int *>(oslot + G::ROWS_BYTES);
 #pragma unroll
@@ -592,13 +632,12 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
             {
               unsigned int sv = (vote[sg] >> (4u * g)) & 1u;
               if (kind == PLG_KIND_II && lscale)
-                sv += lphys >= 0 ? reinterpret_cast<const unsigned int *>(slots + lphys * G::SLOT_BYTES + G::ROWS_BYTES)[sg * 8 + g]
-                                 : (ok[sg] ? ld_coherent_u32(lscale + first_site + sg * 8 + g) : 0u);
+                sv += lphys >= 0 ? reinterpret_cast<const unsigned int *>(slots + lphys * G::SLOT_BYTES + G::ROWS_BYTES)[L.row[sg]]
+                                 : (ok[sg] ? ld_coherent_u32(lscale + first_site + L.row[sg]) : 0u);
               if (rscale)
-                sv += rphys >= 0 ? reinterpret_cast<const unsigned int *>(slots + rphys * G::SLOT_BYTES + G::ROWS_BYTES)[sg * 8 + g]
-                                 : (ok[sg] ? ld_coherent_u32(rscale + first_site + sg * 8 + g) : 0u);
-              ostrip[sg * 8 + g] = sv;
-              if ((pad & 1) && nrows < AW_TILE && ok[sg]) pscale[first_site + sg * 8 + g] = sv; /* ragged last tile */
+                sv += rphys >= 0 ? reinterpret_cast<const unsigned int *>(slots + rphys * G::SLOT_BYTES + G::ROWS_BYTES)[L.row[sg]]
+                                 : (ok[sg] ? ld_coherent_u32(rscale + first_site + L.row[sg]) : 0u);
+              ostrip[L.row[sg]] = sv;
             }
           }
         }
@@ -606,13 +645,48 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&done[it & 1u]);
+        AW_TICK(4)
       }
     }
+#ifdef AW_EXP_TIMING
+    if (blockIdx.x == 3 && lane == 0)
+      printf("warp %u: total %lld | ring %lld  tip-tip %lld  compute(+ready) %lld  vote-wait %lld  epilogue %lld  loop %lld\n", warp,
+             clock64() - t_begin, tb[0], tb[1], tb[2], tb[3], tb[4], tb[6]);
+#endif
     return;
   }
 
   /* ================= DMA warp: tip characters, gathers, stores ================= */
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AW_REGS_DMA));
   const unsigned long long stream = aw_policy_stream();
+  /* The DMA warp of team 0 also feeds the operation ring: whenever it has to wait it checks
+   * whether all consumers have handed back the stage of the next record to load (the record of
+   * operation fill_it, two ahead of the one whose descriptor carried its size). */
+  unsigned int fill_it = AW_STAGES, fill_i = AW_STAGES % n_ops;
+  unsigned int fill_b0 = 0u, fill_b1 = 0u; /* AW_STAGES == 2 */
+  unsigned int known_it = 0; /* sizes are known for operations < known_it + AW_STAGES */
+  auto producer_poll = [&]()
+  {
+    if (team != 0 || fill_it >= total_its || fill_it >= known_it + AW_STAGES) return;
+    const unsigned int fs = fill_it % AW_STAGES;
+    if (!mbar_test_wait(&empty[fs], ((fill_it / AW_STAGES) - 1u) & 1u)) return;
+    if (lane == 0)
+    {
+#ifdef AW_EXP_NORING
+      const unsigned int fb = 128u;
+#else
+      const unsigned int fb = fs ? fill_b1 : fill_b0;
+#endif
+      mbar_arrive_expect_tx(&full[fs], fb);
+      aw_g2s(stage_base + fs * G::REC_BYTES, records + (size_t)fill_i * G::REC_BYTES, fb, &full[fs], keep);
+    }
+    ++fill_it;
+    if (++fill_i == n_ops) fill_i = 0;
+  };
+  auto wait_poll = [&](uint64_t * bar, unsigned int parity)
+  {
+    while (!mbar_test_wait(bar, parity)) producer_poll();
+  };
   int last_store_slot = -1; /* source slot of the most recently committed store group */
 
   /* tip characters three operations ahead (cp.async of 16 bytes per tip row); what that needs of
@@ -641,13 +715,20 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  /* (an empty group after each: the loop commits two groups per iteration and counts on it) */
   load_pend(0, 0);
   issue_codes(0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   load_pend(1, 0);
   issue_codes(1);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   load_pend(2, 0);
   issue_codes(2);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   load_pend(3, 0);
+  issue_codes(3);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  load_pend(4, 0);
 
   /* what must happen before the math warp may touch the result slot of operation `it_x`: the
    * store that last read the slot has drained, tip rows are on their way (completion = bytes on
@@ -659,7 +740,7 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
     uint64_t * rb = &ready[it_x & 1u];
     unsigned char * oslot = slots + out_x * G::SLOT_BYTES;
     const int kind_x = dx.kind;
-    const bool gather = kind_x == PLG_KIND_TT || (kind_x == PLG_KIND_TI && out_x != rphys_x);
+    const bool gather = kind_x == PLG_KIND_TT;
     if (miss_x)
     {
       bulk_wait<0>();
@@ -668,8 +749,7 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
     if (gather)
     {
       const unsigned char * cbuf = codes + (it_x % AW_CODEBUFS) * 32;
-      /* lane r works out the table row of pattern r; the elected lane needs the 16 byte offsets
-       * as warp-uniform values: one shuffle each */
+      /* lane r works out the table row of pattern r */
       unsigned int my_off = 0;
       if (lane < AW_TILE)
       {
@@ -681,33 +761,46 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
         }
         my_off = row * (unsigned int)G::ROWB;
       }
-      unsigned int offs[AW_TILE];
-#pragma unroll
-      for (int r = 0; r < AW_TILE; ++r) offs[r] = __shfl_sync(0xffffffffu, my_off, r);
+      /* 16-byte asynchronous copies through the load/store path (the rows are scattered over
+       * the table: sixteen TMA requests per tile would cost ~700 cycles of TMA time).  A row is
+       * CH chunks: whole warps take its first 32 k chunks, the tails of several rows share a warp
+       * instruction.  Completion: every lane arrives on `ready` when its copies have landed. */
       const unsigned char * src0 = tables + (size_t)dx.rbytes * G::ROWB;
-      fence_proxy_async_smem(); /* the zeroed counts: read by the TMA store of this tile */
-      __syncwarp();
-      if (aw_elect())
+#ifdef AW_EXP_NOGATHER
+      nrows_x = 0;
+#endif
+      constexpr int CH = G::ROWB / 16; /* 40, 20, 10 */
+      constexpr int FULLW = CH / 32, TAIL = CH % 32, RPT = TAIL ? 32 / TAIL : 1; /* rows per tail instruction */
+#pragma unroll
+      for (int r = 0; r < AW_TILE; ++r)
       {
-        mbar_arrive_expect_tx(rb, nrows_x * G::ROWB);
-        if (nrows_x == AW_TILE)
-        {
+        const unsigned int off_r = __shfl_sync(0xffffffffu, my_off, r);
+        if ((unsigned int)r < nrows_x)
 #pragma unroll
-          for (int r = 0; r < AW_TILE; ++r) aw_g2s(oslot + G::row_off(r), src0 + offs[r], G::ROWB, rb, keep);
-        }
-        else
-        {
+          for (int w = 0; w < FULLW; ++w)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(oslot + G::row_off(r) + (w * 32 + lane) * 16)),
+                         "l"(src0 + off_r + (w * 32 + lane) * 16)
+                         : "memory");
+      }
+      if (TAIL)
+      {
 #pragma unroll
-          for (int r = 0; r < AW_TILE; ++r)
-            if ((unsigned int)r < nrows_x) aw_g2s(oslot + G::row_off(r), src0 + offs[r], G::ROWB, rb, keep);
+        for (int r0 = 0; r0 < AW_TILE; r0 += RPT)
+        {
+          const unsigned int rr = r0 + lane / TAIL, c = FULLW * 32 + lane % TAIL;
+          const unsigned int off_r = __shfl_sync(0xffffffffu, my_off, rr & 15u);
+          if (lane < RPT * TAIL && rr < nrows_x)
+          {
+            const unsigned int dst_off = (rr < 8u ? rr * G::ROWB : 8u * G::ROWB + 64u + (rr - 8u) * G::ROWB) + c * 16u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(oslot + dst_off)), "l"(src0 + off_r + c * 16u)
+                         : "memory");
+          }
         }
       }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr(rb)) : "memory");
     }
     else
-    {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(rb);
-    }
+      mbar_arrive(rb);
     __syncwarp();
   };
 
@@ -722,18 +815,24 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
     for (unsigned int i = 0; i < n_ops; ++i, ++it)
     {
       const unsigned int s = it % AW_STAGES;
-      /* tip characters: request those of it + 3; those of it and it + 1 have landed */
-      issue_codes((it + 3u) % AW_CODEBUFS);
-      load_pend(i + 4, pass);
-      asm volatile("cp.async.wait_group 2;" ::: "memory");
+      /* tip characters: request those of it + 4; those of it .. it + 2 must have landed */
+      issue_codes((it + 4u) % AW_CODEBUFS);
+      load_pend(i + 5, pass);
+      /* two groups are committed per iteration (tip characters, then whatever gathers the
+       * iteration issued): all but the last four complete = the characters up to it + 2 */
+      asm volatile("cp.async.wait_group 4;" ::: "memory");
       __syncwarp();
 
-      mbar_wait(&full[s], (it / AW_STAGES) & 1u);
+      wait_poll(&full[s], (it / AW_STAGES) & 1u);
       const FusedOp & d = *reinterpret_cast<const FusedOp *>(stage_base + s * G::REC_BYTES);
-      const unsigned int ahead = d.lbytes >> 16;
+      if (s) fill_b1 = d.lbytes >> 16; /* size of the record of operation it + AW_STAGES */
+      else fill_b0 = d.lbytes >> 16;
+      known_it = it + 1u;
       if (!have)
       {
-        release(s, it, i, ahead);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        release(s);
+        producer_poll();
         continue;
       }
       const int kind = d.kind;
@@ -753,7 +852,7 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
       sl.advance(pslot);
       /* everything this warp needs of the record is in registers: hand the stage back early, the
        * refill then has a whole operation to arrive */
-      release(s, it, i, ahead);
+      release(s);
 
       /* The next operation of this tile.  While the math warp is still busy with this one, tip
        * rows can already be gathered if nobody uses their slot; once it has finished, any slot
@@ -762,25 +861,36 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
       const bool next_here = i + 1 < n_ops;
       const FusedOp & dn = *reinterpret_cast<const FusedOp *>(stage_base + (s ^ 1u) * G::REC_BYTES);
       const unsigned int next_parity = ((it + 1u) / AW_STAGES) & 1u;
-      if (next_here && mbar_try_wait(&full[s ^ 1u], next_parity))
+      bool prepared_blocked = false; /* the next operation's slot is in use by this one: after `done` */
+      auto try_early = [&]()
       {
+        if (prepared || !next_here || !mbar_test_wait(&full[s ^ 1u], next_parity)) return;
         AwSlots sn = sl;
         sn.place(dn.lslot, dn.rslot, dn.pslot);
-        const bool gather_n = dn.kind == PLG_KIND_TT || (dn.kind == PLG_KIND_TI && sn.out != sn.rphys && sn.rphys >= 0);
-        if (gather_n && sn.out != out && sn.out != lphys && sn.out != rphys)
+        const bool miss_n = (dn.kind == PLG_KIND_II && sn.lphys < 0) || (dn.kind != PLG_KIND_TT && sn.rphys < 0);
+        if (!miss_n && sn.out != out && sn.out != lphys && sn.out != rphys)
         {
           prepare(dn, it + 1u, sn.out, sn.rphys, false, nrows);
           prepared = true;
         }
-      }
+        else
+          prepared_blocked = true;
+      };
+      try_early();
 
-      /* the tile is complete when its rows have landed (tip-tip) or the math warp says so */
-      if (kind == PLG_KIND_TT) mbar_wait(&ready[it & 1u], (it >> 1) & 1u);
-      else mbar_wait(&done[it & 1u], (it >> 1) & 1u);
+      /* the tile is complete when its rows have landed (tip-tip) or the math warps say so */
+      {
+        uint64_t * bar = kind == PLG_KIND_TT ? &ready[it & 1u] : &done[it & 1u];
+        while (!mbar_test_wait(bar, (it >> 1) & 1u))
+        {
+          producer_poll();
+          if (!prepared_blocked) try_early();
+        }
+      }
 
       if (next_here && !prepared)
       {
-        mbar_wait(&full[s ^ 1u], next_parity);
+        wait_poll(&full[s ^ 1u], next_parity);
         AwSlots sn = sl;
         sn.place(dn.lslot, dn.rslot, dn.pslot);
         const bool miss_n = (dn.kind == PLG_KIND_II && sn.lphys < 0) || (dn.kind != PLG_KIND_TT && sn.rphys < 0);
@@ -792,25 +902,23 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
         }
       }
 
+      asm volatile("cp.async.commit_group;" ::: "memory"); /* this iteration's gathers */
       unsigned char * const oslot = slots + out * G::SLOT_BYTES;
       if (pad & 1)
       {
-        if (kind == PLG_KIND_TT && mode == 1 && nrows < AW_TILE && lane < nrows) pscale[first_site + lane] = 0u;
+        if (mode == 1 && lane < nrows) pscale[first_site + lane] = reinterpret_cast<const unsigned int *>(oslot + G::ROWS_BYTES)[lane];
+        fence_proxy_async_smem(); /* rows gathered by this warp's cp.async copies (tip-tip): TMA reads them next */
         __syncwarp();
         if (aw_elect())
         {
           double * dst0 = parent + (size_t)first_site * (R * 20);
-          if (nrows == AW_TILE)
+          const unsigned int first_half = min(nrows, 8u);
+#ifdef AW_EXP_NOSTORE
+          if (nrows > 99u)
+#endif
           {
-#pragma unroll
-            for (int r = 0; r < AW_TILE; ++r) aw_s2g(dst0 + (size_t)r * (R * 20), oslot + G::row_off(r), G::ROWB, stream);
-            if (mode == 1) aw_s2g(pscale + first_site, oslot + G::ROWS_BYTES, 64, stream);
-          }
-          else
-          {
-#pragma unroll
-            for (int r = 0; r < AW_TILE; ++r)
-              if ((unsigned int)r < nrows) aw_s2g(dst0 + (size_t)r * (R * 20), oslot + G::row_off(r), G::ROWB, stream);
+          aw_s2g(dst0, oslot, first_half * G::ROWB, stream);
+          if (nrows > 8u) aw_s2g(dst0 + 8 * (R * 20), oslot + G::HALF_BYTES + 64, (nrows - 8u) * G::ROWB, stream);
           }
         }
         last_store_slot = out;
@@ -830,7 +938,7 @@ static size_t walk_smem()
 {
   using G = AwGeom<R>;
   return (size_t)AW_STAGES * G::REC_BYTES + (size_t)AW_TEAMS * AW_SLOTS * G::SLOT_BYTES + AW_TEAMS * AW_CODEBUFS * 32 +
-         (2 * AW_STAGES + 4 * AW_TEAMS) * sizeof(uint64_t) + AW_STAGES * sizeof(unsigned int) + 8;
+         (2 * AW_STAGES + 6 * AW_TEAMS) * sizeof(uint64_t) + AW_TEAMS * 8 * sizeof(unsigned int);
 }
 
 size_t plg_walk_aa_record_bytes(unsigned int rate_cats) { return 128 + 2 * (size_t)rate_cats * 3200; }
@@ -862,7 +970,7 @@ static int launch_walk(plg_context * ctx, const FusedOp * dev_ops, unsigned char
   TipmapArg tm;
   memcpy(tm.map, ctx->tipmap, sizeof(tm.map));
   k_walk_pack_aa<R><<<n_ops, 256, pack_smem, ctx->stream>>>(dev_ops, dev_records, dev_tables, ctx->maxstates, tm);
-  k_walk_aa<R><<<blocks, 2 * AW_TEAMS * 32, smem, ctx->stream>>>(dev_ops, dev_records, dev_tables, n_ops, ctx->d.sites,
+  k_walk_aa<R><<<blocks, AW_WARPS * 32, smem, ctx->stream>>>(dev_ops, dev_records, dev_tables, n_ops, ctx->d.sites,
                                                                  ctx->maxstates);
   return PLG_OK;
 }

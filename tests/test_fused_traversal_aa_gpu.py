@@ -1,10 +1,10 @@
-"""GPU: the 20-state single-kernel traversal (libpll_b200/csrc/gpu/plg_traverse_aa.cu; opt-in with
-PLL_GPU_FUSED_AA=1 for protein partitions with 1, 2 or 4 rate categories) against
+"""GPU: the 20-state single-kernel walk (libpll_b200/csrc/gpu/plg_walk_aa.cu; opt-in with
+PLL_GPU_FUSED_AA=1 for protein partitions with 1, 2 or 4 rate categories and per-site scalers) against
 
   * the level-by-level tensor-core kernels (PLL_GPU_FUSED=0): both run the same DMMA chains in the
     same order, so every CLV and every scaler array must be BIT-identical - plain and
     slot-recycling lists, per-site and per-rate scalers, 1 and 2 tile-cache slots (1 slot forces
-    reads back from HBM), alignment lengths that leave partial 32-pattern tiles and partial
+    reads back from HBM), alignment lengths that leave partial 16-pattern tiles and partial
     8-pattern groups, CLV tips and pattern tips, LG and the LG4M four-matrix mixture;
   * the reference's AVX2 path (oracle/_ref): scalers bit-exact, CLVs within 1e-12 relative
     (DMMA sums the 20 products of a row in another order than the AVX2 lanes), lnL within 1e-10.
@@ -19,19 +19,13 @@ from test_parity_gpu import _caterpillar
 
 pytestmark = pytest.mark.gpu
 
-#: which whole-list kernel the module exercises: "1" = plg_traverse_aa.cu, "2" / "2s" = plg_walk_aa.cu
-#: with one / two warps per tile team
-IMPL = __import__("os").environ.get("PLL_TEST_FUSED_AA", "2")
-
-
 def _select(monkeypatch, fused=True):
-    monkeypatch.setenv("PLL_GPU_FUSED_AA", IMPL[0] if fused else "0")
-    monkeypatch.setenv("PLL_GPU_WALK_SPLIT", "2" if IMPL.endswith("s") else "1")
+    monkeypatch.setenv("PLL_GPU_FUSED_AA", "1" if fused else "0")
 
 
 def _fused_here(rate_scalers):
-    """The second design keeps per-rate scalers on the level-by-level kernels."""
-    return not (IMPL[0] == "2" and rate_scalers)
+    """Per-rate scalers stay on the level-by-level kernels."""
+    return not rate_scalers
 
 
 def _run(gpu_lib, monkeypatch, w, attrs, fused, slots=3, variant="default"):
