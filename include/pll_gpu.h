@@ -325,7 +325,8 @@ PLL_EXPORT int pll_gpu_device_count(void);
  * log-likelihoods / derivatives are the per-slice partial results added on the host in slice
  * order (the only cross-device exchange on the path: reference src/core_likelihood_avx.c:1259
  * `logl +=`, src/core_derivatives_avx2.c:756-765 are the only statements that couple sites).
- * Nothing in the caller changes.  Not combinable with ascertainment-bias correction. */
+ * Nothing in the caller changes (ascertainment-bias correction included: its per-state sites live
+ * in the last slice). */
 PLL_EXPORT int pll_gpu_set_devices(int count);
 /* The slicing rule itself: writes first_site[0 .. n] for `sites` patterns cut into at most
  * `slices` 64-pattern-aligned slices (first_site[n] = sites) and returns n <= slices; first_site

@@ -937,9 +937,10 @@ extern "C" int plg_mem_info(plg_context_t * ctx, size_t * free_bytes, size_t * t
 extern "C" int plg_set_active_sites(plg_context_t * ctx, unsigned int sites)
 {
   PLG_CHECK_CTX(ctx);
-  if (sites == 0 || sites > ctx->d.sites)
+  /* 0 is legal: a slice of a multi-device partition that holds per-state sites only */
+  if (sites > ctx->d.sites)
   {
-    plg_set_error("plg_set_active_sites: %u out of range (1..%u)", sites, ctx->d.sites);
+    plg_set_error("plg_set_active_sites: %u out of range (0..%u)", sites, ctx->d.sites);
     return PLG_E_INVALID;
   }
   ctx->active_sites = sites;

@@ -493,6 +493,7 @@ static int launch_derivatives_dna(plg_context * ctx, const DerArgs & a, const De
   unsigned int nblocks = (sites + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
   const unsigned int cap = (unsigned int)(ctx->sm_count * (per_sm > 0 ? per_sm : 1));
   if (nblocks > cap) nblocks = cap;
+  if (nblocks == 0) nblocks = 1; /* no active pattern: one block still delivers the (zero) sums */
   int rc = plg_ensure_partials(ctx, 2 * (size_t)nblocks);
   if (rc) return rc;
   DerArgs b = a;
@@ -618,6 +619,7 @@ static int launch_derivatives_aa(plg_context * ctx, const DerArgs & a, const Der
   unsigned int nblocks = (sites + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
   const unsigned int cap = (unsigned int)(ctx->sm_count * (per_sm > 0 ? per_sm : 1));
   if (nblocks > cap) nblocks = cap;
+  if (nblocks == 0) nblocks = 1; /* no active pattern: one block still delivers the (zero) sums */
   int rc = plg_ensure_partials(ctx, 2 * (size_t)nblocks);
   if (rc) return rc;
   DerArgs b = a;
@@ -891,6 +893,7 @@ extern "C" int plg_likelihood_derivatives(plg_context_t * ctx, const void * key,
   const unsigned int R = ctx->d.rate_cats, K = ctx->d.states;
   const unsigned int nelem = ctx->active_sites * R;
   unsigned int nblocks = (nelem + PLG_DER_THREADS - 1) / PLG_DER_THREADS;
+  if (nblocks == 0) nblocks = 1; /* no active pattern: one block still delivers the (zero) sums */
   /* persistent: exactly the CTAs that are resident at once (one wave) */
   const unsigned int cap = (unsigned int)ctx->sm_count * 2u;
   if (nblocks > cap) nblocks = cap;

@@ -326,7 +326,7 @@ int plg_gen_loglikelihood(plg_context * ctx, const GenLnl & g, const double * fr
                           const double * prop_invar, double * persite_lnl, double * logl_out)
 {
   const unsigned int R = ctx->d.rate_cats, Kp = ctx->d.states_padded;
-  const unsigned int nblocks = (ctx->active_sites + PLG_GEN_THREADS - 1) / PLG_GEN_THREADS;
+  const unsigned int nblocks = ctx->active_sites ? (ctx->active_sites + PLG_GEN_THREADS - 1) / PLG_GEN_THREADS : 1u;
   int rc = plg_ensure_partials(ctx, nblocks);
   if (rc) return rc;
   bool any_pinv = false;
@@ -499,7 +499,7 @@ int plg_gen_derivatives(plg_context * ctx, const double * sumtable, const double
                         double * d_f, double * dd_f)
 {
   const unsigned int R = ctx->d.rate_cats, K = ctx->d.states, Kp = ctx->d.states_padded;
-  const unsigned int nblocks = (ctx->active_sites + PLG_GEN_THREADS - 1) / PLG_GEN_THREADS;
+  const unsigned int nblocks = ctx->active_sites ? (ctx->active_sites + PLG_GEN_THREADS - 1) / PLG_GEN_THREADS : 1u;
   int rc = plg_ensure_partials(ctx, 2 * (size_t)nblocks);
   if (rc) return rc;
   bool any_pinv = false;

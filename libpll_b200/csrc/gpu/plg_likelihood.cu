@@ -318,6 +318,7 @@ static int launch_lnl_dna(plg_context * ctx, LnlArgs & a, const LnlParams & P)
   unsigned int nblocks = (sites + PLG_LNL_THREADS - 1) / PLG_LNL_THREADS;
   const unsigned int cap = (unsigned int)(ctx->sm_count * (per_sm > 0 ? per_sm : 1));
   if (nblocks > cap) nblocks = cap;
+  if (nblocks == 0) nblocks = 1;
   k_lnl_dna<R, MODE><<<nblocks, PLG_LNL_THREADS, 0, ctx->stream>>>(a, P);
   return PLG_OK;
 }
@@ -550,6 +551,7 @@ static int launch_lnl_aa(plg_context * ctx, LnlArgs & a, const LnlParams & P)
   unsigned int nblocks = (sites + PLG_LNL_THREADS - 1) / PLG_LNL_THREADS;
   const unsigned int cap = (unsigned int)(ctx->sm_count * (per_sm > 0 ? per_sm : 1));
   if (nblocks > cap) nblocks = cap;
+  if (nblocks == 0) nblocks = 1;
   k_lnl_aa<R, MODE><<<nblocks, PLG_LNL_THREADS, 0, ctx->stream>>>(a, P);
   return PLG_OK;
 }
@@ -584,6 +586,7 @@ static int common_args(plg_context * ctx, LnlArgs & a, double * persite_lnl, uns
 {
   const unsigned int nelem = ctx->active_sites * ctx->d.rate_cats;
   *nblocks = (nelem + PLG_LNL_THREADS - 1) / PLG_LNL_THREADS;
+  if (*nblocks == 0) *nblocks = 1; /* no active pattern: one block still delivers the (zero) sum */
   int rc = plg_ensure_partials(ctx, *nblocks);
   if (rc) return rc;
   if (persite_lnl && !ctx->persite_dev)

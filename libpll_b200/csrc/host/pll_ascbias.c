@@ -44,7 +44,7 @@ PLL_EXPORT void pll_set_asc_state_weights(pll_partition_t * partition, const uns
   }
   pll_partition_t * p = &g->pub;
   memcpy(p->pattern_weights + p->sites, state_weights, p->states * sizeof(unsigned int));
-  int rc = plg_set_pattern_weights(g->ctx, p->pattern_weights);
+  int rc = pllg_dev_set_pattern_weights(g, p->pattern_weights);
   if (rc) pllg_fail(rc, "pll_set_asc_state_weights");
 }
 
@@ -58,7 +58,7 @@ static double * fetch_clv_tail(pllg_partition_t * g, unsigned int clv_index)
     pll_fail(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
     return NULL;
   }
-  int rc = plg_get_clv_sites(g->ctx, clv_index, p->sites, p->states, buf);
+  int rc = pllg_dev_get_clv_sites(g, clv_index, p->sites, p->states, buf);
   if (rc)
   {
     pllg_fail(rc, "ascertainment bias correction");
@@ -74,7 +74,7 @@ static int fetch_scaler_tail(pllg_partition_t * g, int scaler_index, unsigned in
   const pll_partition_t * p = &g->pub;
   memset(out, 0, p->states * sizeof(unsigned int));
   if (scaler_index == PLL_SCALE_BUFFER_NONE) return 1;
-  int rc = plg_get_scaler_sites(g->ctx, (unsigned int)scaler_index, p->sites, p->states, out);
+  int rc = pllg_dev_get_scaler_sites(g, (unsigned int)scaler_index, p->sites, p->states, out);
   return rc ? pllg_fail(rc, "ascertainment bias correction") : 1;
 }
 
@@ -232,7 +232,7 @@ int pllg_asc_derivatives(pllg_partition_t * g, int parent_scaler_index, int chil
   if (!ok) pll_fail(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
   if (ok)
   {
-    int rc = plg_get_sumtable_sites(g->ctx, sumtable_key, p->sites, K, sum);
+    int rc = pllg_dev_get_sumtable_sites(g, sumtable_key, p->sites, K, sum);
     if (rc) ok = pllg_fail(rc, "pll_compute_likelihood_derivatives");
   }
   if (ok) ok = fetch_scaler_tail(g, parent_scaler_index, sf) && fetch_scaler_tail(g, child_scaler_index, sf + K);

@@ -143,10 +143,10 @@ PLL_EXPORT int pll_compute_likelihood_derivatives(pll_partition_t * partition,
    * from the per-state site likelihoods */
   const int ab = (int)(p->attributes & PLL_ATTRIB_AB_MASK);
   int rc = PLG_OK;
-  if (ab == PLL_ATTRIB_AB_STAMATAKIS) rc = plg_set_active_sites(g->ctx, p->sites + K);
+  if (ab == PLL_ATTRIB_AB_STAMATAKIS) rc = pllg_dev_set_active_sites(g, p->sites + K);
   if (!rc)
     rc = pllg_dev_likelihood_derivatives(g, sumtable, diagp, p->rate_weights, pinv, freqs, d_f, dd_f);
-  if (ab == PLL_ATTRIB_AB_STAMATAKIS) plg_set_active_sites(g->ctx, p->sites);
+  if (ab == PLL_ATTRIB_AB_STAMATAKIS) pllg_dev_set_active_sites(g, p->sites);
   int ok = rc ? pllg_fail(rc, "pll_compute_likelihood_derivatives") : PLL_SUCCESS;
   if (ok && ab && ab != PLL_ATTRIB_AB_STAMATAKIS)
     ok = pllg_asc_derivatives(g, parent_scaler_index, child_scaler_index, diagp, sumtable, d_f, dd_f);

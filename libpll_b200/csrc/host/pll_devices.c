@@ -204,6 +204,62 @@ int pllg_dev_set_pattern_weights(pllg_partition_t * g, const unsigned int * weig
   FOR_EACH_DEVICE(plg_set_pattern_weights(ctx, weights + lo));
 }
 
+/* The leading `count` patterns of the partition take part in the lnL / derivative reductions
+ * (ascertainment bias: the per-state sites behind the last real pattern do not): every slice gets
+ * its share of that prefix. */
+int pllg_dev_set_active_sites(pllg_partition_t * g, unsigned int count)
+{
+  for (unsigned int d = 0; d < g->ndev; ++d)
+  {
+    const unsigned int lo = g->lo[d], hi = g->lo[d + 1];
+    const unsigned int mine = count <= lo ? 0u : (count >= hi ? hi - lo : count - lo);
+    int rc = plg_set_active_sites(g->ctxs[d], mine);
+    if (rc) return rc;
+  }
+  return PLG_OK;
+}
+
+/* A range of patterns [first, first + count) of a CLV / scale buffer / sumtable, wherever its
+ * pieces live (the per-state sites of the ascertainment-bias correction sit in the last slice, or
+ * straddle the last two) */
+#define FOR_EACH_PIECE(call)                                                   \
+  do                                                                           \
+  {                                                                            \
+    for (unsigned int d = 0; d < g->ndev; ++d)                                 \
+    {                                                                          \
+      const unsigned int a = first > g->lo[d] ? first : g->lo[d];              \
+      const unsigned int b = first + count < g->lo[d + 1] ? first + count : g->lo[d + 1]; \
+      if (a >= b) continue;                                                    \
+      plg_context_t * ctx = g->ctxs[d];                                        \
+      const unsigned int local = a - g->lo[d], n = b - a;                      \
+      const size_t at = a - first;                                             \
+      int rc_ = (call);                                                        \
+      if (rc_) return rc_;                                                     \
+    }                                                                          \
+    return PLG_OK;                                                             \
+  } while (0)
+
+int pllg_dev_get_clv_sites(pllg_partition_t * g, unsigned int clv_index, unsigned int first, unsigned int count,
+                           double * out)
+{
+  const size_t span = clv_span(g);
+  FOR_EACH_PIECE(plg_get_clv_sites(ctx, clv_index, local, n, out + at * span));
+}
+
+int pllg_dev_get_scaler_sites(pllg_partition_t * g, unsigned int scaler_index, unsigned int first,
+                              unsigned int count, unsigned int * out)
+{
+  const size_t span = scaler_span(g);
+  FOR_EACH_PIECE(plg_get_scaler_sites(ctx, scaler_index, local, n, out + at * span));
+}
+
+int pllg_dev_get_sumtable_sites(pllg_partition_t * g, const void * key, unsigned int first, unsigned int count,
+                                double * out)
+{
+  const size_t span = clv_span(g);
+  FOR_EACH_PIECE(plg_get_sumtable_sites(ctx, key, local, n, out + at * span));
+}
+
 int pllg_dev_update_invariant(pllg_partition_t * g, int * invariant_out)
 {
   FOR_EACH_DEVICE(plg_update_invariant(ctx, invariant_out ? invariant_out + lo : NULL));

@@ -64,6 +64,13 @@ int pllg_dev_set_clv(pllg_partition_t * g, unsigned int clv_index, const double 
 int pllg_dev_get_clv(pllg_partition_t * g, unsigned int clv_index, double * clv);
 int pllg_dev_get_scaler(pllg_partition_t * g, unsigned int scaler_index, unsigned int * scaler);
 int pllg_dev_set_pattern_weights(pllg_partition_t * g, const unsigned int * weights);
+int pllg_dev_set_active_sites(pllg_partition_t * g, unsigned int count);
+int pllg_dev_get_clv_sites(pllg_partition_t * g, unsigned int clv_index, unsigned int first, unsigned int count,
+                           double * out);
+int pllg_dev_get_scaler_sites(pllg_partition_t * g, unsigned int scaler_index, unsigned int first,
+                              unsigned int count, unsigned int * out);
+int pllg_dev_get_sumtable_sites(pllg_partition_t * g, const void * key, unsigned int first, unsigned int count,
+                                double * out);
 int pllg_dev_update_invariant(pllg_partition_t * g, int * invariant_out);
 int pllg_dev_set_pmatrix(pllg_partition_t * g, unsigned int matrix_index, const double * pmatrix);
 int pllg_dev_update_pmatrix(pllg_partition_t * g, const unsigned int * matrix_indices,

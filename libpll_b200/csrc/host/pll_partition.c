@@ -242,15 +242,6 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips,
   /* one device context per pattern slice (pll_devices.c); a single one unless the caller asked
    * for more with pll_gpu_set_devices / PLL_GPU_DEVICES */
   int slices = pll_gpu_current_slices();
-  if (slices > 1 && p->asc_bias_alloc)
-  {
-    /* the per-state sites of the correction live behind the last real site; the host epilogues
-     * read them from one context */
-    pll_fail(PLL_ERROR_GPU_UNSUPPORTED,
-             "Ascertainment-bias correction is not available on a partition spread over several devices.");
-    free_host(g);
-    return NULL;
-  }
   int rc = pllg_dev_create(g, &dims, pick_device(), slices);
   if (rc != PLG_OK)
   {
@@ -307,7 +298,7 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips,
   if (p->asc_bias_alloc)
   {
     /* reductions cover the real sites; the per-state sites only feed the correction terms */
-    rc = plg_set_active_sites(g->ctx, sites);
+    rc = pllg_dev_set_active_sites(g, sites);
     if (!rc) rc = pllg_dev_set_pattern_weights(g, p->pattern_weights);
     if (rc)
     {

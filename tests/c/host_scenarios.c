@@ -61,14 +61,14 @@ static unsigned long scenario(unsigned int states, unsigned int cats, int patter
   CHECK(pll_gpu_set_devices(slices));
   pll_partition_t * p = pll_partition_create(tips, inner, states, sites, 2, matrices, cats, inner, attrs);
   pll_gpu_set_devices(0);
-  if ((ab && rate_scalers) || (ab && slices > 1))
+  if (ab && rate_scalers)
   {
     CHECK(p == NULL && pll_errno == PLL_ERROR_GPU_UNSUPPORTED);
     CHECK(null_device_live_contexts() == 0);
     return 0;
   }
   CHECK(p != NULL);
-  CHECK(pll_gpu_partition_devices(p) == (slices > 1 ? 3 : 1));   /* 130 patterns: 64 + 64 + 2 */
+  CHECK(pll_gpu_partition_devices(p) == (slices > 1 ? 3 : 1));   /* 130 patterns (+ states with AB): 64 + 64 + rest */
   CHECK(null_device_live_contexts() == pll_gpu_partition_devices(p));
 
   /* model */

@@ -110,3 +110,45 @@ def test_ascbias_errors(gpu_lib):
     with pytest.raises(PllError):  # p-inv is incompatible with the correction
         part.update_invariant_sites_proportion(0, 0.2)
     part.destroy()
+
+
+@pytest.mark.parametrize("slices,sites", [(2, 128), (3, 200), (4, 61)])
+def test_ascbias_on_a_sliced_partition(gpu_lib, ref_lib, monkeypatch, slices, sites):
+    """pll_gpu_set_devices / PLL_GPU_DEVICES with the correction: the per-state sites behind the
+    last pattern fall into the last slice (with 128 patterns in two slices they ARE the last slice:
+    a context without a single active pattern), the reductions cover each slice's share of the real
+    patterns, the host epilogue fetches the per-state CLVs / scalers / sumtable rows from wherever
+    they live.  Same values as the reference (src/likelihood.c:24-119,
+    src/core_derivatives.c:654-727)."""
+    monkeypatch.setenv("PLL_GPU_DEVICES", str(slices))
+    w = S.make_workload(9, sites, states=4, seed=sites)
+    pg, pr, pidx = _pair(gpu_lib, ref_lib, w, PLL_ATTRIB_PATTERN_TIP, PLL_ATTRIB_ARCH_AVX2)
+    assert gpu_lib.pll_gpu_partition_devices(pg.ptr) >= 2  # 64-pattern aligned slices of sites + states
+    state_weights = np.arange(2, 6, dtype=np.uint32) * 5
+    top = w.tips + w.inner - 1
+    for p in (pg, pr):
+        p.update_prob_matrices(pidx, w.matrix_indices, w.branch_lengths)
+        p.update_partials(w.ops)
+    a, b = w.root_a, w.root_b
+    for ab in TYPES:
+        for p in (pg, pr):
+            p.set_asc_bias_type(ab)
+            if ab in (PLL_ATTRIB_AB_FELSENSTEIN, PLL_ATTRIB_AB_STAMATAKIS):
+                p.set_asc_state_weights(state_weights)
+        args = (a, w.scaler_of(a), b, w.scaler_of(b), w.root_matrix, pidx)
+        lg, lr = pg.edge_loglikelihood(*args), pr.edge_loglikelihood(*args)
+        assert np.isfinite(lr) and abs(lg - lr) <= RTOL * abs(lr), (ab, lg, lr)
+        rg = pg.root_loglikelihood(top, w.scaler_of(top), pidx)
+        rr = pr.root_loglikelihood(top, w.scaler_of(top), pidx)
+        assert abs(rg - rr) <= RTOL * abs(rr), (ab, rg, rr)
+        sg, sr = pg.new_sumtable(), pr.new_sumtable()
+        pg.update_sumtable(a, b, w.scaler_of(a), w.scaler_of(b), pidx, sg)
+        pr.update_sumtable(a, b, w.scaler_of(a), w.scaler_of(b), pidx, sr)
+        for t in (0.05, 0.7):
+            dg = pg.likelihood_derivatives(w.scaler_of(a), w.scaler_of(b), t, pidx, sg)
+            dr = pr.likelihood_derivatives(w.scaler_of(a), w.scaler_of(b), t, pidx, sr)
+            scale = max(abs(dr[0]), float(w.weights.sum()) * 1e-3)
+            assert abs(dg[0] - dr[0]) <= RTOL * scale, (ab, t, dg, dr)
+            assert abs(dg[1] - dr[1]) <= RTOL * max(abs(dr[1]), scale), (ab, t, dg, dr)
+    pg.destroy()
+    pr.destroy()

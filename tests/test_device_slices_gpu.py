@@ -129,12 +129,4 @@ def test_slices_follow_the_environment_and_reject_asc_bias(gpu_lib, monkeypatch)
     part.destroy()
     assert abs(lnl1 - lnl3) <= 1e-12 * abs(lnl1)
 
-    assert gpu_lib.pll_gpu_set_devices(2) == 1
-    try:
-        with pytest.raises(Exception, match="several devices"):
-            gpu_lib.partition(tips=4, clv_buffers=2, states=4, sites=200, rate_matrices=1, prob_matrices=5,
-                              rate_cats=4, scale_buffers=2,
-                              attributes=PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_AB_LEWIS)
-    finally:
-        gpu_lib.pll_gpu_set_devices(0)
     assert gpu_lib.pll_gpu_set_devices(-1) == 0 and gpu_lib.pll_gpu_set_devices(17) == 0
