@@ -153,3 +153,23 @@ def test_repeated_calls_replay_a_graph(gpu_lib, monkeypatch):
     assert part.stats()["graph_launches"] >= 2
     assert part.get_clv(top).tobytes() == first
     part.destroy()
+
+
+def test_the_walk_is_deterministic(gpu_lib, monkeypatch):
+    """Math and DMA warps hand tiles over through mbarriers only; a missed ordering would show as a
+    result that moves between identical calls.  The same 300-operation list 40 times: the root CLV
+    and the log-likelihood must not change by a bit."""
+    monkeypatch.setenv("PLL_GPU_FUSED", "1")
+    _select(monkeypatch)
+    monkeypatch.setenv("PLL_GPU_AA_EXACT", "0")
+    w = S.make_workload(300, 20000, states=20, seed=12)
+    part, pidx = S.build_partition(gpu_lib, w, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP)
+    part.update_prob_matrices(pidx, w.matrix_indices, w.branch_lengths)
+    top = w.tips + w.inner - 1
+    args = (w.root_a, w.scaler_of(w.root_a), w.root_b, w.scaler_of(w.root_b), w.root_matrix, pidx)
+    seen = set()
+    for _ in range(40):
+        part.update_partials(w.ops)
+        seen.add((part.edge_loglikelihood(*args), part.get_clv(top).tobytes()))
+    assert len(seen) == 1
+    part.destroy()
