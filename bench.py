@@ -480,6 +480,13 @@ def leg_c4(lib, part, pidx, tree, walker, sites: int, branches: int = 10, iters:
     t_move = t_sum = t_der = 0.0
     n_der = 0
     lengths = []
+    per_branch = []
+    # warm-up, untimed: the first sumtable of a partition allocates its 128 MB slot and loads the
+    # level-by-level kernels (the traversal of this benchmark runs the fused one): ~90 ms once
+    e0 = walker.edge(root)
+    for _ in range(2):
+        part.update_sumtable(e0[0], e0[2], e0[1], e0[3], pidx, key)
+        part.likelihood_derivatives(e0[1], e0[3], root.contents.length, pidx, key)
     part.synchronize()
     t_all = time.perf_counter()
     for b in range(branches):
@@ -510,7 +517,13 @@ def leg_c4(lib, part, pidx, tree, walker, sites: int, branches: int = 10, iters:
             length = min(max(length, 1e-6), 10.0)
         t_der += time.perf_counter() - t0
         lengths.append(length)
+        per_branch.append((len(ops), t_move, t_sum, t_der))
     total = time.perf_counter() - t_all
+    prev = (0.0, 0.0, 0.0)
+    for b, (n_ops, a, c, d) in enumerate(per_branch):   # where a slow branch spent its time
+        log(f"c4 branch {b}: {n_ops} operations, move {1e6 * (a - prev[0]):.0f} us, "
+            f"sumtable {1e6 * (c - prev[1]):.0f} us, {iters} derivative calls {1e6 * (d - prev[2]):.0f} us")
+        prev = (a, c, d)
     return {
         "c_caller": c_caller_latencies(),
         "what": f"Newton on {branches} branches (the evaluation edge + {branches - 1} re-rooted ones): "
