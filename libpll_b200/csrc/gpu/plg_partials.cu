@@ -717,11 +717,11 @@ struct dmma_geom
 {
   static constexpr int ROW = R * 20;        /* doubles per site                       */
   /* The 8 sites of a unit sit in the ring as two contiguous halves (sites 0..3, sites 4..7), the
-   * second half 64 bytes further modulo 128.  Each half is ONE bulk copy - the TMA unit serves a
-   * request every ~46 cycles per SM whatever its size, so eight row-sized copies per child made
-   * the kernel request-bound (16 x 46 cycles per unit against 480 cycles of DMMA) - and DMMA row
-   * g works on site (g & 1) * 4 + (g >> 1): the two sites of a quarter warp then start 64 bytes
-   * apart modulo 128 and the four lanes of a site read 64 contiguous bytes - conflict free. */
+   * second half 64 bytes further modulo 128.  Each half is ONE bulk copy (two per child instead of
+   * eight row copies: less issue work per unit, no padded rows; measured neutral in time - the
+   * copies were not request-bound, tools/ubench/tma_store_peak.cu) and DMMA row g works on site
+   * (g & 1) * 4 + (g >> 1): the two sites of a quarter warp then start 64 bytes apart modulo 128
+   * and the four lanes of a site read 64 contiguous bytes - conflict free. */
   static constexpr int HALF = 4 * ROW + 8;  /* doubles from the first half to the second */
   static constexpr int UNIT = 8 * ROW + 8;  /* doubles per child per unit (8 sites)      */
 };

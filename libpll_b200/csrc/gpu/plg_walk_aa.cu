@@ -52,11 +52,11 @@ struct AwGeom
 {
   static constexpr int ROWB = R * 160; /* bytes of one pattern row */
   /* A slot holds the 16 pattern rows of a tile as two contiguous halves (rows 0..7, rows 8..15:
-   * each half is ONE bulk copy to or from HBM - the TMA unit serves a request every ~46 cycles
-   * per SM whatever its size, row-sized copies starve it), the second half 64 bytes further
-   * modulo 128.  A DMMA group takes four rows of each half (AwLane::row): the two patterns of
-   * a quarter warp then sit 64 bytes apart modulo 128 and the four lanes of a pattern touch 64
-   * contiguous bytes - fragment loads and stores are bank-conflict free. */
+   * each half is ONE bulk copy to HBM instead of eight row copies the DMA warp would have to issue),
+   * the second half 64 bytes further modulo 128.  A DMMA group takes four rows of each half
+   * (AwLane::row): the two patterns of a quarter warp then sit 64 bytes apart modulo 128 and the
+   * four lanes of a pattern touch 64 contiguous bytes - fragment loads and stores are
+   * bank-conflict free. */
   __host__ __device__ static constexpr int row_off(int s) { return s < 8 ? s * ROWB : 8 * ROWB + 64 + (s - 8) * ROWB; }
   static constexpr int HALF_BYTES = 8 * ROWB;
   static constexpr int ROWS_BYTES = 16 * ROWB + 64;
@@ -762,7 +762,7 @@ k_walk_aa(const FusedOp * __restrict__ ops, const unsigned char * __restrict__ r
         my_off = row * (unsigned int)G::ROWB;
       }
       /* 16-byte asynchronous copies through the load/store path (the rows are scattered over
-       * the table: sixteen TMA requests per tile would cost ~700 cycles of TMA time).  A row is
+       * the table: twenty warp-wide cp.async instead of sixteen single-lane TMA requests).  A row is
        * CH chunks: whole warps take its first 32 k chunks, the tails of several rows share a warp
        * instruction.  Completion: every lane arrives on `ready` when its copies have landed. */
       const unsigned char * src0 = tables + (size_t)dx.rbytes * G::ROWB;
