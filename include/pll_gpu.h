@@ -326,7 +326,9 @@ PLL_EXPORT int pll_gpu_device_count(void);
  * order (the only cross-device exchange on the path: reference src/core_likelihood_avx.c:1259
  * `logl +=`, src/core_derivatives_avx2.c:756-765 are the only statements that couple sites).
  * Nothing in the caller changes (ascertainment-bias correction included: its per-state sites live
- * in the last slice). */
+ * in the last slice).  Value-returning calls issue their per-device launches from one helper
+ * thread per further slice (they spin while calls keep coming, nap when idle; PLL_GPU_HOST_THREADS=0
+ * keeps every launch on the calling thread). */
 PLL_EXPORT int pll_gpu_set_devices(int count);
 /* The slicing rule itself: writes first_site[0 .. n] for `sites` patterns cut into at most
  * `slices` 64-pattern-aligned slices (first_site[n] = sites) and returns n <= slices; first_site

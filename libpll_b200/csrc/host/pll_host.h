@@ -32,6 +32,7 @@ typedef struct pllg_partition
   int grouped;               /* 1: scalar results are combined on the devices (plg_group_*) */
   plg_context_t * ctxs[PLLG_MAX_DEVICES];
   unsigned int lo[PLLG_MAX_DEVICES + 1];
+  struct pllg_pool * pool;   /* helper threads, one per slice but the first (pll_devices.c); NULL: none */
 } pllg_partition_t;
 
 static inline pllg_partition_t * pllg_from(const pll_partition_t * p)
@@ -53,6 +54,9 @@ int pll_gpu_current_slices(void);
  * arguments as the plg_* function of the same name, host arrays indexed by site are offset per
  * slice, scalar results are summed in slice order */
 int pllg_dev_create(pllg_partition_t * g, const plg_dims_t * dims, int first_device, int slices);
+/* message of a device call that failed on a helper thread (plg_last_error is thread-local), or
+ * NULL; reading it clears it */
+const char * pllg_pending_error(void);
 void pllg_dev_destroy(pllg_partition_t * g);
 int pllg_dev_synchronize(pllg_partition_t * g);
 int pllg_dev_set_tipmap(pllg_partition_t * g, const unsigned int * tipmap, unsigned int maxstates);

@@ -43,7 +43,8 @@ int pllg_fail(int rc, const char * where)
     case PLG_E_UNSUPPORTED: code = PLL_ERROR_GPU_UNSUPPORTED; break;
     default: code = PLL_ERROR_GPU_RUNTIME; break;
   }
-  return pll_fail(code, "%s: %s", where, plg_last_error());
+  const char * message = pllg_pending_error();
+  return pll_fail(code, "%s: %s", where, message ? message : plg_last_error());
 }
 
 PLL_EXPORT void * pll_aligned_alloc(size_t size, size_t alignment)

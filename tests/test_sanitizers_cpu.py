@@ -60,7 +60,7 @@ def _build(tmp_path_factory, name, sources):
     out = tmp_path_factory.mktemp(name) / name
     cmd = [gcc, "-std=gnu99", "-g", "-O1", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
            "-fno-omit-frame-pointer", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-I", HOST,
-           "-o", str(out)] + sources + ["-lm"]
+           "-o", str(out)] + sources + ["-lm", "-pthread"]
     built = subprocess.run(cmd, capture_output=True, text=True)
     if built.returncode != 0 and "sanitize" in built.stderr:
         pytest.skip("this gcc has no sanitizer runtime")
