@@ -420,18 +420,48 @@ int pllg_dev_set_pmatrix(pllg_partition_t * g, unsigned int matrix_index, const 
   FOR_EACH_DEVICE(plg_set_pmatrix(ctx, matrix_index, pmatrix));
 }
 
+/* the enqueue-only calls of a branch-length loop also go out side by side (their host part -
+ * staging, planning, launch - is ~15 us per device) */
+struct pmatrix_args
+{
+  const unsigned int * matrix_indices;
+  const double * branch_lengths;
+  unsigned int count;
+  const double * rates, * prop_invar, * eigenvals, * eigenvecs, * inv_eigenvecs;
+};
+
+static int pmatrix_job(pllg_partition_t * g, unsigned int d, void * p)
+{
+  struct pmatrix_args * a = (struct pmatrix_args *)p;
+  return plg_update_pmatrix(g->ctxs[d], a->matrix_indices, a->branch_lengths, a->count, a->rates, a->prop_invar,
+                            a->eigenvals, a->eigenvecs, a->inv_eigenvecs);
+}
+
 int pllg_dev_update_pmatrix(pllg_partition_t * g, const unsigned int * matrix_indices,
                             const double * branch_lengths, unsigned int count, const double * rates,
                             const double * prop_invar, const double * eigenvals,
                             const double * eigenvecs, const double * inv_eigenvecs)
 {
-  FOR_EACH_DEVICE(plg_update_pmatrix(ctx, matrix_indices, branch_lengths, count, rates, prop_invar,
-                                     eigenvals, eigenvecs, inv_eigenvecs));
+  struct pmatrix_args a = {matrix_indices, branch_lengths, count, rates, prop_invar, eigenvals, eigenvecs, inv_eigenvecs};
+  return run_on_slices(g, pmatrix_job, &a);
+}
+
+struct partials_args
+{
+  const pll_operation_t * operations;
+  unsigned int count;
+};
+
+static int partials_job(pllg_partition_t * g, unsigned int d, void * p)
+{
+  struct partials_args * a = (struct partials_args *)p;
+  return plg_update_partials(g->ctxs[d], a->operations, a->count);
 }
 
 int pllg_dev_update_partials(pllg_partition_t * g, const pll_operation_t * operations, unsigned int count)
 {
-  FOR_EACH_DEVICE(plg_update_partials(ctx, operations, count));
+  struct partials_args a = {operations, count};
+  return run_on_slices(g, partials_job, &a);
 }
 
 /* Device group (plg_group_*): all slices enqueue, the devices add their partial results among
@@ -539,15 +569,31 @@ int pllg_dev_root_loglikelihood(pllg_partition_t * g, unsigned int clv_index, in
   return PLG_OK;
 }
 
+struct sumtable_args
+{
+  unsigned int parent_clv_index, child_clv_index;
+  int parent_scaler_index, child_scaler_index;
+  const double * eigenvecs, * left_terms;
+  const void * key;
+  double * host_copy;
+};
+
+static int sumtable_job(pllg_partition_t * g, unsigned int d, void * p)
+{
+  struct sumtable_args * a = (struct sumtable_args *)p;
+  return plg_update_sumtable(g->ctxs[d], a->parent_clv_index, a->child_clv_index, a->parent_scaler_index,
+                             a->child_scaler_index, a->eigenvecs, a->left_terms, a->key,
+                             a->host_copy ? a->host_copy + g->lo[d] * clv_span(g) : NULL);
+}
+
 int pllg_dev_update_sumtable(pllg_partition_t * g, unsigned int parent_clv_index,
                              unsigned int child_clv_index, int parent_scaler_index,
                              int child_scaler_index, const double * eigenvecs,
                              const double * left_terms, const void * key, double * host_copy)
 {
-  const size_t span = clv_span(g);
-  FOR_EACH_DEVICE(plg_update_sumtable(ctx, parent_clv_index, child_clv_index, parent_scaler_index,
-                                      child_scaler_index, eigenvecs, left_terms, key,
-                                      host_copy ? host_copy + lo * span : NULL));
+  struct sumtable_args a = {parent_clv_index, child_clv_index, parent_scaler_index, child_scaler_index,
+                            eigenvecs, left_terms, key, host_copy};
+  return run_on_slices(g, sumtable_job, &a);
 }
 
 /* Releases the device copy of the sumtable a caller is about to free (the host pointer is only a
