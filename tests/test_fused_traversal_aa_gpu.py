@@ -173,3 +173,40 @@ def test_the_walk_is_deterministic(gpu_lib, monkeypatch):
         seen.add((part.edge_loglikelihood(*args), part.get_clv(top).tobytes()))
     assert len(seen) == 1
     part.destroy()
+
+
+@pytest.mark.parametrize("walk", [False, True])
+def test_benchmark_shape_against_the_reference(gpu_lib, ref_lib, monkeypatch, walk):
+    """BASELINE configs[2] itself: the 500-taxon LG+G4 operations list of bench.py's C3 record (173
+    tip-tip / 154 tip-inner / 171 inner-inner operations) on a 6 000-pattern window of the 200 000-
+    pattern alignment, device - level-by-level kernels and the whole-list walk - against the
+    reference's AVX2 path with the same P-matrices: all 498 scaler arrays bit for bit, CLVs within
+    1e-12 relative (DMMA sums a row's 20 products in another order), per-pattern lnL within 1e-10."""
+    monkeypatch.setenv("PLL_GPU_FUSED", "1")
+    _select(monkeypatch, fused=walk)
+    monkeypatch.setenv("PLL_GPU_AA_EXACT", "0")
+    w = S.make_workload(500, 200_000, states=20)
+    lo, hi = 97_000, 103_000
+    rates = ref_lib.gamma_rates(w.alpha, w.rate_cats)
+    pg, pidx = S.build_partition(gpu_lib, w, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP, lo=lo, hi=hi, rates=rates)
+    pr, _ = S.build_partition(ref_lib, w, PLL_ATTRIB_ARCH_AVX2 | PLL_ATTRIB_PATTERN_TIP, lo=lo, hi=hi, rates=rates)
+    pg.update_prob_matrices(pidx, w.matrix_indices, w.branch_lengths)
+    pr.update_prob_matrices(pidx, w.matrix_indices, w.branch_lengths)
+    for m in range(w.prob_matrices):
+        pg.set_pmatrix(m, pr.get_pmatrix(m))
+    pg.reset_stats()
+    pg.update_partials(w.ops)
+    assert (pg.stats()["kernel_launches"] == 2) == walk
+    pr.update_partials(w.ops)
+    for k in range(w.inner):
+        np.testing.assert_array_equal(pg.get_scaler(k), pr.get_scaler(k), err_msg=f"scaler {k}")
+        np.testing.assert_allclose(pg.get_clv(w.tips + k), pr.get_clv(w.tips + k), rtol=1e-12, atol=0,
+                                   err_msg=f"CLV {w.tips + k}")
+    ps_g, ps_r = np.zeros(hi - lo), np.zeros(hi - lo)
+    args = (w.root_a, w.scaler_of(w.root_a), w.root_b, w.scaler_of(w.root_b), w.root_matrix, pidx)
+    lg = pg.edge_loglikelihood(*args, persite=ps_g)
+    lr = pr.edge_loglikelihood(*args, persite=ps_r)
+    np.testing.assert_allclose(ps_g, ps_r, rtol=1e-10, atol=0)
+    assert abs(lg - lr) <= 1e-10 * abs(lr)
+    pg.destroy()
+    pr.destroy()
