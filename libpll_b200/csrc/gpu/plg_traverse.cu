@@ -491,13 +491,11 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
   /* Tip characters are the one per-tile input that still comes from HBM / L2.  A tile covers
    * TILE / R consecutive sites, i.e. TILE / R consecutive bytes of a tip row (rows are padded to
    * 256 bytes, a tile never straddles the padding): while operation i is computed, a few lanes
-   * copy the bytes operation i+2 needs into a triple-buffered strip of shared memory with
-   * cp.async - no register holds them in the meantime (one operation ahead was not enough: the
-   * tip rows are evicted from L2 by the write stream, under load the copy takes longer than an
-   * operation and its wait showed as 6.6 % of the warps' time). */
+   * copy the bytes operation i+1 needs into a double-buffered strip of shared memory with
+   * cp.async - no register holds them in the meantime. */
   constexpr unsigned int TIP_BYTES = TILE / R;           /* per tip row and tile */
   constexpr unsigned int TIP_LANES = TIP_BYTES / 4;      /* 4-byte cp.async each */
-  unsigned char * codes = cache_base + (size_t)NW * per_warp + (size_t)warp * (6 * TIP_BYTES);
+  unsigned char * codes = cache_base + (size_t)NW * per_warp + (size_t)warp * (4 * TIP_BYTES);
   auto prefetch_codes = [&](const FusedStage<R> & st, unsigned int tile_n, bool haven, unsigned int buf)
   {
     const int kind = st.desc.kind;
@@ -525,25 +523,10 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
   }
   unsigned int it = 0;
   const unsigned int total_its = passes * n_ops;
-  /* tile of the operation `ahead` iterations after (pass, i) */
-  auto tile_of = [&](unsigned int pass, unsigned int i, unsigned int ahead, bool & have_t) -> unsigned int
+  if (total_its)
   {
-    unsigned int p = pass, j = i + ahead;
-    while (j >= n_ops) { j -= n_ops; ++p; }
-    have_t = p * NW + warp < my_tiles;
-    return first_tile + p * NW + warp;
-  };
-  for (unsigned int a = 0; a < 2; ++a)
-  {
-    if (a < total_its)
-    {
-      bool have_t;
-      const unsigned int tile_t = tile_of(0, 0, a, have_t);
-      mbar_wait(&full[a % S], (a / S) & 1u);
-      prefetch_codes(stages[a % S], tile_t, have_t, a % 3u);
-    }
-    else
-      asm volatile("cp.async.commit_group;" ::: "memory");
+    mbar_wait(&full[0], 0);
+    prefetch_codes(stages[0], first_tile + warp, warp < my_tiles, 0);
   }
   for (unsigned int pass = 0; pass < passes; ++pass)
   {
@@ -551,20 +534,26 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
     const bool have = pass * NW + warp < my_tiles;
     const unsigned int e0 = tile * TILE + lane;
     const bool tile_full = (tile + 1) * TILE <= nelem;
+    const unsigned int tile_next = tile + NW;
+    const bool have_next = (pass + 1) * NW + warp < my_tiles;
     for (unsigned int i = 0; i < n_ops; ++i, ++it)
     {
       /* stage `it` is known to be full: it was waited for when its tip codes were requested */
       const int s = it % S;
-      const unsigned int buf = it % 3u;
-      asm volatile("cp.async.wait_group 1;" ::: "memory"); /* codes of `it` have landed, those of it + 1 may be on their way */
+      const unsigned int buf = it & 1u;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
       const unsigned char * lcode = codes + (buf * 2 + 0) * TIP_BYTES + lane / R;
       const unsigned char * rcode = codes + (buf * 2 + 1) * TIP_BYTES + lane / R;
-      /* the stage two operations ahead: probed now, needed only after this operation's arithmetic
-       * (a probe costs ~150 cycles of latency even when the stage is there) */
-      const unsigned int itn = it + 2;
-      const bool ahead = itn < total_its;
-      bool next_full = ahead && mbar_try_wait(&full[itn % S], (itn / S) & 1u);
+      if (it + 1 < total_its)
+      {
+        const unsigned int itn = it + 1;
+        mbar_wait(&full[itn % S], (itn / S) & 1u);
+        if (i + 1 == n_ops)
+          prefetch_codes(stages[itn % S], tile_next, have_next, buf ^ 1u);
+        else
+          prefetch_codes(stages[itn % S], tile, have, buf ^ 1u);
+      }
       if (have)
       {
         const FusedStage<R> & st = stages[s];
@@ -575,15 +564,6 @@ k_traverse_dna(const unsigned char * __restrict__ records, unsigned int n_ops, u
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
-      if (ahead)
-      {
-        if (!next_full) mbar_wait(&full[itn % S], (itn / S) & 1u);
-        bool have_t;
-        const unsigned int tile_t = tile_of(pass, i, 2, have_t);
-        prefetch_codes(stages[itn % S], tile_t, have_t, itn % 3u);
-      }
-      else
-        asm volatile("cp.async.commit_group;" ::: "memory");
     }
   }
 }
@@ -597,7 +577,7 @@ static int launch_fused(plg_context * ctx, const FusedOp * dev_ops, unsigned cha
   static_assert(sizeof(FusedOp) == 128, "descriptor must be 128 bytes");
   const size_t smem = fused_stages(R) * sizeof(FusedStage<R>) + 128 +
                       (size_t)PLG_FUSED_WARPS * nslot * EPT * 32 * (32 + 4) +
-                      (size_t)PLG_FUSED_WARPS * 6 * (32 * EPT / R);
+                      (size_t)PLG_FUSED_WARPS * 4 * (32 * EPT / R);
   static size_t configured[PLG_MAX_DEVICES] = {}; /* function attributes are per device */
   if (smem > configured[ctx->device % PLG_MAX_DEVICES])
   {
