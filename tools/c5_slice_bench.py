@@ -11,11 +11,14 @@ import libpll_b200
 from libpll_b200 import synthetic as S
 from libpll_b200.binding import PLL_ATTRIB_ARCH_GPU, PLL_ATTRIB_PATTERN_TIP
 
+import os
+if os.environ.get("PLL_B200_LIB"):  # developer experiments: another build of the library
+    libpll_b200.LIB_PATH = os.path.abspath(os.environ["PLL_B200_LIB"])
 lib = libpll_b200.load()
 tips, total, slots = 5000, 10_000_000, 64
 w = S.recycle_slots(S.make_workload(tips, 64, states=4), slots)
 base = None
-for n in (8, 4, 2, 1):
+for n in ((8,) if os.environ.get("PLL_B200_LIB") else (8, 4, 2, 1)):
     per = (total // n + 63) // 64 * 64
     part = lib.partition(tips=tips, clv_buffers=w.inner, states=4, sites=per, rate_matrices=1,
                          prob_matrices=w.prob_matrices, rate_cats=4, scale_buffers=w.inner,
