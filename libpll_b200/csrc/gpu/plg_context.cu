@@ -158,7 +158,7 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
     const char * fs = getenv("PLL_GPU_FUSED_SLOTS");
     ctx->use_fused = fu ? atoi(fu) : 1;
     const char * fa = getenv("PLL_GPU_FUSED_AA");
-    ctx->use_fused_aa = fa ? atoi(fa) : 0;
+    ctx->use_fused_aa = fa ? (atoi(fa) ? 1 : 0) : 2; /* unset: the walk for lists that recycle slots */
     ctx->fused_slots = fs ? (unsigned int)atoi(fs) : 3u;
     if (ctx->fused_slots < 1) ctx->fused_slots = 1;
     if (ctx->fused_slots > 3) ctx->fused_slots = 3; /* shared-memory budget of plg_traverse.cu */

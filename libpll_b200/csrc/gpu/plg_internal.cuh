@@ -108,8 +108,10 @@ struct plg_context
   unsigned int active_sites; /* leading sites the lnL / derivative reductions cover */
   double * lnl_scratch;      /* one CLV-sized scratch (20-state edge lnL), lazily allocated */
   int use_fused;             /* DNA: whole operations list in one kernel (PLL_GPU_FUSED, default 1) */
-  int use_fused_aa;          /* 20 states: the same on the tensor cores (plg_walk_aa.cu; PLL_GPU_FUSED_AA, default 0:
-                                measured 6 % slower than the level-by-level kernels at BASELINE configs[2]) */
+  int use_fused_aa;          /* 20 states: the same on the tensor cores (plg_walk_aa.cu; PLL_GPU_FUSED_AA): 0 never,
+                                1 always, 2 (default) for lists that recycle CLV / scaler slots - there most stores
+                                are dead and the walk is 16-22 % faster than the level-by-level kernels, which
+                                win by 6 % on lists without recycling */
   unsigned int fused_slots;  /* tiles a warp keeps in shared memory (PLL_GPU_FUSED_SLOTS, default 3) */
   unsigned char * fused_records; /* packed operation records of the non-graph path */
   size_t fused_records_cap;

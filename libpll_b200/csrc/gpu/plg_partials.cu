@@ -1203,7 +1203,8 @@ static int build_plan(plg_context * ctx, const pll_operation_t * operations, uns
   plan.fused_hits = plan.fused_misses = 0;
   /* 20 states: the tensor-core walk (plg_walk_aa.cu) - 1, 2 or 4 rate categories, per-site scalers
    * or none, not in bit-exact mode */
-  const bool aa_walk = K == 20 && ctx->use_fused_aa && !ctx->aa_exact && !ctx->rate_scalers &&
+  const bool aa_walk = K == 20 && (ctx->use_fused_aa == 1 || (ctx->use_fused_aa == 2 && recycled)) &&
+                       !ctx->aa_exact && !ctx->rate_scalers &&
                        plg_walk_aa_supported(R, ctx->pattern_tip ? ctx->maxstates : 1u);
   const unsigned int aa_slots =
       aa_walk ? (ctx->fused_slots < PLG_WALK_AA_SLOTS ? ctx->fused_slots : PLG_WALK_AA_SLOTS) : 0;

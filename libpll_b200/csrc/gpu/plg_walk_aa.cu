@@ -1,7 +1,9 @@
 /*
  * plg_walk_aa.cu - the whole operations list of pll_update_partials in ONE kernel, 20 states,
- * opt-in with PLL_GPU_FUSED_AA=1 (the level-by-level kernels of plg_partials.cu are the default:
- * at BASELINE configs[2] this kernel takes 24.4 ms against their 22.3-23.5 ms).
+ * the default for lists that recycle CLV / scaler slots (most of their stores are dead: 16-22 %
+ * faster than the level-by-level kernels of plg_partials.cu), PLL_GPU_FUSED_AA=1 for every list
+ * (at BASELINE configs[2], one slot per node, it takes 24.4 ms against their 22.3-23.5 ms:
+ * DESIGN.md section 3).
  *
  * Patterns are independent, so a tile of patterns can walk the entire list with the children it
  * has just produced kept on chip; only results leave for HBM (64 GB instead of 128 GB at

@@ -1,5 +1,6 @@
-"""GPU: the 20-state single-kernel walk (libpll_b200/csrc/gpu/plg_walk_aa.cu; opt-in with
-PLL_GPU_FUSED_AA=1 for protein partitions with 1, 2 or 4 rate categories and per-site scalers) against
+"""GPU: the 20-state single-kernel walk (libpll_b200/csrc/gpu/plg_walk_aa.cu; the default for
+operation lists that recycle CLV / scaler slots, PLL_GPU_FUSED_AA=1 forces it for every list of a
+protein partition with 1, 2 or 4 rate categories and per-site scalers) against
 
   * the level-by-level tensor-core kernels (PLL_GPU_FUSED=0): both run the same DMMA chains in the
     same order, so every CLV and every scaler array must be BIT-identical - plain and
@@ -210,3 +211,27 @@ def test_benchmark_shape_against_the_reference(gpu_lib, ref_lib, monkeypatch, wa
     assert abs(lg - lr) <= 1e-10 * abs(lr)
     pg.destroy()
     pr.destroy()
+
+
+def test_default_selection(gpu_lib, monkeypatch):
+    """Without PLL_GPU_FUSED_AA a list that recycles slots (most of its stores are dead: the walk
+    is 16-22 % faster there) runs as pack + walk, a list with one slot per node on the level-by-level
+    kernels; both give the bits of the forced level-by-level run."""
+    monkeypatch.setenv("PLL_GPU_FUSED", "1")
+    monkeypatch.delenv("PLL_GPU_FUSED_AA", raising=False)
+    monkeypatch.setenv("PLL_GPU_AA_EXACT", "0")
+    plain = S.make_workload(60, 1500, states=20, seed=21)
+    recycled = S.recycle_slots(plain, 9)
+    for w, walk in ((plain, False), (recycled, True)):
+        part, pidx = S.build_partition(gpu_lib, w, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP)
+        part.update_prob_matrices(pidx, w.matrix_indices, w.branch_lengths)
+        part.reset_stats()
+        part.update_partials(w.ops)
+        assert (part.stats()["kernel_launches"] == 2) == walk
+        lnl = part.edge_loglikelihood(w.root_a, w.scaler_of(w.root_a), w.root_b, w.scaler_of(w.root_b),
+                                      w.root_matrix, pidx)
+        part.destroy()
+        ref = _run(gpu_lib, monkeypatch, w, PLL_ATTRIB_PATTERN_TIP, fused=False)
+        monkeypatch.setenv("PLL_GPU_FUSED", "1")      # _run switched the whole-list kernels off
+        monkeypatch.delenv("PLL_GPU_FUSED_AA", raising=False)
+        assert lnl == ref[2]

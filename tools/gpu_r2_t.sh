@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 400 python -m pytest tests/test_fused_traversal_aa_gpu.py -x -q -m gpu -k "benchmark_shape or deterministic" 2>&1 | tail -6 > gpurun_out/t_pytest.txt
+timeout -s KILL 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4 > gpurun_out/t_pytest.txt
 cat gpurun_out/t_pytest.txt
