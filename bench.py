@@ -538,6 +538,49 @@ def leg_c4(lib, part, pidx, tree, walker, sites: int, branches: int = 10, iters:
     }
 
 
+def c3_recycled(lib, w, steps: int, slots: int = 64):
+    """The C3 list with its inner CLVs / scale buffers in a pool of recycled slots (the memory-saving
+    mode of large analyses): the library's default for such lists - the whole-list walk k_walk_aa,
+    which stores only the last value of a buffer - next to the level-by-level kernels forced with
+    PLL_GPU_FUSED_AA=0.  Same lnL from both (and from the one-slot-per-node list)."""
+    from libpll_b200 import synthetic as S
+    from libpll_b200.binding import PLL_ATTRIB_ARCH_GPU, PLL_ATTRIB_PATTERN_TIP
+
+    wr = S.recycle_slots(w, slots)
+    out = {"slots": slots, "operations": len(wr.ops)}
+    saved = os.environ.get("PLL_GPU_FUSED_AA")
+    try:
+        for name, env in (("default", None), ("level_by_level", "0")):
+            if env is None:
+                os.environ.pop("PLL_GPU_FUSED_AA", None)
+            else:
+                os.environ["PLL_GPU_FUSED_AA"] = env
+            part, pidx = S.build_partition(lib, wr, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP)
+            root = (wr.root_a, wr.scaler_of(wr.root_a), wr.root_b, wr.scaler_of(wr.root_b), wr.root_matrix, pidx)
+            part.update_prob_matrices(pidx, wr.matrix_indices, wr.branch_lengths)
+            for _ in range(3):
+                part.update_partials(wr.ops)
+                lnl = part.edge_loglikelihood(*root)
+            part.reset_stats()
+            part.timer_start()
+            for _ in range(steps):
+                part.update_partials(wr.ops)
+                lnl = part.edge_loglikelihood(*root)
+            ms = part.timer_stop() / steps
+            st = part.stats()
+            part.destroy()
+            out[name] = {"ms_per_step": ms, "value": len(wr.ops) * w.sites / (ms * 1e-3), "unit": UNIT,
+                         "kernel": "k_walk_aa" if st["kernel_launches"] <= 8 * steps else "k_partial_dmma_aa / k_partial_tt_aa",
+                         "gpu_launches_per_step": st["kernel_launches"] / steps,
+                         "compulsory_GB_per_step": st["compulsory_bytes"] / steps / 1e9, "lnl": lnl}
+    finally:
+        if saved is None:
+            os.environ.pop("PLL_GPU_FUSED_AA", None)
+        else:
+            os.environ["PLL_GPU_FUSED_AA"] = saved
+    return out
+
+
 def leg_c3(lib, steps: int, warmup: int, local_rank: int):
     """BASELINE configs[2]: 500 taxa x 200k patterns, LG+G4 protein, traversal + edge lnL."""
     from libpll_b200 import synthetic as S
@@ -574,6 +617,7 @@ def leg_c3(lib, steps: int, warmup: int, local_rank: int):
     e2e_s = (time.perf_counter() - t0) / steps
     clocks = sampler.stop()
     part.destroy()
+    recycled = c3_recycled(lib, w, steps)
     tt, ti, ii = w.op_kinds()
     peak, peak_src = hbm_peak()
     comp = trav["compulsory_bytes"] / steps
@@ -587,6 +631,7 @@ def leg_c3(lib, steps: int, warmup: int, local_rank: int):
         "value": len(w.ops) * sites / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
         "e2e": {"value": len(w.ops) * sites / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3},
         "gpu_launches": stats["kernel_launches"], "clocks": clocks, "lnl": lnl,
+        "recycled_slots": recycled,
         "roofline": {
             "kernel": "k_walk_aa (whole list, FP64 tensor cores)" if fused else "k_partial_dmma_aa (level by level)",
             "avg_traversal_ms": trav_ms,
