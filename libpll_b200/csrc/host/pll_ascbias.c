@@ -68,13 +68,32 @@ static double * fetch_clv_tail(pllg_partition_t * g, unsigned int clv_index)
   return buf;
 }
 
-/* scaler counts of the trailing sites; zeros when there is no scaler */
+/* scaler counts of the trailing sites; zeros when there is no scaler.
+ *
+ * With PLL_ATTRIB_RATE_SCALERS the reference still reads element `sites + n` of the scaler array
+ * (src/likelihood.c:91, :233, :378-381, src/core_derivatives.c:684-685) although that array is
+ * laid out [site][rate]: what it gets is the count of pattern (sites + n) / R at rate
+ * (sites + n) % R.  The value is well defined (the array holds (sites + states) * R counts), so a
+ * drop-in returns the same one: the patterns that cover those flat elements are fetched and
+ * element `sites + n` picked out of them. */
 static int fetch_scaler_tail(pllg_partition_t * g, int scaler_index, unsigned int * out)
 {
   const pll_partition_t * p = &g->pub;
   memset(out, 0, p->states * sizeof(unsigned int));
   if (scaler_index == PLL_SCALE_BUFFER_NONE) return 1;
-  int rc = pllg_dev_get_scaler_sites(g, (unsigned int)scaler_index, p->sites, p->states, out);
+  const unsigned int R = p->rate_cats;
+  if (!(p->attributes & PLL_ATTRIB_RATE_SCALERS) || R == 1)
+  {
+    int rc = pllg_dev_get_scaler_sites(g, (unsigned int)scaler_index, p->sites, p->states, out);
+    return rc ? pllg_fail(rc, "ascertainment bias correction") : 1;
+  }
+  const unsigned int first = p->sites / R, last = (p->sites + p->states - 1) / R;
+  const unsigned int n = last - first + 1;
+  unsigned int * rows = (unsigned int *)malloc((size_t)n * R * sizeof(unsigned int));
+  if (!rows) return pll_fail(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
+  int rc = pllg_dev_get_scaler_sites(g, (unsigned int)scaler_index, first, n, rows);
+  if (!rc) memcpy(out, rows + (p->sites - (size_t)first * R), p->states * sizeof(unsigned int));
+  free(rows);
   return rc ? pllg_fail(rc, "ascertainment bias correction") : 1;
 }
 

@@ -186,14 +186,6 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips,
     pll_fail(PLL_ERROR_PARAM_INVALID, "Multiple architecture flags specified.");
     return NULL;
   }
-  if ((attributes & (PLL_ATTRIB_AB_MASK | PLL_ATTRIB_AB_FLAG)) && (attributes & PLL_ATTRIB_RATE_SCALERS))
-  {
-    /* the reference indexes the scalers of the per-state sites per SITE (src/likelihood.c:91,
-     * src/core_derivatives.c:684-685), which is meaningless for per-rate arrays */
-    pll_fail(PLL_ERROR_GPU_UNSUPPORTED,
-             "Ascertainment-bias correction cannot be combined with per-rate scalers.");
-    return NULL;
-  }
   if (rate_matrices == 0 || rate_cats == 0 || states == 0 || sites == 0)
   {
     pll_fail(PLL_ERROR_PARAM_INVALID, "Invalid partition dimensions.");

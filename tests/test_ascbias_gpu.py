@@ -97,6 +97,52 @@ def test_ascbias_with_scaling(gpu_lib, ref_lib):
     pr.destroy()
 
 
+@pytest.mark.parametrize("pattern_tip", [True, False])
+def test_ascbias_with_per_rate_scalers(gpu_lib, ref_lib, pattern_tip):
+    """PLL_ATTRIB_RATE_SCALERS with the correction: the reference reads element `sites + n` of a
+    scaler array laid out [site][rate] (src/likelihood.c:91, :378-381, src/core_derivatives.c:684-685),
+    i.e. the count of pattern (sites + n) / R at rate (sites + n) % R; the drop-in returns the same
+    values.  Long caterpillar so that those counts are not zero."""
+    from libpll_b200.binding import PLL_ATTRIB_RATE_SCALERS
+    from test_parity_gpu import _caterpillar
+
+    w = _caterpillar(300, 42, 4, seed=5)
+    extra = PLL_ATTRIB_RATE_SCALERS | (PLL_ATTRIB_PATTERN_TIP if pattern_tip else 0)
+    pg, pr, pidx = _pair(gpu_lib, ref_lib, w, extra, PLL_ATTRIB_ARCH_AVX2)
+    for p in (pg, pr):
+        p.update_prob_matrices(pidx, w.matrix_indices, w.branch_lengths)
+        p.update_partials(w.ops)
+    top = w.tips + w.inner - 1
+    picked = 0  # the flat elements sites .. sites + states - 1 the reference reads
+    for k in range(w.inner):
+        sr, sg = np.asarray(pr.get_scaler(k)).ravel(), np.asarray(pg.get_scaler(k)).ravel()
+        assert np.array_equal(sr, sg)
+        picked += int(sr[w.sites:w.sites + 4].sum())
+    assert picked > 0
+    a, b = w.root_a, w.root_b
+    for ab in TYPES:
+        for p in (pg, pr):
+            p.set_asc_bias_type(ab)
+            p.set_asc_state_weights([5, 6, 7, 8])
+        args = (a, w.scaler_of(a), b, w.scaler_of(b), w.root_matrix, pidx)
+        lg, lr = pg.edge_loglikelihood(*args), pr.edge_loglikelihood(*args)
+        assert np.isfinite(lr) and abs(lg - lr) <= RTOL * abs(lr), (ab, lg, lr)
+        rg = pg.root_loglikelihood(top, w.scaler_of(top), pidx)
+        rr = pr.root_loglikelihood(top, w.scaler_of(top), pidx)
+        assert np.isfinite(rr) and abs(rg - rr) <= RTOL * abs(rr), (ab, rg, rr)
+        sg, sr = pg.new_sumtable(), pr.new_sumtable()
+        pg.update_sumtable(a, b, w.scaler_of(a), w.scaler_of(b), pidx, sg)
+        pr.update_sumtable(a, b, w.scaler_of(a), w.scaler_of(b), pidx, sr)
+        for t in (0.01, 0.2, 1.5):
+            dg = pg.likelihood_derivatives(w.scaler_of(a), w.scaler_of(b), t, pidx, sg)
+            dr = pr.likelihood_derivatives(w.scaler_of(a), w.scaler_of(b), t, pidx, sr)
+            scale = max(abs(dr[0]), float(w.weights.sum()) * 1e-3)
+            assert abs(dg[0] - dr[0]) <= RTOL * scale, (ab, t, dg, dr)
+            assert abs(dg[1] - dr[1]) <= RTOL * max(abs(dr[1]), scale), (ab, t, dg, dr)
+    pg.destroy()
+    pr.destroy()
+
+
 def test_ascbias_errors(gpu_lib):
     w = S.make_workload(6, 50, states=4, seed=1)
     part, _ = S.build_partition(gpu_lib, w, PLL_ATTRIB_ARCH_GPU | PLL_ATTRIB_PATTERN_TIP)
