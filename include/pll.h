@@ -445,7 +445,7 @@ PLL_EXPORT int pll_compute_likelihood_derivatives(pll_partition_t * partition,
 
 /* ---- ascertainment-bias correction (reference src/pll.c:1061-1116).  The partition must be
  * created with PLL_ATTRIB_AB_FLAG or one of the PLL_ATTRIB_AB_* types: it then holds `states`
- * extra per-state sites.  Not combinable with PLL_ATTRIB_RATE_SCALERS on this backend. ---- */
+ * extra per-state sites. ---- */
 PLL_EXPORT int pll_set_asc_bias_type(pll_partition_t * partition, int asc_bias_type);
 PLL_EXPORT void pll_set_asc_state_weights(pll_partition_t * partition,
                                           const unsigned int * state_weights);
@@ -570,6 +570,99 @@ PLL_EXPORT void pll_show_clv(const pll_partition_t * partition,
                              unsigned int clv_index,
                              int scaler_index,
                              unsigned int float_precision);
+
+/* ---- the direct-call surface (reference src/pll.h:864-1000, :1659-1700): plain HOST arrays, no
+ * partition.  Each call uploads its arguments, runs the kernels the partition API runs and downloads
+ * the result (libpll_b200/csrc/host/pll_core.c) - for callers that keep their own arrays; data
+ * that should stay in HBM belongs in a partition.  Array layouts follow the architecture bits in
+ * `attrib` as in the reference (states_padded = states / even / a multiple of 4 for
+ * PLL_ATTRIB_ARCH_CPU / _SSE / _AVX, _AVX2, _GPU).  The `lookup` table of the tip-tip pair is
+ * opaque (same size as the reference's).  PLL_ATTRIB_AB_* bits are not supported here. ---- */
+/* replaces reference src/core_partials.c:82-186 */
+PLL_EXPORT void pll_core_create_lookup(unsigned int states, unsigned int rate_cats, double * lookup,
+                                       const double * left_matrix, const double * right_matrix,
+                                       const unsigned int * tipmap, unsigned int tipmap_size,
+                                       unsigned int attrib);
+/* replaces reference src/core_partials.c:188-260 */
+PLL_EXPORT void pll_core_update_partial_tt(unsigned int states, unsigned int sites, unsigned int rate_cats,
+                                           double * parent_clv, unsigned int * parent_scaler,
+                                           const unsigned char * left_tipchars,
+                                           const unsigned char * right_tipchars,
+                                           const unsigned int * tipmap, unsigned int tipmap_size,
+                                           const double * lookup, unsigned int attrib);
+/* replaces reference src/core_partials.c:262-532 */
+PLL_EXPORT void pll_core_update_partial_ti(unsigned int states, unsigned int sites, unsigned int rate_cats,
+                                           double * parent_clv, unsigned int * parent_scaler,
+                                           const unsigned char * left_tipchars, const double * right_clv,
+                                           const double * left_matrix, const double * right_matrix,
+                                           const unsigned int * right_scaler, const unsigned int * tipmap,
+                                           unsigned int tipmap_size, unsigned int attrib);
+/* replaces reference src/core_partials.c:534-862 */
+PLL_EXPORT void pll_core_update_partial_ii(unsigned int states, unsigned int sites, unsigned int rate_cats,
+                                           double * parent_clv, unsigned int * parent_scaler,
+                                           const double * left_clv, const double * right_clv,
+                                           const double * left_matrix, const double * right_matrix,
+                                           const unsigned int * left_scaler,
+                                           const unsigned int * right_scaler, unsigned int attrib);
+/* replaces reference src/core_pmatrix.c:24-250 */
+PLL_EXPORT int pll_core_update_pmatrix(double ** pmatrix, unsigned int states, unsigned int rate_cats,
+                                       const double * rates, const double * branch_lengths,
+                                       const unsigned int * matrix_indices,
+                                       const unsigned int * params_indices, const double * prop_invar,
+                                       double * const * eigenvals, double * const * eigenvecs,
+                                       double * const * inv_eigenvecs, unsigned int count,
+                                       unsigned int attrib);
+/* replace reference src/core_derivatives.c:125-296 (ii), :298-446 (ti), :501-732 */
+PLL_EXPORT int pll_core_update_sumtable_ii(unsigned int states, unsigned int sites, unsigned int rate_cats,
+                                           const double * parent_clv, const double * child_clv,
+                                           const unsigned int * parent_scaler,
+                                           const unsigned int * child_scaler, double * const * eigenvecs,
+                                           double * const * inv_eigenvecs, double * const * freqs,
+                                           double * sumtable, unsigned int attrib);
+PLL_EXPORT int pll_core_update_sumtable_ti(unsigned int states, unsigned int sites, unsigned int rate_cats,
+                                           const double * parent_clv, const unsigned char * left_tipchars,
+                                           const unsigned int * parent_scaler, double * const * eigenvecs,
+                                           double * const * inv_eigenvecs, double * const * freqs,
+                                           const unsigned int * tipmap, unsigned int tipmap_size,
+                                           double * sumtable, unsigned int attrib);
+PLL_EXPORT int pll_core_likelihood_derivatives(unsigned int states, unsigned int sites,
+                                               unsigned int rate_cats, const double * rate_weights,
+                                               const unsigned int * parent_scaler,
+                                               const unsigned int * child_scaler, const int * invariant,
+                                               const unsigned int * pattern_weights, double branch_length,
+                                               const double * prop_invar, double * const * freqs,
+                                               const double * rates, double * const * eigenvals,
+                                               const double * sumtable, double * d_f, double * dd_f,
+                                               unsigned int attrib);
+/* replace reference src/core_likelihood.c:25-209 (root), :211-596 (edge ti), :598-1002 (edge ii) */
+PLL_EXPORT double pll_core_root_loglikelihood(unsigned int states, unsigned int sites, unsigned int rate_cats,
+                                              const double * clv, const unsigned int * scaler,
+                                              double * const * frequencies, const double * rate_weights,
+                                              const unsigned int * pattern_weights,
+                                              const double * invar_proportion, const int * invar_indices,
+                                              const unsigned int * freqs_indices, double * persite_lnl,
+                                              unsigned int attrib);
+PLL_EXPORT double pll_core_edge_loglikelihood_ti(unsigned int states, unsigned int sites,
+                                                 unsigned int rate_cats, const double * parent_clv,
+                                                 const unsigned int * parent_scaler,
+                                                 const unsigned char * tipchars, const unsigned int * tipmap,
+                                                 unsigned int tipmap_size, const double * pmatrix,
+                                                 double * const * frequencies, const double * rate_weights,
+                                                 const unsigned int * pattern_weights,
+                                                 const double * invar_proportion, const int * invar_indices,
+                                                 const unsigned int * freqs_indices, double * persite_lnl,
+                                                 unsigned int attrib);
+PLL_EXPORT double pll_core_edge_loglikelihood_ii(unsigned int states, unsigned int sites,
+                                                 unsigned int rate_cats, const double * parent_clv,
+                                                 const unsigned int * parent_scaler, const double * child_clv,
+                                                 const unsigned int * child_scaler, const double * pmatrix,
+                                                 double * const * frequencies, const double * rate_weights,
+                                                 const unsigned int * pattern_weights,
+                                                 const double * invar_proportion, const int * invar_indices,
+                                                 const unsigned int * freqs_indices, double * persite_lnl,
+                                                 unsigned int attrib);
+/* frees the calling thread's scratch device state of the pll_core_* calls (optional) */
+PLL_EXPORT void pll_gpu_core_release(void);
 
 #ifdef __cplusplus
 }

@@ -163,6 +163,10 @@ PLL_EXPORT int plg_set_pattern_weights(plg_context_t * ctx, const unsigned int *
  * computes invariant[] on the device from the resident tips and copies it to `invariant_out`
  * (sites ints; may be NULL to keep it device-only). */
 PLL_EXPORT int plg_update_invariant(plg_context_t * ctx, int * invariant_out);
+/* The caller's own invariant[] array (sites ints: -1 or the state index) instead of the tip scan;
+ * the `invariant` / `invar_indices` argument of the reference's pll_core_* calls
+ * (src/pll.h:943-1000). */
+PLL_EXPORT int plg_set_invariant(plg_context_t * ctx, const int * invariant);
 PLL_EXPORT int plg_set_pmatrix(plg_context_t * ctx, unsigned int matrix_index,
                                const double * pmatrix);
 PLL_EXPORT int plg_get_pmatrix(plg_context_t * ctx, unsigned int matrix_index,
@@ -260,6 +264,9 @@ PLL_EXPORT int plg_update_sumtable(plg_context_t * ctx,
                                    const double * left_terms,
                                    const void * key,
                                    double * host_copy);
+/* Uploads a host sumtable (sites x rate_cats x states_padded doubles) into the device slot of
+ * `key`: the table argument of the reference's pll_core_likelihood_derivatives (src/pll.h:943-961). */
+PLL_EXPORT int plg_set_sumtable(plg_context_t * ctx, const void * key, const double * table);
 /* Releases the device slot of `key` (all slots are released by plg_destroy). */
 PLL_EXPORT int plg_free_sumtable(plg_context_t * ctx, const void * key);
 

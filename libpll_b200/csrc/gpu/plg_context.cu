@@ -126,7 +126,7 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   ctx->clv_first = ctx->pattern_tip ? dims->tips : 0;
   ctx->clv = NULL; ctx->scalers = NULL; ctx->tipchars = NULL; ctx->pmatrix = NULL;
   ctx->weights = NULL; ctx->invariant = NULL; ctx->has_invariant = false;
-  ctx->maxstates = 0; ctx->log2_maxstates = 0;
+  ctx->maxstates = 0; ctx->log2_maxstates = 0; ctx->tipmap_epoch = 0;
   memset(ctx->tipmap, 0, sizeof(ctx->tipmap));
   ctx->stage_host = NULL; ctx->stage_dev = NULL; ctx->stage_size = 0; ctx->stage_off = 0;
   ctx->tables = NULL; ctx->tables_cap = 0; ctx->partials = NULL; ctx->partials_cap = 0;
@@ -705,6 +705,9 @@ extern "C" int plg_set_tipmap(plg_context_t * ctx, const unsigned int * tipmap,
     plg_set_error("plg_set_tipmap: maxstates %u > 256", maxstates);
     return PLG_E_INVALID;
   }
+  /* captured operation lists carry the map by value: a changed map must not replay them */
+  if (maxstates != ctx->maxstates || (tipmap && memcmp(ctx->tipmap, tipmap, maxstates * sizeof(unsigned int)) != 0))
+    ctx->tipmap_epoch++;
   memset(ctx->tipmap, 0, sizeof(ctx->tipmap));
   if (tipmap) memcpy(ctx->tipmap, tipmap, maxstates * sizeof(unsigned int));
   ctx->maxstates = maxstates;
@@ -854,6 +857,23 @@ extern "C" int plg_update_invariant(plg_context_t * ctx, int * invariant_out)
   PLG_LAUNCH_CHECK(ctx);
   ctx->has_invariant = true;
   if (invariant_out) return d2h(ctx, invariant_out, ctx->invariant, (size_t)sites * sizeof(int));
+  return PLG_OK;
+}
+
+/* The caller's own invariant[] (the `invariant` / `invar_indices` argument of the reference's
+ * pll_core_* entry points, src/pll.h:943-1000): sites ints, -1 or the state index. */
+extern "C" int plg_set_invariant(plg_context_t * ctx, const int * invariant)
+{
+  PLG_CHECK_CTX(ctx);
+  if (!invariant)
+  {
+    plg_set_error("plg_set_invariant: null array");
+    return PLG_E_INVALID;
+  }
+  int rc = h2d(ctx, ctx->invariant, invariant, (size_t)ctx->d.sites * sizeof(int));
+  if (rc) return rc;
+  PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->has_invariant = true;
   return PLG_OK;
 }
 

@@ -862,6 +862,28 @@ extern "C" int plg_update_sumtable(plg_context_t * ctx, unsigned int parent_clv_
   return PLG_OK;
 }
 
+/* A sumtable the caller holds on the host (sites x rate_cats x states_padded doubles, the layout
+ * plg_update_sumtable writes) becomes the device slot of `key`: the input side of the reference's
+ * pll_core_likelihood_derivatives (src/pll.h:943-961), which receives the table as an argument. */
+extern "C" int plg_set_sumtable(plg_context_t * ctx, const void * key, const double * table)
+{
+  PLG_CHECK_CTX(ctx);
+  if (!key || !table)
+  {
+    plg_set_error("plg_set_sumtable: null argument");
+    return PLG_E_INVALID;
+  }
+  plg_release_l2(ctx);
+  double * dev = NULL;
+  int rc = sumtable_slot(ctx, key, &dev);
+  if (rc) return rc;
+  const size_t bytes = (size_t)ctx->d.sites * ctx->span * sizeof(double);
+  PLG_CUDA(cudaMemcpyAsync(dev, table, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PLG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.h2d_bytes += bytes;
+  return PLG_OK;
+}
+
 extern "C" int plg_free_sumtable(plg_context_t * ctx, const void * key)
 {
   PLG_CHECK_CTX(ctx);

@@ -134,6 +134,7 @@ struct plg_context
 
   unsigned int maxstates;
   unsigned int log2_maxstates;
+  unsigned long long tipmap_epoch; /* bumped when the map's content changes: part of the graph-cache key */
   unsigned int tipmap[PLL_ASCII_SIZE];
 
   /* pinned-host / device staging ring for small per-call constants and op tables */

@@ -1726,7 +1726,7 @@ extern "C" int plg_update_partials(plg_context_t * ctx, const pll_operation_t * 
   const bool try_graph = ctx->use_graphs && !ctx->profiling && count >= 2;
   if (try_graph)
   {
-    key = fnv1a(operations, key_bytes) ^ ((uint64_t)ctx->maxstates << 56);
+    key = fnv1a(operations, key_bytes) ^ ((uint64_t)ctx->maxstates << 56) ^ (ctx->tipmap_epoch * 0x9E3779B97F4A7C15ull);
     auto hit = ctx->graphs->find(key);
     if (hit != ctx->graphs->end() && hit->second->key_bytes.size() == key_bytes &&
         memcmp(hit->second->key_bytes.data(), operations, key_bytes) == 0)

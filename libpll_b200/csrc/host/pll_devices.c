@@ -33,6 +33,15 @@ PLL_EXPORT int pll_gpu_set_devices(int count)
   return PLL_SUCCESS;
 }
 
+/* sets this thread's slice count and returns the previous raw setting (scratch partitions of
+ * pll_core.c live on one device whatever the caller selected for its own partitions) */
+int pllg_swap_slices(int count)
+{
+  const int old = g_slices;
+  g_slices = count;
+  return old;
+}
+
 int pll_gpu_current_slices(void)
 {
   if (g_slices > 0) return g_slices;

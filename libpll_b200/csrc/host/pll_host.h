@@ -50,6 +50,8 @@ int pll_gpu_mirror_mode(void);
 /* number of pattern slices pll_partition_create would use in this thread (pll_devices.c) */
 int pll_gpu_current_slices(void);
 
+int pllg_swap_slices(int count);
+
 /* the plg_* device ABI fanned out over the partition's pattern slices (pll_devices.c): same
  * arguments as the plg_* function of the same name, host arrays indexed by site are offset per
  * slice, scalar results are summed in slice order */
