@@ -12,8 +12,8 @@ import numpy as np
 import pytest
 
 from libpll_b200 import synthetic as S
-from libpll_b200.binding import (PLL_ATTRIB_ARCH_AVX2, PLL_ATTRIB_ARCH_CPU, PLL_ATTRIB_PATTERN_TIP,
-                                 PLL_ATTRIB_RATE_SCALERS)
+from libpll_b200.binding import (PLL_ATTRIB_ARCH_AVX2, PLL_ATTRIB_ARCH_CPU, PLL_ATTRIB_ARCH_SSE,
+                                 PLL_ATTRIB_PATTERN_TIP, PLL_ATTRIB_RATE_SCALERS)
 
 pytestmark = pytest.mark.gpu
 
@@ -124,7 +124,8 @@ def _clv_close(got, want, states):
 
 
 CASES = [(4, 4, PLL_ATTRIB_ARCH_AVX2, False), (4, 4, PLL_ATTRIB_ARCH_AVX2, True), (20, 4, PLL_ATTRIB_ARCH_AVX2, False),
-         (5, 3, PLL_ATTRIB_ARCH_CPU, False)]
+         (5, 3, PLL_ATTRIB_ARCH_CPU, False), (4, 1, PLL_ATTRIB_ARCH_AVX2, False), (20, 2, PLL_ATTRIB_ARCH_AVX2, True),
+         (5, 2, PLL_ATTRIB_ARCH_SSE, False)]
 
 
 @pytest.mark.parametrize("states,cats,arch,rate_scalers", CASES)
@@ -208,8 +209,10 @@ def test_core_pmatrix(gpu_lib, ref_lib, states, cats, arch, rate_scalers):
 @pytest.mark.parametrize("pinv", [0.0, 0.25])
 @pytest.mark.parametrize("states,cats,arch,rate_scalers", CASES)
 def test_core_likelihood_sumtable_derivatives(gpu_lib, ref_lib, states, cats, arch, rate_scalers, pinv):
-    if pinv and arch == PLL_ATTRIB_ARCH_CPU:
+    if pinv and arch != PLL_ATTRIB_ARCH_AVX2:
         pytest.skip("one p-inv case per alphabet size is enough")
+    if arch == PLL_ATTRIB_ARCH_SSE:
+        pytest.skip("the reference's SSE log-likelihood of an odd alphabet is not reproducible (NaN on a repeated call)")
     c = Case(ref_lib, states, cats, arch, rate_scalers, pinv=pinv)
     p, w = c.part.p, c.w
     tm, tms = c.tipmap()
