@@ -61,12 +61,6 @@ static unsigned long scenario(unsigned int states, unsigned int cats, int patter
   CHECK(pll_gpu_set_devices(slices));
   pll_partition_t * p = pll_partition_create(tips, inner, states, sites, 2, matrices, cats, inner, attrs);
   pll_gpu_set_devices(0);
-  if (ab && rate_scalers)
-  {
-    CHECK(p == NULL && pll_errno == PLL_ERROR_GPU_UNSUPPORTED);
-    CHECK(null_device_live_contexts() == 0);
-    return 0;
-  }
   CHECK(p != NULL);
   CHECK(pll_gpu_partition_devices(p) == (slices > 1 ? 3 : 1));   /* 130 patterns (+ states with AB): 64 + 64 + rest */
   CHECK(null_device_live_contexts() == pll_gpu_partition_devices(p));
@@ -253,6 +247,68 @@ int main(void)
     l = pll_compute_edge_loglikelihood(p, 5, 0, 6, 1, 2, params, NULL);
     CHECK(l == -400.0);   /* the null device returns -(patterns of the slice): 192 + 192 + 16 summed */
     pll_partition_destroy(p);
+    CHECK(null_device_live_contexts() == 0);
+  }
+
+  /* the direct-call surface (pll_core_*, host arrays): every array is touched over the extent the
+   * reference's callers allocate, for caller paddings equal to and different from the device's */
+  {
+    const unsigned int cstates[] = {4, 5, 20}, cattr[] = {PLL_ATTRIB_ARCH_AVX2, PLL_ATTRIB_ARCH_CPU, PLL_ATTRIB_ARCH_SSE};
+    for (unsigned int s = 0; s < 3; ++s)
+      for (unsigned int a = 0; a < 3; ++a)
+        for (int rs = 0; rs < 2; ++rs)
+        {
+          const unsigned int K = cstates[s], R = 3, sites = 37, attrib = cattr[a] | (rs ? PLL_ATTRIB_RATE_SCALERS : 0);
+          const unsigned int Kp = (cattr[a] == PLL_ATTRIB_ARCH_CPU) ? K : (cattr[a] == PLL_ATTRIB_ARCH_SSE ? ((K + 1) & ~1u) : ((K + 3) & ~3u));
+          const size_t clv_len = (size_t)sites * R * Kp, mat_len = (size_t)R * K * Kp, sc_len = sites * (rs ? R : 1);
+          double * clv[3], * mat[3], * ev[3], * iv[3], * fr[3], * el[3];
+          double * table = (double *)calloc(clv_len, sizeof(double));
+          double * lookup = (double *)calloc(1024 * R + 1024 * (size_t)R * Kp, sizeof(double));
+          unsigned int * sc[3];
+          for (int i = 0; i < 3; ++i)
+          {
+            clv[i] = (double *)calloc(clv_len, sizeof(double));
+            mat[i] = (double *)calloc(mat_len, sizeof(double));
+            ev[i] = (double *)calloc((size_t)K * Kp, sizeof(double));
+            iv[i] = (double *)calloc((size_t)K * Kp, sizeof(double));
+            fr[i] = (double *)calloc(Kp, sizeof(double));
+            el[i] = (double *)calloc(Kp, sizeof(double));
+            sc[i] = (unsigned int *)calloc(sc_len, sizeof(unsigned int));
+          }
+          unsigned char * chars = (unsigned char *)calloc(sites, 1);
+          unsigned int tipmap[32], weights[37], idx[3] = {0, 1, 2}, mi[3] = {2, 0, 1};
+          int inv[37];
+          for (unsigned int i = 0; i < 32; ++i) tipmap[i] = 1u << (i % K);
+          for (unsigned int i = 0; i < sites; ++i) { chars[i] = (unsigned char)(1 + i % 3); weights[i] = 1; inv[i] = -1; }
+          double rates[3] = {0.5, 1.0, 1.5}, rw[3] = {0.3, 0.3, 0.4}, pinv[3] = {0.1, 0.1, 0.1}, bl[3] = {0.1, 0.2, 0.3}, d1, d2;
+          pll_errno = 0;
+          pll_core_update_partial_ii(K, sites, R, clv[0], sc[0], clv[1], clv[2], mat[0], mat[1], sc[1], sc[2], attrib);
+          pll_core_update_partial_ii(K, sites, R, clv[0], NULL, clv[1], clv[2], mat[0], mat[1], NULL, NULL, attrib);
+          pll_core_update_partial_ti(K, sites, R, clv[0], sc[0], chars, clv[2], mat[0], mat[1], sc[2], tipmap, 32, attrib);
+          pll_core_create_lookup(K, R, lookup, mat[0], mat[1], tipmap, 32, attrib);
+          pll_core_update_partial_tt(K, sites, R, clv[0], sc[0], chars, chars, tipmap, 32, lookup, attrib);
+          CHECK(pll_errno == 0);
+          CHECK(pll_core_update_pmatrix(mat, K, R, rates, bl, mi, idx, pinv, el, ev, iv, 3, attrib));
+          CHECK(pll_core_update_sumtable_ii(K, sites, R, clv[1], clv[2], sc[1], sc[2], ev, iv, fr, table, attrib));
+          CHECK(pll_core_update_sumtable_ti(K, sites, R, clv[1], chars, sc[1], ev, iv, fr, tipmap, 32, table, attrib));
+          CHECK(pll_core_likelihood_derivatives(K, sites, R, rw, sc[1], sc[2], inv, weights, 0.3, pinv, fr, rates, el,
+                                                table, &d1, &d2, attrib));
+          double l = pll_core_root_loglikelihood(K, sites, R, clv[1], sc[1], fr, rw, weights, pinv, inv, idx, table, attrib);
+          CHECK(l == -(double)sites);
+          l = pll_core_edge_loglikelihood_ii(K, sites, R, clv[1], sc[1], clv[2], sc[2], mat[0], fr, rw, weights, NULL,
+                                             NULL, idx, NULL, attrib);
+          CHECK(l == -(double)sites);
+          l = pll_core_edge_loglikelihood_ti(K, sites, R, clv[1], sc[1], chars, tipmap, 32, mat[0], fr, rw, weights,
+                                             pinv, inv, idx, table, attrib);
+          CHECK(l == -(double)sites);
+          /* ascertainment-bias bits belong to the partition API */
+          CHECK(!pll_core_update_sumtable_ii(K, sites, R, clv[1], clv[2], sc[1], sc[2], ev, iv, fr, table,
+                                             attrib | PLL_ATTRIB_AB_LEWIS) && pll_errno == PLL_ERROR_GPU_UNSUPPORTED);
+          for (int i = 0; i < 3; ++i) { free(clv[i]); free(mat[i]); free(ev[i]); free(iv[i]); free(fr[i]); free(el[i]); free(sc[i]); }
+          free(table); free(lookup); free(chars);
+        }
+    CHECK(null_device_live_contexts() > 0);    /* the cached scratch partitions */
+    pll_gpu_core_release();
     CHECK(null_device_live_contexts() == 0);
   }
 

@@ -172,6 +172,12 @@ int plg_update_invariant(plg_context_t * ctx, int * invariant_out)
   if (invariant_out) touch_out(invariant_out, ctx->d.sites * sizeof(int), 0xff); /* -1 everywhere */
   return PLG_OK;
 }
+int plg_set_invariant(plg_context_t * ctx, const int * invariant)
+{
+  MAYBE_FAIL();
+  touch_in(invariant, ctx->d.sites * sizeof(int));
+  return PLG_OK;
+}
 int plg_set_pmatrix(plg_context_t * ctx, unsigned int matrix_index, const double * pmatrix)
 {
   if (matrix_index >= ctx->d.prob_matrices) return PLG_E_INVALID;
@@ -276,6 +282,12 @@ int plg_update_sumtable(plg_context_t * ctx, unsigned int parent_clv_index, unsi
   else
     touch_in(left_terms, R * K * Kp * sizeof(double));
   if (host_copy) touch_out(host_copy, ctx->d.sites * span(ctx) * sizeof(double), 0);
+  return PLG_OK;
+}
+int plg_set_sumtable(plg_context_t * ctx, const void * key, const double * table)
+{
+  MAYBE_FAIL();
+  touch_in(table, (size_t)ctx->d.sites * span(ctx) * sizeof(double));
   return PLG_OK;
 }
 int plg_free_sumtable(plg_context_t * ctx, const void * key) { return PLG_OK; }

@@ -79,4 +79,4 @@ def test_host_layer_against_the_null_device(tmp_path_factory):
                                       PLL_GPU_MIRROR=mirror))
         assert run.returncode == 0, run.stderr[-4000:]
         m = re.search(r"scenarios=(\d+) refused=(\d+)", run.stderr)
-        assert m and int(m.group(1)) == 360 and int(m.group(2)) == 216, run.stderr[-500:]
+        assert m and int(m.group(1)) == 576 and int(m.group(2)) == 0, run.stderr[-500:]
