@@ -245,6 +245,20 @@ PLL_EXPORT int plg_root_loglikelihood(plg_context_t * ctx,
                                       double * persite_lnl,
                                       double * logl_out);
 
+/* plg_root_loglikelihood with one scaler count per pattern supplied by the caller (host array of
+ * ctx->sites entries) instead of a scale buffer: with PLL_ATTRIB_RATE_SCALERS the reference's root
+ * kernels read element n of the [site][rate] array for pattern n (src/core_likelihood_avx.c:176-178),
+ * which on a partition cut into pattern slices lives in another slice - the host layer gathers the
+ * counts and hands every slice its own. */
+PLL_EXPORT int plg_root_loglikelihood_counts(plg_context_t * ctx,
+                                             unsigned int clv_index,
+                                             const unsigned int * site_counts,
+                                             const double * freqs,
+                                             const double * rate_weights,
+                                             const double * prop_invar,
+                                             double * persite_lnl,
+                                             double * logl_out);
+
 /* replaces: pll_core_update_sumtable_ii / _ti (reference src/core_derivatives.c:125-446,
  * src/core_derivatives_avx.c:25-207,462-645, src/core_derivatives_avx2.c:24-521).
  * `eigenvecs` is [rate_cats][states][states_padded] gathered by params_indices.  `left_terms`

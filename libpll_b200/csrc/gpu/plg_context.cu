@@ -126,7 +126,7 @@ extern "C" int plg_create(const plg_dims_t * dims, int device, plg_context_t ** 
   ctx->clv_first = ctx->pattern_tip ? dims->tips : 0;
   ctx->clv = NULL; ctx->scalers = NULL; ctx->tipchars = NULL; ctx->pmatrix = NULL;
   ctx->weights = NULL; ctx->invariant = NULL; ctx->has_invariant = false;
-  ctx->maxstates = 0; ctx->log2_maxstates = 0; ctx->tipmap_epoch = 0;
+  ctx->maxstates = 0; ctx->log2_maxstates = 0; ctx->tipmap_epoch = 0; ctx->root_counts = NULL;
   memset(ctx->tipmap, 0, sizeof(ctx->tipmap));
   ctx->stage_host = NULL; ctx->stage_dev = NULL; ctx->stage_size = 0; ctx->stage_off = 0;
   ctx->tables = NULL; ctx->tables_cap = 0; ctx->partials = NULL; ctx->partials_cap = 0;
@@ -297,6 +297,7 @@ extern "C" void plg_destroy(plg_context_t * ctx)
   cudaFree(ctx->pmatrix);
   cudaFree(ctx->weights);
   cudaFree(ctx->invariant);
+  cudaFree(ctx->root_counts);
   cudaFree(ctx->stage_dev);
   cudaFree(ctx->tables);
   cudaFree(ctx->partials);

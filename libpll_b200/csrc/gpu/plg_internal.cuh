@@ -134,6 +134,7 @@ struct plg_context
 
   unsigned int maxstates;
   unsigned int log2_maxstates;
+  unsigned int * root_counts;      /* per-pattern counts of plg_root_loglikelihood_counts (lazy) */
   unsigned long long tipmap_epoch; /* bumped when the map's content changes: part of the graph-cache key */
   unsigned int tipmap[PLL_ASCII_SIZE];
 

@@ -779,24 +779,17 @@ extern "C" int plg_edge_loglikelihood(plg_context_t * ctx, unsigned int parent_c
   return fetch_result(ctx, persite_lnl, logl_out);
 }
 
-extern "C" int plg_root_loglikelihood(plg_context_t * ctx, unsigned int clv_index,
-                                      int scaler_index, const double * freqs,
-                                      const double * rate_weights, const double * prop_invar,
-                                      double * persite_lnl, double * logl_out)
+/* root log-likelihood with the scaler counts at `pscale` (device; NULL: none) */
+static int root_loglikelihood(plg_context * ctx, unsigned int clv_index, const unsigned int * pscale,
+                              const double * freqs, const double * rate_weights, const double * prop_invar,
+                              double * persite_lnl, double * logl_out)
 {
-  PLG_CHECK_CTX(ctx);
-  if (clv_index < ctx->clv_first || clv_index >= ctx->d.tips + ctx->d.clv_buffers ||
-      scaler_index >= (int)ctx->d.scale_buffers || !logl_out)
-  {
-    plg_set_error("plg_root_loglikelihood: index out of range");
-    return PLG_E_INVALID;
-  }
   if (!plg_fast_path(ctx))
   {
     GenLnl g;
     memset(&g, 0, sizeof(g));
     g.clvp = plg_clv_ptr(ctx, clv_index);
-    g.pscale = plg_scaler_ptr(ctx, scaler_index);
+    g.pscale = pscale;
     g.root = 1;
     return plg_gen_loglikelihood(ctx, g, freqs, rate_weights, prop_invar, persite_lnl, logl_out);
   }
@@ -809,7 +802,7 @@ extern "C" int plg_root_loglikelihood(plg_context_t * ctx, unsigned int clv_inde
   rc = common_args(ctx, a, persite_lnl, &nblocks);
   if (rc) return rc;
   a.clvp = plg_clv_ptr(ctx, clv_index);
-  a.pscale = plg_scaler_ptr(ctx, scaler_index);
+  a.pscale = pscale;
   /* the root kernels index the scaler per site even in per-rate mode
    * (reference src/core_likelihood_avx.c:176-178) */
   a.per_rate_scaling = 0;
@@ -824,4 +817,46 @@ extern "C" int plg_root_loglikelihood(plg_context_t * ctx, unsigned int clv_inde
   }
   PLG_LAUNCH_CHECK(ctx);
   return fetch_result(ctx, persite_lnl, logl_out);
+}
+
+extern "C" int plg_root_loglikelihood(plg_context_t * ctx, unsigned int clv_index,
+                                      int scaler_index, const double * freqs,
+                                      const double * rate_weights, const double * prop_invar,
+                                      double * persite_lnl, double * logl_out)
+{
+  PLG_CHECK_CTX(ctx);
+  if (clv_index < ctx->clv_first || clv_index >= ctx->d.tips + ctx->d.clv_buffers ||
+      scaler_index >= (int)ctx->d.scale_buffers || !logl_out)
+  {
+    plg_set_error("plg_root_loglikelihood: index out of range");
+    return PLG_E_INVALID;
+  }
+  return root_loglikelihood(ctx, clv_index, plg_scaler_ptr(ctx, scaler_index), freqs, rate_weights, prop_invar,
+                            persite_lnl, logl_out);
+}
+
+/* The same with one scaler count per pattern handed over by the caller (host array, sites
+ * entries).  With per-rate scalers the reference's root kernels read element n of the
+ * [site][rate] array for pattern n (src/core_likelihood_avx.c:176-178); on a partition cut into
+ * pattern slices that element lives in another slice, so the host layer collects the counts
+ * (libpll_b200/csrc/host/pll_devices.c) and passes each slice its own. */
+extern "C" int plg_root_loglikelihood_counts(plg_context_t * ctx, unsigned int clv_index,
+                                             const unsigned int * site_counts, const double * freqs,
+                                             const double * rate_weights, const double * prop_invar,
+                                             double * persite_lnl, double * logl_out)
+{
+  PLG_CHECK_CTX(ctx);
+  if (clv_index < ctx->clv_first || clv_index >= ctx->d.tips + ctx->d.clv_buffers || !site_counts || !logl_out)
+  {
+    plg_set_error("plg_root_loglikelihood_counts: invalid argument");
+    return PLG_E_INVALID;
+  }
+  if (!ctx->root_counts)
+    PLG_CUDA(cudaMalloc(&ctx->root_counts, (size_t)ctx->d.sites * sizeof(unsigned int)));
+  /* pageable source: consumed when the call returns */
+  PLG_CUDA(cudaMemcpyAsync(ctx->root_counts, site_counts, (size_t)ctx->d.sites * sizeof(unsigned int),
+                           cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.h2d_bytes += (size_t)ctx->d.sites * sizeof(unsigned int);
+  return root_loglikelihood(ctx, clv_index, ctx->root_counts, freqs, rate_weights, prop_invar, persite_lnl,
+                            logl_out);
 }

@@ -551,6 +551,7 @@ struct root_args
   const double * freqs, * rate_weights, * prop_invar;
   double * persite_lnl;
   double part[PLLG_MAX_DEVICES];
+  const unsigned int * flat; /* see pllg_dev_root_loglikelihood; NULL: the slices' own scale buffers */
 };
 
 static int root_job(pllg_partition_t * g, unsigned int d, void * p)
@@ -558,6 +559,10 @@ static int root_job(pllg_partition_t * g, unsigned int d, void * p)
   struct root_args * a = (struct root_args *)p;
   int rc = g->grouped ? PLG_OK : begin_deferred(g, d);
   if (rc) return rc;
+  if (a->flat)
+    return plg_root_loglikelihood_counts(g->ctxs[d], a->clv_index, a->flat + g->lo[d], a->freqs, a->rate_weights,
+                                         a->prop_invar, a->persite_lnl ? a->persite_lnl + g->lo[d] : NULL,
+                                         &a->part[d]);
   return plg_root_loglikelihood(g->ctxs[d], a->clv_index, a->scaler_index, a->freqs, a->rate_weights, a->prop_invar,
                                 a->persite_lnl ? a->persite_lnl + g->lo[d] : NULL, &a->part[d]);
 }
@@ -566,12 +571,43 @@ int pllg_dev_root_loglikelihood(pllg_partition_t * g, unsigned int clv_index, in
                                 const double * freqs, const double * rate_weights,
                                 const double * prop_invar, double * persite_lnl, double * logl_out)
 {
-  struct root_args a = {clv_index, scaler_index, freqs, rate_weights, prop_invar, persite_lnl, {0}};
+  struct root_args a = {clv_index, scaler_index, freqs, rate_weights, prop_invar, persite_lnl, {0}, NULL};
+  unsigned int * flat = NULL;
+  const unsigned int R = g->pub.rate_cats;
+  if (g->ndev > 1 && (g->pub.attributes & PLL_ATTRIB_RATE_SCALERS) && R > 1 && scaler_index != PLL_SCALE_BUFFER_NONE)
+  {
+    /* The reference's root kernels read element n of the per-rate scaler array [site][rate] for
+     * pattern n (src/core_likelihood_avx.c:176-178, src/core_likelihood.c:197-198): the count of
+     * pattern n / R at rate n % R.  For a slice that starts at pattern lo > 0 those elements belong
+     * to an earlier slice, so they are collected here (the first ceil(sites / R) patterns hold them
+     * all) and every slice gets the elements [lo, hi) of the flat array. */
+    const unsigned int need = (g->sites_alloc + R - 1) / R;
+    flat = (unsigned int *)malloc((size_t)need * R * sizeof(unsigned int));
+    if (!flat) return PLG_E_NOMEM;
+    int grc = pllg_dev_get_scaler_sites(g, (unsigned int)scaler_index, 0, need, flat);
+    if (grc)
+    {
+      free(flat);
+      return grc;
+    }
+    a.flat = flat;
+  }
   int rc = group_begin(g);
-  if (rc) return rc;
+  if (rc)
+  {
+    free(flat);
+    return rc;
+  }
   rc = run_on_slices(g, root_job, &a);
-  if (g->grouped) return group_finish(g, rc, logl_out, NULL);
-  if ((rc = collect_all(g, rc))) return rc;
+  if (g->grouped)
+  {
+    rc = group_finish(g, rc, logl_out, NULL);
+    free(flat);
+    return rc;
+  }
+  rc = collect_all(g, rc);
+  free(flat);
+  if (rc) return rc;
   double total = a.part[0];
   for (unsigned int d = 1; d < g->ndev; ++d) total += a.part[d];
   *logl_out = total;

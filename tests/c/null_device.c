@@ -268,6 +268,16 @@ int plg_root_loglikelihood(plg_context_t * ctx, unsigned int clv_index, int scal
   if (persite_lnl) touch_out(persite_lnl, ctx->active_sites * sizeof(double), 0);
   return deliver(ctx, logl_out, NULL);
 }
+int plg_root_loglikelihood_counts(plg_context_t * ctx, unsigned int clv_index, const unsigned int * site_counts,
+                                  const double * freqs, const double * rate_weights, const double * prop_invar,
+                                  double * persite_lnl, double * logl_out)
+{
+  MAYBE_FAIL();
+  touch_in(site_counts, ctx->d.sites * sizeof(unsigned int));
+  touch_model(ctx, freqs, rate_weights, prop_invar);
+  if (persite_lnl) touch_out(persite_lnl, ctx->active_sites * sizeof(double), 0);
+  return deliver(ctx, logl_out, NULL);
+}
 int plg_update_sumtable(plg_context_t * ctx, unsigned int parent_clv_index, unsigned int child_clv_index,
                         int parent_scaler_index, int child_scaler_index, const double * eigenvecs,
                         const double * left_terms, const void * key, double * host_copy)

@@ -97,8 +97,8 @@ def test_ascbias_with_scaling(gpu_lib, ref_lib):
     pr.destroy()
 
 
-@pytest.mark.parametrize("pattern_tip", [True, False])
-def test_ascbias_with_per_rate_scalers(gpu_lib, ref_lib, pattern_tip):
+@pytest.mark.parametrize("pattern_tip,slices,sites", [(True, 1, 42), (False, 1, 42), (True, 3, 150)])
+def test_ascbias_with_per_rate_scalers(gpu_lib, ref_lib, monkeypatch, pattern_tip, slices, sites):
     """PLL_ATTRIB_RATE_SCALERS with the correction: the reference reads element `sites + n` of a
     scaler array laid out [site][rate] (src/likelihood.c:91, :378-381, src/core_derivatives.c:684-685),
     i.e. the count of pattern (sites + n) / R at rate (sites + n) % R; the drop-in returns the same
@@ -106,9 +106,12 @@ def test_ascbias_with_per_rate_scalers(gpu_lib, ref_lib, pattern_tip):
     from libpll_b200.binding import PLL_ATTRIB_RATE_SCALERS
     from test_parity_gpu import _caterpillar
 
-    w = _caterpillar(300, 42, 4, seed=5)
+    if slices > 1:  # the flat elements then come from whichever pattern slices hold them
+        monkeypatch.setenv("PLL_GPU_DEVICES", str(slices))
+    w = _caterpillar(300, sites, 4, seed=5)
     extra = PLL_ATTRIB_RATE_SCALERS | (PLL_ATTRIB_PATTERN_TIP if pattern_tip else 0)
     pg, pr, pidx = _pair(gpu_lib, ref_lib, w, extra, PLL_ATTRIB_ARCH_AVX2)
+    assert gpu_lib.pll_gpu_partition_devices(pg.ptr) == slices
     for p in (pg, pr):
         p.update_prob_matrices(pidx, w.matrix_indices, w.branch_lengths)
         p.update_partials(w.ops)

@@ -130,3 +130,42 @@ def test_slices_follow_the_environment_and_reject_asc_bias(gpu_lib, monkeypatch)
     assert abs(lnl1 - lnl3) <= 1e-12 * abs(lnl1)
 
     assert gpu_lib.pll_gpu_set_devices(-1) == 0 and gpu_lib.pll_gpu_set_devices(17) == 0
+
+
+@pytest.mark.parametrize("states,tips,sites", [(4, 300, 150), (4, 300, 192), (20, 140, 150)])
+def test_root_loglikelihood_of_a_sliced_partition_with_per_rate_scalers(gpu_lib, ref_lib, states, tips, sites):
+    """The reference's root kernels read element n of the per-rate scaler array [site][rate] for
+    pattern n (src/core_likelihood_avx.c:176-178, src/core_likelihood.c:197-198) - the count of pattern
+    n / R at rate n % R.  On a sliced partition those elements live in an earlier slice; the host
+    layer gathers them (pllg_dev_root_loglikelihood).  A long caterpillar, so that the counts are not
+    zero: root and edge log-likelihood and the per-pattern values against the reference."""
+    from test_parity_gpu import _caterpillar
+
+    w = _caterpillar(tips, sites, states, seed=5)
+    rates = ref_lib.gamma_rates(w.alpha, w.rate_cats)
+    extra = PLL_ATTRIB_PATTERN_TIP | PLL_ATTRIB_RATE_SCALERS
+    pr, pidx = S.build_partition(ref_lib, w, PLL_ATTRIB_ARCH_AVX2 | extra, rates=rates)
+    assert gpu_lib.pll_gpu_set_devices(3) == 1
+    try:
+        pg, _ = S.build_partition(gpu_lib, w, PLL_ATTRIB_ARCH_GPU | extra, rates=rates)
+    finally:
+        gpu_lib.pll_gpu_set_devices(0)
+    assert gpu_lib.pll_gpu_partition_devices(pg.ptr) == 3
+    for p in (pg, pr):
+        p.update_prob_matrices(pidx, w.matrix_indices, w.branch_lengths)
+        p.update_partials(w.ops)
+    top = w.tips + w.inner - 1
+    counts = np.asarray(pr.get_scaler(w.scaler_of(top))).ravel()
+    assert np.array_equal(counts, np.asarray(pg.get_scaler(w.scaler_of(top))).ravel())
+    assert counts[:sites].any() and len(set(counts[:sites].tolist())) > 1   # the flat elements differ
+    sg, sr = np.zeros(sites), np.zeros(sites)
+    rg = pg.root_loglikelihood(top, w.scaler_of(top), pidx, persite=sg)
+    rr = pr.root_loglikelihood(top, w.scaler_of(top), pidx, persite=sr)
+    assert np.isfinite(rr) and abs(rg - rr) <= RTOL * abs(rr), (rg, rr)
+    assert np.allclose(sg, sr, rtol=RTOL, atol=0)
+    a, b = w.root_a, w.root_b
+    args = (a, w.scaler_of(a), b, w.scaler_of(b), w.root_matrix, pidx)
+    eg, er = pg.edge_loglikelihood(*args), pr.edge_loglikelihood(*args)
+    assert abs(eg - er) <= RTOL * abs(er), (eg, er)
+    pg.destroy()
+    pr.destroy()
