@@ -11,17 +11,18 @@ import numpy as np
 import pytest
 
 from libpll_b200 import trees as T
-from libpll_b200.binding import OP_DTYPE, PLL_ATTRIB_ARCH_AVX2, PLL_ATTRIB_ARCH_GPU, PLL_ATTRIB_PATTERN_TIP
+from libpll_b200.binding import (OP_DTYPE, PLL_ATTRIB_ARCH_AVX2, PLL_ATTRIB_ARCH_GPU, PLL_ATTRIB_PATTERN_TIP,
+                                 PLL_ATTRIB_RATE_SCALERS)
 from test_utree_cpu import random_newick
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-10
 
 
-def _partition(lib, arch, tree, seqs, sites):
+def _partition(lib, arch, tree, seqs, sites, extra=0):
     part = lib.partition(tips=tree.tips, clv_buffers=tree.inner, states=4, sites=sites, rate_matrices=1,
                          prob_matrices=2 * tree.tips - 3, rate_cats=4, scale_buffers=tree.inner,
-                         attributes=arch | PLL_ATTRIB_PATTERN_TIP)
+                         attributes=arch | PLL_ATTRIB_PATTERN_TIP | extra)
     part.set_frequencies(0, [0.3, 0.2, 0.25, 0.25])
     part.set_subst_params(0, [1.2, 3.1, 0.9, 1.1, 3.3, 1.0])
     part.set_category_rates(lib.gamma_rates(0.7, 4))
@@ -30,14 +31,23 @@ def _partition(lib, arch, tree, seqs, sites):
     return part
 
 
-def test_partial_traversals_follow_the_reference(gpu_lib, ref_lib):
+@pytest.mark.parametrize("tips,sites,rate_scalers,slices", [(90, 1200, False, 1), (600, 200, False, 1), (600, 200, True, 1),
+                                                            (600, 300, False, 3), (600, 300, True, 3)])
+def test_partial_traversals_follow_the_reference(gpu_lib, ref_lib, tips, sites, rate_scalers, slices):
+    """600 tips: deep enough that every re-rooting also re-accumulates scaler counts (per site or per
+    rate) along the re-oriented path; 3 slices: one partition over three device contexts"""
     lib = T.bind(gpu_lib)
-    tips, sites = 90, 1200
     tree = T.Tree(lib, newick=random_newick(tips, 17))
     rng = np.random.default_rng(4)
     seqs = {f"t{i}": "".join(rng.choice(list("ACGT-R"), sites, p=[.28, .22, .24, .22, .03, .01])) for i in range(tips)}
-    pg = _partition(gpu_lib, PLL_ATTRIB_ARCH_GPU, tree, seqs, sites)
-    pr = _partition(ref_lib, PLL_ATTRIB_ARCH_AVX2, tree, seqs, sites)
+    extra = PLL_ATTRIB_RATE_SCALERS if rate_scalers else 0
+    assert gpu_lib.pll_gpu_set_devices(slices) == 1
+    try:
+        pg = _partition(gpu_lib, PLL_ATTRIB_ARCH_GPU, tree, seqs, sites, extra)
+    finally:
+        gpu_lib.pll_gpu_set_devices(0)
+    assert gpu_lib.pll_gpu_partition_devices(pg.ptr) == slices
+    pr = _partition(ref_lib, PLL_ATTRIB_ARCH_AVX2, tree, seqs, sites, extra)
     pidx = np.zeros(4, np.uint32)
 
     oriented = {}  # record address -> is the CLV of its node oriented along this record?
@@ -86,6 +96,8 @@ def test_partial_traversals_follow_the_reference(gpu_lib, ref_lib):
         assert abs(g - r) <= RTOL * abs(r), (g, r)
         assert abs(g - g0) <= 1e-9 * abs(g0), "moving the virtual root must not change the likelihood"
     assert 0 < np.mean(sizes) < tree.inner / 2, "the traversals should really be partial"
+    if tips >= 600:
+        assert sum(int(np.asarray(pr.get_scaler(k)).sum()) for k in range(tree.inner)) > 0
     pg.destroy()
     pr.destroy()
     tree.destroy()
