@@ -103,3 +103,51 @@ def test_switch_combinations(gpu_lib, ref_lib, states, kind, pattern_tip, rate_s
         pg.destroy()
         pr.destroy()
     assert checked >= 2 and scaled > 0
+
+
+@pytest.mark.parametrize("slices", [1, 3])
+@pytest.mark.parametrize("rate_scalers", [False, True])
+@pytest.mark.parametrize("recycled", [False, True])
+@pytest.mark.parametrize("states,variant", [(4, "default"), (20, "default"), (20, "lg4m")])
+def test_list_shapes_and_models(gpu_lib, ref_lib, states, variant, recycled, rate_scalers, slices):
+    """The other axis: lists that recycle CLV / scaler slots (32 slots for 500 / 160 taxa: WAR / WAW
+    hazards, dead stores, the 20-state whole-list kernel) x one / four rate matrices (LG4M: a
+    different matrix and frequency vector per category) x scaler mode x slices x tip kind, each list
+    run twice (the second time as a replayed CUDA graph, after new branch lengths)."""
+    w = S.make_workload(500 if states == 4 else 160, 300, states=states, seed=31)
+    w.branch_lengths = np.full(w.prob_matrices, 2.0)
+    if recycled:
+        w = S.recycle_slots(w, 32)
+    rates = ref_lib.gamma_rates(w.alpha, w.rate_cats)
+    for pattern_tip in (True, False):
+        extra = (PLL_ATTRIB_PATTERN_TIP if pattern_tip else 0) | (PLL_ATTRIB_RATE_SCALERS if rate_scalers else 0)
+        assert gpu_lib.pll_gpu_set_devices(slices) == 1
+        try:
+            pg, pidx = S.build_partition(gpu_lib, w, PLL_ATTRIB_ARCH_GPU | extra, variant=variant, rates=rates)
+        finally:
+            gpu_lib.pll_gpu_set_devices(0)
+        pr, _ = S.build_partition(ref_lib, w, PLL_ATTRIB_ARCH_AVX2 | extra, variant=variant, rates=rates)
+        a, b = w.root_a, w.root_b
+        for rep in range(2):
+            for p in (pg, pr):
+                p.update_prob_matrices(pidx, w.matrix_indices, w.branch_lengths * (1.0 + 0.1 * rep))
+                p.update_partials(w.ops)
+            sg, sr = np.zeros(w.sites), np.zeros(w.sites)
+            args = (a, w.scaler_of(a), b, w.scaler_of(b), w.root_matrix, pidx)
+            eg, er = pg.edge_loglikelihood(*args, persite=sg), pr.edge_loglikelihood(*args, persite=sr)
+            assert np.isfinite(er) and abs(eg - er) <= RTOL * abs(er), ("edge", pattern_tip, rep, eg, er)
+            assert np.allclose(sg, sr, rtol=RTOL, atol=0), ("edge per pattern", pattern_tip, rep)
+            inner = a if a >= w.tips else b
+            rg = pg.root_loglikelihood(inner, w.scaler_of(inner), pidx)
+            rr = pr.root_loglikelihood(inner, w.scaler_of(inner), pidx)
+            assert np.isfinite(rr) and abs(rg - rr) <= RTOL * abs(rr), ("root", pattern_tip, rep, rg, rr)
+            tg, tr = pg.new_sumtable(), pr.new_sumtable()
+            pg.update_sumtable(a, b, w.scaler_of(a), w.scaler_of(b), pidx, tg)
+            pr.update_sumtable(a, b, w.scaler_of(a), w.scaler_of(b), pidx, tr)
+            dg = pg.likelihood_derivatives(w.scaler_of(a), w.scaler_of(b), 0.3, pidx, tg)
+            dr = pr.likelihood_derivatives(w.scaler_of(a), w.scaler_of(b), 0.3, pidx, tr)
+            scale = max(abs(dr[0]), float(w.weights.sum()) * 1e-3)
+            assert _same(dg[0], dr[0], scale) and _same(dg[1], dr[1], max(abs(dr[1]), scale)), (pattern_tip, rep, dg, dr)
+        assert sum(int(np.asarray(pr.get_scaler(w.scaler_of(x))).sum()) for x in (a, b) if x >= w.tips) > 0
+        pg.destroy()
+        pr.destroy()
